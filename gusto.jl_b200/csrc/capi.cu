@@ -1,0 +1,524 @@
+// libgusto_b200.so: CUDA kernels (sm_100a) + the C ABI declared in include/gusto_b200.h.
+// Product path only: there is no CPU fallback; every entry point fails with GUSTO_E_NODEVICE / GUSTO_E_CUDA when
+// no B200 is usable.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/gusto_b200.h"
+#include "common.cuh"
+#include "linearize.cuh"
+#include "ipm.cuh"
+#include "evaluate.cuh"
+
+using namespace gusto;
+
+// ------------------------------------------------------------------------------------------ TMA helpers
+namespace {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ kernels
+constexpr int LIN_KNOTS_PER_CTA = 8;      // one warp per knot
+constexpr int IPM_THREADS = 64;
+constexpr int EVAL_THREADS = 128;
+
+// K1+K2.  Grid: ceil(B*N/8) CTAs of 8 warps.  The 8 knots' states and controls are contiguous in HBM
+// ([B][N][NX] knot-major) and are staged into shared memory with two TMA bulk copies per CTA.
+template <int M>
+__global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p) {
+  using T = Traits<M>;
+  constexpr int NX = T::NX, NU = T::NU, KPC = LIN_KNOTS_PER_CTA;
+  __shared__ alignas(16) double sx[KPC * NX];
+  __shared__ alignas(16) double su[KPC * NU];
+  __shared__ double ws[KPC][NX * NX + NX];
+  __shared__ alignas(8) unsigned long long mbar;
+  const BatchDesc& d = *dp;
+  const int total = d.B * d.N;
+  const int k0 = blockIdx.x * KPC;
+  const int nk = (total - k0) < KPC ? (total - k0) : KPC;
+  const uint32_t bx = (uint32_t)(nk * NX * sizeof(double)), bu = (uint32_t)(nk * NU * sizeof(double));
+  const double* gx = p.Xp + (size_t)k0 * NX;
+  const double* gu = p.Up + (size_t)k0 * NU;
+  const bool use_tma = (bx % 16u == 0u) && (bu % 16u == 0u);
+  if (use_tma) {
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, bx + bu);
+      tma_bulk_g2s(sx, gx, bx, &mbar);
+      tma_bulk_g2s(su, gu, bu, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+  } else {   // ragged tail CTA whose byte count is not a multiple of 16
+    for (int i = threadIdx.x; i < nk * NX; i += blockDim.x) sx[i] = gx[i];
+    for (int i = threadIdx.x; i < nk * NU; i += blockDim.x) su[i] = gu[i];
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5;
+  if (warp < nk) {
+    const int gk = k0 + warp;
+    linearize_knot<M>(d, p, gk / d.N, gk % d.N, sx + warp * NX, su + warp * NU, ws[warp]);
+  }
+}
+
+// K3.  Grid: B CTAs (one problem instance each).
+template <int M>
+__global__ void __launch_bounds__(IPM_THREADS) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
+                                                          double* scratch, size_t stride, double* info) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  if (p.active && !p.active[b]) return;      // converged / failed instance: frozen (CTA-uniform exit)
+  ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem, info + (size_t)b * IPM_NINFO);
+}
+
+// K4.  Grid: B CTAs.
+template <int M>
+__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
+  using T = Traits<M>;
+  __shared__ double red[EVAL_THREADS];
+  const int b = blockIdx.x;
+  if (p.active && !p.active[b]) return;
+  evaluate_instance<M>(*dp, p, b, p.Xn + (size_t)b * dp->N * T::NX, p.Un + (size_t)b * dp->N * T::NU,
+                       out + (size_t)b * EVAL_NOUT, red);
+}
+
+// accept: candidate -> accepted trajectory for flagged instances; install next omega / Delta.
+__global__ void accept_kernel(BatchPtrs p, int N, int nx, int nu, const uint8_t* accept, const double* omega,
+                              const double* delta) {
+  const int b = blockIdx.x;
+  if (accept[b]) {
+    const size_t ox = (size_t)b * N * nx, ou = (size_t)b * N * nu;
+    for (int i = threadIdx.x; i < N * nx; i += blockDim.x) p.Xp[ox + i] = p.Xn[ox + i];
+    for (int i = threadIdx.x; i < N * nu; i += blockDim.x) p.Up[ou + i] = p.Un[ou + i];
+  }
+  if (threadIdx.x == 0) {
+    if (omega) p.omega[b] = omega[b];
+    if (delta) p.delta[b] = delta[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ context
+struct gusto_ctx {
+  gusto_config cfg;
+  int nx = 0, nu = 0;
+  BatchDesc hdesc;
+  BatchDesc* ddesc = nullptr;
+  BatchPtrs p;
+  double *d_tf = nullptr, *d_xinit = nullptr, *d_glo = nullptr, *d_ghi = nullptr;
+  double *d_scratch = nullptr, *d_info = nullptr, *d_eval = nullptr, *d_omega_in = nullptr, *d_delta_in = nullptr;
+  uint8_t* d_accept = nullptr;
+  uint8_t* d_active = nullptr;
+  size_t scratch_stride = 0;
+  int ipm_smem = 0;
+  IpmParams prm;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t tev[2] = {};
+  bool timed[4] = {false, false, false, false};
+  int64_t launches = 0;
+  std::string err;
+};
+
+static std::string g_err;
+
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return GUSTO_E_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+static void dims_of(int model, int* nx, int* nu) {
+  switch (model) {
+    case DUBINS: *nx = 3; *nu = 1; break;
+    case FREEFLYER_SE2: *nx = 6; *nu = 3; break;
+    case ASTROBEE_SE3: *nx = 12; *nu = 6; break;
+    case ASTROBEE_SE3_MANIFOLD: *nx = 13; *nu = 6; break;
+    default: *nx = 0; *nu = 0;
+  }
+}
+static size_t scratch_doubles_of(int model, int N, int n_obs) {
+  switch (model) {
+    case DUBINS: return IpmLayout<DUBINS>::scratch_doubles(N, 0);
+    case FREEFLYER_SE2: return IpmLayout<FREEFLYER_SE2>::scratch_doubles(N, n_obs);
+    case ASTROBEE_SE3: return IpmLayout<ASTROBEE_SE3>::scratch_doubles(N, n_obs);
+    default: return IpmLayout<ASTROBEE_SE3_MANIFOLD>::scratch_doubles(N, n_obs);
+  }
+}
+static int ipm_smem_doubles_of(int model, int N) {
+  switch (model) {
+    case DUBINS: return IpmLayout<DUBINS>::smem_doubles(N, IPM_THREADS);
+    case FREEFLYER_SE2: return IpmLayout<FREEFLYER_SE2>::smem_doubles(N, IPM_THREADS);
+    case ASTROBEE_SE3: return IpmLayout<ASTROBEE_SE3>::smem_doubles(N, IPM_THREADS);
+    default: return IpmLayout<ASTROBEE_SE3_MANIFOLD>::smem_doubles(N, IPM_THREADS);
+  }
+}
+
+extern "C" {
+
+int32_t gusto_version(void) { return 100; }
+
+const char* gusto_last_error(const gusto_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const double* obs_a, const double* obs_b,
+                     gusto_ctx** out) {
+  if (!cfg || !out) { g_err = "gusto_create: null argument"; return GUSTO_E_ARG; }
+  *out = nullptr;
+  int nx, nu;
+  dims_of(cfg->model_id, &nx, &nu);
+  if (nx == 0) { g_err = "gusto_create: unknown model_id"; return GUSTO_E_ARG; }
+  if (cfg->N < 3 || cfg->B < 1) { g_err = "gusto_create: need N >= 3 and B >= 1"; return GUSTO_E_ARG; }
+  if (cfg->n_obs < 0 || cfg->n_obs > MAX_OBS) { g_err = "gusto_create: n_obs out of range (max 64)"; return GUSTO_E_ARG; }
+  if (cfg->n_obs > 0 && (!obs_kind || !obs_a || !obs_b)) { g_err = "gusto_create: obstacle table missing"; return GUSTO_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_err = "gusto_create: no CUDA device (this library has no CPU path)";
+    return GUSTO_E_NODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_err = "gusto_create: bad device ordinal"; return GUSTO_E_ARG; }
+  gusto_ctx* ctx = new (std::nothrow) gusto_ctx();
+  if (!ctx) { g_err = "gusto_create: out of host memory"; return GUSTO_E_ALLOC; }
+  ctx->cfg = *cfg;
+  ctx->nx = nx; ctx->nu = nu;
+  auto fail = [&](int code) { g_err = ctx->err; gusto_destroy(ctx); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(GUSTO_E_CUDA); }
+  BatchDesc& h = ctx->hdesc;
+  memset(&h, 0, sizeof(h));
+  h.model_id = cfg->model_id; h.N = cfg->N; h.B = cfg->B; h.n_obs = (cfg->model_id == DUBINS) ? 0 : cfg->n_obs;
+  for (int i = 0; i < 16; ++i) h.rp[i] = cfg->robot_params[i];
+  for (int i = 0; i < 10; ++i) h.sp[i] = cfg->scp_params[i];
+  for (int i = 0; i < MAX_NX; ++i) h.goal_type[i] = i < nx ? cfg->goal_type[i] : 0;
+  for (int i = 0; i < h.n_obs; ++i) {
+    h.obs_kind[i] = obs_kind[i];
+    for (int a = 0; a < 3; ++a) { h.obs_a[i][a] = obs_a[i * 3 + a]; h.obs_b[i][a] = obs_b[i * 3 + a]; }
+  }
+  ctx->prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
+  ctx->prm.nref = cfg->ipm_nref > 0 ? cfg->ipm_nref : 2;
+  ctx->prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
+  ctx->prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : 1e-6;
+  ctx->prm.delta_d = cfg->ipm_delta_d > 0 ? cfg->ipm_delta_d : 1e-10;
+
+  const size_t B = cfg->B, N = cfg->N, no = h.n_obs > 0 ? h.n_obs : 1;
+  auto alloc = [&](double** ptr, size_t n) {
+    if (cudaMalloc((void**)ptr, n * sizeof(double)) != cudaSuccess) { ctx->err = "cudaMalloc failed"; return false; }
+    return cudaMemsetAsync(*ptr, 0, n * sizeof(double), 0) == cudaSuccess;
+  };
+  bool ok = true;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreate(&ctx->tev[i]) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&ctx->ddesc, sizeof(BatchDesc)) == cudaSuccess;
+  ok = ok && cudaMemcpy(ctx->ddesc, &h, sizeof(BatchDesc), cudaMemcpyHostToDevice) == cudaSuccess;
+  BatchPtrs& p = ctx->p;
+  memset(&p, 0, sizeof(p));
+  ok = ok && alloc(&ctx->d_tf, B) && alloc(&ctx->d_xinit, B * nx) && alloc(&ctx->d_glo, B * nx) && alloc(&ctx->d_ghi, B * nx);
+  ok = ok && alloc(&p.Xp, B * N * nx) && alloc(&p.Up, B * N * nu) && alloc(&p.Xn, B * N * nx) && alloc(&p.Un, B * N * nu);
+  ok = ok && alloc(&p.omega, B) && alloc(&p.delta, B) && alloc(&ctx->d_omega_in, B) && alloc(&ctx->d_delta_in, B);
+  ok = ok && alloc(&p.f, B * N * nx) && alloc(&p.A, B * N * nx * nx) && alloc(&p.g, B * N * nx) && alloc(&p.rows, B * N * no * 5);
+  ctx->scratch_stride = scratch_doubles_of(cfg->model_id, (int)N, h.n_obs);
+  ok = ok && alloc(&ctx->d_scratch, B * ctx->scratch_stride);
+  ok = ok && alloc(&ctx->d_info, B * IPM_NINFO) && alloc(&ctx->d_eval, B * EVAL_NOUT);
+  ok = ok && cudaMalloc((void**)&ctx->d_accept, B) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&ctx->d_active, B) == cudaSuccess && cudaMemset(ctx->d_active, 1, B) == cudaSuccess;
+  if (!ok) { if (ctx->err.empty()) ctx->err = std::string("gusto_create: ") + cudaGetErrorString(cudaGetLastError()); return fail(GUSTO_E_ALLOC); }
+  p.active = ctx->d_active;
+  p.tf = ctx->d_tf; p.x_init = ctx->d_xinit; p.goal_lo = ctx->d_glo; p.goal_hi = ctx->d_ghi;
+  // initial penalties: omega0, Delta0
+  {
+    double* tmp = new double[2 * B];
+    for (size_t i = 0; i < B; ++i) { tmp[i] = cfg->scp_params[SP_OMEGA0]; tmp[B + i] = cfg->scp_params[SP_DELTA0]; }
+    cudaMemcpy(p.omega, tmp, B * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.delta, tmp + B, B * sizeof(double), cudaMemcpyHostToDevice);
+    delete[] tmp;
+  }
+  ctx->ipm_smem = ipm_smem_doubles_of(cfg->model_id, (int)N) * (int)sizeof(double);
+  cudaError_t e = cudaSuccess;
+  switch (cfg->model_id) {
+    case DUBINS: e = cudaFuncSetAttribute(ipm_kernel<DUBINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
+    case FREEFLYER_SE2: e = cudaFuncSetAttribute(ipm_kernel<FREEFLYER_SE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
+    case ASTROBEE_SE3: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
+    default: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3_MANIFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GUSTO_E_CUDA); }
+  if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "gusto_create: device sync failed"; return fail(GUSTO_E_CUDA); }
+  *out = ctx;
+  return GUSTO_OK;
+}
+
+int32_t gusto_destroy(gusto_ctx* ctx) {
+  if (!ctx) return GUSTO_OK;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  BatchPtrs& p = ctx->p;
+  void* ptrs[] = {ctx->ddesc, ctx->d_tf, ctx->d_xinit, ctx->d_glo, ctx->d_ghi, p.Xp, p.Up, p.Xn, p.Un, p.omega, p.delta,
+                  ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i) if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GUSTO_OK;
+}
+
+#define NEED(c) do { if (!ctx) { g_err = "null context"; return GUSTO_E_ARG; } if (!(c)) { ctx->err = "null argument"; return GUSTO_E_ARG; } } while (0)
+#define H2D(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream))
+
+int32_t gusto_set_problems(gusto_ctx* ctx, const double* x_init, const double* goal_lo, const double* goal_hi, const double* tf) {
+  NEED(x_init && goal_lo && goal_hi && tf);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B;
+  H2D(ctx->d_xinit, x_init, B * ctx->nx); H2D(ctx->d_glo, goal_lo, B * ctx->nx); H2D(ctx->d_ghi, goal_hi, B * ctx->nx);
+  H2D(ctx->d_tf, tf, B);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+static int32_t copy_traj(gusto_ctx* ctx, double* dX, double* dU, const double* X, const double* U, bool to_dev, double* hX, double* hU) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t nX = (size_t)ctx->cfg.B * ctx->cfg.N * ctx->nx, nU = (size_t)ctx->cfg.B * ctx->cfg.N * ctx->nu;
+  if (to_dev) { H2D(dX, X, nX); H2D(dU, U, nU); }
+  else { D2H(hX, dX, nX); D2H(hU, dU, nU); }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+int32_t gusto_set_trajectory(gusto_ctx* ctx, const double* X, const double* U) { NEED(X && U); return copy_traj(ctx, ctx->p.Xp, ctx->p.Up, X, U, true, nullptr, nullptr); }
+int32_t gusto_set_candidate(gusto_ctx* ctx, const double* X, const double* U) { NEED(X && U); return copy_traj(ctx, ctx->p.Xn, ctx->p.Un, X, U, true, nullptr, nullptr); }
+int32_t gusto_get_trajectory(gusto_ctx* ctx, double* X, double* U) { NEED(X && U); return copy_traj(ctx, ctx->p.Xp, ctx->p.Up, nullptr, nullptr, false, X, U); }
+int32_t gusto_get_candidate(gusto_ctx* ctx, double* X, double* U) { NEED(X && U); return copy_traj(ctx, ctx->p.Xn, ctx->p.Un, nullptr, nullptr, false, X, U); }
+
+int32_t gusto_set_penalties(gusto_ctx* ctx, const double* omega, const double* delta) {
+  NEED(omega && delta);
+  CK(cudaSetDevice(ctx->cfg.device));
+  H2D(ctx->p.omega, omega, ctx->cfg.B); H2D(ctx->p.delta, delta, ctx->cfg.B);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+static int32_t launch_linearize(gusto_ctx* ctx) {
+  const int total = ctx->cfg.B * ctx->cfg.N;
+  const int grid = (total + LIN_KNOTS_PER_CTA - 1) / LIN_KNOTS_PER_CTA;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  switch (ctx->cfg.model_id) {
+    case DUBINS: linearize_kernel<DUBINS><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
+    case FREEFLYER_SE2: linearize_kernel<FREEFLYER_SE2><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
+    case ASTROBEE_SE3: linearize_kernel<ASTROBEE_SE3><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
+    default: linearize_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timed[0] = true; ctx->launches++;
+  return GUSTO_OK;
+}
+static int32_t launch_solve(gusto_ctx* ctx) {
+  const int grid = ctx->cfg.B;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  switch (ctx->cfg.model_id) {
+    case DUBINS: ipm_kernel<DUBINS><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
+    case FREEFLYER_SE2: ipm_kernel<FREEFLYER_SE2><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
+    case ASTROBEE_SE3: ipm_kernel<ASTROBEE_SE3><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
+    default: ipm_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed[1] = true; ctx->launches++;
+  return GUSTO_OK;
+}
+static int32_t launch_evaluate(gusto_ctx* ctx) {
+  const int grid = ctx->cfg.B;
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  switch (ctx->cfg.model_id) {
+    case DUBINS: evaluate_kernel<DUBINS><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
+    case FREEFLYER_SE2: evaluate_kernel<FREEFLYER_SE2><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
+    case ASTROBEE_SE3: evaluate_kernel<ASTROBEE_SE3><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
+    default: evaluate_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timed[2] = true; ctx->launches++;
+  return GUSTO_OK;
+}
+
+int32_t gusto_linearize(gusto_ctx* ctx) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = launch_linearize(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_get_blocks(gusto_ctx* ctx, double* f, double* A, double* g, double* rows) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t BN = (size_t)ctx->cfg.B * ctx->cfg.N;
+  if (f) D2H(f, ctx->p.f, BN * ctx->nx);
+  if (A) D2H(A, ctx->p.A, BN * ctx->nx * ctx->nx);
+  if (g) D2H(g, ctx->p.g, BN * ctx->nx);
+  if (rows && ctx->hdesc.n_obs > 0) D2H(rows, ctx->p.rows, BN * ctx->hdesc.n_obs * 5);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_solve_subproblem(gusto_ctx* ctx, double* info) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = launch_solve(ctx);
+  if (rc) return rc;
+  if (info) D2H(info, ctx->d_info, (size_t)ctx->cfg.B * IPM_NINFO);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_evaluate(gusto_ctx* ctx, double* out) {
+  NEED(out);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = launch_evaluate(ctx);
+  if (rc) return rc;
+  D2H(out, ctx->d_eval, (size_t)ctx->cfg.B * EVAL_NOUT);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+static int32_t launch_accept(gusto_ctx* ctx, const uint8_t* acc_dev, const double* om_dev, const double* de_dev) {
+  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  accept_kernel<<<ctx->cfg.B, 128, 0, ctx->stream>>>(ctx->p, ctx->cfg.N, ctx->nx, ctx->nu, acc_dev, om_dev, de_dev);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  ctx->timed[3] = true; ctx->launches++;
+  return GUSTO_OK;
+}
+
+int32_t gusto_accept(gusto_ctx* ctx, const uint8_t* accept, const double* omega, const double* delta) {
+  NEED(accept);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B;
+  CK(cudaMemcpyAsync(ctx->d_accept, accept, B, cudaMemcpyHostToDevice, ctx->stream));
+  if (omega) H2D(ctx->d_omega_in, omega, B);
+  if (delta) H2D(ctx->d_delta_in, delta, B);
+  int32_t rc = launch_accept(ctx, ctx->d_accept, omega ? ctx->d_omega_in : nullptr, delta ? ctx->d_delta_in : nullptr);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_set_active(gusto_ctx* ctx, const uint8_t* active) {
+  NEED(active);
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->d_active, active, ctx->cfg.B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_iterate(gusto_ctx* ctx, double* out, double* info) {
+  NEED(out);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc;
+  if ((rc = launch_linearize(ctx))) return rc;
+  if ((rc = launch_solve(ctx))) return rc;
+  if ((rc = launch_evaluate(ctx))) return rc;
+  D2H(out, ctx->d_eval, (size_t)ctx->cfg.B * EVAL_NOUT);
+  if (info) D2H(info, ctx->d_info, (size_t)ctx->cfg.B * IPM_NINFO);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_iterate_device(gusto_ctx* ctx) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc;
+  if ((rc = launch_linearize(ctx))) return rc;
+  if ((rc = launch_solve(ctx))) return rc;
+  if ((rc = launch_evaluate(ctx))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_accept_device(gusto_ctx* ctx, const uint8_t* accept_dev, const double* omega_dev, const double* delta_dev) {
+  NEED(accept_dev);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = launch_accept(ctx, accept_dev, omega_dev, delta_dev);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_last_kernel_ms(gusto_ctx* ctx, float* ms) {
+  NEED(ms);
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = 0.f;
+    if (ctx->timed[i]) CK(cudaEventElapsedTime(&ms[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+  }
+  return GUSTO_OK;
+}
+
+int32_t gusto_timer_start(gusto_ctx* ctx) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return GUSTO_OK;
+}
+int32_t gusto_timer_stop(gusto_ctx* ctx, float* ms) {
+  NEED(ms);
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->tev[1]));
+  CK(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
+  return GUSTO_OK;
+}
+
+int64_t gusto_launch_count(const gusto_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t gusto_device_ptr(gusto_ctx* ctx, int32_t which, void** ptr, int64_t* n) {
+  NEED(ptr && n);
+  const int64_t B = ctx->cfg.B, N = ctx->cfg.N;
+  switch (which) {
+    case 0: *ptr = ctx->d_eval; *n = B * EVAL_NOUT; break;
+    case 1: *ptr = ctx->d_info; *n = B * IPM_NINFO; break;
+    case 2: *ptr = ctx->p.Xp; *n = B * N * ctx->nx; break;
+    case 3: *ptr = ctx->p.Up; *n = B * N * ctx->nu; break;
+    case 4: *ptr = ctx->p.Xn; *n = B * N * ctx->nx; break;
+    case 5: *ptr = ctx->p.Un; *n = B * N * ctx->nu; break;
+    case 6: *ptr = ctx->p.omega; *n = B; break;
+    case 7: *ptr = ctx->p.delta; *n = B; break;
+    case 8: *ptr = ctx->d_active; *n = B; break;   /* bytes, not doubles */
+    default: ctx->err = "gusto_device_ptr: bad selector"; return GUSTO_E_ARG;
+  }
+  return GUSTO_OK;
+}
+
+int64_t gusto_stream_handle(gusto_ctx* ctx) { return ctx ? (int64_t)(uintptr_t)ctx->stream : 0; }
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+"""ctypes binding over the C ABI (include/gusto_b200.h) and the host-side GuSTO outer loop.
+
+`solve_gusto_batch` is the batched counterpart of `solve_gusto_jump!` (/root/reference/src/scp/scp_gusto.jl:49-176):
+the accept/reject logic, the Delta/omega schedule and the convergence test run here on the host, per instance,
+exactly as in the reference (:119-174); everything numerical runs in the CUDA kernels behind the C ABI.  The same
+loop is mirrored in Julia in julia/GuSTOB200.jl.
+
+There is no CPU path: if libgusto_b200.so is missing or no GPU is usable every entry point raises.
+"""
+import ctypes
+import os
+import time
+from dataclasses import dataclass, field
+import numpy as np
+
+from . import models as M
+from .problems import BatchProblem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgusto_b200.so")
+EVAL_NOUT = 8
+SOLVE_NINFO = 8
+EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)
+SCP_STATUS = ("NA", "OK", "InaccurateModel", "ViolatesConstraints", "TrustRegionViolated", "SolverFailed", "Inactive")
+ST_NA, ST_OK, ST_INACCURATE, ST_VIOLATES, ST_TRVIOLATED, ST_SOLVERFAIL, ST_INACTIVE = range(7)
+
+
+class GustoConfig(ctypes.Structure):
+    _fields_ = [("model_id", ctypes.c_int32), ("N", ctypes.c_int32), ("B", ctypes.c_int32), ("n_obs", ctypes.c_int32),
+                ("robot_params", ctypes.c_double * 16), ("scp_params", ctypes.c_double * 10),
+                ("goal_type", ctypes.c_int32 * 16), ("device", ctypes.c_int32),
+                ("ipm_max_iter", ctypes.c_int32), ("ipm_nref", ctypes.c_int32),
+                ("ipm_tol", ctypes.c_double), ("ipm_delta_p", ctypes.c_double), ("ipm_delta_d", ctypes.c_double)]
+
+
+def make_config(bp: BatchProblem, device=0, ipm_max_iter=0, ipm_nref=0, ipm_tol=0.0, ipm_delta_p=0.0, ipm_delta_d=0.0):
+    kind, a, b = bp.obstacle_table()
+    cfg = GustoConfig()
+    cfg.model_id, cfg.N, cfg.B, cfg.n_obs = bp.model.model_id, bp.N, bp.B, int(kind.shape[0])
+    cfg.robot_params[:] = list(bp.robot_params())
+    cfg.scp_params[:] = list(bp.model.scp_params)
+    gt = np.zeros(16, dtype=np.int32)
+    gt[:bp.model.x_dim] = bp.goal_type
+    cfg.goal_type[:] = list(gt)
+    cfg.device = device
+    cfg.ipm_max_iter, cfg.ipm_nref = ipm_max_iter, ipm_nref
+    cfg.ipm_tol, cfg.ipm_delta_p, cfg.ipm_delta_d = ipm_tol, ipm_delta_p, ipm_delta_d
+    return cfg, (np.ascontiguousarray(kind, dtype=np.int32), np.ascontiguousarray(a), np.ascontiguousarray(b))
+
+
+_DP = ctypes.POINTER(ctypes.c_double)
+_IP = ctypes.POINTER(ctypes.c_int32)
+_BP = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_DP)
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """Load libgusto_b200.so and declare every symbol of include/gusto_b200.h.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(gusto-b200 has no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.gusto_create.argtypes = [ctypes.POINTER(GustoConfig), _IP, _DP, _DP, ctypes.POINTER(vp)]
+    lib.gusto_destroy.argtypes = [vp]
+    lib.gusto_last_error.argtypes = [vp]
+    lib.gusto_last_error.restype = ctypes.c_char_p
+    lib.gusto_version.restype = i32
+    lib.gusto_set_problems.argtypes = [vp, _DP, _DP, _DP, _DP]
+    for name in ("gusto_set_trajectory", "gusto_get_trajectory", "gusto_get_candidate", "gusto_set_candidate",
+                 "gusto_set_penalties"):
+        getattr(lib, name).argtypes = [vp, _DP, _DP]
+    lib.gusto_linearize.argtypes = [vp]
+    lib.gusto_get_blocks.argtypes = [vp, _DP, _DP, _DP, _DP]
+    lib.gusto_solve_subproblem.argtypes = [vp, _DP]
+    lib.gusto_evaluate.argtypes = [vp, _DP]
+    lib.gusto_accept.argtypes = [vp, _BP, _DP, _DP]
+    lib.gusto_set_active.argtypes = [vp, _BP]
+    lib.gusto_iterate.argtypes = [vp, _DP, _DP]
+    lib.gusto_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    lib.gusto_timer_start.argtypes = [vp]
+    lib.gusto_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    lib.gusto_launch_count.argtypes = [vp]
+    lib.gusto_launch_count.restype = i64
+    lib.gusto_device_ptr.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.gusto_iterate_device.argtypes = [vp]
+    lib.gusto_accept_device.argtypes = [vp, vp, vp, vp]
+    lib.gusto_stream_handle.argtypes = [vp]
+    lib.gusto_stream_handle.restype = i64
+    for name in ("gusto_create", "gusto_destroy", "gusto_set_problems", "gusto_set_trajectory", "gusto_get_trajectory",
+                 "gusto_get_candidate", "gusto_set_candidate", "gusto_set_penalties", "gusto_linearize",
+                 "gusto_get_blocks", "gusto_solve_subproblem", "gusto_evaluate", "gusto_accept", "gusto_set_active",
+                 "gusto_iterate", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
+                 "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop"):
+        getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+class GustoError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One gusto_ctx: a batch of B instances resident on one GPU."""
+
+    def __init__(self, bp: BatchProblem, device=0, **ipm_opts):
+        self.lib = load_library()
+        self.bp = bp
+        self.B, self.N, self.nx, self.nu = bp.B, bp.N, bp.model.x_dim, bp.model.u_dim
+        cfg, (kind, a, b) = make_config(bp, device, **ipm_opts)
+        self.n_obs = int(kind.shape[0]) if bp.model.model_id != M.DUBINS else 0
+        self._ctx = ctypes.c_void_p()
+        rc = self.lib.gusto_create(ctypes.byref(cfg), kind.ctypes.data_as(_IP), _dp(a), _dp(b), ctypes.byref(self._ctx))
+        if rc != 0:
+            raise GustoError(f"gusto_create failed ({rc}): {self.lib.gusto_last_error(None).decode()}")
+        self._chk(self.lib.gusto_set_problems(self._ctx, _dp(np.ascontiguousarray(bp.x_init)),
+                                              _dp(np.ascontiguousarray(bp.goal_lo)), _dp(np.ascontiguousarray(bp.goal_hi)),
+                                              _dp(np.ascontiguousarray(bp.tf))))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise GustoError(f"gusto call failed ({rc}): {self.lib.gusto_last_error(self._ctx).decode()}")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.gusto_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data movement
+    def set_trajectory(self, X, U):
+        self._chk(self.lib.gusto_set_trajectory(self._ctx, _dp(np.ascontiguousarray(X)), _dp(np.ascontiguousarray(U))))
+
+    def set_candidate(self, X, U):
+        self._chk(self.lib.gusto_set_candidate(self._ctx, _dp(np.ascontiguousarray(X)), _dp(np.ascontiguousarray(U))))
+
+    def _get(self, fn, X=None, U=None):
+        X = np.empty((self.B, self.N, self.nx)) if X is None else X
+        U = np.empty((self.B, self.N, self.nu)) if U is None else U
+        self._chk(fn(self._ctx, _dp(X), _dp(U)))
+        return X, U
+
+    def get_trajectory(self, X=None, U=None):
+        return self._get(self.lib.gusto_get_trajectory, X, U)
+
+    def get_candidate(self, X=None, U=None):
+        return self._get(self.lib.gusto_get_candidate, X, U)
+
+    def set_penalties(self, omega, delta):
+        self._chk(self.lib.gusto_set_penalties(self._ctx, _dp(np.ascontiguousarray(omega, dtype=np.float64)),
+                                               _dp(np.ascontiguousarray(delta, dtype=np.float64))))
+
+    def set_active(self, active):
+        a = np.ascontiguousarray(active, dtype=np.uint8)
+        self._chk(self.lib.gusto_set_active(self._ctx, a.ctypes.data_as(_BP)))
+
+    # -- kernels
+    def linearize(self):
+        self._chk(self.lib.gusto_linearize(self._ctx))
+
+    def get_blocks(self):
+        BN = self.B * self.N
+        f = np.empty((self.B, self.N, self.nx)); A = np.empty((self.B, self.N, self.nx, self.nx))
+        g = np.empty((self.B, self.N, self.nx)); rows = np.zeros((self.B, self.N, self.n_obs, 5))
+        self._chk(self.lib.gusto_get_blocks(self._ctx, _dp(f), _dp(A), _dp(g), _dp(rows) if self.n_obs else None))
+        return f, A, g, rows
+
+    def solve_subproblem(self, info=None):
+        info = np.empty((self.B, SOLVE_NINFO)) if info is None else info
+        self._chk(self.lib.gusto_solve_subproblem(self._ctx, _dp(info)))
+        return info
+
+    def evaluate(self, out=None):
+        out = np.empty((self.B, EVAL_NOUT)) if out is None else out
+        self._chk(self.lib.gusto_evaluate(self._ctx, _dp(out)))
+        return out
+
+    def accept(self, accept, omega=None, delta=None):
+        a = np.ascontiguousarray(accept, dtype=np.uint8)
+        self._chk(self.lib.gusto_accept(self._ctx, a.ctypes.data_as(_BP),
+                                        _dp(None if omega is None else np.ascontiguousarray(omega, dtype=np.float64)),
+                                        _dp(None if delta is None else np.ascontiguousarray(delta, dtype=np.float64))))
+
+    def iterate(self, out=None, info=None):
+        out = np.empty((self.B, EVAL_NOUT)) if out is None else out
+        info = np.empty((self.B, SOLVE_NINFO)) if info is None else info
+        self._chk(self.lib.gusto_iterate(self._ctx, _dp(out), _dp(info)))
+        return out, info
+
+    def iterate_device(self):
+        self._chk(self.lib.gusto_iterate_device(self._ctx))
+
+    def accept_device(self, accept_ptr, omega_ptr, delta_ptr):
+        self._chk(self.lib.gusto_accept_device(self._ctx, accept_ptr, omega_ptr, delta_ptr))
+
+    def device_ptr(self, which):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        self._chk(self.lib.gusto_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def kernel_ms(self):
+        ms = (ctypes.c_float * 4)()
+        self._chk(self.lib.gusto_last_kernel_ms(self._ctx, ms))
+        return dict(linearize=ms[0], solve=ms[1], evaluate=ms[2], accept=ms[3])
+
+    def timer_start(self):
+        self._chk(self.lib.gusto_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self._chk(self.lib.gusto_timer_stop(self._ctx, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.lib.gusto_launch_count(self._ctx))
+
+
+# ------------------------------------------------------------------------------------------- outer loop
+@dataclass
+class BatchSCPSolution:
+    """Per-instance SCPSolution histories (types.jl:150-173) + SCPParam_GuSTO vectors (scp_gusto.jl:15-19)."""
+    X: np.ndarray
+    U: np.ndarray
+    converged: np.ndarray
+    successful: np.ndarray
+    iterations: np.ndarray
+    J_true: list = field(default_factory=list)            # list of [B] arrays, one per history entry
+    J_full: list = field(default_factory=list)
+    scp_status: list = field(default_factory=list)        # int codes, SCP_STATUS
+    solver_status: list = field(default_factory=list)
+    accept_solution: list = field(default_factory=list)
+    convergence_measure: list = field(default_factory=list)
+    Delta_vec: list = field(default_factory=list)
+    omega_vec: list = field(default_factory=list)
+    rho_vec: list = field(default_factory=list)
+    tr_ok_vec: list = field(default_factory=list)
+    ineq_ok_vec: list = field(default_factory=list)
+    newton_iters: list = field(default_factory=list)
+    iter_elapsed_times: list = field(default_factory=list)
+    total_time: float = 0.0
+    batch_iterations: int = 0
+
+
+def gusto_update(ev, solver_ok, active, Delta, omega, iterations, conv_prev, sp, force=False):
+    """Vectorised accept/reject + Delta/omega schedule + convergence test of scp_gusto.jl:119-174 for one outer
+    iteration.  All arguments are [B] arrays; returns the new state.  Pure host logic (also used by the gloo tests)."""
+    D0, w_max, rho0, rho1 = sp[M.SP_DELTA0], sp[M.SP_OMEGAMAX], sp[M.SP_RHO0], sp[M.SP_RHO1]
+    b_succ, b_fail, g_fail, thr = sp[M.SP_BSUCC], sp[M.SP_BFAIL], sp[M.SP_GFAIL], sp[M.SP_CONVTHR]
+    conv, tr_ok, ineq_ok, rho = ev[:, EV_CONV], ev[:, EV_TR_OK] > 0.5, ev[:, EV_INEQ_OK] > 0.5, ev[:, EV_RHO]
+    run = active & solver_ok
+    failed = active & ~solver_ok                                  # :107-111 early return
+    inaccurate = run & tr_ok & (rho > rho1)
+    accepted = run & tr_ok & ~(rho > rho1)
+    tr_viol = run & ~tr_ok
+    status = np.full(active.shape, ST_INACTIVE, dtype=np.int32)
+    status[failed] = ST_SOLVERFAIL
+    status[inaccurate] = ST_INACCURATE
+    status[accepted & ineq_ok] = ST_OK
+    status[accepted & ~ineq_ok] = ST_VIOLATES
+    status[tr_viol] = ST_TRVIOLATED
+    Delta_n, omega_n = Delta.copy(), omega.copy()
+    Delta_n[inaccurate] = b_fail * Delta[inaccurate]
+    grow = accepted & (rho < rho0)
+    Delta_n[grow] = np.minimum(b_succ * Delta[grow], D0)
+    esc = (accepted & ~ineq_ok) | tr_viol
+    omega_n[esc] = g_fail * omega[esc]
+    iterations_n = iterations + run.astype(iterations.dtype)
+    omega_exceeded = run & (omega_n > w_max)                      # :163-166
+    conv_test = accepted & ~omega_exceeded & (iterations_n > 2) & (conv + conv_prev <= thr)   # :167-174
+    converged_now = conv_test
+    successful_now = conv_test & ineq_ok
+    done = failed | omega_exceeded | (converged_now & (not force))
+    return dict(accept=accepted, status=status, Delta=Delta_n, omega=omega_n, iterations=iterations_n,
+                converged_now=converged_now, successful_now=successful_now, done=done, run=run)
+
+
+def solve_gusto_batch(engine: Engine, X0=None, U0=None, max_iter=30, force=False, verbose=False, all_done=None):
+    """Batched solve_gusto_jump!.  `all_done(local_done_flags) -> bool` lets a multi-GPU caller plug in the status
+    all-gather (one collective per outer iteration); default is the local decision."""
+    bp = engine.bp
+    B = bp.B
+    sp = bp.model.scp_params
+    if X0 is None:
+        X0, U0 = bp.init_traj_straightline()
+    t0 = time.perf_counter()
+    engine.set_trajectory(X0, U0)
+    Delta = np.full(B, sp[M.SP_DELTA0]); omega = np.full(B, sp[M.SP_OMEGA0])
+    engine.set_penalties(omega, Delta)
+    # :72-75  initialize_model_params!, J_true[1] = cost_true(traj), rho_vec[2] = ratio(traj, traj)
+    engine.set_candidate(X0, U0)
+    engine.linearize()
+    ev0 = engine.evaluate()
+    S = BatchSCPSolution(X0, U0, np.zeros(B, bool), np.zeros(B, bool), np.zeros(B, np.int64))
+    S.J_true.append(ev0[:, EV_JTRUE].copy()); S.J_full.append(ev0[:, EV_JTRUE].copy())
+    S.scp_status.append(np.full(B, ST_NA, np.int32)); S.solver_status.append(np.full(B, -1, np.int32))
+    S.accept_solution.append(np.ones(B, bool)); S.convergence_measure.append(np.zeros(B))
+    S.Delta_vec.append(Delta.copy()); S.omega_vec.append(omega.copy())
+    S.rho_vec += [np.zeros(B), ev0[:, EV_RHO].copy()]
+    S.tr_ok_vec.append(np.zeros(B, bool)); S.ineq_ok_vec.append(np.zeros(B, bool))
+    active = np.ones(B, bool)
+    iter_cap = max_iter
+    out = np.empty((B, EVAL_NOUT)); info = np.empty((B, SOLVE_NINFO))
+    for it in range(iter_cap):
+        ti = time.perf_counter()
+        engine.set_active(active)
+        engine.iterate(out, info)
+        solver_ok = info[:, 0] == 0
+        st = gusto_update(out, solver_ok, active, Delta, omega, S.iterations, S.convergence_measure[-1], sp, force)
+        engine.accept(st["accept"], st["omega"], st["Delta"])
+        J_prev = S.J_true[-1]
+        S.J_true.append(np.where(st["accept"], out[:, EV_JTRUE], J_prev))
+        S.J_full.append(np.where(st["run"], info[:, 4], S.J_full[-1]))
+        S.scp_status.append(st["status"]); S.solver_status.append(np.where(active, info[:, 0], -1).astype(np.int32))
+        S.accept_solution.append(st["accept"])
+        S.convergence_measure.append(np.where(st["run"], out[:, EV_CONV], S.convergence_measure[-1]))
+        S.rho_vec.append(np.where(st["run"] & (out[:, EV_TR_OK] > 0.5), out[:, EV_RHO], np.nan))
+        S.tr_ok_vec.append(out[:, EV_TR_OK] > 0.5); S.ineq_ok_vec.append(out[:, EV_INEQ_OK] > 0.5)
+        S.newton_iters.append(np.where(active, info[:, 1], 0))
+        Delta, omega = st["Delta"], st["omega"]
+        S.Delta_vec.append(Delta.copy()); S.omega_vec.append(omega.copy())
+        S.iterations = st["iterations"]
+        S.converged |= st["converged_now"]; S.successful |= st["successful_now"]
+        active = active & ~st["done"]
+        S.iter_elapsed_times.append(time.perf_counter() - ti)
+        S.batch_iterations += 1
+        if verbose:
+            print(f"[gusto] it {it + 1:2d} active {int(active.sum()):5d} accepted {int(st['accept'].sum()):5d} "
+                  f"converged {int(S.converged.sum()):5d} newton {info[:, 1].mean():.1f} "
+                  f"ms/it {1e3 * S.iter_elapsed_times[-1]:.2f}")
+        finished = (not active.any()) if all_done is None else all_done(~active)
+        if finished:
+            break
+    S.X, S.U = engine.get_trajectory()
+    S.total_time = time.perf_counter() - t0
+    return S

@@ -1,0 +1,138 @@
+/* gusto_b200.h -- C ABI of the B200-native batched GuSTO SCP hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.  A Julia host binds it with
+ * `ccall` (gusto.jl_b200/julia/GuSTOB200.jl), the tests and bench bind it with ctypes (gusto.jl_b200/host.py).
+ *
+ * It replaces, inside `solve_gusto_jump!` (reference: /root/reference/src/scp/scp_gusto.jl:49-176), everything
+ * that is not the outer accept/reject logic:
+ *     gusto_linearize          <- update_model_params! (:95) + the cc.func row evaluations of
+ *                                 add_constraints_gusto_jump! (:192-251): f_dyn/A_dyn/B_dyn, dynamics_constraints,
+ *                                 ncsi_*_convexified + BulletCollision.distance (dynamics/astrobee_se3.jl:130-305)
+ *     gusto_solve_subproblem   <- Model(with_optimizer(...)) (:82-92), add_variables_jump! (:178-190),
+ *                                 add_objective_gusto_jump! (:253-314), JuMP.optimize! (:104), JuMP.value (:114)
+ *     gusto_evaluate           <- convergence_metric (:115, traj_opt.jl:74-85), trust_region_satisfied_gusto (:120),
+ *                                 convex_ineq_satisfied_gusto_jump (:121), trust_region_ratio_gusto (:124),
+ *                                 cost_true (:146), JuMP.objective_value (:116)
+ *     gusto_accept             <- copy!(SCPS.traj, new_traj) (:147) and the Delta/omega pushes (:125-145,156)
+ * The trust-region update and convergence test themselves (:119-174) stay in the host language.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (GUSTO_E_*); it never throws.  gusto_last_error() returns a
+ *     message for the last failure on that context (or a global one when ctx is NULL).
+ *   - all arrays are Float64, dense, instance-major / knot-major: X is [B][N][n_x], which is exactly the memory of a
+ *     Julia Array{Float64,3} of size (n_x, N, B); U is [B][N][n_u].
+ *   - the library never keeps a caller pointer after the call returns (Julia arrays may move after GC.@preserve).
+ *   - a context owns one CUDA stream; calls on one context are serialised and block until host outputs are written.
+ */
+#ifndef GUSTO_B200_H
+#define GUSTO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gusto_ctx gusto_ctx;
+
+/* model_id: which DynamicsModel plugin (src/dynamics/*.jl) the batch uses */
+enum { GUSTO_DUBINS = 0, GUSTO_FREEFLYER_SE2 = 1, GUSTO_ASTROBEE_SE3 = 2, GUSTO_ASTROBEE_SE3_MANIFOLD = 3 };
+/* obstacle kinds: HyperRectangle (a = min corner, b = max corner) / HyperSphere (a = centre, b[0] = radius) */
+enum { GUSTO_OBS_BOX = 0, GUSTO_OBS_SPHERE = 1 };
+/* goal_type per state coordinate: none / PointGoal (equality) / BoxGoal (inequality)  (src/goals.jl) */
+enum { GUSTO_GOAL_FREE = 0, GUSTO_GOAL_POINT = 1, GUSTO_GOAL_BOX = 2 };
+/* per-instance convex-solver status (MOI-like): OPTIMAL / ITERATION_LIMIT / NUMERICAL_ERROR */
+enum { GUSTO_SOLVER_OPTIMAL = 0, GUSTO_SOLVER_ITERATION_LIMIT = 1, GUSTO_SOLVER_NUMERICAL = 2 };
+enum {
+  GUSTO_OK = 0, GUSTO_E_ARG = -1, GUSTO_E_CUDA = -2, GUSTO_E_ALLOC = -3, GUSTO_E_STATE = -4, GUSTO_E_NODEVICE = -5
+};
+
+/* number of doubles per instance written by gusto_evaluate / gusto_solve_subproblem */
+#define GUSTO_EVAL_NOUT 8 /* conv, tr_ok, ineq_ok, rho, J_true, J_full, max_k|dX_k|^2, max soft-row value */
+#define GUSTO_SOLVE_NINFO 8 /* status, newton iterations, residual, mu, objective, 0, 0, 0 */
+
+typedef struct {
+  int32_t model_id;        /* GUSTO_* model                                                        */
+  int32_t N;               /* knots            (SCPProblem.N, types.jl:78-86)                      */
+  int32_t B;               /* instances in this context (this rank's shard)                        */
+  int32_t n_obs;           /* collision components: keepout_zones..., obstacle_set... (types.jl:19) */
+  double robot_params[16]; /* 0 mass | 1-3 Jxx,Jyy,Jzz | 4 radius | 5 v_max | 6 a_max | 7 w_max | 8 alpha_max |
+                              9 clearance | 10 dubins v | 11 dubins k | 12-14 dubins x_max | 15 dubins u_max
+                              (robot/astrobee3D.jl:16-30, robot/freeflyer.jl:29-50, dynamics/dubins_car.jl:20-33) */
+  double scp_params[10];   /* Delta0, omega0, omega_max, eps, rho0, rho1, beta_succ, beta_fail, gamma_fail,
+                              convergence_threshold  (SCPParam_GuSTO(model), SCPParam(model))      */
+  int32_t goal_type[16];   /* per state coordinate, shared by the batch                                          */
+  int32_t device;          /* CUDA device ordinal                                                                */
+  /* convex-solver controls (0 selects the default) */
+  int32_t ipm_max_iter;    /* default 60   */
+  int32_t ipm_nref;        /* default 2    */
+  double ipm_tol;          /* default 1e-8 */
+  double ipm_delta_p;      /* default 1e-6 */
+  double ipm_delta_d;      /* default 1e-10 */
+} gusto_config;
+
+/* Create a context for a batch of B instances sharing robot / model / environment.
+ * obs_kind[n_obs], obs_a[n_obs*3], obs_b[n_obs*3] describe the collision components (may be NULL when n_obs == 0). */
+int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const double* obs_a, const double* obs_b,
+                     gusto_ctx** out);
+int32_t gusto_destroy(gusto_ctx* ctx);
+const char* gusto_last_error(const gusto_ctx* ctx);
+int32_t gusto_version(void);
+
+/* Per-instance problem data: x_init[B*n_x], goal_lo/goal_hi[B*n_x] (PointGoal: lo == hi == point), tf[B]
+ * (ProblemDefinition.x_init / goal_set, TrajectoryOptimizationProblem.tf_guess; types.jl:32-63). */
+int32_t gusto_set_problems(gusto_ctx* ctx, const double* x_init, const double* goal_lo, const double* goal_hi,
+                           const double* tf);
+/* Accepted ("previous") trajectory SCPS.traj: X[B*N*n_x], U[B*N*n_u]. */
+int32_t gusto_set_trajectory(gusto_ctx* ctx, const double* X, const double* U);
+int32_t gusto_get_trajectory(gusto_ctx* ctx, double* X, double* U);
+/* Candidate trajectory of the last gusto_solve_subproblem (new_traj, scp_gusto.jl:114). */
+int32_t gusto_get_candidate(gusto_ctx* ctx, double* X, double* U);
+int32_t gusto_set_candidate(gusto_ctx* ctx, const double* X, const double* U);
+/* Current penalty weight and trust-region size per instance: omega[B], delta[B] (param.alg.omega_vec[end], Delta_vec[end]). */
+int32_t gusto_set_penalties(gusto_ctx* ctx, const double* omega, const double* delta);
+
+/* K1+K2: linearize dynamics and obstacle rows about the accepted trajectory, for all B*N knots. */
+int32_t gusto_linearize(gusto_ctx* ctx);
+/* Test hook: copy the blocks out.  Any pointer may be NULL.  f[B*N*n_x], A[B*N*n_x*n_x] (row-major per knot),
+ * g[B*N*n_x] (= f - A Xp - B Up), rows[B*N*n_obs*5] (nhat_x, nhat_y, nhat_z, off, dist0). */
+int32_t gusto_get_blocks(gusto_ctx* ctx, double* f, double* A, double* g, double* rows);
+
+/* K3: solve the convex subproblem of every instance; info[B*GUSTO_SOLVE_NINFO] (may be NULL). */
+int32_t gusto_solve_subproblem(gusto_ctx* ctx, double* info);
+/* K4: evaluate the candidate against the accepted trajectory; out[B*GUSTO_EVAL_NOUT]. */
+int32_t gusto_evaluate(gusto_ctx* ctx, double* out);
+/* accept[b] != 0: candidate becomes the accepted trajectory of instance b.  omega/delta (may be NULL) are the values
+ * for the NEXT iteration (the obstacle toggle distance Delta/8 + clearance follows, scp_gusto.jl:156). */
+int32_t gusto_accept(gusto_ctx* ctx, const uint8_t* accept, const double* omega, const double* delta);
+
+/* active[b] == 0 freezes instance b: solve / evaluate skip it (converged or failed instances, scp_gusto.jl:172-173).
+ * All instances are active after gusto_create. */
+int32_t gusto_set_active(gusto_ctx* ctx, const uint8_t* active);
+
+/* One fused outer iteration for callers that keep everything on the device between iterations:
+ * linearize -> solve -> evaluate, a single D2H copy of out[B*GUSTO_EVAL_NOUT] and info[B*GUSTO_SOLVE_NINFO]. */
+int32_t gusto_iterate(gusto_ctx* ctx, double* out, double* info);
+
+/* Timing of the last call of each kernel on this context, in milliseconds (CUDA events on the context's stream):
+ * ms[0] linearize, ms[1] solve, ms[2] evaluate, ms[3] accept. */
+int32_t gusto_last_kernel_ms(gusto_ctx* ctx, float* ms);
+/* Device-clock stopwatch: two CUDA events recorded on the context's stream (start synchronises the stream first). */
+int32_t gusto_timer_start(gusto_ctx* ctx);
+int32_t gusto_timer_stop(gusto_ctx* ctx, float* ms);
+/* Number of kernel launches issued by this context since creation. */
+int64_t gusto_launch_count(const gusto_ctx* ctx);
+
+/* Device pointers for zero-copy plumbing (torch.distributed all_gather of the evaluation/status block).
+ * which: 0 eval_out[B*8], 1 solve_info[B*8], 2 Xp, 3 Up, 4 Xn, 5 Un, 6 omega, 7 delta, 8 active (B bytes). */
+int32_t gusto_device_ptr(gusto_ctx* ctx, int32_t which, void** ptr, int64_t* n_doubles);
+/* Device-only variants (no host copies): run on the context stream and return after the stream is synchronised. */
+int32_t gusto_iterate_device(gusto_ctx* ctx);
+int32_t gusto_accept_device(gusto_ctx* ctx, const uint8_t* accept_dev, const double* omega_dev, const double* delta_dev);
+/* Handle of the context's CUDA stream (cudaStream_t as integer) so that a torch stream can wait on it. */
+int64_t gusto_stream_handle(gusto_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUSTO_B200_H */

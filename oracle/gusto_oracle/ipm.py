@@ -94,7 +94,8 @@ def solve_qcqp(qp, tol=1e-8, max_iter=200, verbose=False):
         mu_aff = float((s + a_aff * ds) @ (lam + a_aff * dlam)) / max(m, 1)
         sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
         # corrector
-        dz, dnu, ds, dlam = direction(s * lam - sigma * mu + ds * dlam)
+        # centering target never below 0.1*tol: keeps lam/s bounded once the iterate is converged in mu
+        dz, dnu, ds, dlam = direction(s * lam - max(sigma * mu, 0.1 * tol) + ds * dlam)
         tau = min(max(0.995, 1.0 - mu), 0.999999) if mu < 1 else 0.995
         a_p, a_d = max_step(s, ds, tau), max_step(lam, dlam, tau)
         z = z + a_p * dz

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY -- single-thread host simulation of the CUDA kernel bodies.
+//
+// Compiles gusto.jl_b200/csrc/{linearize,ipm,evaluate}.cuh with -DGUSTO_HOSTSIM (G_TID = 0, G_NTHR = 1, barriers are
+// no-ops) so that the kernels' arithmetic can be checked against the oracle in the GPU-less build container
+// (pytest -m "not gpu").  It is built into tests/hostsim/_build/, is never linked into libgusto_b200.so and is never
+// reachable from the product path; it proves nothing about races or memory spaces -- the -m gpu tests do that.
+#define GUSTO_HOSTSIM 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/gusto_b200.h"
+#include "../../gusto.jl_b200/csrc/common.cuh"
+#include "../../gusto.jl_b200/csrc/linearize.cuh"
+#include "../../gusto.jl_b200/csrc/ipm.cuh"
+#include "../../gusto.jl_b200/csrc/evaluate.cuh"
+
+using namespace gusto;
+
+template <int M>
+static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stages, double* info, double* eval) {
+  using T = Traits<M>;
+  using L = IpmLayout<M>;
+  const int N = d.N, B = d.B;
+  if (stages & 1) {
+    std::vector<double> ws(T::NX * T::NX + T::NX);
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < N; ++k)
+        linearize_knot<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data());
+  }
+  if (stages & 2) {
+    std::vector<double> scratch(L::scratch_doubles(N, d.n_obs)), smem(L::smem_doubles(N, 1));
+    for (int b = 0; b < B; ++b) ipm_solve_instance<M>(d, p, prm, b, scratch.data(), smem.data(), info + (size_t)b * IPM_NINFO);
+  }
+  if (stages & 4) {
+    double red[4];
+    for (int b = 0; b < B; ++b)
+      evaluate_instance<M>(d, p, b, p.Xn + (size_t)b * N * T::NX, p.Un + (size_t)b * N * T::NU, eval + (size_t)b * EVAL_NOUT, red);
+  }
+}
+
+extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind, const double* obs_a, const double* obs_b,
+                               const double* x_init, const double* goal_lo, const double* goal_hi, const double* tf,
+                               double* Xp, double* Up, double* Xn, double* Un, double* omega, double* delta,
+                               double* f, double* A, double* g, double* rows, int stages, double* info, double* eval) {
+  BatchDesc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = cfg->model_id; d.N = cfg->N; d.B = cfg->B; d.n_obs = cfg->model_id == DUBINS ? 0 : cfg->n_obs;
+  for (int i = 0; i < 16; ++i) d.rp[i] = cfg->robot_params[i];
+  for (int i = 0; i < 10; ++i) d.sp[i] = cfg->scp_params[i];
+  for (int i = 0; i < MAX_NX; ++i) d.goal_type[i] = cfg->goal_type[i];
+  for (int i = 0; i < d.n_obs; ++i) {
+    d.obs_kind[i] = obs_kind[i];
+    for (int a = 0; a < 3; ++a) { d.obs_a[i][a] = obs_a[i * 3 + a]; d.obs_b[i][a] = obs_b[i * 3 + a]; }
+  }
+  BatchPtrs p;
+  p.active = nullptr;
+  p.tf = tf; p.x_init = x_init; p.goal_lo = goal_lo; p.goal_hi = goal_hi;
+  p.Xp = Xp; p.Up = Up; p.Xn = Xn; p.Un = Un; p.omega = omega; p.delta = delta; p.f = f; p.A = A; p.g = g; p.rows = rows;
+  IpmParams prm;
+  prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
+  prm.nref = cfg->ipm_nref > 0 ? cfg->ipm_nref : 2;
+  prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
+  prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : 1e-6;
+  prm.delta_d = cfg->ipm_delta_d > 0 ? cfg->ipm_delta_d : 1e-10;
+  switch (cfg->model_id) {
+    case DUBINS: run<DUBINS>(d, p, prm, stages, info, eval); break;
+    case FREEFLYER_SE2: run<FREEFLYER_SE2>(d, p, prm, stages, info, eval); break;
+    case ASTROBEE_SE3: run<ASTROBEE_SE3>(d, p, prm, stages, info, eval); break;
+    case ASTROBEE_SE3_MANIFOLD: run<ASTROBEE_SE3_MANIFOLD>(d, p, prm, stages, info, eval); break;
+    default: return -1;
+  }
+  return 0;
+}

@@ -1,0 +1,144 @@
+"""GPU parity tests (run on the B200): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (FP64 everywhere; stated per north_star):
+  L1 component parity  f, A, g, obstacle rows, evaluation scalars ............ 1e-12 relative
+  L2 solve parity      objective rel-diff <= 1e-6, |dX| <= 1e-4, |dU| <= 1e-5, hard rows <= 1e-7
+  L3 end-to-end        final J_true rel-diff <= 1e-3, identical accept/convergence decisions on the tested instances
+"""
+import numpy as np
+import pytest
+
+from util import gb, orc, to_oracle
+from gusto_oracle.scp import solve_subproblem, evaluate, solve_gusto
+from gusto_oracle.subproblem import linearize, obstacle_rows
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("dubins", dict(B=3, N=30)), ("freeflyerSE2", dict(B=5, N=40)), ("astrobeeSE3", dict(B=6, N=50)),
+         ("astrobeeSE3manifold", dict(B=3, N=60))]
+
+
+def rel(a, b, floor=1.0):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(floor, float(np.max(np.abs(b))) if np.size(b) else floor)
+
+
+@pytest.fixture(scope="module")
+def engines(host):
+    made = {}
+    for name, kw in CASES:
+        bp = gb.problems.CONFIGS[name](**kw)
+        made[name] = (bp, host.Engine(bp, device=0))
+    yield made
+    for _, e in made.values():
+        e.close()
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_linearize_blocks_match_oracle(engines, name):
+    bp, eng = engines[name]
+    X0, U0 = bp.init_traj_straightline()
+    rng = np.random.default_rng(1)
+    X = X0 + 0.05 * rng.normal(size=X0.shape)
+    U = U0 + 0.05 * rng.normal(size=U0.shape)
+    eng.set_trajectory(X, U)
+    eng.linearize()
+    f, A, g, rows = eng.get_blocks()
+    toggle = bp.model.scp_params[0] / 8 + bp.model.clearance
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        lin = linearize(p, X[b], U[b])
+        assert rel(f[b], lin["f"]) < 1e-12 and rel(A[b], lin["A"]) < 1e-12 and rel(g[b], lin["g"]) < 1e-12
+        if p.n_obs:
+            r = obstacle_rows(p, X[b], toggle)
+            assert rel(rows[b][..., :3], r["nhat"]) < 1e-12
+            assert rel(rows[b][..., 3], r["off"]) < 1e-12 and rel(rows[b][..., 4], r["dist0"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+@pytest.mark.parametrize("omega", [1.0, 25.0])
+def test_subproblem_and_evaluation_match_oracle(engines, name, omega):
+    bp, eng = engines[name]
+    sp = bp.model.scp_params
+    X0, U0 = bp.init_traj_straightline()
+    eng.set_trajectory(X0, U0)
+    eng.set_penalties(np.full(bp.B, omega), np.full(bp.B, sp[0]))
+    eng.set_active(np.ones(bp.B, np.uint8))
+    out, info = eng.iterate()
+    Xn, Un = eng.get_candidate()
+    toggle = sp[0] / 8 + bp.model.clearance
+    assert np.all(info[:, 0] == 0), info
+    for b in range(min(bp.B, 3)):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, _ = solve_subproblem(p, X0[b], U0[b], omega, sp[0], toggle, sp[3])
+        assert st == "OPTIMAL"
+        assert abs(info[b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
+        assert np.max(np.abs(Xn[b] - Xs)) < 1e-4 and np.max(np.abs(Un[b] - Us)) < 1e-5
+        # evaluation scalars on the GPU's own candidate
+        ev = evaluate(p, Xn[b], Un[b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
+        assert abs(out[b, 0] - ev["conv"]) <= 1e-12 * max(1.0, ev["conv"])
+        assert bool(out[b, 1]) == ev["tr_ok"] and bool(out[b, 2]) == ev["ineq_ok"]
+        assert abs(out[b, 3] - ev["rho"]) <= 1e-10 * max(1e-3, abs(ev["rho"]))
+        assert abs(out[b, 4] - ev["J_true"]) <= 1e-12 * max(1.0, ev["J_true"])
+        assert abs(out[b, 5] - ev["J_full"]) <= 1e-9 * max(1.0, abs(ev["J_full"]))
+        # hard rows of the candidate: init, goal, dynamics defect of the linearised model
+        assert np.max(np.abs(Xn[b, 0] - bp.x_init[b])) < 1e-7
+        sel = bp.goal_type == 1
+        assert np.max(np.abs(Xn[b, -1][sel] - bp.goal_lo[b][sel])) < 1e-7
+
+
+@pytest.mark.parametrize("name", ["dubins", "freeflyerSE2", "astrobeeSE3"])
+def test_full_scp_matches_oracle(engines, host, name):
+    bp, eng = engines[name]
+    S = host.solve_gusto_batch(eng, max_iter=30)
+    for b in range(min(bp.B, 2)):
+        R = solve_gusto(to_oracle(bp, b), max_iter=30)
+        assert bool(S.converged[b]) == R.converged and bool(S.successful[b]) == R.successful
+        assert int(S.iterations[b]) == R.iterations
+        assert abs(S.J_true[-1][b] - R.J_true[-1]) <= 1e-3 * max(1e-6, abs(R.J_true[-1]))
+        acc = [bool(a[b]) for a in S.accept_solution[:R.iterations + 1]]
+        assert acc == R.accept_solution
+
+
+def test_shard_equivalence_and_ragged_batch(host):
+    """B*N not a multiple of the 8 knots a linearize CTA stages; shards of a batch give bit-identical results."""
+    bp = gb.problems.config_astrobee_se3(B=5, N=21, seed=3)
+    X0, U0 = bp.init_traj_straightline()
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0)
+    out, info = e.iterate()
+    Xn, Un = e.get_candidate()
+    e.close()
+    for rank in range(2):
+        bs = bp.shard(rank, 2)
+        lo = rank * bp.B // 2
+        es = host.Engine(bs, device=0)
+        es.set_trajectory(X0[lo:lo + bs.B], U0[lo:lo + bs.B])
+        o2, i2 = es.iterate()
+        X2, U2 = es.get_candidate()
+        es.close()
+        assert np.array_equal(X2, Xn[lo:lo + bs.B]) and np.array_equal(U2, Un[lo:lo + bs.B])
+        assert np.array_equal(o2, out[lo:lo + bs.B])
+
+
+def test_inactive_instances_are_frozen(host):
+    bp = gb.problems.config_freeflyer_se2(B=4, N=20, seed=5)
+    X0, U0 = bp.init_traj_straightline()
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0)
+    e.set_candidate(X0, U0)
+    e.set_active(np.array([1, 0, 1, 0], np.uint8))
+    e.iterate()
+    Xn, _ = e.get_candidate()
+    assert np.array_equal(Xn[1], X0[1]) and np.array_equal(Xn[3], X0[3])
+    assert not np.array_equal(Xn[0], X0[0])
+    e.close()
+
+
+def test_errors_are_reported_not_thrown(host):
+    bp = gb.problems.config_dubins(B=1, N=30)
+    cfg, (kind, a, b) = host.make_config(bp)
+    cfg.N = 2
+    import ctypes
+    ctx = ctypes.c_void_p()
+    rc = host.load_library().gusto_create(ctypes.byref(cfg), None, None, None, ctypes.byref(ctx))
+    assert rc < 0 and b"N >= 3" in host.load_library().gusto_last_error(None)

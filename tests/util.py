@@ -1,0 +1,78 @@
+"""Shared helpers for the test-suite: package loader, oracle bridge and the kernel host-simulation harness."""
+import ctypes
+import importlib.util
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+
+def load_package():
+    if "gusto_b200" in sys.modules:
+        return sys.modules["gusto_b200"]
+    d = os.path.join(ROOT, "gusto.jl_b200")
+    spec = importlib.util.spec_from_file_location("gusto_b200", os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gusto_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+gb = load_package()
+import gusto_oracle as orc  # noqa: E402
+from gusto_oracle.subproblem import Problem  # noqa: E402
+
+
+def to_oracle(bp, b):
+    """Instance b of a BatchProblem as an oracle Problem (checks that both sides carry the same parameter tables)."""
+    m = orc.get_model(bp.model.name)
+    assert np.array_equal(m.robot_params, bp.robot_params()), "robot parameter tables differ"
+    assert np.array_equal(m.scp_params, bp.model.scp_params), "SCP parameter tables differ"
+    return Problem(m, bp.N, float(bp.tf[b]), bp.x_init[b].copy(), bp.goal_type.copy(), bp.goal_lo[b].copy(),
+                   bp.goal_hi[b].copy(), bp.obstacle_table())
+
+
+# ------------------------------------------------------------------------------------ host simulation of the kernels
+_HS = None
+
+
+def hostsim_lib():
+    global _HS
+    if _HS is not None:
+        return _HS
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out = os.path.join(ROOT, "tests", "hostsim", "_build", "libgusto_hostsim.so")
+    deps = [src] + [os.path.join(ROOT, "gusto.jl_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "gusto.jl_b200", "csrc"))]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", out])
+    _HS = ctypes.CDLL(out)
+    return _HS
+
+
+def hostsim_iterate(bp, Xp, Up, omega, delta, stages=7, Xn=None, Un=None, **ipm_opts):
+    """Run linearize (1) | solve (2) | evaluate (4) of the kernel bodies on the host.  Returns a dict of arrays."""
+    host = gb.engine()
+    cfg, (kind, a, b) = host.make_config(bp, 0, **ipm_opts)
+    B, N, nx, nu = bp.B, bp.N, bp.model.x_dim, bp.model.u_dim
+    no = int(kind.shape[0]) if bp.model.model_id != gb.models.DUBINS else 0
+    dp = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    Xp = np.ascontiguousarray(Xp, dtype=np.float64).copy(); Up = np.ascontiguousarray(Up, dtype=np.float64).copy()
+    Xn = np.zeros((B, N, nx)) if Xn is None else np.ascontiguousarray(Xn, dtype=np.float64).copy()
+    Un = np.zeros((B, N, nu)) if Un is None else np.ascontiguousarray(Un, dtype=np.float64).copy()
+    omega = np.ascontiguousarray(np.broadcast_to(omega, (B,)), dtype=np.float64).copy()
+    delta = np.ascontiguousarray(np.broadcast_to(delta, (B,)), dtype=np.float64).copy()
+    f = np.zeros((B, N, nx)); A = np.zeros((B, N, nx, nx)); g = np.zeros((B, N, nx)); rows = np.zeros((B, N, max(no, 1), 5))
+    info = np.zeros((B, 8)); ev = np.zeros((B, 8))
+    x_init = np.ascontiguousarray(bp.x_init); glo = np.ascontiguousarray(bp.goal_lo); ghi = np.ascontiguousarray(bp.goal_hi)
+    tf = np.ascontiguousarray(bp.tf)
+    rc = hostsim_lib().hostsim_iterate(ctypes.byref(cfg), kind.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), dp(a), dp(b),
+                                       dp(x_init), dp(glo), dp(ghi), dp(tf), dp(Xp), dp(Up), dp(Xn), dp(Un), dp(omega),
+                                       dp(delta), dp(f), dp(A), dp(g), dp(rows), ctypes.c_int(stages), dp(info), dp(ev))
+    assert rc == 0
+    return dict(f=f, A=A, g=g, rows=rows[:, :, :no], Xn=Xn, Un=Un, info=info, eval=ev)
