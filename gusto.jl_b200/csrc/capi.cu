@@ -46,7 +46,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 
 // ------------------------------------------------------------------------------------------------ kernels
 constexpr int LIN_KNOTS_PER_CTA = 8;      // one warp per knot
-constexpr int IPM_THREADS = 64;
+#ifndef GUSTO_IPM_THREADS
+#define GUSTO_IPM_THREADS 64
+#endif
+#ifndef GUSTO_IPM_MINBLOCKS
+#define GUSTO_IPM_MINBLOCKS 7
+#endif
+constexpr int IPM_THREADS = GUSTO_IPM_THREADS;
 constexpr int EVAL_THREADS = 128;
 
 // K1+K2.  Grid: ceil(B*N/8) CTAs of 8 warps.  The 8 knots' states and controls are contiguous in HBM
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
 
 // K3.  Grid: B CTAs (one problem instance each).
 template <int M>
-__global__ void __launch_bounds__(IPM_THREADS) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
+__global__ void __launch_bounds__(IPM_THREADS, GUSTO_IPM_MINBLOCKS) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
                                                           double* scratch, size_t stride, double* info) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;

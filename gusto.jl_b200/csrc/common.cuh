@@ -13,6 +13,7 @@
 
 #ifdef GUSTO_HOSTSIM
 #define GDEV inline
+#define GDEV_NOINLINE inline
 #define GHD inline
 #define G_TID 0
 #define G_NTHR 1
@@ -23,6 +24,7 @@
 #else
 #include <cuda_runtime.h>
 #define GDEV __device__ __forceinline__
+#define GDEV_NOINLINE __device__ __noinline__
 #define GHD __host__ __device__ __forceinline__
 #define G_TID ((int)threadIdx.x)
 #define G_NTHR ((int)blockDim.x)
@@ -33,6 +35,25 @@
 #endif
 
 #define G_PAR_FOR(i, n) for (int i = G_TID; i < (n); i += G_NTHR)
+// loops executed by the first warp only (callers guard with `if (G_TID < G_WARP)`), separated by G_SYNCWARP()
+#ifdef GUSTO_HOSTSIM
+#define G_WARP 1
+#else
+#define G_WARP 32
+#endif
+#define G_W0_FOR(i, n) for (int i = G_TID; i < (n); i += G_WARP)
+
+// 8-byte asynchronous global->shared copy (LDGSTS): lets the block-tridiagonal sweeps prefetch the next block's factor
+// while the current one is applied.  Host simulation: a plain copy.
+#ifdef GUSTO_HOSTSIM
+inline void g_cp_async8(double* dst, const double* src) { *dst = *src; }
+inline void g_cp_async_wait() {}
+#else
+__device__ __forceinline__ void g_cp_async8(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 namespace gusto {
 

@@ -29,6 +29,12 @@
 
 namespace gusto {
 
+#ifdef GUSTO_HOSTSIM
+GDEV long long g_clock() { return 0; }
+#else
+GDEV long long g_clock() { return clock64(); }
+#endif
+
 struct IpmParams {
   int max_iter;      // Newton iterations cap
   int nref;          // refinement steps on the corrector solve
@@ -39,7 +45,7 @@ struct IpmParams {
 
 enum : int { IPM_OPTIMAL = 0, IPM_ITERATION_LIMIT = 1, IPM_NUMERICAL = 2 };
 constexpr int SLOT_W = 6;   // s, lam, t, lamb, pa (ds*dlam of the predictor), pb (dt*dlamb of the predictor)
-constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, -, -, -
+constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cycles: assemble+slots, factorize, kkt solves
 
 template <int M> struct IpmLayout {
   using T = Traits<M>;
@@ -58,7 +64,7 @@ template <int M> struct IpmLayout {
     return 6 * nz + 5 * ne + (size_t)N * nslots(n_obs) * SLOT_W + (size_t)N * NX * NX * 6 + (size_t)N * NU * NU * 2 +
            (size_t)N * NU * NX + (size_t)(N + 1) * NX * NX * 2;
   }
-  GHD static int smem_doubles(int N, int nthr) { return (N + 1) * NX + 3 * NX * NX + nthr + 16; }
+  GHD static int smem_doubles(int N, int nthr) { return (N + 1) * NX + 4 * NX * NX + 16 + nthr + 16; }
 };
 
 template <int M> struct IpmCtx {
@@ -73,7 +79,7 @@ template <int M> struct IpmCtx {
   double *z, *nu, *r, *dz, *t1, *res, *e, *rnu, *dnu, *resnu, *enu, *bS, *slot;
   double *Hx, *Ci, *CA, *W, *Hu, *Cu, *GT, *Ld, *Lo;
   // shared
-  double *sy, *sD, *sLo, *sLi, *red;
+  double *sy, *sD, *sLo, *sLi, *sB4, *stmp, *red;
 };
 
 // ------------------------------------------------------------------------------------------------- slots
@@ -233,7 +239,7 @@ template <int M> GDEV double apply_AT_entry(const IpmCtx<M>& c, const double* nu
 }
 
 // out = (H + dp I)^-1 in   per knot, using the inverse Cholesky factors Ci, Cu  (H^-1 = Ci' Ci)
-template <int M> GDEV void apply_Hinv(const IpmCtx<M>& c, const double* in, double* out) {
+template <int M> GDEV_NOINLINE void apply_Hinv(const IpmCtx<M>& c, const double* in, double* out) {
   constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU, NV = IpmCtx<M>::NV;
   G_PAR_FOR(k, c.N) {
     const double* Ci = c.Ci + (size_t)k * NX * NX;
@@ -247,47 +253,74 @@ template <int M> GDEV void apply_Hinv(const IpmCtx<M>& c, const double* in, doub
 }
 
 // Block-tridiagonal solve  S y = b  in shared memory (sy holds b on entry, the solution on exit).
-template <int M> GDEV void schur_solve(const IpmCtx<M>& c) {
-  constexpr int NX = IpmCtx<M>::NX;
+// The sweep is a chain of 2(N+1) dependent NX x NX mat-vecs.  It runs on the first warp only (warp-level barriers);
+// the factor blocks of the NEXT row are prefetched from HBM/L2 into a shared-memory double buffer with cp.async
+// while the current block is applied, so the chain never waits on a global load.
+template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
+  constexpr int NX = IpmCtx<M>::NX, NN = NX * NX;
   const int N = c.N;
   double* y = c.sy;
-  double* tmp = c.sD;   // NX scratch
-  for (int j = 0; j <= N; ++j) {      // forward: y_j = Ld_j (b_j - Lo_j y_{j-1})
-    const double* Ld = c.Ld + (size_t)j * NX * NX;
-    const double* Lo = c.Lo + (size_t)j * NX * NX;
-    G_PAR_FOR(i, NX) {
-      double a = y[j * NX + i];
-      if (j > 0) for (int m = 0; m < NX; ++m) a -= Lo[i * NX + m] * y[(j - 1) * NX + m];
-      tmp[i] = a;
+  double* tmp = c.stmp;
+  double* bLd[2] = {c.sD, c.sLo};
+  double* bLo[2] = {c.sLi, c.sB4};
+  if (G_TID < G_WARP) {
+    // ---- forward: y_j = Ld_j (b_j - Lo_j y_{j-1})
+    G_W0_FOR(it, NN) { g_cp_async8(&bLd[0][it], c.Ld + it); }
+    g_cp_async_wait();
+    G_SYNCWARP();
+    for (int j = 0; j <= N; ++j) {
+      const int cur = j & 1, nxt = cur ^ 1;
+      if (j < N) {
+        const double* Ldn = c.Ld + (size_t)(j + 1) * NN;
+        const double* Lon = c.Lo + (size_t)(j + 1) * NN;
+        G_W0_FOR(it, NN) { g_cp_async8(&bLd[nxt][it], Ldn + it); g_cp_async8(&bLo[nxt][it], Lon + it); }
+      }
+      G_W0_FOR(i, NX) {
+        double a = y[j * NX + i];
+        if (j > 0) for (int m = 0; m < NX; ++m) a -= bLo[cur][i * NX + m] * y[(j - 1) * NX + m];
+        tmp[i] = a;
+      }
+      G_SYNCWARP();
+      G_W0_FOR(i, NX) {
+        double a = 0;
+        for (int m = 0; m <= i; ++m) a += bLd[cur][i * NX + m] * tmp[m];
+        y[j * NX + i] = a;
+      }
+      g_cp_async_wait();
+      G_SYNCWARP();
     }
-    G_SYNC();
-    G_PAR_FOR(i, NX) {
-      double a = 0;
-      for (int m = 0; m <= i; ++m) a += Ld[i * NX + m] * tmp[m];
-      y[j * NX + i] = a;
+    // ---- backward: nu_j = Ld_j' (y_j - Lo_{j+1}' nu_{j+1}).  After the forward sweep buffer (N & 1) holds Ld_N, Lo_N.
+    for (int j = N; j >= 0; --j) {
+      const int cur = j & 1, nxt = cur ^ 1;     // bLd[cur] = Ld_j ; bLo[nxt] = Lo_{j+1} (staged while row j+1 was applied)
+      if (j > 0) {
+        const double* Ldn = c.Ld + (size_t)(j - 1) * NN;
+        G_W0_FOR(it, NN) { g_cp_async8(&bLd[nxt][it], Ldn + it); }
+      }
+      G_W0_FOR(i, NX) {
+        double a = y[j * NX + i];
+        if (j < N) for (int m = 0; m < NX; ++m) a -= bLo[nxt][m * NX + i] * y[(j + 1) * NX + m];
+        tmp[i] = a;
+      }
+      G_SYNCWARP();
+      // Lo_{j+1} is consumed: its buffer can take Lo_j (needed at step j-1 as "Lo_{(j-1)+1}")
+      if (j > 0) {
+        const double* Lon = c.Lo + (size_t)j * NN;
+        G_W0_FOR(it, NN) { g_cp_async8(&bLo[cur][it], Lon + it); }
+      }
+      G_W0_FOR(i, NX) {
+        double a = 0;
+        for (int m = i; m < NX; ++m) a += bLd[cur][m * NX + i] * tmp[m];
+        y[j * NX + i] = a;
+      }
+      g_cp_async_wait();
+      G_SYNCWARP();
     }
-    G_SYNC();
   }
-  for (int j = N; j >= 0; --j) {      // backward: nu_j = Ld_j' (y_j - Lo_{j+1}' nu_{j+1})
-    const double* Ld = c.Ld + (size_t)j * NX * NX;
-    const double* Lo = c.Lo + (size_t)(j + 1) * NX * NX;
-    G_PAR_FOR(i, NX) {
-      double a = y[j * NX + i];
-      if (j < N) for (int m = 0; m < NX; ++m) a -= Lo[m * NX + i] * y[(j + 1) * NX + m];
-      tmp[i] = a;
-    }
-    G_SYNC();
-    G_PAR_FOR(i, NX) {
-      double a = 0;
-      for (int m = i; m < NX; ++m) a += Ld[m * NX + i] * tmp[m];
-      y[j * NX + i] = a;
-    }
-    G_SYNC();
-  }
+  G_SYNC();
 }
 
 // [dz; dnu] = Ktilde^-1 [r; rnu]  with Ktilde = [[H + dp I, A'], [A, -(dd) ]] via the Schur complement.
-template <int M> GDEV void kkt_solve(const IpmCtx<M>& c, const double* r, const double* rnu, double* dz, double* dnu) {
+template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* r, const double* rnu, double* dz, double* dnu) {
   constexpr int NX = IpmCtx<M>::NX, NV = IpmCtx<M>::NV;
   const int N = c.N;
   apply_Hinv<M>(c, r, c.t1);
@@ -326,18 +359,22 @@ template <int M> GDEV void kkt_solve_refined(const IpmCtx<M>& c, const double* r
 }
 
 // ------------------------------------------------------------------------------------------ factorisation
-template <int M> GDEV bool factorize(const IpmCtx<M>& c, const IpmParams& prm) {
+template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c, const IpmParams& prm) {
   constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU;
   const int N = c.N;
   const double hh = 0.5 * c.h;
   double bad = 0.0;
-  // (1) per knot: Cholesky of Hx + dp I (into W[k][0] as scratch), inverse Cholesky of Hu + dp I, GT = Theta G'
+  // (1) per knot, on thread-local copies: Cholesky of Hx + dp I and its inverse Ci; inverse Cholesky Cu of Hu + dp I;
+  //     GT = Theta G'
   G_PAR_FOR(k, N) {
-    double* C = c.W + (size_t)k * 3 * NX * NX;
+    double C[NX * NX], Cinv[NX * NX];
     const double* Hx = c.Hx + (size_t)k * NX * NX;
     for (int i = 0; i < NX * NX; ++i) C[i] = Hx[i];
     for (int i = 0; i < NX; ++i) C[i * NX + i] += prm.delta_p;
     if (!chol_lower<NX>(C)) bad = 1.0;
+    for (int j = 0; j < NX; ++j) tri_inv_col<NX>(C, j, Cinv);
+    double* gCi = c.Ci + (size_t)k * NX * NX;
+    for (int i = 0; i < NX * NX; ++i) gCi[i] = Cinv[i];
     double Hu[NU * NU], Cu[NU * NU];
     for (int i = 0; i < NU * NU; ++i) { Hu[i] = c.Hu[(size_t)k * NU * NU + i]; Cu[i] = 0.0; }
     for (int i = 0; i < NU; ++i) Hu[i * NU + i] += prm.delta_p;
@@ -357,12 +394,6 @@ template <int M> GDEV bool factorize(const IpmCtx<M>& c, const IpmParams& prm) {
         }
         GT[a * NX + i] = s;
       }
-  }
-  G_SYNC();
-  // (2) Ci = C^-1 column by column
-  G_PAR_FOR(it, N * NX) {
-    const int k = it / NX, col = it - k * NX;
-    tri_inv_col<NX>(c.W + (size_t)k * 3 * NX * NX, col, c.Ci + (size_t)k * NX * NX);
   }
   G_SYNC();
   // (3) CA = h/2 * Ci * A'   (CA[m][j] = h/2 sum_q Ci[m][q] A[j][q])
@@ -454,7 +485,7 @@ struct Resid { double rz, rp, rc, mu, npair; };
 
 // phase 0: build Hx, Hu and the predictor rhs (sigma*mu = 0, no second-order term); also residual norms.
 // phase 1: corrector rhs with centering target `smu` and the stored predictor products.
-template <int M> GDEV void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out) {
+template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const int N = c.N;
@@ -543,7 +574,7 @@ template <int M> GDEV void assemble(const IpmCtx<M>& c, int phase, double smu, R
 
 // Per-slot step from dz; mode 0: predictor (returns max steps and stores nothing), mode 1: store predictor products,
 // mode 2: apply step (alpha_p, alpha_d).  Returns through amax[0..1] the largest primal/dual step to the boundary.
-template <int M> GDEV void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* amax,
+template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* amax,
                                       double* mu_aff) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NV = L::NV;
@@ -601,7 +632,7 @@ template <int M> GDEV void slot_steps(const IpmCtx<M>& c, int phase, double smu,
 }
 
 // Keep every complementarity pair above 1e-4 * mu (wide neighbourhood of the central path), as the oracle does.
-template <int M> GDEV void recenter(const IpmCtx<M>& c) {
+template <int M> GDEV_NOINLINE void recenter(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
@@ -658,7 +689,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   c.W = q; q += (size_t)N * NX * NX * 3;
   c.Hu = q; q += (size_t)N * NU * NU; c.Cu = q; q += (size_t)N * NU * NU; c.GT = q; q += (size_t)N * NU * NX;
   c.Ld = q; q += (size_t)(N + 1) * NX * NX; c.Lo = q; q += (size_t)(N + 1) * NX * NX;
-  c.sy = smem; c.sD = c.sy + (N + 1) * NX; c.sLo = c.sD + NX * NX; c.sLi = c.sLo + NX * NX; c.red = c.sLi + NX * NX;
+  c.sy = smem; c.sD = c.sy + (N + 1) * NX; c.sLo = c.sD + NX * NX; c.sLi = c.sLo + NX * NX; c.sB4 = c.sLi + NX * NX;
+  c.stmp = c.sB4 + NX * NX; c.red = c.stmp + 16;
 
   // ---- start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); slacks one unit inside
   G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; c.z[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
@@ -682,12 +714,15 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   G_SYNC();
 
   int status = IPM_ITERATION_LIMIT, it_done = 0;
+  long long cyc_asm = 0, cyc_fac = 0, cyc_sol = 0, cyc_slot = 0, tc0;
   double res = 1e300, mu = 0;
   const double scd = 1.0 + c.omega;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
     it_done = iter;
     Resid R;
+    tc0 = g_clock();
     assemble<M>(c, 0, 0.0, &R);
+    cyc_asm += g_clock() - tc0;
     mu = R.mu;
     res = R.rz / scd;
     res = R.rp > res ? R.rp : res; res = R.rc > res ? R.rc : res; res = mu > res ? mu : res;
@@ -696,26 +731,38 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
 #endif
     if (res <= prm.tol) { status = IPM_OPTIMAL; break; }
     if (!(res == res) || res > 1e200) { status = IPM_NUMERICAL; break; }
-    if (!factorize<M>(c, prm)) {
+    tc0 = g_clock();
+    const bool fac_ok = factorize<M>(c, prm);
+    cyc_fac += g_clock() - tc0;
+    if (!fac_ok) {
 #ifdef GUSTO_HOSTSIM
       if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  factorize: non-positive pivot\n");
 #endif
     }
     // predictor
+    tc0 = g_clock();
     kkt_solve_refined<M>(c, c.r, c.rnu, c.dz, c.dnu, 0);
+    cyc_sol += g_clock() - tc0;
     double am[2], mu_aff = 0;
+    tc0 = g_clock();
     slot_steps<M>(c, 0, 0.0, 0, 0, 0, am, &mu_aff);
     double a_aff = am[0] < am[1] ? am[0] : am[1];
     a_aff = a_aff < 1.0 ? a_aff : 1.0;
     slot_steps<M>(c, 0, 0.0, 1, a_aff, a_aff, am, &mu_aff);
+    cyc_slot += g_clock() - tc0;
     mu_aff = R.npair > 0 ? mu_aff / R.npair : 0.0;
     double sigma = mu > 0 ? (mu_aff / mu) : 0.0;
     sigma = sigma * sigma * sigma;
     double smu = sigma * mu;
     smu = smu > 0.1 * prm.tol ? smu : 0.1 * prm.tol;
     // corrector
+    tc0 = g_clock();
     assemble<M>(c, 1, smu, &R);
+    cyc_asm += g_clock() - tc0;
+    tc0 = g_clock();
     kkt_solve_refined<M>(c, c.r, c.rnu, c.dz, c.dnu, prm.nref);
+    cyc_sol += g_clock() - tc0;
+    tc0 = g_clock();
     slot_steps<M>(c, 1, smu, 0, 0, 0, am, &mu_aff);
     double tau = 0.995;
     if (mu < 1.0) { tau = 1.0 - mu; tau = tau > 0.995 ? tau : 0.995; tau = tau < 0.999999 ? tau : 0.999999; }
@@ -726,6 +773,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     G_PAR_FOR(it, (N + 1) * NX) c.nu[it] += ad * c.dnu[it];
     G_SYNC();
     recenter<M>(c);
+    cyc_slot += g_clock() - tc0;
   }
   if (status == IPM_ITERATION_LIMIT && res <= 1e3 * prm.tol) status = IPM_OPTIMAL;
   {   // a NaN/Inf anywhere in the iterate is a numerical failure, never an answer
@@ -749,7 +797,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   obj = block_sum(obj, c.red);
   if (G_TID == 0) {
     info[0] = (double)status; info[1] = (double)it_done; info[2] = res; info[3] = mu; info[4] = obj;
-    info[5] = 0; info[6] = 0; info[7] = 0;
+    info[5] = (double)(cyc_asm + cyc_slot); info[6] = (double)cyc_fac; info[7] = (double)cyc_sol;   // SM cycles per phase
   }
 }
 

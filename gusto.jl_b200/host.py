@@ -17,7 +17,7 @@ from . import models as M
 from .problems import BatchProblem
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgusto_b200.so")
+LIB_PATH = os.environ.get("GUSTO_B200_LIB", os.path.join(_HERE, "libgusto_b200.so"))
 EVAL_NOUT = 8
 SOLVE_NINFO = 8
 EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)

@@ -49,7 +49,7 @@ enum {
 
 /* number of doubles per instance written by gusto_evaluate / gusto_solve_subproblem */
 #define GUSTO_EVAL_NOUT 8 /* conv, tr_ok, ineq_ok, rho, J_true, J_full, max_k|dX_k|^2, max soft-row value */
-#define GUSTO_SOLVE_NINFO 8 /* status, newton iterations, residual, mu, objective, 0, 0, 0 */
+#define GUSTO_SOLVE_NINFO 8 /* status, newton iterations, residual, mu, objective, SM cycles: assembly, factorisation, KKT solves */
 
 typedef struct {
   int32_t model_id;        /* GUSTO_* model                                                        */

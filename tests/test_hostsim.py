@@ -1,0 +1,80 @@
+"""Kernel bodies (linearize / IPM solve / evaluate) run through the single-thread host simulation and compared with
+the oracle.  This checks the CUDA sources' arithmetic in the GPU-less container; races, memory spaces and the C ABI
+are covered by the -m gpu tests.  The host simulation is test infrastructure (tests/hostsim), not a product path.
+"""
+import numpy as np
+import pytest
+
+from util import gb, orc, to_oracle, hostsim_iterate
+from gusto_oracle.scp import solve_subproblem, evaluate, solve_gusto
+from gusto_oracle.subproblem import linearize, obstacle_rows
+
+CASES = [("dubins", dict(B=2, N=30)), ("freeflyerSE2", dict(B=2, N=40)), ("astrobeeSE3", dict(B=2, N=50)),
+         ("astrobeeSE3manifold", dict(B=2, N=60))]
+
+
+def err(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) if np.size(a) else 0.0
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_linearize_body_is_exact(name, kw):
+    bp = gb.problems.CONFIGS[name](**kw)
+    X0, U0 = bp.init_traj_straightline()
+    rng = np.random.default_rng(0)
+    X = X0 + 0.1 * rng.normal(size=X0.shape); U = U0 + 0.1 * rng.normal(size=U0.shape)
+    hs = hostsim_iterate(bp, X, U, 1.0, bp.model.scp_params[0], stages=1)
+    toggle = bp.model.scp_params[0] / 8 + bp.model.clearance
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        lin = linearize(p, X[b], U[b])
+        assert err(hs["f"][b], lin["f"]) < 1e-13 and err(hs["A"][b], lin["A"]) < 1e-13 and err(hs["g"][b], lin["g"]) < 1e-12
+        if p.n_obs:
+            r = obstacle_rows(p, X[b], toggle)
+            assert err(hs["rows"][b][..., :3], r["nhat"]) < 1e-13 and err(hs["rows"][b][..., 3], r["off"]) < 1e-12
+            assert err(hs["rows"][b][..., 4], r["dist0"]) < 1e-13
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("omega", [1.0, 25.0])
+def test_solve_and_evaluate_bodies_match_oracle(name, kw, omega):
+    bp = gb.problems.CONFIGS[name](**kw)
+    sp = bp.model.scp_params
+    X0, U0 = bp.init_traj_straightline()
+    hs = hostsim_iterate(bp, X0, U0, omega, sp[0])
+    toggle = sp[0] / 8 + bp.model.clearance
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[b], U0[b], omega, sp[0], toggle, sp[3])
+        assert st == "OPTIMAL" and hs["info"][b, 0] == 0
+        assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
+        assert abs(hs["info"][b, 1] - r.iters) <= 3          # same algorithm: Newton iteration counts agree
+        xtol = 1e-3 if name == "astrobeeSE3manifold" else 1e-4
+        assert err(hs["Xn"][b], Xs) < xtol and err(hs["Un"][b], Us) < 1e-5
+        ev = evaluate(p, hs["Xn"][b], hs["Un"][b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
+        o = hs["eval"][b]
+        assert abs(o[0] - ev["conv"]) < 1e-12 and bool(o[1]) == ev["tr_ok"] and bool(o[2]) == ev["ineq_ok"]
+        assert abs(o[3] - ev["rho"]) <= 1e-10 * max(1e-3, abs(ev["rho"]))
+        assert abs(o[4] - ev["J_true"]) <= 1e-12 * max(1.0, ev["J_true"]) and abs(o[5] - ev["J_full"]) <= 1e-9 * max(1.0, abs(ev["J_full"]))
+
+
+def test_trust_region_and_penalty_paths_are_exercised():
+    """Small Delta / large omega: the trust-region hinge and obstacle hinges are active in the solve."""
+    bp = gb.problems.config_astrobee_se3_notebook(N=30)
+    X0, U0 = bp.init_traj_straightline()
+    p = to_oracle(bp, 0)
+    for omega, Delta in [(100.0, 0.3), (1e4, 10.0), (1.0, 0.01)]:
+        toggle = Delta / 8 + bp.model.clearance
+        hs = hostsim_iterate(bp, X0, U0, omega, Delta)
+        Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[0], U0[0], omega, Delta, toggle, bp.model.scp_params[3])
+        assert st == "OPTIMAL" and hs["info"][0, 0] == 0
+        assert abs(hs["info"][0, 4] - obj) <= 1e-5 * max(1.0, abs(obj)), (omega, Delta, hs["info"][0, 4], obj)
+        assert err(hs["Un"][0], Us) < 1e-4
+
+
+def test_numerical_failure_is_reported_as_status_not_as_an_answer():
+    bp = gb.problems.config_astrobee_se3(B=1, N=20, seed=1)
+    X0, U0 = bp.init_traj_straightline()
+    X0[0, 3, 0] = np.nan
+    hs = hostsim_iterate(bp, X0, U0, 1.0, 10.0, stages=3)
+    assert hs["info"][0, 0] == 2

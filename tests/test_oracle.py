@@ -1,0 +1,148 @@
+"""CPU tests of the oracle itself (parity is unpinned by the reference: it has no tests; see oracle/__init__.py).
+
+What can be pinned is pinned here: the closed-form Jacobians against finite differences of f (the reference derived
+them symbolically, scripts/symbolic_math.m), the signed distance against brute force, the interior-point solver
+against an independent SciPy solver, the SCP loop against the one recorded reference run
+(examples/freeflyerSE2.ipynb cell 3) as a loose band, and the committed golden vectors.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.optimize as sopt
+
+from util import gb, orc, to_oracle, ROOT
+from gusto_oracle.models import f_dyn, A_dyn, B_dyn, get_model
+from gusto_oracle.sdf import signed_distance, Obstacle, BOX, SPHERE, pack_obstacles
+from gusto_oracle.subproblem import build_qcqp
+from gusto_oracle.ipm import solve_qcqp
+from gusto_oracle.scp import solve_gusto, solve_subproblem, penalized_cost
+
+
+@pytest.mark.parametrize("name", orc.MODELS)
+def test_jacobians_match_finite_differences(name):
+    m = get_model(name)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=m.n_x) * 0.3
+    u = rng.normal(size=m.n_u) * 0.3
+    A = A_dyn(m, x)
+    B = B_dyn(m)
+    h = 1e-6
+    for j in range(m.n_x):
+        e = np.zeros(m.n_x); e[j] = h
+        assert np.allclose((f_dyn(m, x + e, u) - f_dyn(m, x - e, u)) / (2 * h), A[:, j], atol=1e-8)
+    for j in range(m.n_u):
+        e = np.zeros(m.n_u); e[j] = h
+        assert np.allclose((f_dyn(m, x, u + e) - f_dyn(m, x, u - e)) / (2 * h), B[:, j], atol=1e-8)
+
+
+def test_signed_distance_box_and_sphere_against_brute_force():
+    rng = np.random.default_rng(1)
+    R = 0.26
+    lo, hi = np.array([-1.0, -0.5, 0.0]), np.array([0.5, 1.0, 2.0])
+    obs = pack_obstacles([Obstacle(BOX, lo, hi), Obstacle(SPHERE, np.array([2.0, 0.0, 1.0]), np.array([0.4, 0, 0]))])
+    pts = rng.uniform(-3, 3, size=(200, 3))
+    d, n = signed_distance(pts, obs, R)
+    # brute force: distance to a dense sampling of the box surface
+    g = np.linspace(0, 1, 41)
+    faces = []
+    for ax in range(3):
+        for side in (lo, hi):
+            a, b = [i for i in range(3) if i != ax]
+            P = np.zeros((41 * 41, 3))
+            P[:, a] = np.repeat(lo[a] + g * (hi[a] - lo[a]), 41); P[:, b] = np.tile(lo[b] + g * (hi[b] - lo[b]), 41); P[:, ax] = side[ax]
+            faces.append(P)
+    S = np.concatenate(faces)
+    for p, db in zip(pts, d[:, 0]):
+        dist = np.min(np.linalg.norm(S - p, axis=1))
+        inside = np.all(p > lo) and np.all(p < hi)
+        assert abs((-dist if inside else dist) - R - db) < 0.04
+    assert np.allclose(d[:, 1], np.linalg.norm(pts - np.array([2.0, 0, 1.0]), axis=1) - 0.4 - R)
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0)
+    # first-order model: d(r + dr) ~ d(r) + n.dr
+    dr = 1e-6 * rng.normal(size=pts.shape)
+    d2, _ = signed_distance(pts + dr, obs, R)
+    assert np.allclose(d2 - d, np.einsum("kij,kj->ki", n, dr), atol=1e-9)
+
+
+def test_sdf_planar_mode_has_no_z_normal():
+    obs = pack_obstacles([Obstacle(BOX, np.array([0., 0., -5.]), np.array([1., 1., 5.]))])
+    d, n = signed_distance(np.array([[2.0, 0.5, 0.0], [0.5, 0.4, 0.0]]), obs, 0.157, ws_dim=2)
+    assert np.allclose(d[:, 0], [1.0 - 0.157, -0.4 - 0.157]) and np.all(n[..., 2] == 0)
+    assert np.allclose(n[0, 0], [1, 0, 0]) and np.allclose(n[1, 0], [0, -1, 0])
+
+
+def test_ipm_matches_independent_scipy_solver_on_a_small_subproblem():
+    """Same QCQP (dubins N=6, control ball + soft state box) solved by SLSQP on the penalised, slack-free form."""
+    bp = gb.problems.config_dubins(B=1, N=6)
+    p = to_oracle(bp, 0)
+    m = p.model
+    Xp, Up = p.init_traj_straightline()
+    omega, Delta, eps = 1.0, m.scp_params[0], m.scp_params[3]
+    qp = build_qcqp(p, Xp, Up, omega, Delta, 0.0, eps)
+    r = solve_qcqp(qp)
+    assert r.status == "OPTIMAL"
+    n = qp.nX + qp.nU
+    # SLSQP on (X,U) only: soft rows are inactive here (|x| << 100), so the problem is cost s.t. eq + control ball
+    A, b = qp.Aeq.toarray()[:, :n], qp.beq
+    cons = [{"type": "eq", "fun": lambda z: A @ z - b, "jac": lambda z: A}]
+    for k in range(p.N - 1):
+        cons.append({"type": "ineq", "fun": (lambda z, k=k: m.robot_params[15] ** 2 - z[qp.nX + k] ** 2)})
+    res = sopt.minimize(lambda z: 0.5 * z @ (qp.P[:n] * z), qp.z0[:n], jac=lambda z: qp.P[:n] * z, constraints=cons,
+                        method="SLSQP", options=dict(ftol=1e-14, maxiter=500))
+    assert res.success
+    assert abs(res.fun - r.obj) <= 1e-6 * max(1.0, abs(r.obj))
+    assert np.max(np.abs(res.x - r.z[:n])) < 1e-4
+
+
+def test_ipm_objective_equals_penalised_cost_and_hard_rows_hold():
+    bp = gb.problems.config_astrobee_se3_notebook(N=30)
+    p = to_oracle(bp, 0)
+    m = p.model
+    Xp, Up = p.init_traj_straightline()
+    toggle = m.scp_params[0] / 8 + m.robot_params[9]
+    for omega in (1.0, 100.0):
+        X, U, obj, st, lin, rows, r = solve_subproblem(p, Xp, Up, omega, m.scp_params[0], toggle, m.scp_params[3])
+        assert st == "OPTIMAL"
+        J = penalized_cost(p, X, U, Xp, rows, omega, m.scp_params[0], m.scp_params[3])
+        assert abs(J - obj) <= 1e-5 * max(1.0, abs(obj))
+        assert np.max(np.abs(X[0] - p.x_init)) < 1e-8 and np.max(np.abs(X[-1] - p.goal_lo)) < 1e-8
+        assert np.all(np.linalg.norm(U[:-1, :3], axis=1) / m.robot_params[0] <= m.robot_params[6] + 1e-7)
+
+
+@pytest.mark.parametrize("name,kw", [("dubins", {}), ("freeflyerSE2", dict(B=2)), ("astrobeeSE3", dict(B=2)),
+                                      ("astrobeeSE3manifold", dict(B=1))])
+def test_scp_converges_on_every_model(name, kw):
+    bp = gb.problems.CONFIGS[name](**kw)
+    S = solve_gusto(to_oracle(bp, 0))
+    assert S.converged and S.successful
+    assert len(S.J_true) == S.iterations + 1 and len(S.accept_solution) == S.iterations + 1      # quirk q10
+    assert S.Delta_vec[0] == bp.model.scp_params[0] and S.omega_vec[0] == 1.0
+
+
+@pytest.mark.slow
+def test_freeflyer_notebook_run_is_inside_the_recorded_band():
+    """examples/freeflyerSE2.ipynb cell 3 (Gurobi + Bullet, N=200): converged, 28 iterations, first accepted
+    J_true = 0.152419, final J_true = 0.111656, omega escalates 1 -> 10 -> 100.  Bullet's cylinder hull and Gurobi's
+    tolerances are not reproducible here, so this is a loose band (N=100 to keep the CPU suite short)."""
+    bp = gb.problems.config_freeflyer_notebook(N=100)
+    S = solve_gusto(to_oracle(bp, 0), max_iter=40)
+    assert S.converged
+    assert 0.05 < S.J_true[1] < 0.5          # recorded 0.1524 at N=200
+    assert 0.03 < S.J_true[-1] < 0.3         # recorded 0.1117
+    assert 5 <= S.iterations <= 40
+
+
+def test_golden_vectors():
+    """Vectors generated by tests/golden/make_golden.py from this oracle (committed so that drift is visible)."""
+    path = os.path.join(ROOT, "tests", "golden", "oracle_golden.npz")
+    G = np.load(path)
+    for name in orc.MODELS:
+        m = get_model(name)
+        x, u = G[f"{name}_x"], G[f"{name}_u"]
+        assert np.allclose(f_dyn(m, x, u), G[f"{name}_f"], rtol=0, atol=1e-14)
+        assert np.allclose(A_dyn(m, x), G[f"{name}_A"], rtol=0, atol=1e-14)
+    bp = gb.problems.config_astrobee_se3(B=2, N=20, seed=11)
+    S = solve_gusto(to_oracle(bp, 0))
+    assert abs(S.J_true[-1] - float(G["se3_scp_J"])) <= 1e-6 * float(G["se3_scp_J"]) and S.iterations == int(G["se3_scp_iters"])
