@@ -43,16 +43,24 @@
 #endif
 #define G_W0_FOR(i, n) for (int i = G_TID; i < (n); i += G_WARP)
 
-// 8-byte asynchronous global->shared copy (LDGSTS): lets the block-tridiagonal sweeps prefetch the next block's factor
-// while the current one is applied.  Host simulation: a plain copy.
+// Asynchronous global->shared copies (LDGSTS): the block-tridiagonal sweeps prefetch the next block's factor while the
+// current one is applied.  16-byte form needs 16-byte aligned source and destination.  Host simulation: plain copies.
 #ifdef GUSTO_HOSTSIM
 inline void g_cp_async8(double* dst, const double* src) { *dst = *src; }
+inline void g_cp_async16(double* dst, const double* src) { dst[0] = src[0]; dst[1] = src[1]; }
+inline void g_cp_async_commit() {}
 inline void g_cp_async_wait() {}
+template <int N> inline void g_cp_async_wait_group() {}
 #else
 __device__ __forceinline__ void g_cp_async8(double* dst, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void g_cp_async16(double* dst, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void g_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void g_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
 namespace gusto {
@@ -73,18 +81,76 @@ constexpr int MAX_NU = 6;
 constexpr int MAX_OBS = 64;
 
 // Compile-time description of a dynamics model (mirrors the reference's per-model files, see models.cuh).
+//   NX, NU, WS (workspace dims of the obstacle rows), which soft/hard row families exist (SCPConstraints(SCPP) of the
+//   model file), and the STRUCTURE the convex solve exploits:
+//   * x-blocks / u-blocks: a partition of the state / control coordinates such that every inequality row except the
+//     state trust region has its gradient inside one block (position | velocity | attitude | rate).  The reduced
+//     Hessian of a knot is then  dg*I + blockdiag(blocks) + kappa_tr * g g'  (Sherman-Morrison invertible).
+//   * a_row/a_col: the static sparsity pattern of A = df/dx (entries that can be non-zero), ANZ entries.
+//   * b_row(a): the single state row driven by control a (B = df/du has one entry per column).
+#define GUSTO_BLOCKS(NAME, CNT, O0, N0, O1, N1, O2, N2, O3, N3)                                            \
+  static constexpr int NAME##_CNT = CNT;                                                                    \
+  GHD static constexpr int NAME##_off(int b) { return b == 0 ? O0 : b == 1 ? O1 : b == 2 ? O2 : O3; }      \
+  GHD static constexpr int NAME##_n(int b) { return b == 0 ? N0 : b == 1 ? N1 : b == 2 ? N2 : N3; }        \
+  GHD static constexpr int NAME##_pk(int b) {   /* offset of block b in the packed-lower storage */        \
+    int o = 0;                                                                                              \
+    for (int q = 0; q < b; ++q) o += NAME##_n(q) * (NAME##_n(q) + 1) / 2;                                   \
+    return o;                                                                                               \
+  }                                                                                                         \
+  GHD static constexpr int NAME##_of(int i) {   /* block containing coordinate i */                        \
+    int b = 0;                                                                                              \
+    for (int q = 0; q < CNT; ++q) if (i >= NAME##_off(q)) b = q;                                            \
+    return b;                                                                                               \
+  }
+
 template <int M> struct Traits;
 template <> struct Traits<DUBINS> {
   static constexpr int NX = 3, NU = 1, WS = 0, HAS_TR = 0, NNORM = 0, NLIN = 6, HAS_QUAT = 0, NBALL = 1;
+  GUSTO_BLOCKS(XB, 3, 0, 1, 1, 1, 2, 1, 0, 0)
+  GUSTO_BLOCKS(UB, 1, 0, 1, 0, 0, 0, 0, 0, 0)
+  static constexpr int ANZ = 2;
+  GHD static constexpr int a_row(int e) { return e; }
+  GHD static constexpr int a_col(int) { return 2; }
+  GHD static constexpr int b_row(int) { return 2; }
 };
 template <> struct Traits<FREEFLYER_SE2> {
   static constexpr int NX = 6, NU = 3, WS = 2, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2;
+  GUSTO_BLOCKS(XB, 4, 0, 2, 2, 1, 3, 2, 5, 1)
+  GUSTO_BLOCKS(UB, 2, 0, 2, 2, 1, 0, 0, 0, 0)
+  static constexpr int ANZ = 3;
+  GHD static constexpr int a_row(int e) { return e; }
+  GHD static constexpr int a_col(int e) { return 3 + e; }
+  GHD static constexpr int b_row(int a) { return 3 + a; }
 };
 template <> struct Traits<ASTROBEE_SE3> {
   static constexpr int NX = 12, NU = 6, WS = 3, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2;
+  GUSTO_BLOCKS(XB, 4, 0, 3, 3, 3, 6, 3, 9, 3)
+  GUSTO_BLOCKS(UB, 2, 0, 3, 3, 3, 0, 0, 0, 0)
+  // rows 0-2: identity on v | rows 6-8: MRP kinematics wrt (p, w) | rows 9-11: gyroscopic wrt w (off-diagonal)
+  static constexpr int ANZ = 27;
+  GHD static constexpr int a_row(int e) { return e < 3 ? e : e < 21 ? 6 + (e - 3) / 6 : 9 + (e - 21) / 2; }
+  GHD static constexpr int a_col(int e) {
+    if (e < 3) return 3 + e;
+    if (e < 21) return 6 + (e - 3) % 6;
+    const int r = (e - 21) / 2, q = (e - 21) % 2;       // row 9+r: the two columns of {9,10,11} other than 9+r
+    return 9 + (q + (q >= r ? 1 : 0));
+  }
+  GHD static constexpr int b_row(int a) { return a < 3 ? 3 + a : 6 + a; }
 };
 template <> struct Traits<ASTROBEE_SE3_MANIFOLD> {
   static constexpr int NX = 13, NU = 6, WS = 3, HAS_TR = 0, NNORM = 2, NLIN = 1, HAS_QUAT = 1, NBALL = 2;
+  GUSTO_BLOCKS(XB, 4, 0, 3, 3, 3, 6, 4, 10, 3)
+  GUSTO_BLOCKS(UB, 2, 0, 3, 3, 3, 0, 0, 0, 0)
+  // rows 0-2: identity on v | rows 6-9: quaternion kinematics wrt (q, w) minus the zero diagonal | rows 10-12: gyroscopic
+  static constexpr int ANZ = 33;
+  GHD static constexpr int a_row(int e) { return e < 3 ? e : e < 27 ? 6 + (e - 3) / 6 : 10 + (e - 27) / 2; }
+  GHD static constexpr int a_col(int e) {
+    if (e < 3) return 3 + e;
+    if (e < 27) { const int r = (e - 3) / 6, q = (e - 3) % 6; return 6 + (q + (q >= r ? 1 : 0)); }
+    const int r = (e - 27) / 2, q = (e - 27) % 2;
+    return 10 + (q + (q >= r ? 1 : 0));
+  }
+  GHD static constexpr int b_row(int a) { return a < 3 ? 3 + a : 7 + a; }
 };
 
 // Everything a kernel needs that is shared by the whole batch.  Passed by value (fits the 4 KB param space).

@@ -8,15 +8,25 @@
 // Method: infeasible-start primal-dual interior point with Mehrotra predictor-corrector (same algorithm as
 // oracle/gusto_oracle/ipm.py, so iterates can be compared one-to-one), specialised to the problem structure:
 //   * every inequality touches one knot only; its slack t and both multipliers are eliminated analytically,
-//     leaving a block-diagonal reduced Hessian  H = blkdiag(Hx_k [NXxNX], Hu_k [NUxNU]);
+//     leaving a block-diagonal reduced Hessian  H = blkdiag(Hx_k, Hu_k);
+//   * inside a knot every row except the state trust region lives in ONE coordinate block (position | velocity |
+//     attitude | rate, Traits<M>::XB_*), so  Hx_k = blockdiag(<=4x4 blocks) + kappa_tr g g'  and its inverse is
+//     blockdiag(P_b) - coef w w'  (Sherman-Morrison); nothing larger than 4x4 is ever factorised per knot;
+//   * A_k = df/dx is used through its static sparsity pattern (Traits<M>::a_row/a_col, 27 of 144 entries for SE3);
 //   * the equality rows (init, trapezoid dynamics, point goal) are block-bidiagonal, so the Schur complement
-//     S = A (H + dp I)^-1 A' is block-tridiagonal with N+1 blocks of NX x NX and is factorised by a block
-//     Cholesky sweep; Newton directions are then recovered with `nref` steps of iterative refinement against
-//     the unregularised KKT matrix (H alone is only positive SEMI-definite: the cost has no state term).
+//     S = Aeq (H + dp I)^-1 Aeq' is block-tridiagonal with N+1 blocks of NX x NX.  It is factorised as a block
+//     L D L' with explicit D_j^-1 (Gauss-Jordan in shared memory on one warp while the other warp prefetches the
+//     next block row), so each solve is two chains of N dependent NX x NX mat-vecs streamed through a cp.async
+//     ring plus one fully parallel D^-1 pass;
+//   * Newton directions are recovered with `nref` steps of iterative refinement against the unregularised KKT
+//     matrix (H alone is only positive SEMI-definite: the cost has no state term).
 // A first-order splitting (ADMM, prototyped in tools/admm_proto.py) was rejected: GuSTO's accept test compares
 // soft rows against eps = 1e-6 (astrobee_se3.jl:31, scp_gusto.jl:318-327), and with a trapezoid double
 // integrator over 70 s ADMM needs >2000 iterations for 1e-6 residuals while this method needs 8-25 for 1e-8.
 //
+// Memory: the iterate z, the direction dz and the Schur right-hand side live in shared memory; multipliers, slack
+// records (compacted to the obstacle rows inside the toggle distance), per-knot block inverses and the
+// block-tridiagonal factor live in a per-instance global scratch that stays L2-resident.
 // All arithmetic is FP64 (the reference is Float64 throughout).
 #pragma once
 #include "common.cuh"
@@ -44,588 +54,1028 @@ struct IpmParams {
 };
 
 enum : int { IPM_OPTIMAL = 0, IPM_ITERATION_LIMIT = 1, IPM_NUMERICAL = 2 };
-constexpr int SLOT_W = 6;   // s, lam, t, lamb, pa (ds*dlam of the predictor), pb (dt*dlamb of the predictor)
+constexpr int SLOT_W = 6;     // s, lam, t, lamb, pa (ds*dlam of the predictor), pb (dt*dlamb of the predictor)
+constexpr int OROW_W = 5;     // compacted obstacle row: nhat[3], off, knot
 constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cycles: assemble+slots, factorize, kkt solves
+constexpr int RING_STAGES = 8;
+
+GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
 template <int M> struct IpmLayout {
   using T = Traits<M>;
-  static constexpr int NX = T::NX, NU = T::NU, NV = NX + NU;
+  static constexpr int NX = T::NX, NU = T::NU, NV = NX + NU, NN = NX * NX, ANZ = T::ANZ;
+  static constexpr int LDR = NX | 1;                      // odd row stride of a ring tile: conflict-free both ways
+  static constexpr int TILE = NX * LDR;
+  // special (non-obstacle) slots of a knot
   static constexpr int S_TR = 0;
-  static constexpr int S_NORM = 1;
+  static constexpr int S_NORM = T::HAS_TR;
   static constexpr int S_LIN = S_NORM + T::NNORM;
-  static constexpr int S_QUAT = S_LIN + T::NLIN;          // hinge, then hard row
+  static constexpr int S_QUAT = S_LIN + T::NLIN;           // hinge, then hard row
   static constexpr int S_BALL = S_QUAT + 2 * T::HAS_QUAT;
-  static constexpr int S_BOX = S_BALL + T::NBALL;         // 2*NX goal-box rows (upper, lower per coordinate)
-  static constexpr int S_OBS = S_BOX + 2 * NX;
-  GHD static int nslots(int n_obs) { return S_OBS + n_obs; }
+  static constexpr int SP = S_BALL + T::NBALL;
+  static constexpr int NBOX = 2 * NX;                      // goal-box rows (upper, lower per coordinate), knot N-1 only
+  static constexpr int XPK = T::XB_pk(T::XB_CNT), UPK = T::UB_pk(T::UB_CNT);
+  // per-knot record: Hb[XPK] P[XPK] w[NX] aw[NX] Hub[UPK] Th[UPK] kap coef
+  static constexpr int KD_HB = 0, KD_P = XPK, KD_W = 2 * XPK, KD_AW = KD_W + NX, KD_HU = KD_AW + NX, KD_TH = KD_HU + UPK,
+                       KD_KAP = KD_TH + UPK, KD_COEF = KD_KAP + 1, KDW = KD_COEF + 1;
+  GHD static size_t rnd(size_t v) { return (v + 1) & ~(size_t)1; }   // keep every array 16-byte aligned
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
-    const size_t nz = (size_t)N * NV, ne = (size_t)(N + 1) * NX;
-    return 6 * nz + 5 * ne + (size_t)N * nslots(n_obs) * SLOT_W + (size_t)N * NX * NX * 6 + (size_t)N * NU * NU * 2 +
-           (size_t)N * NU * NX + (size_t)(N + 1) * NX * NX * 2;
+    const size_t nz = rnd((size_t)N * NV), ne = rnd((size_t)(N + 1) * NX), no = T::WS > 0 ? n_obs : 0;
+    return 3 * nz + 4 * ne + rnd((size_t)N * ANZ) + rnd((size_t)N * SP * SLOT_W) + (size_t)NBOX * SLOT_W +
+           rnd((size_t)N * no * SLOT_W) + rnd((size_t)N * no * OROW_W) + rnd((size_t)N * KDW) + (size_t)(N + 1) * 2 * NN;
   }
-  GHD static int smem_doubles(int N, int nthr) { return (N + 1) * NX + 4 * NX * NX + 16 + nthr + 16; }
+  GHD static int work_doubles(int N) {      // dz | sy | ring, also the 8 factorisation tiles
+    const int ne = (N + 1) * NX;
+    const int ring = RING_STAGES * TILE > ne ? RING_STAGES * TILE : ne;
+    const int w = N * NV + ne + ring, f = 9 * NN + 16;
+    return w > f ? w : f;
+  }
+  static constexpr int TAB_DOUBLES = (NX * (NX + 1) + 7) / 8;    // (row, col) of the packed lower triangle, as bytes
+  GHD static int seg_doubles(int N) { return (N + 4) / 2 + 2; }
+  GHD static int smem_doubles(int N, int nthr) { return N * NV + work_doubles(N) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES; }
 };
 
 template <int M> struct IpmCtx {
   using L = IpmLayout<M>;
   static constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const BatchDesc* d;
-  int N, n_obs, S, b;
-  double h, omega, Delta, toggle, eps;
+  const double* rp;
+  int N, n_obs, b, nact, pmask, bmask;
+  double h, hh, omega, Delta, toggle, eps, dp, dd;
   const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
-  double Bm[NX * NU];     // constant B
+  double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
   // global scratch
-  double *z, *nu, *r, *dz, *t1, *res, *e, *rnu, *dnu, *resnu, *enu, *bS, *slot;
-  double *Hx, *Ci, *CA, *W, *Hu, *Cu, *GT, *Ld, *Lo;
+  double *nu, *dnu, *r, *rnu, *t1, *res, *resnu, *Ac, *sslot, *bslot, *ost, *orow, *kd, *fac;
   // shared
-  double *sy, *sD, *sLo, *sLi, *sB4, *stmp, *red;
+  double *z, *dz, *sy, *ring, *red;
+  int* seg;
+  unsigned char* tab;     // [2][NX(NX+1)/2]: row / column of packed-lower entry t
 };
 
-// ------------------------------------------------------------------------------------------------- slots
-struct SlotEval {
+// ------------------------------------------------------------------------------------------- slot algebra
+// One inequality  c0(z) [- t] + s = 0, s >= 0 (multiplier lam) [, t >= 0 (multiplier lamb), cost omega*t].
+// After eliminating (s, lam [, t, lamb]) the row contributes  kap * gv gv' + lam * hess  to H and  -gv * bt  to the rhs.
+struct Pair { double rc, rt, wa, wb, ba, bb, iw, kap, bt, la; };
+
+GDEV void pair_eval(const double* st, bool has_t, double c0, double omega, double smu, int phase, Pair& q) {
+  const double sa = st[0], la = st[1];
+  const double isa = 1.0 / sa;
+  q.la = la;
+  q.wa = la * isa;
+  if (has_t) {
+    const double t = st[2], lb = st[3];
+    const double it = 1.0 / t;
+    q.rc = c0 - t + sa; q.rt = omega - la - lb;
+    q.wb = lb * it;
+    const double rsa = sa * la - smu + (phase ? st[4] : 0.0), rsb = t * lb - smu + (phase ? st[5] : 0.0);
+    q.ba = (la * q.rc - rsa) * isa; q.bb = -rsb * it;
+    q.iw = 1.0 / (q.wa + q.wb);
+    q.kap = q.wa * q.wb * q.iw;
+    q.bt = q.ba - q.wa * (q.ba + q.bb - q.rt) * q.iw;
+  } else {
+    q.rc = c0 + sa; q.rt = 0.0; q.wb = 0.0; q.bb = 0.0; q.iw = 0.0;
+    const double rs = sa * la - smu + (phase ? st[4] : 0.0);
+    q.ba = (la * q.rc - rs) * isa;
+    q.kap = q.wa;
+    q.bt = q.ba;
+  }
+}
+
+struct Stat { double rz, rc, mus, np; };   // running max |dual residual|, max |row residual|, sum s*lam, #pairs
+GDEV void pair_stat(const double* st, bool has_t, const Pair& q, Stat& S) {
+  S.rc = fabs(q.rc) > S.rc ? fabs(q.rc) : S.rc;
+  if (!(q.rc == q.rc)) S.rc = 1e300;
+  S.mus += st[0] * st[1]; S.np += 1.0;
+  if (has_t) { S.rz = fabs(q.rt) > S.rz ? fabs(q.rt) : S.rz; S.mus += st[2] * st[3]; S.np += 1.0; }
+}
+
+// Step of one row given gdz = gv . dz.   mode 0: largest steps to the boundary; mode 1: same + store the predictor
+// products and the complementarity at step ap; mode 2: apply (ap, ad).
+struct StepAcc { double amp, amd, mus; };
+GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a) {
+  const double sa = st[0], la = st[1];
+  if (has_t) {
+    const double t = st[2], lb = st[3];
+    const double dt = (q.wa * gdz + q.ba + q.bb - q.rt) * q.iw;
+    const double dla = q.wa * (gdz - dt) + q.ba, dlb = -q.wb * dt + q.bb, ds = -q.rc - (gdz - dt);
+    if (mode == 2) {
+      st[0] = sa + ap * ds; st[2] = t + ap * dt; st[1] = la + ad * dla; st[3] = lb + ad * dlb;
+    } else {
+      if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
+      if (dt < 0) { const double v = -t / dt; a.amp = v < a.amp ? v : a.amp; }
+      if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
+      if (dlb < 0) { const double v = -lb / dlb; a.amd = v < a.amd ? v : a.amd; }
+      if (mode == 1) { st[4] = ds * dla; st[5] = dt * dlb; a.mus += (sa + ap * ds) * (la + ap * dla) + (t + ap * dt) * (lb + ap * dlb); }
+    }
+  } else {
+    const double dla = q.wa * gdz + q.ba, ds = -q.rc - gdz;
+    if (mode == 2) { st[0] = sa + ap * ds; st[1] = la + ad * dla; }
+    else {
+      if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
+      if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
+      if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; a.mus += (sa + ap * ds) * (la + ap * dla); }
+    }
+  }
+}
+
+GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega) {
+  for (int i = 0; i < SLOT_W; ++i) st[i] = 0.0;
+  if (!valid) return;
+  if (has_t) {
+    const double t = (c0 > 0 ? c0 : 0.0) + 1.0;
+    const double sa = t - c0;
+    st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = 0.5 * omega; st[2] = t; st[3] = 0.5 * omega;
+  } else {
+    st[0] = -c0 > 1e-2 ? -c0 : 1e-2; st[1] = 1e-2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- special slots
+// The rows of a knot other than trust region / obstacles / goal box: each lives on <= 4 coordinates [i0, i0+n) of x
+// (or u for the control balls), inside one Hessian block.
+struct SpecEval {
   bool valid, is_u, has_t;
-  int i0, i1;             // variable range the gradient lives on
-  double c0;              // constraint value without the -t term
-  double gv[MAX_NX];      // gradient on [i0, i1)
-  double hq[MAX_NX];      // diagonal of the constraint Hessian on [i0, i1)
+  int i0, n;
+  double c0;
+  double gv[4], hq[4];     // gradient and diagonal of the constraint Hessian on [i0, i0+n)
 };
 
-template <int M>
-GDEV void slot_eval(const IpmCtx<M>& c, int k, int s, const double* x, const double* u, SlotEval& o) {
+template <int M> GHD constexpr bool spec_is_u(int s) { return s >= IpmLayout<M>::S_BALL; }
+template <int M> GHD constexpr int spec_i0(int s) {
   using L = IpmLayout<M>;
-  using T = Traits<M>;
-  constexpr int NX = L::NX;
-  const double* rp = c.d->rp;
-  o.valid = false; o.is_u = false; o.has_t = true; o.i0 = 0; o.i1 = 0; o.c0 = 0.0;
-  if (s == L::S_TR) {
-    if (!T::HAS_TR) return;
-    // stri_state_trust_region (astrobee_se3.jl:308-311) in slack-scaled form: |x - xp|^2 - Delta/omega - t <= 0
-    o.valid = true; o.i0 = 0; o.i1 = NX;
-    double v = -c.Delta / c.omega;
-    for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; o.gv[i] = 2.0 * dxi; o.hq[i] = 2.0; v += dxi * dxi; }
-    o.c0 = v;
-  } else if (s < L::S_LIN) {
+  return s < L::S_LIN ? norm_i0<M>(s - L::S_NORM) : s < L::S_QUAT ? lin_i<M>(s - L::S_LIN) : s < L::S_BALL ? 6 : ball_i0<M>(s - L::S_BALL);
+}
+template <int M> GHD constexpr int spec_block(int s) {      // Hessian block (x-blocks, or u-blocks for the balls)
+  return spec_is_u<M>(s) ? Traits<M>::UB_of(spec_i0<M>(s)) : Traits<M>::XB_of(spec_i0<M>(s));
+}
+
+// s in [S_NORM, SP); x, u: the knot's state/control; xp: previous state of the knot.
+template <int M>
+GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const double* u, SpecEval& o) {
+  using L = IpmLayout<M>;
+  const double* rp = c.rp;
+  o.valid = true; o.is_u = false; o.has_t = true; o.i0 = 0; o.n = 0; o.c0 = 0.0;
+  for (int a = 0; a < 4; ++a) { o.gv[a] = 0.0; o.hq[a] = 0.0; }
+  if (s < L::S_LIN) {
+    // csi_translational_velocity_bound / csi_angular_velocity_bound: |x[i0:i1)|^2 - lim^2 - t <= 0
     int i0, i1; double lim;
     norm_row<M>(s - L::S_NORM, rp, &i0, &i1, &lim);
-    o.valid = true; o.i0 = i0; o.i1 = i1;
+    o.i0 = i0; o.n = i1 - i0;
     double v = -lim * lim;
-    for (int i = i0; i < i1; ++i) { o.gv[i - i0] = 2.0 * x[i]; o.hq[i - i0] = 2.0; v += x[i] * x[i]; }
+    for (int a = 0; a < 4; ++a) if (a < i1 - i0) { o.gv[a] = 2.0 * x[i0 + a]; o.hq[a] = 2.0; v += x[i0 + a] * x[i0 + a]; }
     o.c0 = v;
   } else if (s < L::S_QUAT) {
     int i; double sign, bound;
     lin_row<M>(s - L::S_LIN, rp, &i, &sign, &bound);
-    o.valid = true; o.i0 = i; o.i1 = i + 1; o.gv[0] = sign; o.hq[0] = 0.0; o.c0 = sign * x[i] - bound;
+    o.i0 = i; o.n = 1; o.gv[0] = sign; o.c0 = sign * x[i] - bound;
   } else if (s < L::S_BALL) {
     // cse_quaternion_norm (astrobee_se3_manifold.jl:308-313): e = a.q - 1, a = qp/|qp|.
     //   hinge  e - eps/omega - t <= 0 (t >= 0)       and the hard row  -e - eps/omega <= 0   
-    const double* qp = c.Xp + k * NX + 6;
+    const double* qp = c.Xp + k * L::NX + 6;
     const double nq = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
     double ev = -1.0;
     for (int i = 0; i < 4; ++i) ev += qp[i] / nq * x[6 + i];
     const bool hinge = (s == L::S_QUAT);
-    o.valid = true; o.i0 = 6; o.i1 = 10; o.has_t = hinge;
-    for (int i = 0; i < 4; ++i) { o.gv[i] = (hinge ? 1.0 : -1.0) * qp[i] / nq; o.hq[i] = 0.0; }
+    o.i0 = 6; o.n = 4; o.has_t = hinge;
+    for (int i = 0; i < 4; ++i) o.gv[i] = (hinge ? 1.0 : -1.0) * qp[i] / nq;
     o.c0 = (hinge ? ev : -ev) - c.eps / c.omega;
-  } else if (s < L::S_BOX) {
-    if (k >= c.N - 1) return;       // control bounds cover k = 1..N-1 only (astrobee_se3.jl:370-371, quirk q3)
+  } else {
+    // control balls cover k = 1..N-1 only (astrobee_se3.jl:370-371, quirk q3)
+    o.is_u = true; o.has_t = false;
     int i0, i1; double scale[3], rad;
     ctrl_ball<M>(s - L::S_BALL, rp, &i0, &i1, scale, &rad);
-    o.valid = true; o.is_u = true; o.has_t = false; o.i0 = i0; o.i1 = i1;
+    o.i0 = i0; o.n = i1 - i0;
+    if (k >= c.N - 1) { o.valid = false; return; }
     double v = -rad * rad;
-    for (int i = i0; i < i1; ++i) {
-      const double s2 = scale[i - i0] * scale[i - i0];
-      o.gv[i - i0] = 2.0 * s2 * u[i]; o.hq[i - i0] = 2.0 * s2; v += s2 * u[i] * u[i];
+    for (int a = 0; a < 3; ++a) if (a < i1 - i0) {
+      const double s2 = scale[a] * scale[a];
+      o.gv[a] = 2.0 * s2 * u[i0 + a]; o.hq[a] = 2.0 * s2; v += s2 * u[i0 + a] * u[i0 + a];
     }
-    o.c0 = v;
-  } else if (s < L::S_OBS) {
-    // csbci_goal_constraints (dynamics.jl:37-42): X[i,N] - ub <= 0, lb - X[i,N] <= 0, hard
-    const int j = s - L::S_BOX, i = j >> 1;
-    if (k != c.N - 1 || c.d->goal_type[i] != GOAL_BOX) return;
-    o.valid = true; o.has_t = false; o.i0 = i; o.i1 = i + 1; o.hq[0] = 0.0;
-    if ((j & 1) == 0) { o.gv[0] = 1.0; o.c0 = x[i] - c.goal_hi[i]; }
-    else { o.gv[0] = -1.0; o.c0 = c.goal_lo[i] - x[i]; }
-  } else {
-    // ncsi_obstacle_avoidance_constraints_convexified (astrobee_se3.jl:282-305): off - nhat.r - t <= 0 if dist0 < toggle
-    const int i = s - L::S_OBS;
-    const double* row = c.rows + ((size_t)k * c.n_obs + i) * 5;
-    if (!(row[4] < c.toggle)) return;
-    o.valid = true; o.i0 = 0; o.i1 = T::WS;
-    double v = row[3];
-    for (int a = 0; a < T::WS; ++a) { o.gv[a] = -row[a]; o.hq[a] = 0.0; v -= row[a] * x[a]; }
     o.c0 = v;
   }
 }
 
-// ------------------------------------------------------------------------------ small dense helpers (row-major)
-template <int n> GDEV bool chol_lower(double* H) {          // in place, lower triangle; upper left untouched
+// stri_state_trust_region (astrobee_se3.jl:308-311) in slack-scaled form: |x - xp|^2 - Delta/omega - t <= 0
+template <int M> GDEV double tr_c0(const IpmCtx<M>& c, int k, const double* x) {
+  constexpr int NX = IpmCtx<M>::NX;
+  double v = -c.Delta / c.omega;
+  for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; }
+  return v;
+}
+// csbci_goal_constraints (dynamics.jl:37-42): X[i,N] - ub <= 0 (j even), lb - X[i,N] <= 0 (j odd); hard
+template <int M> GDEV double box_c0(const IpmCtx<M>& c, int j, const double* x) {
+  const int i = j >> 1;
+  return (j & 1) == 0 ? x[i] - c.goal_hi[i] : c.goal_lo[i] - x[i];
+}
+
+// ------------------------------------------------------------------------------------- small SPD blocks
+// P = (H + dp I)^-1 for a packed-lower SPD block of order n <= 4 (Cholesky, triangular inverse, Li' Li).
+template <int n> GDEV bool spd_inv_packed(const double* H, double dp, double* P) {
+  double Lc[n * (n + 1) / 2], Li[n * (n + 1) / 2];
   bool ok = true;
+#pragma unroll
   for (int j = 0; j < n; ++j) {
-    double djj = H[j * n + j];
-    for (int m = 0; m < j; ++m) djj -= H[j * n + m] * H[j * n + m];
-    if (!(djj > 0.0)) { ok = false; djj = 1e-300; }
-    const double l = sqrt(djj);
-    H[j * n + j] = l;
+    double dj = H[tri(j, j)] + dp;
+#pragma unroll
+    for (int m = 0; m < j; ++m) dj -= Lc[tri(j, m)] * Lc[tri(j, m)];
+    if (!(dj > 0.0)) { ok = false; dj = 1e-300; }
+    const double il = 1.0 / sqrt(dj);
+    Lc[tri(j, j)] = il;                       // the diagonal holds 1 / l_jj
+#pragma unroll
     for (int i = j + 1; i < n; ++i) {
-      double v = H[i * n + j];
-      for (int m = 0; m < j; ++m) v -= H[i * n + m] * H[j * n + m];
-      H[i * n + j] = v / l;
+      double v = H[tri(i, j)];
+#pragma unroll
+      for (int m = 0; m < j; ++m) v -= Lc[tri(i, m)] * Lc[tri(j, m)];
+      Lc[tri(i, j)] = v * il;
     }
   }
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    Li[tri(j, j)] = Lc[tri(j, j)];
+#pragma unroll
+    for (int i = j + 1; i < n; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = j; m < i; ++m) s += Lc[tri(i, m)] * Li[tri(m, j)];
+      Li[tri(i, j)] = -s * Lc[tri(i, i)];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int m = i; m < n; ++m) s += Li[tri(m, i)] * Li[tri(m, j)];
+      P[tri(i, j)] = s;
+    }
   return ok;
 }
-// column `col` of the inverse of lower-triangular C, written into out[:, col] (full column, zeros above col)
-template <int n> GDEV void tri_inv_col(const double* C, int col, double* out) {
-  double y[n];
+
+// out[0:n) = Sym(packed) * v[0:n)
+template <int n> GDEV void sym_mv(const double* Pk, const double* v, double* out) {
+#pragma unroll
   for (int i = 0; i < n; ++i) {
-    if (i < col) { y[i] = 0.0; continue; }
-    double v = (i == col) ? 1.0 : 0.0;
-    for (int m = col; m < i; ++m) v -= C[i * n + m] * y[m];
-    y[i] = v / C[i * n + i];
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) s += Pk[tri(i, j)] * v[j];
+    out[i] = s;
   }
-  for (int i = 0; i < n; ++i) out[i * n + col] = y[i];
 }
 
 // ------------------------------------------------------------------------------------- structured operators
-// Row j of the equality system (j = 0..N), applied to a primal vector v (layout [k][NV]):
+// Equality system, row j = 0..N, applied to a primal vector v (layout [k][NV]):
 //   j = 0      : x_0
 //   1..N-1     : (I + h/2 A_{j-1}) x_{j-1} + G u_{j-1} - (I - h/2 A_j) x_j + G u_j          (G = h/2 B)
 //   j = N      : M x_{N-1}      (M = diag(goal_type == POINT))
-template <int M> GDEV double apply_A_entry(const IpmCtx<M>& c, const double* v, int j, int i) {
-  constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU, NV = IpmCtx<M>::NV;
-  const double hh = 0.5 * c.h;
-  if (j == 0) return v[i];
-  if (j == c.N) return c.d->goal_type[i] == GOAL_POINT ? v[(c.N - 1) * NV + i] : 0.0;
-  const double* vp = v + (j - 1) * NV;
-  const double* vc = v + j * NV;
-  const double* Ap = c.A + (size_t)(j - 1) * NX * NX + i * NX;
-  const double* Ac = c.A + (size_t)j * NX * NX + i * NX;
-  double acc = vp[i] - vc[i];
-  for (int m = 0; m < NX; ++m) acc += hh * (Ap[m] * vp[m] + Ac[m] * vc[m]);
-  for (int m = 0; m < NU; ++m) acc += hh * c.Bm[i * NU + m] * (vp[NX + m] + vc[NX + m]);
-  return acc;
+template <int M> GDEV void aeq_row(const IpmCtx<M>& c, const double* v, int j, double* out) {
+  using T = Traits<M>;
+  constexpr int NX = T::NX, NU = T::NU, NV = NX + NU, ANZ = T::ANZ;
+  const int N = c.N;
+  if (j == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) out[i] = v[i];
+  } else if (j == N) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) out[i] = ((c.pmask >> i) & 1) ? v[(N - 1) * NV + i] : 0.0;
+  } else {
+    const double* vp = v + (j - 1) * NV;
+    const double* vc = v + j * NV;
+    const double* Ap = c.Ac + (size_t)(j - 1) * ANZ;
+    const double* Ak = c.Ac + (size_t)j * ANZ;
+    double acc[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int e = 0; e < ANZ; ++e) acc[T::a_row(e)] += Ap[e] * vp[T::a_col(e)] + Ak[e] * vc[T::a_col(e)];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) acc[T::b_row(a)] += c.bv[a] * (vp[NX + a] + vc[NX + a]);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) out[i] = vp[i] - vc[i] + c.hh * acc[i];
+  }
 }
-// Entry (k, i) of A' nu (i < NX: state part, i >= NX: control part)
-template <int M> GDEV double apply_AT_entry(const IpmCtx<M>& c, const double* nu, int k, int i) {
-  constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU;
-  const double hh = 0.5 * c.h;
+// (Aeq' nu) at knot k: out[0:NX) state part, out[NX:NV) control part
+template <int M> GDEV void aeqT_knot(const IpmCtx<M>& c, const double* nu, int k, double* out) {
+  using T = Traits<M>;
+  constexpr int NX = T::NX, NU = T::NU, ANZ = T::ANZ;
   const int N = c.N;
   const double* nk = nu + k * NX;          // row k       (knot k as "current")
   const double* nn = nu + (k + 1) * NX;    // row k + 1   (knot k as "previous")
-  const double* Ak = c.A + (size_t)k * NX * NX;
-  if (i < NX) {
-    double acc;
-    if (k == 0) acc = nk[i]; else acc = -nk[i];
-    if (k == N - 1) acc += c.d->goal_type[i] == GOAL_POINT ? nn[i] : 0.0; else acc += nn[i];
+  const double* Ak = c.Ac + (size_t)k * ANZ;
+  double wv[NX], acc[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    const double a = nk[i], b2 = nn[i];
+    wv[i] = (k > 0 ? a : 0.0) + (k < N - 1 ? b2 : 0.0);
+    out[i] = (k == 0 ? a : -a) + (k == N - 1 ? (((c.pmask >> i) & 1) ? b2 : 0.0) : b2);
+    acc[i] = 0.0;
+  }
+#pragma unroll
+  for (int e = 0; e < ANZ; ++e) acc[T::a_col(e)] += Ak[e] * wv[T::a_row(e)];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) out[i] += c.hh * acc[i];
+#pragma unroll
+  for (int a = 0; a < NU; ++a) out[NX + a] = c.hh * c.bv[a] * wv[T::b_row(a)];
+}
+
+// out = (H_k + dp I)^-1 in  for knot k:  state part blockdiag(P_b) - coef w w', control part blockdiag(Th_b)
+template <int M, int B0 = 0> GDEV void phi_x_blocks(const double* P, const double* in, double* out) {
+  using T = Traits<M>;
+  if constexpr (B0 < T::XB_CNT) {
+    sym_mv<T::XB_n(B0)>(P + T::XB_pk(B0), in + T::XB_off(B0), out + T::XB_off(B0));
+    phi_x_blocks<M, B0 + 1>(P, in, out);
+  }
+}
+template <int M, int B0 = 0> GDEV void phi_u_blocks(const double* P, const double* in, double* out) {
+  using T = Traits<M>;
+  if constexpr (B0 < T::UB_CNT) {
+    sym_mv<T::UB_n(B0)>(P + T::UB_pk(B0), in + T::UB_off(B0), out + T::UB_off(B0));
+    phi_u_blocks<M, B0 + 1>(P, in, out);
+  }
+}
+template <int M> GDEV void apply_phi(const IpmCtx<M>& c, int k, const double* in, double* out) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX;
+  const double* kd = c.kd + (size_t)k * L::KDW;
+  phi_x_blocks<M>(kd + L::KD_P, in, out);
+  if (T::HAS_TR) {
+    const double* w = kd + L::KD_W;
     double s = 0.0;
-    for (int m = 0; m < NX; ++m) {
-      double w = 0.0;
-      if (k > 0) w += nk[m];
-      if (k < N - 1) w += nn[m];
-      s += Ak[m * NX + i] * w;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s += w[i] * in[i];
+    s *= kd[L::KD_COEF];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) out[i] -= s * w[i];
+  }
+  phi_u_blocks<M>(kd + L::KD_TH, in + NX, out + NX);
+}
+// out = H_k in  (unregularised)
+template <int M> GDEV void apply_H(const IpmCtx<M>& c, int k, const double* in, double* out) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  const double* kd = c.kd + (size_t)k * L::KDW;
+  phi_x_blocks<M>(kd + L::KD_HB, in, out);
+  if (T::HAS_TR) {
+    double gvec[NX], s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { gvec[i] = 2.0 * (c.z[k * NV + i] - c.Xp[k * NX + i]); s += gvec[i] * in[i]; }
+    s *= kd[L::KD_KAP];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) out[i] += s * gvec[i];
+  }
+  phi_u_blocks<M>(kd + L::KD_HU, in + NX, out + NX);
+}
+
+// ------------------------------------------------------------------------- assembly of H, rhs, residuals
+struct Resid { double rz, rp, rc, mu, npair; };
+
+// accumulate one row into a block:  gz += lam gv,  rr -= gv bt,  Hb += lam hess + kap gv gv'   (block-local indices)
+template <int n> GDEV void block_add(double* Hb, double* gzb, double* rrb, int i0, int m, const double* gv, const double* hq,
+                                     const Pair& q, int phase) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) if (a < m && i0 + a < n) {
+    gzb[i0 + a] += q.la * gv[a];
+    rrb[i0 + a] -= gv[a] * q.bt;
+    if (phase == 0) {
+      Hb[tri(i0 + a, i0 + a)] += q.la * hq[a];
+#pragma unroll
+      for (int b2 = 0; b2 <= a; ++b2) Hb[tri(i0 + a, i0 + b2)] += q.kap * gv[a] * gv[b2];
     }
-    return acc + hh * s;
-  } else {
-    const int a = i - NX;
-    double s = 0.0;
-    for (int m = 0; m < NX; ++m) {
-      double w = 0.0;
-      if (k > 0) w += nk[m];
-      if (k < N - 1) w += nn[m];
-      s += c.Bm[m * NU + a] * w;
-    }
-    return hh * s;
   }
 }
 
-// out = (H + dp I)^-1 in   per knot, using the inverse Cholesky factors Ci, Cu  (H^-1 = Ci' Ci)
-template <int M> GDEV_NOINLINE void apply_Hinv(const IpmCtx<M>& c, const double* in, double* out) {
-  constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU, NV = IpmCtx<M>::NV;
-  G_PAR_FOR(k, c.N) {
-    const double* Ci = c.Ci + (size_t)k * NX * NX;
-    const double* Cu = c.Cu + (size_t)k * NU * NU;
-    double t[NX], tu[NU > 0 ? NU : 1];
-    for (int i = 0; i < NX; ++i) { double a = 0; for (int m = 0; m <= i; ++m) a += Ci[i * NX + m] * in[k * NV + m]; t[i] = a; }
-    for (int i = 0; i < NX; ++i) { double a = 0; for (int m = i; m < NX; ++m) a += Ci[m * NX + i] * t[m]; out[k * NV + i] = a; }
-    for (int i = 0; i < NU; ++i) { double a = 0; for (int m = 0; m <= i; ++m) a += Cu[i * NU + m] * in[k * NV + NX + m]; tu[i] = a; }
-    for (int i = 0; i < NU; ++i) { double a = 0; for (int m = i; m < NU; ++m) a += Cu[m * NU + i] * tu[m]; out[k * NV + NX + i] = a; }
-  }
-}
+template <int M> struct KnotAcc {       // what the state blocks of a knot share
+  double la_tr, bt_tr, kap_tr, gw;
+  Stat st;
+};
 
-// Block-tridiagonal solve  S y = b  in shared memory (sy holds b on entry, the solution on exit).
-// The sweep is a chain of 2(N+1) dependent NX x NX mat-vecs.  It runs on the first warp only (warp-level barriers);
-// the factor blocks of the NEXT row are prefetched from HBM/L2 into a shared-memory double buffer with cp.async
-// while the current block is applied, so the chain never waits on a global load.
-template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
-  constexpr int NX = IpmCtx<M>::NX, NN = NX * NX;
-  const int N = c.N;
-  double* y = c.sy;
-  double* tmp = c.stmp;
-  double* bLd[2] = {c.sD, c.sLo};
-  double* bLo[2] = {c.sLi, c.sB4};
-  if (G_TID < G_WARP) {
-    // ---- forward: y_j = Ld_j (b_j - Lo_j y_{j-1})
-    G_W0_FOR(it, NN) { g_cp_async8(&bLd[0][it], c.Ld + it); }
-    g_cp_async_wait();
-    G_SYNCWARP();
-    for (int j = 0; j <= N; ++j) {
-      const int cur = j & 1, nxt = cur ^ 1;
-      if (j < N) {
-        const double* Ldn = c.Ld + (size_t)(j + 1) * NN;
-        const double* Lon = c.Lo + (size_t)(j + 1) * NN;
-        G_W0_FOR(it, NN) { g_cp_async8(&bLd[nxt][it], Ldn + it); g_cp_async8(&bLo[nxt][it], Lon + it); }
+template <int M, int B0>
+GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double* gz, KnotAcc<M>& ka, bool& ok) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  if constexpr (B0 < T::XB_CNT) {
+    constexpr int n = T::XB_n(B0), off = T::XB_off(B0), npk = n * (n + 1) / 2;
+    double Hb[npk], rr[n], gtr[n];
+#pragma unroll
+    for (int i = 0; i < npk; ++i) Hb[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) { rr[i] = 0.0; gtr[i] = 0.0; }
+    if (T::HAS_TR) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        gtr[i] = 2.0 * (x[off + i] - c.Xp[k * NX + off + i]);
+        gz[off + i] += ka.la_tr * gtr[i];
+        rr[i] -= gtr[i] * ka.bt_tr;
+        Hb[tri(i, i)] = 2.0 * ka.la_tr;
       }
-      G_W0_FOR(i, NX) {
-        double a = y[j * NX + i];
-        if (j > 0) for (int m = 0; m < NX; ++m) a -= bLo[cur][i * NX + m] * y[(j - 1) * NX + m];
-        tmp[i] = a;
-      }
-      G_SYNCWARP();
-      G_W0_FOR(i, NX) {
-        double a = 0;
-        for (int m = 0; m <= i; ++m) a += bLd[cur][i * NX + m] * tmp[m];
-        y[j * NX + i] = a;
-      }
-      g_cp_async_wait();
-      G_SYNCWARP();
     }
-    // ---- backward: nu_j = Ld_j' (y_j - Lo_{j+1}' nu_{j+1}).  After the forward sweep buffer (N & 1) holds Ld_N, Lo_N.
-    for (int j = N; j >= 0; --j) {
-      const int cur = j & 1, nxt = cur ^ 1;     // bLd[cur] = Ld_j ; bLo[nxt] = Lo_{j+1} (staged while row j+1 was applied)
-      if (j > 0) {
-        const double* Ldn = c.Ld + (size_t)(j - 1) * NN;
-        G_W0_FOR(it, NN) { g_cp_async8(&bLd[nxt][it], Ldn + it); }
-      }
-      G_W0_FOR(i, NX) {
-        double a = y[j * NX + i];
-        if (j < N) for (int m = 0; m < NX; ++m) a -= bLo[nxt][m * NX + i] * y[(j + 1) * NX + m];
-        tmp[i] = a;
-      }
-      G_SYNCWARP();
-      // Lo_{j+1} is consumed: its buffer can take Lo_j (needed at step j-1 as "Lo_{(j-1)+1}")
-      if (j > 0) {
-        const double* Lon = c.Lo + (size_t)j * NN;
-        G_W0_FOR(it, NN) { g_cp_async8(&bLo[cur][it], Lon + it); }
-      }
-      G_W0_FOR(i, NX) {
-        double a = 0;
-        for (int m = i; m < NX; ++m) a += bLd[cur][m * NX + i] * tmp[m];
-        y[j * NX + i] = a;
-      }
-      g_cp_async_wait();
-      G_SYNCWARP();
+    // special rows living in this block
+#pragma unroll
+    for (int s = L::S_NORM; s < L::S_BALL; ++s) {
+      if (spec_block<M>(s) != B0) continue;
+      SpecEval o;
+      spec_eval<M>(c, k, s, x, x + NX, o);
+      const double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      Pair q;
+      pair_eval(st, o.has_t, o.c0, c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, o.has_t, q, ka.st);
+      block_add<n>(Hb, gz + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
     }
-  }
-  G_SYNC();
-}
-
-// [dz; dnu] = Ktilde^-1 [r; rnu]  with Ktilde = [[H + dp I, A'], [A, -(dd) ]] via the Schur complement.
-template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* r, const double* rnu, double* dz, double* dnu) {
-  constexpr int NX = IpmCtx<M>::NX, NV = IpmCtx<M>::NV;
-  const int N = c.N;
-  apply_Hinv<M>(c, r, c.t1);
-  G_SYNC();
-  G_PAR_FOR(it, (N + 1) * NX) { const int j = it / NX, i = it - j * NX; c.sy[it] = apply_A_entry<M>(c, c.t1, j, i) - rnu[it]; }
-  G_SYNC();
-  schur_solve<M>(c);
-  G_PAR_FOR(it, (N + 1) * NX) dnu[it] = c.sy[it];
-  G_SYNC();
-  G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; c.t1[it] = r[it] - apply_AT_entry<M>(c, dnu, k, i); }
-  G_SYNC();
-  apply_Hinv<M>(c, c.t1, dz);
-  G_SYNC();
-}
-
-// Refinement against the exact KKT matrix [[H, A'], [A, 0]].
-template <int M> GDEV void kkt_solve_refined(const IpmCtx<M>& c, const double* r, const double* rnu, double* dz, double* dnu, int nref) {
-  constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU, NV = IpmCtx<M>::NV;
-  const int N = c.N;
-  kkt_solve<M>(c, r, rnu, dz, dnu);
-  for (int it_ref = 0; it_ref < nref; ++it_ref) {
-    G_PAR_FOR(it, N * NV) {
-      const int k = it / NV, i = it - k * NV;
-      double a = r[it] - apply_AT_entry<M>(c, dnu, k, i);
-      if (i < NX) { const double* H = c.Hx + (size_t)k * NX * NX + i * NX; for (int m = 0; m < NX; ++m) a -= H[m] * dz[k * NV + m]; }
-      else { const double* H = c.Hu + (size_t)k * NU * NU + (i - NX) * NU; for (int m = 0; m < NU; ++m) a -= H[m] * dz[k * NV + NX + m]; }
-      c.res[it] = a;
+    // convexified obstacle rows (compacted): off - nhat.r - t <= 0
+    if (T::WS > 0 && B0 == T::XB_of(0)) {
+      constexpr int WS = T::WS > 0 ? T::WS : 1;
+      const int s0 = c.seg[k], s1 = c.seg[k + 1];
+      for (int p = s0; p < s1; ++p) {
+        const double* row = c.orow + (size_t)p * OROW_W;
+        const double* st = c.ost + (size_t)p * SLOT_W;
+        double gv[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
+        double v = row[3];
+#pragma unroll
+        for (int a = 0; a < WS; ++a) { gv[a] = -row[a]; v -= row[a] * x[a]; }
+        Pair q;
+        pair_eval(st, true, v, c.omega, smu, phase, q);
+        if (phase == 0) pair_stat(st, true, q, ka.st);
+        block_add<n>(Hb, gz + off, rr, 0, WS, gv, hq, q, phase);
+      }
     }
-    G_PAR_FOR(it, (N + 1) * NX) { const int j = it / NX, i = it - j * NX; c.resnu[it] = rnu[it] - apply_A_entry<M>(c, dz, j, i); }
-    G_SYNC();
-    kkt_solve<M>(c, c.res, c.resnu, c.e, c.enu);
-    G_PAR_FOR(it, N * NV) dz[it] += c.e[it];
-    G_PAR_FOR(it, (N + 1) * NX) dnu[it] += c.enu[it];
-    G_SYNC();
-  }
-}
-
-// ------------------------------------------------------------------------------------------ factorisation
-template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c, const IpmParams& prm) {
-  constexpr int NX = IpmCtx<M>::NX, NU = IpmCtx<M>::NU;
-  const int N = c.N;
-  const double hh = 0.5 * c.h;
-  double bad = 0.0;
-  // (1) per knot, on thread-local copies: Cholesky of Hx + dp I and its inverse Ci; inverse Cholesky Cu of Hu + dp I;
-  //     GT = Theta G'
-  G_PAR_FOR(k, N) {
-    double C[NX * NX], Cinv[NX * NX];
-    const double* Hx = c.Hx + (size_t)k * NX * NX;
-    for (int i = 0; i < NX * NX; ++i) C[i] = Hx[i];
-    for (int i = 0; i < NX; ++i) C[i * NX + i] += prm.delta_p;
-    if (!chol_lower<NX>(C)) bad = 1.0;
-    for (int j = 0; j < NX; ++j) tri_inv_col<NX>(C, j, Cinv);
-    double* gCi = c.Ci + (size_t)k * NX * NX;
-    for (int i = 0; i < NX * NX; ++i) gCi[i] = Cinv[i];
-    double Hu[NU * NU], Cu[NU * NU];
-    for (int i = 0; i < NU * NU; ++i) { Hu[i] = c.Hu[(size_t)k * NU * NU + i]; Cu[i] = 0.0; }
-    for (int i = 0; i < NU; ++i) Hu[i * NU + i] += prm.delta_p;
-    if (!chol_lower<NU>(Hu)) bad = 1.0;
-    for (int j = 0; j < NU; ++j) tri_inv_col<NU>(Hu, j, Cu);
-    double* gCu = c.Cu + (size_t)k * NU * NU;
-    for (int i = 0; i < NU * NU; ++i) gCu[i] = Cu[i];
-    // Theta = Cu' Cu ; GT[a][i] = sum_b Theta[a][b] * G[i][b]
-    double* GT = c.GT + (size_t)k * NU * NX;
-    for (int a = 0; a < NU; ++a)
-      for (int i = 0; i < NX; ++i) {
-        double s = 0;
-        for (int b2 = 0; b2 < NU; ++b2) {
-          double th = 0;
-          for (int m = (a > b2 ? a : b2); m < NU; ++m) th += Cu[m * NU + a] * Cu[m * NU + b2];
-          s += th * hh * c.Bm[i * NU + b2];
+    // goal box rows (last knot only)
+    if (k == c.N - 1 && c.bmask != 0) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        if (!((c.bmask >> (off + i)) & 1)) continue;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int j = 2 * (off + i) + side;
+          const double* st = c.bslot + (size_t)j * SLOT_W;
+          double gv[4] = {side == 0 ? 1.0 : -1.0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
+          Pair q;
+          pair_eval(st, false, box_c0<M>(c, j, x), c.omega, smu, phase, q);
+          if (phase == 0) pair_stat(st, false, q, ka.st);
+          block_add<n>(Hb, gz + off, rr, i, 1, gv, hq, q, phase);
         }
-        GT[a * NX + i] = s;
       }
-  }
-  G_SYNC();
-  // (3) CA = h/2 * Ci * A'   (CA[m][j] = h/2 sum_q Ci[m][q] A[j][q])
-  G_PAR_FOR(it, N * NX) {
-    const int k = it / NX, j = it - k * NX;
-    const double* Ci = c.Ci + (size_t)k * NX * NX;
-    const double* Aj = c.A + (size_t)k * NX * NX + j * NX;
-    double* CA = c.CA + (size_t)k * NX * NX;
-    for (int m = 0; m < NX; ++m) { double s = 0; for (int q = 0; q <= m; ++q) s += Ci[m * NX + q] * Aj[q]; CA[m * NX + j] = hh * s; }
-  }
-  G_SYNC();
-  // (4) W_LL, W_RR, W_RL column by column:  YL = Ci*Lx', YR = Ci*Rx',  W_XY = YX' YY + [flags] G Theta G'
-  G_PAR_FOR(it, N * NX) {
-    const int k = it / NX, j = it - k * NX;
-    const double* Ci = c.Ci + (size_t)k * NX * NX;
-    const double* CA = c.CA + (size_t)k * NX * NX;
-    const double* GT = c.GT + (size_t)k * NU * NX;
-    double* W = c.W + (size_t)k * 3 * NX * NX;
-    const bool first = (k == 0), last = (k == N - 1);
-    const double mj = (c.d->goal_type[j] == GOAL_POINT) ? 1.0 : 0.0;
-    double ylj[NX], yrj[NX];
-    for (int m = 0; m < NX; ++m) {
-      ylj[m] = first ? Ci[m * NX + j] : (CA[m * NX + j] - Ci[m * NX + j]);
-      yrj[m] = last ? Ci[m * NX + j] * mj : (CA[m * NX + j] + Ci[m * NX + j]);
     }
-    for (int i = 0; i < NX; ++i) {
-      const double mi = (c.d->goal_type[i] == GOAL_POINT) ? 1.0 : 0.0;
-      double ll = 0, rr = 0, rl = 0, xi = 0;
-      for (int m = 0; m < NX; ++m) {
-        const double yli = first ? Ci[m * NX + i] : (CA[m * NX + i] - Ci[m * NX + i]);
-        const double yri = last ? Ci[m * NX + i] * mi : (CA[m * NX + i] + Ci[m * NX + i]);
-        ll += yli * ylj[m]; rr += yri * yrj[m]; rl += yri * ylj[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      c.r[k * NV + off + i] = rr[i] - gz[off + i];
+      if (phase == 0) { const double a = fabs(gz[off + i]); ka.st.rz = a > ka.st.rz ? a : ka.st.rz; if (!(a == a)) ka.st.rz = 1e300; }
+    }
+    if (phase == 0) {
+      double* kd = c.kd + (size_t)k * L::KDW;
+      double P[npk];
+      if (!spd_inv_packed<n>(Hb, c.dp, P)) ok = false;
+#pragma unroll
+      for (int i = 0; i < npk; ++i) { kd[L::KD_HB + T::XB_pk(B0) + i] = Hb[i]; kd[L::KD_P + T::XB_pk(B0) + i] = P[i]; }
+      if (T::HAS_TR) {
+        double w[n];
+        sym_mv<n>(P, gtr, w);
+#pragma unroll
+        for (int i = 0; i < n; ++i) { kd[L::KD_W + off + i] = w[i]; ka.gw += w[i] * gtr[i]; }
       }
-      for (int a = 0; a < NU; ++a) xi += hh * c.Bm[i * NU + a] * GT[a * NX + j];
-      W[0 * NX * NX + i * NX + j] = ll + (first ? 0.0 : xi);
-      W[1 * NX * NX + i * NX + j] = rr + (last ? 0.0 : xi);
-      W[2 * NX * NX + i * NX + j] = rl + ((first || last) ? 0.0 : xi);
+    }
+    assemble_xblock<M, B0 + 1>(c, k, phase, smu, x, gz, ka, ok);
+  }
+}
+
+template <int M, int B0>
+GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double wk, double* gz, KnotAcc<M>& ka, bool& ok) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  if constexpr (B0 < T::UB_CNT) {
+    constexpr int n = T::UB_n(B0), off = T::UB_off(B0), npk = n * (n + 1) / 2;
+    double Hb[npk], rr[n];
+#pragma unroll
+    for (int i = 0; i < npk; ++i) Hb[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) { rr[i] = 0.0; Hb[tri(i, i)] = 2.0 * wk; }
+#pragma unroll
+    for (int s = L::S_BALL; s < L::SP; ++s) {
+      if (spec_block<M>(s) != B0) continue;
+      SpecEval o;
+      spec_eval<M>(c, k, s, x, x + NX, o);
+      if (!o.valid) continue;
+      const double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      Pair q;
+      pair_eval(st, false, o.c0, c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, false, q, ka.st);
+      block_add<n>(Hb, gz + NX + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      c.r[k * NV + NX + off + i] = rr[i] - gz[NX + off + i];
+      if (phase == 0) { const double a = fabs(gz[NX + off + i]); ka.st.rz = a > ka.st.rz ? a : ka.st.rz; if (!(a == a)) ka.st.rz = 1e300; }
+    }
+    if (phase == 0) {
+      double* kd = c.kd + (size_t)k * L::KDW;
+      double P[npk];
+      if (!spd_inv_packed<n>(Hb, c.dp, P)) ok = false;
+#pragma unroll
+      for (int i = 0; i < npk; ++i) { kd[L::KD_HU + T::UB_pk(B0) + i] = Hb[i]; kd[L::KD_TH + T::UB_pk(B0) + i] = P[i]; }
+    }
+    assemble_ublock<M, B0 + 1>(c, k, phase, smu, x, wk, gz, ka, ok);
+  }
+}
+
+// phase 0: build the per-knot Hessian blocks, their inverses and the predictor rhs (sigma*mu = 0, no second-order
+//          term); also the residual norms.  Returns false through *ok_out when a block is not positive definite.
+// phase 1: corrector rhs with centering target `smu` and the stored predictor products.
+template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out, bool* ok_out) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
+  const int N = c.N;
+  Stat S; S.rz = 0; S.rc = 0; S.mus = 0; S.np = 0;
+  bool ok = true;
+  G_PAR_FOR(k, N) {
+    const double* x = c.z + k * NV;
+    const double* u = x + NX;
+    double gz[NV];
+    aeqT_knot<M>(c, c.nu, k, gz);
+    const double wk = (k == 0 || k == N - 1) ? 0.5 * c.h : c.h;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) gz[NX + i] += 2.0 * wk * u[i];
+    KnotAcc<M> ka;
+    ka.la_tr = 0; ka.bt_tr = 0; ka.kap_tr = 0; ka.gw = 0; ka.st = S;
+    if (T::HAS_TR) {
+      const double* st = c.sslot + ((size_t)k * L::SP + L::S_TR) * SLOT_W;
+      Pair q;
+      pair_eval(st, true, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, true, q, ka.st);
+      ka.la_tr = q.la; ka.bt_tr = q.bt; ka.kap_tr = q.kap;
+    }
+    assemble_xblock<M, 0>(c, k, phase, smu, x, gz, ka, ok);
+    assemble_ublock<M, 0>(c, k, phase, smu, x, wk, gz, ka, ok);
+    S = ka.st;
+    if (phase == 0) {
+      double* kd = c.kd + (size_t)k * L::KDW;
+      kd[L::KD_KAP] = ka.kap_tr;
+      kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr / (1.0 + ka.kap_tr * ka.gw) : 0.0;
+      if (T::HAS_TR) {       // aw = A_k w  (sparse)
+        const double* Ak = c.Ac + (size_t)k * ANZ;
+        double aw[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) aw[i] = 0.0;
+#pragma unroll
+        for (int e = 0; e < ANZ; ++e) aw[T::a_row(e)] += Ak[e] * kd[L::KD_W + T::a_col(e)];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) kd[L::KD_AW + i] = aw[i];
+      }
     }
   }
+  if (phase == 0) {
+    // equality residual r_p = Aeq z - b  ;  rnu = -r_p
+    double rpmax = 0;
+    G_PAR_FOR(j, N + 1) {
+      double v[NX];
+      aeq_row<M>(c, c.z, j, v);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double t = v[i];
+        if (j == 0) t -= c.x_init[i];
+        else if (j == N) t -= ((c.pmask >> i) & 1) ? c.goal_lo[i] : 0.0;
+        else t += c.hh * (c.g[(j - 1) * NX + i] + c.g[j * NX + i]);
+        c.rnu[j * NX + i] = -t;
+        const double a = fabs(t);
+        rpmax = a > rpmax ? a : rpmax;
+        if (!(a == a)) rpmax = 1e300;
+      }
+    }
+    out->rz = block_max(S.rz, c.red);
+    out->rp = block_max(rpmax, c.red);
+    out->rc = block_max(S.rc, c.red);
+    const double ms = block_sum(S.mus, c.red), np = block_sum(S.np, c.red);
+    out->npair = np;
+    out->mu = np > 0 ? ms / np : 0.0;
+    if (!(out->mu == out->mu)) out->mu = 1e300;
+    *ok_out = block_max(ok ? 0.0 : 1.0, c.red) == 0.0;
+  } else {
+    G_SYNC();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Schur complement
+// Row I of (Phi, A Phi, Phi A', A Phi A') of knot k, Phi = blockdiag(P_b) - coef w w'.  I is a compile-time index so
+// that the sparse products collapse to the handful of entries that exist.
+template <int M, int I> GHD constexpr int ymask() {       // coordinates where row I of A*blockdiag() can be non-zero
+  using T = Traits<M>;
+  int m = 0;
+  for (int e = 0; e < T::ANZ; ++e)
+    if (T::a_row(e) == I) { const int b = T::XB_of(T::a_col(e)); for (int j = 0; j < T::XB_n(b); ++j) m |= 1 << (T::XB_off(b) + j); }
+  return m;
+}
+template <int M, int I>
+GDEV void knot_rows(const IpmCtx<M>& c, int k, double* phi, double* y, double* yt, double* zz) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, ANZ = L::ANZ;
+  constexpr int bI = T::XB_of(I), offI = T::XB_off(bI), nI = T::XB_n(bI);
+  constexpr int YM = ymask<M, I>();
+  const double* kd = c.kd + (size_t)k * L::KDW;
+  const double* P = kd + L::KD_P;
+  const double* Ak = c.Ac + (size_t)k * ANZ;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) { phi[j] = 0.0; y[j] = 0.0; yt[j] = 0.0; zz[j] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < nI; ++j) phi[offI + j] = P[T::XB_pk(bI) + tri(I - offI, j)];
+#pragma unroll
+  for (int e = 0; e < ANZ; ++e) {
+    if (T::a_row(e) != I) continue;
+    const int cc = T::a_col(e), bb = T::XB_of(cc), ob = T::XB_off(bb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < T::XB_n(bb)) y[ob + j] += Ak[e] * P[T::XB_pk(bb) + tri(cc - ob, j)];
+  }
+#pragma unroll
+  for (int e = 0; e < ANZ; ++e) if (T::XB_of(T::a_col(e)) == bI) yt[T::a_row(e)] += phi[T::a_col(e)] * Ak[e];
+#pragma unroll
+  for (int e = 0; e < ANZ; ++e) if ((YM >> T::a_col(e)) & 1) zz[T::a_row(e)] += y[T::a_col(e)] * Ak[e];
+  if (T::HAS_TR) {
+    const double* w = kd + L::KD_W;
+    const double* aw = kd + L::KD_AW;
+    const double cw = kd[L::KD_COEF] * w[I], ca = kd[L::KD_COEF] * aw[I];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { phi[j] -= cw * w[j]; y[j] -= ca * w[j]; yt[j] -= cw * aw[j]; zz[j] -= ca * aw[j]; }
+  }
+}
+
+// Row I of S_jj and of S_{j+1,j}.  Knot k appears in row k as "current" (coefficient Lk = aL A_k + bL I; row 0 is
+// x_0 itself) and in row k+1 as "previous" (Rk = aR A_k + diag(dR); row N is the masked goal row).
+template <int M> GHD constexpr int ctrl_of_row(int I) { int r = -1; for (int a = 0; a < Traits<M>::NU; ++a) if (Traits<M>::b_row(a) == I) r = a; return r; }
+template <int M, int I> GDEV void schur_rows(const IpmCtx<M>& c, int j) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NN = L::NN;
+  const int N = c.N;
+  double dd[NX], od[NX], phi[NX], y[NX], yt[NX], zz[NX];
+#pragma unroll
+  for (int q = 0; q < NX; ++q) { dd[q] = 0.0; od[q] = 0.0; }
+  // control coupling Xi = G Theta G' touches only rows b_row(a)
+  constexpr int aI = ctrl_of_row<M>(I);
+  if (j < N) {
+    knot_rows<M, I>(c, j, phi, y, yt, zz);
+    const double aL = j == 0 ? 0.0 : c.hh, bL = j == 0 ? 1.0 : -1.0;
+    const bool last = (j == N - 1);
+    const double aR = last ? 0.0 : c.hh;
+    const double dRI = last ? (double)((c.pmask >> I) & 1) : 1.0;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) {
+      dd[q] = aL * aL * zz[q] + aL * bL * (y[q] + yt[q]) + bL * bL * phi[q];
+      od[q] = aR * aL * zz[q] + aR * bL * y[q] + aL * dRI * yt[q] + bL * dRI * phi[q];
+    }
+    if constexpr (aI >= 0) {
+      if (j >= 1) {
+        const double* Th = c.kd + (size_t)j * L::KDW + L::KD_TH;
+        constexpr int ub = T::UB_of(aI), uo = T::UB_off(ub);
+#pragma unroll
+        for (int b2 = 0; b2 < T::UB_n(ub); ++b2) {
+          const double xi = c.hh * c.hh * c.bv[aI] * c.bv[uo + b2] * Th[T::UB_pk(ub) + tri(aI - uo, b2)];
+          dd[T::b_row(uo + b2)] += xi;
+          if (j <= N - 2) od[T::b_row(uo + b2)] += xi;
+        }
+      }
+    }
+  }
+  if (j >= 1) {
+    const int k = j - 1;
+    knot_rows<M, I>(c, k, phi, y, yt, zz);
+    const bool last = (k == N - 1);
+    const double aR = last ? 0.0 : c.hh;
+    const double dRI = last ? (double)((c.pmask >> I) & 1) : 1.0;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) {
+      const double dRq = last ? (double)((c.pmask >> q) & 1) : 1.0;
+      dd[q] += aR * aR * zz[q] + aR * (y[q] * dRq + dRI * yt[q]) + dRI * phi[q] * dRq;
+    }
+    if constexpr (aI >= 0) {
+      if (k <= N - 2) {
+        const double* Th = c.kd + (size_t)k * L::KDW + L::KD_TH;
+        constexpr int ub = T::UB_of(aI), uo = T::UB_off(ub);
+#pragma unroll
+        for (int b2 = 0; b2 < T::UB_n(ub); ++b2)
+          dd[T::b_row(uo + b2)] += c.hh * c.hh * c.bv[aI] * c.bv[uo + b2] * Th[T::UB_pk(ub) + tri(aI - uo, b2)];
+      }
+    }
+  }
+  if (j == N && !((c.pmask >> I) & 1)) dd[I] += 1.0;        // free goal coordinates: keep the block non-singular
+  dd[I] += c.dd * dd[I] + 1e-300;
+  double* Sd = c.fac + (size_t)(2 * j) * NN + I * NX;
+#pragma unroll
+  for (int q = 0; q < NX; ++q) Sd[q] = dd[q];
+  if (j < N) {
+    double* So = c.fac + (size_t)(2 * (j + 1) + 1) * NN + I * NX;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) So[q] = od[q];
+  }
+}
+template <int M, int I = 0> GDEV void schur_rows_dispatch(const IpmCtx<M>& c, int j, int i) {
+  if constexpr (I < Traits<M>::NX) {
+    if (i == I) schur_rows<M, I>(c, j);
+    else schur_rows_dispatch<M, I + 1>(c, j, i);
+  }
+}
+
+// Factorisation of the block-tridiagonal S.  Block Cholesky recurrence (numerically the stable form: every update is a
+// symmetric  D_j = S_jj - Lo_j Lo_j'  with Lo_j = S_{j,j-1} L_{j-1}^-T), but what is STORED is the block L D L' form the
+// solves want:  slot (j,0) S_jj -> D_j^-1 = Li_j' Li_j,  slot (j,1) S_{j,j-1} -> V_j = Lo_j Li_{j-1} (= S_{j,j-1} D_{j-1}^-1),
+// so that a solve is two chains of single mat-vecs plus one parallel D^-1 pass.  Li_j = L_j^-1 comes out of one
+// Gaussian elimination of [D_j | I] in shared memory (NX dependent pivot steps on warp 0 -- the critical path of the
+// whole kernel) while the other warp stages block row j+1.  Returns false on a non-positive pivot.
+template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NN = L::NN, NT = NX * (NX + 1) / 2;
+  const int N = c.N;
+  // (1) Schur blocks.  Items ordered row-index-major so that a warp shares the compile-time row index.
+  G_PAR_FOR(it, (N + 1) * NX) {
+    const int i = it / (N + 1), j = it - i * (N + 1);
+    schur_rows_dispatch<M>(c, j, i);
+  }
   G_SYNC();
-  // (5) block-tridiagonal Cholesky sweep over rows j = 0..N (sequential in j, parallel inside a block)
-  double* D = c.sD; double* Lo = c.sLo; double* Li = c.sLi;
+  // (2) sweep over block rows
+  double* tile = c.dz;                       // dz | sy | ring are dead here: 9 tiles of NN doubles + NX pivots
+  double* W = tile;                          // D_j, eliminated in place (lower triangle)
+  double* Wr = tile + NN;                    // I -> unit-lower elimination history (L~^-1)
+  double* Li = tile + 2 * NN;
+  double* Sdd[2] = {tile + 3 * NN, tile + 4 * NN};
+  double* Sod[2] = {tile + 5 * NN, tile + 6 * NN};
+  double* Lo[2] = {tile + 7 * NN, tile + 8 * NN};
+  double* rs = tile + 9 * NN;                // 1 / sqrt(pivot)
+  const int pf0 = G_NTHR > G_WARP ? G_WARP : 0;            // threads [pf0, NTHR) prefetch while warp 0 eliminates
+  const int npf = G_NTHR - pf0;
+  double bad = 0.0;
+  G_PAR_FOR(it, NN) Sdd[0][it] = c.fac[it];
+  G_SYNC();
   for (int j = 0; j <= N; ++j) {
-    G_PAR_FOR(it, NX * NX) {
+    const int cur = j & 1, nxt = cur ^ 1;
+    // (a) D_j = S_jj - Lo_j Lo_j'  (lower triangle);  Wr = I
+    G_PAR_FOR(it, NN) {
       const int i = it / NX, q = it - i * NX;
-      double v = 0.0;
-      if (j < N) v += c.W[(size_t)j * 3 * NX * NX + it];
-      if (j > 0) v += c.W[(size_t)(j - 1) * 3 * NX * NX + NX * NX + it];
-      if (j == N && i == q && c.d->goal_type[i] != GOAL_POINT) v += 1.0;
-      if (i == q) v += prm.delta_d * v + 1e-300;
-      if (j > 0) for (int m = 0; m < NX; ++m) v -= Lo[i * NX + m] * Lo[q * NX + m];
-      D[it] = v;
+      Wr[it] = (i == q) ? 1.0 : 0.0;
+      if (q > i) continue;
+      double v = Sdd[cur][it];
+      if (j > 0) for (int m = 0; m < NX; ++m) v -= Lo[cur][i * NX + m] * Lo[cur][q * NX + m];
+      W[it] = v;
     }
     G_SYNC();
-    for (int q = 0; q < NX; ++q) {         // right-looking Cholesky, column q
-      if (G_TID == 0) { double p = D[q * NX + q]; if (!(p > 0.0)) { bad = 1.0; p = 1e-300; } D[q * NX + q] = sqrt(p); }
-      G_SYNC();
-      G_PAR_FOR(i, NX) if (i > q) D[i * NX + q] /= D[q * NX + q];
-      G_SYNC();
-      G_PAR_FOR(it, NX * NX) { const int i = it / NX, m = it - i * NX; if (m > q && i >= m) D[i * NX + m] -= D[i * NX + q] * D[m * NX + q]; }
-      G_SYNC();
-    }
-    G_PAR_FOR(it, NX * NX) Li[it] = 0.0;
-    G_SYNC();
-    G_PAR_FOR(col, NX) tri_inv_col<NX>(D, col, Li);
-    G_SYNC();
-    double* gLd = c.Ld + (size_t)j * NX * NX;
-    G_PAR_FOR(it, NX * NX) gLd[it] = Li[it];
-    if (j < N) {                          // Lo_{j+1} = W_RL_j * L_jj^-T   (Lo[i][q] = sum_m W_RL[i][m] Li[q][m])
-      const double* WRL = c.W + (size_t)j * 3 * NX * NX + 2 * NX * NX;
-      double* gLo = c.Lo + (size_t)(j + 1) * NX * NX;
-      G_SYNC();
-      G_PAR_FOR(it, NX * NX) {
-        const int i = it / NX, q = it - i * NX;
-        double s = 0; for (int m = 0; m <= q; ++m) s += WRL[i * NX + m] * Li[q * NX + m];
-        D[it] = s;                      // D is free again; stage through it so that Lo is not overwritten while read
+    // (b) warp 0: eliminate column q from the rows below it, in W (columns > q) and in Wr (columns <= q)
+    if (G_TID < G_WARP) {
+      for (int q = 0; q < NX; ++q) {
+        double piv = W[q * NX + q];
+        if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
+        const double ip = 1.0 / piv;
+        if (G_LANE == q % G_NLANE) rs[q] = sqrt(ip);
+        G_W0_FOR(t, NT) {
+          const int i = c.tab[t], e = c.tab[NT + t];
+          if (i <= q) continue;
+          const double mult = W[i * NX + q] * ip;
+          if (e <= q) Wr[i * NX + e] -= mult * Wr[q * NX + e];
+          else W[i * NX + e] -= mult * W[e * NX + q];
+        }
+        G_SYNCWARP();
       }
-      G_SYNC();
-      G_PAR_FOR(it, NX * NX) { Lo[it] = D[it]; gLo[it] = D[it]; }
+    }
+    if (j < N && G_TID >= pf0) {
+      const double* gd = c.fac + (size_t)(2 * (j + 1)) * NN;
+      for (int it = G_TID - pf0; it < 2 * NN; it += npf) {
+        if (it < NN) Sdd[nxt][it] = gd[it]; else Sod[nxt][it - NN] = gd[it];
+      }
     }
     G_SYNC();
+    // (c1) Li = diag(rs) * Wr  (lower triangular)
+    G_PAR_FOR(it, NN) { const int i = it / NX, m = it - i * NX; Li[it] = m <= i ? Wr[it] * rs[i] : 0.0; }
+    G_SYNC();
+    // (c2) D_j^-1 = Li' Li -> global;  Lo_{j+1} = S_{j+1,j} Li'
+    double* gD = c.fac + (size_t)(2 * j) * NN;
+    G_PAR_FOR(it, NN) {
+      const int i = it / NX, q = it - i * NX;
+      if (q <= i) {
+        double s = 0.0;
+        for (int m = i; m < NX; ++m) s += Li[m * NX + i] * Li[m * NX + q];
+        gD[i * NX + q] = s;
+        gD[q * NX + i] = s;
+      }
+      if (j < N) {
+        double s = 0.0;
+        for (int m = 0; m <= q; ++m) s += Sod[nxt][i * NX + m] * Li[q * NX + m];
+        Lo[nxt][it] = s;
+      }
+    }
+    G_SYNC();
+    // (c3) V_{j+1} = Lo_{j+1} Li -> global   (no barrier needed before the next (a): disjoint tiles)
+    if (j < N) {
+      double* gV = c.fac + (size_t)(2 * (j + 1) + 1) * NN;
+      G_PAR_FOR(it, NN) {
+        const int i = it / NX, q = it - i * NX;
+        double s = 0.0;
+        for (int m = q; m < NX; ++m) s += Lo[nxt][i * NX + m] * Li[m * NX + q];
+        gV[it] = s;
+      }
+    }
   }
   bad = block_max(bad, c.red);
   return bad == 0.0;
 }
 
-// ------------------------------------------------------------------------------- assembly of H, rhs, residuals
-struct Resid { double rz, rp, rc, mu, npair; };
-
-// phase 0: build Hx, Hu and the predictor rhs (sigma*mu = 0, no second-order term); also residual norms.
-// phase 1: corrector rhs with centering target `smu` and the stored predictor products.
-template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out) {
+// ------------------------------------------------------------------------------------------------ KKT solves
+// cp.async ring over the R tiles of the factor (global -> shared, RING_STAGES deep), used by warp 0 only.
+template <int M> GDEV void ring_fetch(const IpmCtx<M>& c, int j) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
-  const int N = c.N;
-  double rzmax = 0, rcmax = 0, musum = 0, npair = 0;
-  G_PAR_FOR(k, N) {
-    const double* x = c.z + k * NV;
-    const double* u = x + NX;
-    double Hx[NX * NX], Hu[NU * NU], rx[NX], ru[NU], gz[NV];
-    if (phase == 0) { for (int i = 0; i < NX * NX; ++i) Hx[i] = 0; for (int i = 0; i < NU * NU; ++i) Hu[i] = 0; }
-    // gradient of the Lagrangian without inequality terms: cost 2 w_k u  + A' nu
-    const double wk = (k == 0 || k == N - 1) ? 0.5 * c.h : c.h;
-    for (int i = 0; i < NV; ++i) gz[i] = apply_AT_entry<M>(c, c.nu, k, i);
-    for (int i = 0; i < NU; ++i) { gz[NX + i] += 2.0 * wk * u[i]; if (phase == 0) Hu[i * NU + i] = 2.0 * wk; }
-    for (int i = 0; i < NX; ++i) rx[i] = 0;
-    for (int i = 0; i < NU; ++i) ru[i] = 0;
-    for (int s = 0; s < c.S; ++s) {
-      SlotEval o;
-      slot_eval<M>(c, k, s, x, u, o);
-      if (!o.valid) continue;
-      double* st = c.slot + ((size_t)k * c.S + s) * SLOT_W;
-      const double sa = st[0], la = st[1];
-      double kap, bt;
-      if (o.has_t) {
-        const double t = st[2], lb = st[3];
-        const double rca = o.c0 - t + sa, rt = c.omega - la - lb;
-        const double wa = la / sa, wb = lb / t;
-        const double rsa = sa * la - smu + (phase ? st[4] : 0.0), rsb = t * lb - smu + (phase ? st[5] : 0.0);
-        const double ba = (la * rca - rsa) / sa, bb = -rsb / t;
-        kap = wa * wb / (wa + wb);
-        bt = ba - wa * (ba + bb - rt) / (wa + wb);
-        if (phase == 0) {
-          rcmax = fabs(rca) > rcmax ? fabs(rca) : rcmax;
-          rzmax = fabs(rt) > rzmax ? fabs(rt) : rzmax;
-          musum += sa * la + t * lb; npair += 2;
-        }
-      } else {
-        const double rc = o.c0 + sa;
-        const double rs = sa * la - smu + (phase ? st[4] : 0.0);
-        kap = la / sa;
-        bt = (la * rc - rs) / sa;
-        if (phase == 0) { rcmax = fabs(rc) > rcmax ? fabs(rc) : rcmax; musum += sa * la; npair += 1; }
-      }
-      const int n = o.i1 - o.i0;
-      double* gdst = o.is_u ? (gz + NX) : gz;
-      double* rdst = o.is_u ? ru : rx;
-      for (int a = 0; a < n; ++a) { gdst[o.i0 + a] += la * o.gv[a]; rdst[o.i0 + a] -= o.gv[a] * bt; }
-      if (phase == 0) {
-        double* H = o.is_u ? Hu : Hx;
-        const int ld = o.is_u ? NU : NX;
-        for (int a = 0; a < n; ++a) {
-          H[(o.i0 + a) * ld + o.i0 + a] += la * o.hq[a];
-          for (int b2 = 0; b2 < n; ++b2) H[(o.i0 + a) * ld + o.i0 + b2] += kap * o.gv[a] * o.gv[b2];
-        }
-      }
-    }
-    for (int i = 0; i < NX; ++i) { c.r[k * NV + i] = rx[i] - gz[i]; if (phase == 0) rzmax = fabs(gz[i]) > rzmax ? fabs(gz[i]) : rzmax; }
-    for (int i = 0; i < NU; ++i) { c.r[k * NV + NX + i] = ru[i] - gz[NX + i]; if (phase == 0) rzmax = fabs(gz[NX + i]) > rzmax ? fabs(gz[NX + i]) : rzmax; }
-    if (phase == 0) {
-      double* gHx = c.Hx + (size_t)k * NX * NX; for (int i = 0; i < NX * NX; ++i) gHx[i] = Hx[i];
-      double* gHu = c.Hu + (size_t)k * NU * NU; for (int i = 0; i < NU * NU; ++i) gHu[i] = Hu[i];
-    }
+  constexpr int NX = L::NX, NN = L::NN;
+  if (j >= 1 && j <= c.N) {
+    const double* src = c.fac + (size_t)(2 * j + 1) * NN;
+    double* dst = c.ring + (j % RING_STAGES) * L::TILE;
+    G_W0_FOR(it, NN) { const int i = it / NX, m = it - i * NX; g_cp_async8(dst + i * L::LDR + m, src + it); }
   }
-  if (phase == 0) {
-    // equality residual r_p = A z - b  ;  rnu = -r_p
-    double rpmax = 0;
-    G_PAR_FOR(it, (N + 1) * NX) {
-      const int j = it / NX, i = it - j * NX;
-      double v = apply_A_entry<M>(c, c.z, j, i);
-      if (j == 0) v -= c.x_init[i];
-      else if (j == N) v -= (c.d->goal_type[i] == GOAL_POINT) ? c.goal_lo[i] : 0.0;
-      else v += 0.5 * c.h * (c.g[(j - 1) * NX + i] + c.g[j * NX + i]);
-      c.rnu[it] = -v;
-      rpmax = fabs(v) > rpmax ? fabs(v) : rpmax;
-    }
-    out->rz = block_max(rzmax, c.red);
-    out->rp = block_max(rpmax, c.red);
-    out->rc = block_max(rcmax, c.red);
-    const double ms = block_sum(musum, c.red), np = block_sum(npair, c.red);
-    out->npair = np;
-    out->mu = np > 0 ? ms / np : 0.0;
-    if (!(out->mu == out->mu)) out->mu = 1e300;
-  } else {
-    G_SYNC();
-  }
+  g_cp_async_commit();
 }
 
-// Per-slot step from dz; mode 0: predictor (returns max steps and stores nothing), mode 1: store predictor products,
-// mode 2: apply step (alpha_p, alpha_d).  Returns through amax[0..1] the largest primal/dual step to the boundary.
-template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* amax,
-                                      double* mu_aff) {
+// Block-tridiagonal solve  S nu = b  (sy holds b on entry, nu on exit):
+//   forward  w_j = b_j - R_j w_{j-1};   middle  v_j = D_j^-1 w_j (all threads);   backward  nu_j = v_j - R_{j+1}' nu_{j+1}.
+template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NN = L::NN, LDR = L::LDR, S = RING_STAGES;
+  const int N = c.N;
+  double* y = c.sy;
+  if (G_TID < G_WARP) {
+    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(c, jj);
+    for (int j = 1; j <= N; ++j) {
+      g_cp_async_wait_group<S - 2>();             // tile j has landed (at most S-2 younger groups in flight)
+      G_SYNCWARP();                               // ... for every lane; everyone is done with tile j-1
+      ring_fetch<M>(c, j + S - 1);                // reuses the slot of tile j-1
+      const double* R = c.ring + (j % S) * L::TILE;
+      G_W0_FOR(i, NX) {
+        double a0 = y[j * NX + i], a1 = 0.0;
+#pragma unroll
+        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[i * LDR + m] * y[(j - 1) * NX + m]; a1 -= R[i * LDR + m + 1] * y[(j - 1) * NX + m + 1]; }
+        if (NX & 1) a0 -= R[i * LDR + NX - 1] * y[(j - 1) * NX + NX - 1];
+        y[j * NX + i] = a0 + a1;
+      }
+    }
+    g_cp_async_wait();
+  }
+  G_SYNC();
+  // middle: v = D^-1 w, staged through the (idle) ring so that no row is overwritten while still being read
+  double* v = c.ring;
+  G_PAR_FOR(it, (N + 1) * NX) {
+    const int j = it / NX, i = it - j * NX;
+    const double* Di = c.fac + (size_t)(2 * j) * NN + i * NX;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int m = 0; m + 1 < NX; m += 2) { a0 += Di[m] * y[j * NX + m]; a1 += Di[m + 1] * y[j * NX + m + 1]; }
+    if (NX & 1) a0 += Di[NX - 1] * y[j * NX + NX - 1];
+    v[it] = a0 + a1;
+  }
+  G_SYNC();
+  G_PAR_FOR(it, (N + 1) * NX) y[it] = v[it];
+  G_SYNC();
+  if (G_TID < G_WARP) {
+    // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
+    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(c, N - jj);
+    for (int j = N - 1; j >= 0; --j) {
+      g_cp_async_wait_group<S - 2>();
+      G_SYNCWARP();
+      ring_fetch<M>(c, j + 1 - (S - 1));          // reuses the slot of tile j+2
+      const double* R = c.ring + ((j + 1) % S) * L::TILE;
+      G_W0_FOR(i, NX) {
+        double a0 = y[j * NX + i], a1 = 0.0;
+#pragma unroll
+        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * LDR + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * LDR + i] * y[(j + 1) * NX + m + 1]; }
+        if (NX & 1) a0 -= R[(NX - 1) * LDR + i] * y[(j + 1) * NX + NX - 1];
+        y[j * NX + i] = a0 + a1;
+      }
+    }
+    g_cp_async_wait();
+  }
+  G_SYNC();
+}
+
+// [dz; dnu] (+)= Ktilde^-1 [rin; rnuin]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]] via the Schur complement.
+template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* rin, const double* rnuin, bool accumulate) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
-  double amp = 1e300, amd = 1e300, musum = 0;
-  G_PAR_FOR(it, N * c.S) {
-    const int k = it / c.S, s = it - k * c.S;
+  G_PAR_FOR(k, N) {
+    double in[NV], out[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) in[i] = rin[k * NV + i];
+    apply_phi<M>(c, k, in, out);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = out[i];
+  }
+  G_SYNC();
+  G_PAR_FOR(j, N + 1) {
+    double v[NX];
+    aeq_row<M>(c, c.t1, j, v);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) c.sy[j * NX + i] = v[i] - rnuin[j * NX + i];
+  }
+  G_SYNC();
+  schur_solve<M>(c);
+  G_PAR_FOR(k, N) {
+    double in[NV], out[NV];
+    aeqT_knot<M>(c, c.sy, k, in);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) in[i] = rin[k * NV + i] - in[i];
+    apply_phi<M>(c, k, in, out);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c.dz[k * NV + i] = accumulate ? c.dz[k * NV + i] + out[i] : out[i];
+  }
+  G_PAR_FOR(it, (N + 1) * NX) c.dnu[it] = accumulate ? c.dnu[it] + c.sy[it] : c.sy[it];
+  G_SYNC();
+}
+
+// Solve, then `nref` refinement steps against the exact KKT matrix [[H, Aeq'], [Aeq, 0]].
+template <int M> GDEV void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  const int N = c.N;
+  kkt_solve<M>(c, c.r, c.rnu, false);
+  for (int it_ref = 0; it_ref < nref; ++it_ref) {
+    G_PAR_FOR(k, N) {
+      double at[NV], hd[NV], dk[NV];
+      aeqT_knot<M>(c, c.dnu, k, at);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) dk[i] = c.dz[k * NV + i];
+      apply_H<M>(c, k, dk, hd);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) c.res[k * NV + i] = c.r[k * NV + i] - hd[i] - at[i];
+    }
+    G_PAR_FOR(j, N + 1) {
+      double v[NX];
+      aeq_row<M>(c, c.dz, j, v);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) c.resnu[j * NX + i] = c.rnu[j * NX + i] - v[i];
+    }
+    G_SYNC();
+    kkt_solve<M>(c, c.res, c.resnu, true);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- slot passes
+// Flat pass over every live row.  FN(st, has_t, c0, gdz) is called once per row; `want_gdz` says whether the
+// directional derivative gv.dz is needed.
+template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool want_gdz, FN&& fn) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  const int N = c.N;
+  G_PAR_FOR(it, N * L::SP) {
+    const int k = it / L::SP, s = it - k * L::SP;
     const double* x = c.z + k * NV;
-    const double* u = x + NX;
-    SlotEval o;
-    slot_eval<M>(c, k, s, x, u, o);
-    if (!o.valid) continue;
-    double* st = c.slot + (size_t)it * SLOT_W;
-    const double* dv = c.dz + k * NV + (o.is_u ? NX : 0) + o.i0;
-    double gdz = 0;
-    for (int a = 0; a < o.i1 - o.i0; ++a) gdz += o.gv[a] * dv[a];
-    const double sa = st[0], la = st[1];
-    if (o.has_t) {
-      const double t = st[2], lb = st[3];
-      const double rca = o.c0 - t + sa, rt = c.omega - la - lb;
-      const double wa = la / sa, wb = lb / t;
-      const double rsa = sa * la - smu + (phase ? st[4] : 0.0), rsb = t * lb - smu + (phase ? st[5] : 0.0);
-      const double ba = (la * rca - rsa) / sa, bb = -rsb / t;
-      const double dt = (wa * gdz + ba + bb - rt) / (wa + wb);
-      const double dla = wa * (gdz - dt) + ba, dlb = -wb * dt + bb, ds = -rca - (gdz - dt);
-      if (mode == 2) {
-        st[0] = sa + ap * ds; st[2] = t + ap * dt; st[1] = la + ad * dla; st[3] = lb + ad * dlb;
-      } else {
-        if (ds < 0) { const double a = -sa / ds; amp = a < amp ? a : amp; }
-        if (dt < 0) { const double a = -t / dt; amp = a < amp ? a : amp; }
-        if (dla < 0) { const double a = -la / dla; amd = a < amd ? a : amd; }
-        if (dlb < 0) { const double a = -lb / dlb; amd = a < amd ? a : amd; }
-        if (mode == 1) { st[4] = ds * dla; st[5] = dt * dlb; musum += (sa + ap * ds) * (la + ap * dla) + (t + ap * dt) * (lb + ap * dlb); }
-      }
+    double* st = c.sslot + (size_t)it * SLOT_W;
+    if (T::HAS_TR && s == L::S_TR) {
+      double v = -c.Delta / c.omega, gdz = 0.0;
+      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; gdz += 2.0 * dxi * c.dz[k * NV + i]; }
+      fn(st, true, v, gdz);
     } else {
-      const double rc = o.c0 + sa;
-      const double rs = sa * la - smu + (phase ? st[4] : 0.0);
-      const double wa = la / sa, ba = (la * rc - rs) / sa;
-      const double dla = wa * gdz + ba, ds = -rc - gdz;
-      if (mode == 2) { st[0] = sa + ap * ds; st[1] = la + ad * dla; }
-      else {
-        if (ds < 0) { const double a = -sa / ds; amp = a < amp ? a : amp; }
-        if (dla < 0) { const double a = -la / dla; amd = a < amd ? a : amd; }
-        if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; musum += (sa + ap * ds) * (la + ap * dla); }
-      }
+      SpecEval o;
+      spec_eval<M>(c, k, s, x, x + NX, o);
+      if (!o.valid) continue;
+      double gdz = 0.0;
+      if (want_gdz) { const double* dv = c.dz + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[a]; }
+      fn(st, o.has_t, o.c0, gdz);
     }
   }
+  if (c.bmask != 0) {
+    G_PAR_FOR(j, L::NBOX) {
+      if (!((c.bmask >> (j >> 1)) & 1)) continue;
+      const double* x = c.z + (N - 1) * NV;
+      const double gdz = ((j & 1) == 0 ? 1.0 : -1.0) * c.dz[(N - 1) * NV + (j >> 1)];
+      fn(c.bslot + (size_t)j * SLOT_W, false, box_c0<M>(c, j, x), gdz);
+    }
+  }
+  if (T::WS > 0) {
+    constexpr int WS = T::WS > 0 ? T::WS : 1;
+    G_PAR_FOR(p, c.nact) {
+      const double* row = c.orow + (size_t)p * OROW_W;
+      const int k = (int)row[4];
+      const double* x = c.z + k * NV;
+      const double* dv = c.dz + k * NV;
+      double v = row[3], gdz = 0.0;
+#pragma unroll
+      for (int a = 0; a < WS; ++a) { v -= row[a] * x[a]; gdz -= row[a] * dv[a]; }
+      fn(c.ost + (size_t)p * SLOT_W, true, v, gdz);
+    }
+  }
+}
+
+// mode 0: step lengths of the current direction; mode 1: + predictor products and mu at step ap; mode 2: apply.
+template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* amax,
+                                               double* mu_aff) {
+  StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.mus = 0.0;
+  const double omega = c.omega;
+  for_each_row<M>(c, true, [&](double* st, bool has_t, double c0, double gdz) {
+    Pair q;
+    pair_eval(st, has_t, c0, omega, smu, phase, q);
+    pair_step(st, has_t, q, gdz, mode, ap, ad, acc);
+  });
   if (mode != 2) {
-    amax[0] = -block_max(-amp, c.red);
-    amax[1] = -block_max(-amd, c.red);
-    if (mode == 1) *mu_aff = block_sum(musum, c.red);
+    amax[0] = -block_max(-acc.amp, c.red);
+    amax[1] = -block_max(-acc.amd, c.red);
+    if (mode == 1) *mu_aff = block_sum(acc.mus, c.red);
   } else {
     G_SYNC();
   }
@@ -633,85 +1083,127 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
 
 // Keep every complementarity pair above 1e-4 * mu (wide neighbourhood of the central path), as the oracle does.
 template <int M> GDEV_NOINLINE void recenter(const IpmCtx<M>& c) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NV = L::NV;
-  const int N = c.N;
   double musum = 0, npair = 0;
-  G_PAR_FOR(it, N * c.S) {
-    const int k = it / c.S, s = it - k * c.S;
-    SlotEval o;
-    slot_eval<M>(c, k, s, c.z + k * NV, c.z + k * NV + NX, o);
-    if (!o.valid) continue;
-    const double* st = c.slot + (size_t)it * SLOT_W;
+  for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) {
     musum += st[0] * st[1]; npair += 1;
-    if (o.has_t) { musum += st[2] * st[3]; npair += 1; }
-  }
+    if (has_t) { musum += st[2] * st[3]; npair += 1; }
+  });
   const double ms = block_sum(musum, c.red), np = block_sum(npair, c.red);
   const double floor_ = np > 0 ? 1e-4 * ms / np : 0.0;
-  G_PAR_FOR(it, N * c.S) {
-    const int k = it / c.S, s = it - k * c.S;
-    SlotEval o;
-    slot_eval<M>(c, k, s, c.z + k * NV, c.z + k * NV + NX, o);
-    if (!o.valid) continue;
-    double* st = c.slot + (size_t)it * SLOT_W;
+  for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) {
     if (st[0] * st[1] < floor_) st[1] = floor_ / st[0];
-    if (o.has_t && st[2] * st[3] < floor_) st[3] = floor_ / st[2];
+    if (has_t && st[2] * st[3] < floor_) st[3] = floor_ / st[2];
+  });
+  G_SYNC();
+}
+
+// --------------------------------------------------------------------------------------------------- setup
+template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
+  const int N = c.N;
+  // start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); multipliers 0
+  G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; c.z[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
+  G_PAR_FOR(it, (N + 1) * NX) c.nu[it] = 0.0;
+  // A_k on its sparsity pattern
+  G_PAR_FOR(it, N * ANZ) { const int k = it / ANZ, e = it - k * ANZ; c.Ac[it] = c.A[(size_t)k * NX * NX + T::a_row(e) * NX + T::a_col(e)]; }
+  // obstacle rows inside the toggle distance, compacted knot by knot (astrobee_se3.jl:293)
+  if (T::WS > 0) {
+    G_PAR_FOR(k, N) {
+      int cnt = 0;
+      for (int i = 0; i < c.n_obs; ++i) cnt += (c.rows[((size_t)k * c.n_obs + i) * 5 + 4] < c.toggle) ? 1 : 0;
+      c.seg[k + 1] = cnt;
+    }
+    G_SYNC();
+    if (G_TID == 0) { c.seg[0] = 0; for (int k = 0; k < N; ++k) c.seg[k + 1] += c.seg[k]; }
+    G_SYNC();
+  } else {
+    G_PAR_FOR(k, N + 1) c.seg[k] = 0;
+    G_SYNC();
+  }
+  c.nact = c.seg[N];
+  if (T::WS > 0) {
+    G_PAR_FOR(k, N) {
+      int p = c.seg[k];
+      const double* x = c.z + k * NV;
+      for (int i = 0; i < c.n_obs; ++i) {
+        const double* row = c.rows + ((size_t)k * c.n_obs + i) * 5;
+        if (!(row[4] < c.toggle)) continue;
+        double* o = c.orow + (size_t)p * OROW_W;
+        double v = row[3];
+        for (int a = 0; a < 3; ++a) { o[a] = row[a]; if (a < T::WS) v -= row[a] * x[a]; }
+        o[3] = row[3]; o[4] = (double)k;
+        slot_init(c.ost + (size_t)p * SLOT_W, true, true, v, c.omega);
+        ++p;
+      }
+    }
+  }
+  // special rows: slacks one unit inside
+  G_PAR_FOR(it, N * L::SP) {
+    const int k = it / L::SP, s = it - k * L::SP;
+    const double* x = c.z + k * NV;
+    double* st = c.sslot + (size_t)it * SLOT_W;
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, true, true, tr_c0<M>(c, k, x), c.omega);
+    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, o.valid, o.has_t, o.c0, c.omega); }
+  }
+  G_PAR_FOR(j, L::NBOX) {
+    const bool valid = (c.bmask >> (j >> 1)) & 1;
+    slot_init(c.bslot + (size_t)j * SLOT_W, valid, false, valid ? box_c0<M>(c, j, c.z + (N - 1) * NV) : 0.0, c.omega);
   }
   G_SYNC();
 }
 
 // ------------------------------------------------------------------------------------------------ driver
-// scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance.
+// scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance (16-byte aligned).
 // smem:    IpmLayout<M>::smem_doubles() doubles of shared memory.
 // On exit Xn/Un of the instance hold the solution and info[IPM_NINFO] = {status, iters, res, mu, obj,...}.
 template <int M>
 GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmParams& prm, int b, double* scratch,
                              double* smem, double* info) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, NN = L::NN;
   const int N = d.N;
   IpmCtx<M> c;
-  c.d = &d; c.N = N; c.n_obs = (Traits<M>::WS > 0) ? d.n_obs : 0; c.S = L::nslots(c.n_obs); c.b = b;
-  c.h = p.tf[b] / (N - 1); c.omega = p.omega[b]; c.Delta = p.delta[b];
-  c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];
+  c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
+  c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
+  c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS]; c.dp = prm.delta_p; c.dd = prm.delta_d;
+  c.pmask = 0; c.bmask = 0;
+  for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
   c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
   c.A = p.A + (size_t)b * N * NX * NX; c.g = p.g + (size_t)b * N * NX;
   c.rows = p.rows + (size_t)b * N * d.n_obs * 5;
   c.x_init = p.x_init + (size_t)b * NX; c.goal_lo = p.goal_lo + (size_t)b * NX; c.goal_hi = p.goal_hi + (size_t)b * NX;
-  for (int i = 0; i < NX * NU; ++i) c.Bm[i] = 0.0;
-  dyn_B<M>(d.rp, c.Bm);
-  const size_t nz = (size_t)N * NV, ne = (size_t)(N + 1) * NX;
-  double* q = scratch;
-  c.z = q; q += nz; c.r = q; q += nz; c.dz = q; q += nz; c.t1 = q; q += nz; c.res = q; q += nz; c.e = q; q += nz;
-  c.nu = q; q += ne; c.rnu = q; q += ne; c.dnu = q; q += ne; c.resnu = q; q += ne; c.enu = q; q += ne;
-  c.slot = q; q += (size_t)N * c.S * SLOT_W;
-  c.Hx = q; q += (size_t)N * NX * NX; c.Ci = q; q += (size_t)N * NX * NX; c.CA = q; q += (size_t)N * NX * NX;
-  c.W = q; q += (size_t)N * NX * NX * 3;
-  c.Hu = q; q += (size_t)N * NU * NU; c.Cu = q; q += (size_t)N * NU * NU; c.GT = q; q += (size_t)N * NU * NX;
-  c.Ld = q; q += (size_t)(N + 1) * NX * NX; c.Lo = q; q += (size_t)(N + 1) * NX * NX;
-  c.sy = smem; c.sD = c.sy + (N + 1) * NX; c.sLo = c.sD + NX * NX; c.sLi = c.sLo + NX * NX; c.sB4 = c.sLi + NX * NX;
-  c.stmp = c.sB4 + NX * NX; c.red = c.stmp + 16;
-
-  // ---- start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); slacks one unit inside
-  G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; c.z[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
-  G_PAR_FOR(it, (N + 1) * NX) c.nu[it] = 0.0;
-  G_SYNC();
-  G_PAR_FOR(it, N * c.S) {
-    const int k = it / c.S, s = it - k * c.S;
-    SlotEval o;
-    slot_eval<M>(c, k, s, c.z + k * NV, c.z + k * NV + NX, o);
-    double* st = c.slot + (size_t)it * SLOT_W;
-    for (int i = 0; i < SLOT_W; ++i) st[i] = 0.0;
-    if (!o.valid) continue;
-    if (o.has_t) {
-      const double t = (o.c0 > 0 ? o.c0 : 0.0) + 1.0;
-      const double sa = t - o.c0;
-      st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = 0.5 * c.omega; st[2] = t; st[3] = 0.5 * c.omega;
-    } else {
-      st[0] = -o.c0 > 1e-2 ? -o.c0 : 1e-2; st[1] = 1e-2;
-    }
+  {
+    double Bm[NX * NU];
+    for (int i = 0; i < NX * NU; ++i) Bm[i] = 0.0;
+    dyn_B<M>(d.rp, Bm);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) c.bv[a] = Bm[T::b_row(a) * NU + a];
   }
-  G_SYNC();
+  const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs;
+  double* q = scratch;
+  c.r = q; q += nz; c.t1 = q; q += nz; c.res = q; q += nz;
+  c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne; c.resnu = q; q += ne;
+  c.Ac = q; q += L::rnd((size_t)N * L::ANZ);
+  c.sslot = q; q += L::rnd((size_t)N * L::SP * SLOT_W);
+  c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
+  c.ost = q; q += L::rnd((size_t)N * no * SLOT_W);
+  c.orow = q; q += L::rnd((size_t)N * no * OROW_W);
+  c.kd = q; q += L::rnd((size_t)N * L::KDW);
+  c.fac = q; q += (size_t)(N + 1) * 2 * NN;
+  c.z = smem; c.dz = c.z + N * NV; c.sy = c.dz + N * NV; c.ring = c.sy + (N + 1) * NX;
+  c.red = c.z + N * NV + L::work_doubles(N);
+  c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
+  c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
+  G_PAR_FOR(t, NX * (NX + 1) / 2) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    c.tab[t] = (unsigned char)i; c.tab[NX * (NX + 1) / 2 + t] = (unsigned char)(t - i * (i + 1) / 2);
+  }
+
+  setup<M>(c);
 
   int status = IPM_ITERATION_LIMIT, it_done = 0;
   long long cyc_asm = 0, cyc_fac = 0, cyc_sol = 0, cyc_slot = 0, tc0;
@@ -720,8 +1212,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
     it_done = iter;
     Resid R;
+    bool blocks_ok = true;
     tc0 = g_clock();
-    assemble<M>(c, 0, 0.0, &R);
+    assemble<M>(c, 0, 0.0, &R, &blocks_ok);
     cyc_asm += g_clock() - tc0;
     mu = R.mu;
     res = R.rz / scd;
@@ -732,16 +1225,16 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     if (res <= prm.tol) { status = IPM_OPTIMAL; break; }
     if (!(res == res) || res > 1e200) { status = IPM_NUMERICAL; break; }
     tc0 = g_clock();
-    const bool fac_ok = factorize<M>(c, prm);
+    const bool fac_ok = factorize<M>(c);
     cyc_fac += g_clock() - tc0;
-    if (!fac_ok) {
+    if (!(fac_ok && blocks_ok)) {
 #ifdef GUSTO_HOSTSIM
       if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  factorize: non-positive pivot\n");
 #endif
     }
     // predictor
     tc0 = g_clock();
-    kkt_solve_refined<M>(c, c.r, c.rnu, c.dz, c.dnu, 0);
+    kkt_solve_refined<M>(c, 0);
     cyc_sol += g_clock() - tc0;
     double am[2], mu_aff = 0;
     tc0 = g_clock();
@@ -757,10 +1250,10 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     smu = smu > 0.1 * prm.tol ? smu : 0.1 * prm.tol;
     // corrector
     tc0 = g_clock();
-    assemble<M>(c, 1, smu, &R);
+    assemble<M>(c, 1, smu, &R, &blocks_ok);
     cyc_asm += g_clock() - tc0;
     tc0 = g_clock();
-    kkt_solve_refined<M>(c, c.r, c.rnu, c.dz, c.dnu, prm.nref);
+    kkt_solve_refined<M>(c, prm.nref);
     cyc_sol += g_clock() - tc0;
     tc0 = g_clock();
     slot_steps<M>(c, 1, smu, 0, 0, 0, am, &mu_aff);
@@ -788,11 +1281,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     for (int i = 0; i < NX; ++i) p.Xn[((size_t)b * N + k) * NX + i] = c.z[k * NV + i];
     for (int i = 0; i < NU; ++i) { const double uv = c.z[k * NV + NX + i]; p.Un[((size_t)b * N + k) * NU + i] = uv; obj += wk * uv * uv; }
   }
-  G_PAR_FOR(it, N * c.S) {
-    const int k = it / c.S, s = it - k * c.S;
-    SlotEval o;
-    slot_eval<M>(c, k, s, c.z + k * NV, c.z + k * NV + NX, o);
-    if (o.valid && o.has_t) obj += c.omega * c.slot[(size_t)it * SLOT_W + 2];
+  {
+    const double omega = c.omega;
+    for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) { if (has_t) obj += omega * st[2]; });
   }
   obj = block_sum(obj, c.red);
   if (G_TID == 0) {

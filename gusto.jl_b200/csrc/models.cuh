@@ -153,34 +153,46 @@ template <> GDEV void dyn_A<DUBINS>(const double* x, const double* rp, double* A
 template <> GDEV void dyn_B<DUBINS>(const double* rp, double* Bm) { Bm[2] = rp[RP_DUB_K]; }
 
 // ------------------------------------------------------------------------------ per-model constraint tables
+// Index ranges are constexpr so that the convex solve can place every row in its Hessian block at compile time.
 // Soft quadratic state rows |x[i0:i1)|^2 - lim^2 (csi_translational_velocity_bound / csi_angular_velocity_bound:
 // astrobee_se3.jl:244-252, astrobee_se3_manifold.jl:321-329, freeflyer_se2.jl:225-233).
+template <int M> GHD constexpr int norm_i0(int j) {
+  return M == ASTROBEE_SE3 ? (j == 0 ? 3 : 9) : M == ASTROBEE_SE3_MANIFOLD ? (j == 0 ? 3 : 10) : M == FREEFLYER_SE2 ? (j == 0 ? 3 : 5) : 0;
+}
+template <int M> GHD constexpr int norm_i1(int j) {
+  return M == ASTROBEE_SE3 || M == ASTROBEE_SE3_MANIFOLD ? norm_i0<M>(j) + 3 : M == FREEFLYER_SE2 ? (j == 0 ? 5 : 6) : 0;
+}
 template <int M> GDEV void norm_row(int j, const double* rp, int* i0, int* i1, double* lim) {
-  if (M == ASTROBEE_SE3) { *i0 = j == 0 ? 3 : 9; *i1 = *i0 + 3; }
-  else if (M == ASTROBEE_SE3_MANIFOLD) { *i0 = j == 0 ? 3 : 10; *i1 = *i0 + 3; }
-  else if (M == FREEFLYER_SE2) { *i0 = j == 0 ? 3 : 5; *i1 = j == 0 ? 5 : 6; }
-  else { *i0 = 0; *i1 = 0; }
+  *i0 = norm_i0<M>(j); *i1 = norm_i1<M>(j);
   *lim = j == 0 ? rp[RP_VMAX] : rp[RP_WMAX];
 }
 // Soft linear state rows sign*x[i] - bound (csi_orientation_sign astrobee_se3_manifold.jl:316-319;
 // csi_max/min_bound_constraints dynamics.jl:56-64 for dubins).
+template <int M> GHD constexpr int lin_i(int j) { return M == ASTROBEE_SE3_MANIFOLD ? 6 : M == DUBINS ? j % 3 : 0; }
 template <int M> GDEV void lin_row(int j, const double* rp, int* i, double* sign, double* bound) {
-  if (M == ASTROBEE_SE3_MANIFOLD) { *i = 6; *sign = -1.0; *bound = 0.0; }
-  else if (M == DUBINS) { *i = j % 3; *sign = j < 3 ? 1.0 : -1.0; *bound = rp[RP_DUB_XMAX0 + (j % 3)]; }
-  else { *i = 0; *sign = 0.0; *bound = 0.0; }
+  *i = lin_i<M>(j);
+  if (M == ASTROBEE_SE3_MANIFOLD) { *sign = -1.0; *bound = 0.0; }
+  else if (M == DUBINS) { *sign = j < 3 ? 1.0 : -1.0; *bound = rp[RP_DUB_XMAX0 + (j % 3)]; }
+  else { *sign = 0.0; *bound = 0.0; }
 }
 // Hard control balls |scale .* u[i0:i1)|^2 <= rad^2 for k = 1..N-1 (cci_translational_accel_bound /
 // cci_angular_accel_bound: astrobee_se3.jl:255-263, freeflyer_se2.jl:236-245; cci_max/min_bound dynamics.jl:73-81).
+template <int M> GHD constexpr int ball_i0(int j) {
+  return M == ASTROBEE_SE3 || M == ASTROBEE_SE3_MANIFOLD ? 3 * j : M == FREEFLYER_SE2 ? (j == 0 ? 0 : 2) : 0;
+}
+template <int M> GHD constexpr int ball_i1(int j) {
+  return M == ASTROBEE_SE3 || M == ASTROBEE_SE3_MANIFOLD ? 3 * j + 3 : M == FREEFLYER_SE2 ? (j == 0 ? 2 : 3) : 1;
+}
 template <int M> GDEV void ctrl_ball(int j, const double* rp, int* i0, int* i1, double* scale, double* rad) {
+  *i0 = ball_i0<M>(j); *i1 = ball_i1<M>(j);
   if (M == ASTROBEE_SE3 || M == ASTROBEE_SE3_MANIFOLD) {
-    *i0 = 3 * j; *i1 = 3 * j + 3;
     if (j == 0) { scale[0] = scale[1] = scale[2] = 1.0 / rp[RP_MASS]; *rad = rp[RP_AMAX]; }
     else { scale[0] = 1.0 / rp[RP_JXX]; scale[1] = 1.0 / rp[RP_JYY]; scale[2] = 1.0 / rp[RP_JZZ]; *rad = rp[RP_ALMAX]; }
   } else if (M == FREEFLYER_SE2) {
-    if (j == 0) { *i0 = 0; *i1 = 2; scale[0] = scale[1] = 1.0 / rp[RP_MASS]; *rad = rp[RP_AMAX]; }
-    else { *i0 = 2; *i1 = 3; scale[0] = 1.0 / rp[RP_JXX]; *rad = rp[RP_ALMAX]; }
+    if (j == 0) { scale[0] = scale[1] = 1.0 / rp[RP_MASS]; *rad = rp[RP_AMAX]; }
+    else { scale[0] = 1.0 / rp[RP_JXX]; *rad = rp[RP_ALMAX]; }
   } else {
-    *i0 = 0; *i1 = 1; scale[0] = 1.0; *rad = rp[RP_DUB_UMAX];
+    scale[0] = 1.0; *rad = rp[RP_DUB_UMAX];
   }
 }
 
