@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
 template <int M>
 __global__ void __launch_bounds__(IPM_THREADS, GUSTO_IPM_MINBLOCKS) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
                                                           double* scratch, size_t stride, double* info) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int b = blockIdx.x;
   if (p.active && !p.active[b]) return;      // converged / failed instance: frozen (CTA-uniform exit)
   ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem, info + (size_t)b * IPM_NINFO);

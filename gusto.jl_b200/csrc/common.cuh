@@ -63,6 +63,27 @@ __device__ __forceinline__ void g_cp_async_wait() { asm volatile("cp.async.wait_
 template <int N> __device__ __forceinline__ void g_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+// 16-byte shared/global accesses (LDS.128 / LDG.128) and the fast FP64 reciprocal (MUFU.RCP64H + Newton steps).
+#ifdef GUSTO_HOSTSIM
+struct g_d2 { double x, y; };
+inline g_d2 g_ld2(const double* p) { g_d2 v; v.x = p[0]; v.y = p[1]; return v; }
+inline void g_st2(double* p, double a, double b) { p[0] = a; p[1] = b; }
+inline double g_rcp(double x) { return 1.0 / x; }
+#else
+typedef double2 g_d2;
+__device__ __forceinline__ g_d2 g_ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void g_st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ double g_rcp(double x) { return __drcp_rn(x); }
+#endif
+
+// Address-space hint: pointers that travel through the per-instance context struct come back as generic pointers;
+// telling the compiler they are shared turns LD.E/ST.E (64-bit generic path) back into LDS/STS.
+#ifdef GUSTO_HOSTSIM
+#define G_ASSUME_SHARED(p) ((void)0)
+#else
+#define G_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#endif
+
 namespace gusto {
 
 enum ModelId : int { DUBINS = 0, FREEFLYER_SE2 = 1, ASTROBEE_SE3 = 2, ASTROBEE_SE3_MANIFOLD = 3 };

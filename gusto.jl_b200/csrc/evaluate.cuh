@@ -16,6 +16,7 @@ namespace gusto {
 constexpr int EVAL_NOUT = 8;   // conv, tr_ok, ineq_ok, rho, J_true, J_full, max_k |dX_k|^2, max soft row value
 
 GDEV double block_sum(double v, double* red) {
+  G_ASSUME_SHARED(red);
   red[G_TID] = v;
   G_SYNC();
   double s = 0.0;
@@ -24,6 +25,7 @@ GDEV double block_sum(double v, double* red) {
   return s;
 }
 GDEV double block_max(double v, double* red) {   // NaN-propagating: a NaN anywhere yields +huge
+  G_ASSUME_SHARED(red);
   red[G_TID] = (v == v) ? v : 1e300;
   G_SYNC();
   double s = red[0];

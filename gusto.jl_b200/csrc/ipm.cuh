@@ -64,8 +64,15 @@ GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * 
 template <int M> struct IpmLayout {
   using T = Traits<M>;
   static constexpr int NX = T::NX, NU = T::NU, NV = NX + NU, NN = NX * NX, ANZ = T::ANZ;
-  static constexpr int LDR = NX | 1;                      // odd row stride of a ring tile: conflict-free both ways
-  static constexpr int TILE = NX * LDR;
+  static constexpr int GLD = (NX + 1) & ~1;               // row stride of a factor tile in global memory (16-byte rows)
+  static constexpr int GT = NX * GLD;
+  static constexpr int LDT = 2 * (((NX + 1) / 2) | 1);     // row stride of a shared-memory tile: even, LDT/2 odd -> LDS.128 conflict-free
+  static constexpr int TILE = NX * LDT;
+  static constexpr int CG = NX <= 12 ? 3 : 4;              // output columns per thread task in the tile products
+  static constexpr int NG = (NX + CG - 1) / CG;
+  static constexpr int NTASK = NX * NG;                    // tasks of a full product
+  GHD static constexpr int nlt() { int n = 0; for (int i = 0; i < NX; ++i) for (int g = 0; g < NG; ++g) if (g * CG <= i) ++n; return n; }
+  static constexpr int NLT = nlt();                        // tasks touching the lower triangle
   // special (non-obstacle) slots of a knot
   static constexpr int S_TR = 0;
   static constexpr int S_NORM = T::HAS_TR;
@@ -83,17 +90,19 @@ template <int M> struct IpmLayout {
   GHD static size_t scratch_doubles(int N, int n_obs) {
     const size_t nz = rnd((size_t)N * NV), ne = rnd((size_t)(N + 1) * NX), no = T::WS > 0 ? n_obs : 0;
     return 3 * nz + 4 * ne + rnd((size_t)N * ANZ) + rnd((size_t)N * SP * SLOT_W) + (size_t)NBOX * SLOT_W +
-           rnd((size_t)N * no * SLOT_W) + rnd((size_t)N * no * OROW_W) + rnd((size_t)N * KDW) + (size_t)(N + 1) * 2 * NN;
+           rnd((size_t)N * no * SLOT_W) + rnd((size_t)N * no * OROW_W) + rnd((size_t)N * KDW) + (size_t)(N + 1) * 2 * GT;
   }
   GHD static int work_doubles(int N) {      // dz | sy | ring, also the 8 factorisation tiles
-    const int ne = (N + 1) * NX;
+    const int ne = (int)rnd((size_t)(N + 1) * NX);
     const int ring = RING_STAGES * TILE > ne ? RING_STAGES * TILE : ne;
-    const int w = N * NV + ne + ring, f = 9 * NN + 16;
-    return w > f ? w : f;
+    const int w = (int)rnd((size_t)N * NV) + ne + ring, f = 10 * TILE + 2 * NX + 4;
+    return (w > f ? w : f) + 2;
   }
-  static constexpr int TAB_DOUBLES = (NX * (NX + 1) + 7) / 8;    // (row, col) of the packed lower triangle, as bytes
+  // byte tables: (row, col) of the packed lower triangle, then (row, group) of the lower-triangular product tasks
+  static constexpr int TAB_DOUBLES = (NX * (NX + 1) + 2 * NLT + 7) / 8;
   GHD static int seg_doubles(int N) { return (N + 4) / 2 + 2; }
-  GHD static int smem_doubles(int N, int nthr) { return N * NV + work_doubles(N) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES; }
+  static constexpr int CTX_DOUBLES = 80;                   // the per-instance context struct (IpmCtx) lives in shared memory too
+  GHD static int smem_doubles(int N, int nthr) { return CTX_DOUBLES + (int)rnd((size_t)N * NV) + work_doubles(N) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES; }
 };
 
 template <int M> struct IpmCtx {
@@ -110,8 +119,15 @@ template <int M> struct IpmCtx {
   // shared
   double *z, *dz, *sy, *ring, *red;
   int* seg;
-  unsigned char* tab;     // [2][NX(NX+1)/2]: row / column of packed-lower entry t
+  mutable long long prof[5];      // thread-0 cycle counters: schur rows, factor sweep, forward chain, middle pass, backward chain
+  unsigned char* tab;     // [2][NX(NX+1)/2]: row / column of packed-lower entry t; then [2][NLT]: row / group of lower task
 };
+
+// shared-memory members, with the address space made known to the compiler
+template <int M> GDEV double* sh_z(const IpmCtx<M>& c) { double* p = c.z; G_ASSUME_SHARED(p); return p; }
+template <int M> GDEV double* sh_dz(const IpmCtx<M>& c) { double* p = c.dz; G_ASSUME_SHARED(p); return p; }
+template <int M> GDEV double* sh_sy(const IpmCtx<M>& c) { double* p = c.sy; G_ASSUME_SHARED(p); return p; }
+template <int M> GDEV int* sh_seg(const IpmCtx<M>& c) { return c.seg; }   // (an address-space assumption on this one miscompiles with nvcc 12.9)
 
 // ------------------------------------------------------------------------------------------- slot algebra
 // One inequality  c0(z) [- t] + s = 0, s >= 0 (multiplier lam) [, t >= 0 (multiplier lamb), cost omega*t].
@@ -421,7 +437,7 @@ template <int M> GDEV void apply_H(const IpmCtx<M>& c, int k, const double* in, 
   if (T::HAS_TR) {
     double gvec[NX], s = 0.0;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { gvec[i] = 2.0 * (c.z[k * NV + i] - c.Xp[k * NX + i]); s += gvec[i] * in[i]; }
+    for (int i = 0; i < NX; ++i) { gvec[i] = 2.0 * (sh_z<M>(c)[k * NV + i] - c.Xp[k * NX + i]); s += gvec[i] * in[i]; }
     s *= kd[L::KD_KAP];
 #pragma unroll
     for (int i = 0; i < NX; ++i) out[i] += s * gvec[i];
@@ -488,7 +504,7 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
     // convexified obstacle rows (compacted): off - nhat.r - t <= 0
     if (T::WS > 0 && B0 == T::XB_of(0)) {
       constexpr int WS = T::WS > 0 ? T::WS : 1;
-      const int s0 = c.seg[k], s1 = c.seg[k + 1];
+      const int s0 = sh_seg<M>(c)[k], s1 = sh_seg<M>(c)[k + 1];
       for (int p = s0; p < s1; ++p) {
         const double* row = c.orow + (size_t)p * OROW_W;
         const double* st = c.ost + (size_t)p * SLOT_W;
@@ -592,7 +608,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
   Stat S; S.rz = 0; S.rc = 0; S.mus = 0; S.np = 0;
   bool ok = true;
   G_PAR_FOR(k, N) {
-    const double* x = c.z + k * NV;
+    const double* x = sh_z<M>(c) + k * NV;
     const double* u = x + NX;
     double gz[NV];
     aeqT_knot<M>(c, c.nu, k, gz);
@@ -632,7 +648,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
     double rpmax = 0;
     G_PAR_FOR(j, N + 1) {
       double v[NX];
-      aeq_row<M>(c, c.z, j, v);
+      aeq_row<M>(c, sh_z<M>(c), j, v);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         double t = v[i];
@@ -762,13 +778,13 @@ template <int M, int I> GDEV void schur_rows(const IpmCtx<M>& c, int j) {
   }
   if (j == N && !((c.pmask >> I) & 1)) dd[I] += 1.0;        // free goal coordinates: keep the block non-singular
   dd[I] += c.dd * dd[I] + 1e-300;
-  double* Sd = c.fac + (size_t)(2 * j) * NN + I * NX;
+  double* Sd = c.fac + (size_t)(2 * j) * L::GT + I * L::GLD;
 #pragma unroll
-  for (int q = 0; q < NX; ++q) Sd[q] = dd[q];
+  for (int q = 0; q < L::GLD; q += 2) g_st2(Sd + q, dd[q], q + 1 < NX ? dd[q + 1 < NX ? q + 1 : q] : 0.0);
   if (j < N) {
-    double* So = c.fac + (size_t)(2 * (j + 1) + 1) * NN + I * NX;
+    double* So = c.fac + (size_t)(2 * (j + 1) + 1) * L::GT + I * L::GLD;
 #pragma unroll
-    for (int q = 0; q < NX; ++q) So[q] = od[q];
+    for (int q = 0; q < L::GLD; q += 2) g_st2(So + q, od[q], q + 1 < NX ? od[q + 1 < NX ? q + 1 : q] : 0.0);
   }
 }
 template <int M, int I = 0> GDEV void schur_rows_dispatch(const IpmCtx<M>& c, int j, int i) {
@@ -778,178 +794,263 @@ template <int M, int I = 0> GDEV void schur_rows_dispatch(const IpmCtx<M>& c, in
   }
 }
 
+// acc[c] = sum_m X[i][m] * Y[q0 + c][m]  over one shared-memory tile row pair (rows are LDT apart, MLEN = GLD terms)
+template <int M> GDEV void abt_task(const double* X, const double* Y, int i, int q0, double* acc) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, LDT = L::LDT, CG = L::CG;
+#pragma unroll
+  for (int c2 = 0; c2 < CG; ++c2) acc[c2] = 0.0;
+#pragma unroll
+  for (int m = 0; m < L::GLD; m += 2) {
+    const g_d2 xv = g_ld2(X + i * LDT + m);
+#pragma unroll
+    for (int c2 = 0; c2 < CG; ++c2) {
+      const int q = q0 + c2 < NX ? q0 + c2 : NX - 1;      // clamped: the caller drops columns >= NX
+      const g_d2 yv = g_ld2(Y + q * LDT + m);
+      acc[c2] += xv.x * yv.x;
+      acc[c2] += xv.y * yv.y;
+    }
+  }
+}
+
 // Factorisation of the block-tridiagonal S.  Block Cholesky recurrence (numerically the stable form: every update is a
 // symmetric  D_j = S_jj - Lo_j Lo_j'  with Lo_j = S_{j,j-1} L_{j-1}^-T), but what is STORED is the block L D L' form the
 // solves want:  slot (j,0) S_jj -> D_j^-1 = Li_j' Li_j,  slot (j,1) S_{j,j-1} -> V_j = Lo_j Li_{j-1} (= S_{j,j-1} D_{j-1}^-1),
 // so that a solve is two chains of single mat-vecs plus one parallel D^-1 pass.  Li_j = L_j^-1 comes out of one
 // Gaussian elimination of [D_j | I] in shared memory (NX dependent pivot steps on warp 0 -- the critical path of the
-// whole kernel) while the other warp stages block row j+1.  Returns false on a non-positive pivot.
+// whole kernel) while the other warp stages block row j+1.  All tile products are row-by-row dot products over
+// zero-padded tiles (LDS.128, a 1 x CG register tile per thread).  Returns false on a non-positive pivot.
 template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NN = L::NN, NT = NX * (NX + 1) / 2;
+  constexpr int NX = L::NX, NT = NX * (NX + 1) / 2, LDT = L::LDT, TILE = L::TILE, GLD = L::GLD, GT = L::GT;
+  constexpr int CG = L::CG, NG = L::NG, NTASK = L::NTASK, NLT = L::NLT;
   const int N = c.N;
+  long long tc0 = g_clock();
   // (1) Schur blocks.  Items ordered row-index-major so that a warp shares the compile-time row index.
   G_PAR_FOR(it, (N + 1) * NX) {
     const int i = it / (N + 1), j = it - i * (N + 1);
     schur_rows_dispatch<M>(c, j, i);
   }
-  G_SYNC();
-  // (2) sweep over block rows
-  double* tile = c.dz;                       // dz | sy | ring are dead here: 9 tiles of NN doubles + NX pivots
+  // (2) sweep over block rows.  dz | sy | ring are dead here: 10 tiles + pivots.
+  double* tile = sh_dz<M>(c);
   double* W = tile;                          // D_j, eliminated in place (lower triangle)
-  double* Wr = tile + NN;                    // I -> unit-lower elimination history (L~^-1)
-  double* Li = tile + 2 * NN;
-  double* Sdd[2] = {tile + 3 * NN, tile + 4 * NN};
-  double* Sod[2] = {tile + 5 * NN, tile + 6 * NN};
-  double* Lo[2] = {tile + 7 * NN, tile + 8 * NN};
-  double* rs = tile + 9 * NN;                // 1 / sqrt(pivot)
+  double* Wr = tile + TILE;                  // I -> unit-lower elimination history (L~^-1)
+  double* Li = tile + 2 * TILE;              // L_j^-1 (lower, explicit zeros) and its transpose
+  double* LiT = tile + 3 * TILE;
+  double* Sdd[2] = {tile + 4 * TILE, tile + 5 * TILE};
+  double* Sod[2] = {tile + 6 * TILE, tile + 7 * TILE};
+  double* Lo[2] = {tile + 8 * TILE, tile + 9 * TILE};
+  double* ipv = tile + 10 * TILE;            // 1 / pivot, then 1 / sqrt(pivot)
+  const unsigned char* const tab = c.tab;
+  G_ASSUME_SHARED(tab);
+  const unsigned char* const tab2 = tab + 2 * NT;
+  double* const fac = c.fac;
   const int pf0 = G_NTHR > G_WARP ? G_WARP : 0;            // threads [pf0, NTHR) prefetch while warp 0 eliminates
   const int npf = G_NTHR - pf0;
   double bad = 0.0;
-  G_PAR_FOR(it, NN) Sdd[0][it] = c.fac[it];
+  G_PAR_FOR(it, 10 * TILE) tile[it] = 0.0;
+  G_SYNC();
+  if (G_TID == 0) c.prof[0] += g_clock() - tc0;
+  tc0 = g_clock();
+  // my entries of the packed lower triangle during the elimination (warp 0)
+  int ei[3], ee[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int t = G_TID + r * G_WARP;
+    ei[r] = t < NT ? tab[t] : 0; ee[r] = t < NT ? tab[NT + t] : 0;
+  }
+  G_PAR_FOR(it, NX * GLD / 2) {
+    const int i = it / (GLD / 2), m = 2 * (it - i * (GLD / 2));
+    const g_d2 v = g_ld2(fac + i * GLD + m);
+    g_st2(W + i * LDT + m, v.x, v.y);
+  }
+  G_PAR_FOR(i, NX) Wr[i * LDT + i] = 1.0;
   G_SYNC();
   for (int j = 0; j <= N; ++j) {
     const int cur = j & 1, nxt = cur ^ 1;
-    // (a) D_j = S_jj - Lo_j Lo_j'  (lower triangle);  Wr = I
-    G_PAR_FOR(it, NN) {
-      const int i = it / NX, q = it - i * NX;
-      Wr[it] = (i == q) ? 1.0 : 0.0;
-      if (q > i) continue;
-      double v = Sdd[cur][it];
-      if (j > 0) for (int m = 0; m < NX; ++m) v -= Lo[cur][i * NX + m] * Lo[cur][q * NX + m];
-      W[it] = v;
-    }
-    G_SYNC();
-    // (b) warp 0: eliminate column q from the rows below it, in W (columns > q) and in Wr (columns <= q)
+    // (E) warp 0: eliminate column q from the rows below it, in W (columns > q) and in Wr (columns <= q)
     if (G_TID < G_WARP) {
       for (int q = 0; q < NX; ++q) {
-        double piv = W[q * NX + q];
+        double piv = W[q * LDT + q];
         if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
-        const double ip = 1.0 / piv;
-        if (G_LANE == q % G_NLANE) rs[q] = sqrt(ip);
-        G_W0_FOR(t, NT) {
-          const int i = c.tab[t], e = c.tab[NT + t];
+        const double ip = g_rcp(piv);
+        if (G_LANE == 0) ipv[q] = ip;
+#ifdef GUSTO_HOSTSIM
+        for (int t = 0; t < NT; ++t) {
+          const int i = tab[t], e = tab[NT + t];
+#else
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int i = ei[r], e = ee[r];
+#endif
           if (i <= q) continue;
-          const double mult = W[i * NX + q] * ip;
-          if (e <= q) Wr[i * NX + e] -= mult * Wr[q * NX + e];
-          else W[i * NX + e] -= mult * W[e * NX + q];
+          const double mult = W[i * LDT + q] * ip;
+          if (e <= q) Wr[i * LDT + e] -= mult * Wr[q * LDT + e];
+          else W[i * LDT + e] -= mult * W[e * LDT + q];
         }
         G_SYNCWARP();
       }
+      G_W0_FOR(q, NX) ipv[q] = sqrt(ipv[q]);
     }
     if (j < N && G_TID >= pf0) {
-      const double* gd = c.fac + (size_t)(2 * (j + 1)) * NN;
-      for (int it = G_TID - pf0; it < 2 * NN; it += npf) {
-        if (it < NN) Sdd[nxt][it] = gd[it]; else Sod[nxt][it - NN] = gd[it];
+      const double* gd = fac + (size_t)(2 * (j + 1)) * GT;
+      for (int it = G_TID - pf0; it < NX * GLD; it += npf) {      // two tiles, 16 bytes at a time
+        const int tl = it / (NX * GLD / 2), rem = it - tl * (NX * GLD / 2);
+        const int i = rem / (GLD / 2), m = 2 * (rem - i * (GLD / 2));
+        const g_d2 v = g_ld2(gd + tl * GT + i * GLD + m);
+        g_st2((tl == 0 ? Sdd[nxt] : Sod[nxt]) + i * LDT + m, v.x, v.y);
       }
     }
     G_SYNC();
-    // (c1) Li = diag(rs) * Wr  (lower triangular)
-    G_PAR_FOR(it, NN) { const int i = it / NX, m = it - i * NX; Li[it] = m <= i ? Wr[it] * rs[i] : 0.0; }
-    G_SYNC();
-    // (c2) D_j^-1 = Li' Li -> global;  Lo_{j+1} = S_{j+1,j} Li'
-    double* gD = c.fac + (size_t)(2 * j) * NN;
-    G_PAR_FOR(it, NN) {
-      const int i = it / NX, q = it - i * NX;
-      if (q <= i) {
-        double s = 0.0;
-        for (int m = i; m < NX; ++m) s += Li[m * NX + i] * Li[m * NX + q];
-        gD[i * NX + q] = s;
-        gD[q * NX + i] = s;
-      }
-      if (j < N) {
-        double s = 0.0;
-        for (int m = 0; m <= q; ++m) s += Sod[nxt][i * NX + m] * Li[q * NX + m];
-        Lo[nxt][it] = s;
-      }
+    // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose
+    G_PAR_FOR(it, NX * NX) {
+      const int i = it / NX, m = it - i * NX;
+      const double v = m <= i ? Wr[i * LDT + m] * ipv[i] : 0.0;
+      Li[i * LDT + m] = v;
+      LiT[m * LDT + i] = v;
     }
     G_SYNC();
-    // (c3) V_{j+1} = Lo_{j+1} Li -> global   (no barrier needed before the next (a): disjoint tiles)
+    // (C2) Lo_{j+1} = S_{j+1,j} Li'
     if (j < N) {
-      double* gV = c.fac + (size_t)(2 * (j + 1) + 1) * NN;
-      G_PAR_FOR(it, NN) {
-        const int i = it / NX, q = it - i * NX;
-        double s = 0.0;
-        for (int m = q; m < NX; ++m) s += Lo[nxt][i * NX + m] * Li[m * NX + q];
-        gV[it] = s;
+      G_PAR_FOR(task, NTASK) {
+        const int i = task / NG, q0 = (task - i * NG) * CG;
+        double acc[CG];
+        abt_task<M>(Sod[nxt], Li, i, q0, acc);
+#pragma unroll
+        for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) Lo[nxt][i * LDT + q0 + c2] = acc[c2];
       }
     }
+    G_SYNC();
+    // (X) V_{j+1} = Lo_{j+1} Li -> global;  D_j^-1 = Li' Li -> global;  D_{j+1} = S_{j+1,j+1} - Lo_{j+1} Lo_{j+1}' -> W;  Wr = I
+    {
+      double* gD = fac + (size_t)(2 * j) * GT;
+      double* gV = fac + (size_t)(2 * (j + 1) + 1) * GT;
+      const int nt = j < N ? NTASK + 2 * NLT : NLT;
+      G_PAR_FOR(task, nt) {
+        double acc[CG];
+        if (task < NLT) {                                   // D_j^-1, lower tasks mirrored
+          const int i = tab2[task], q0 = tab2[NLT + task] * CG;
+          abt_task<M>(LiT, LiT, i, q0, acc);
+#pragma unroll
+          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 <= i) { gD[i * GLD + q0 + c2] = acc[c2]; gD[(q0 + c2) * GLD + i] = acc[c2]; }
+        } else if (task < 2 * NLT) {                        // D_{j+1}, lower tasks (the strict upper triangle of W is never read)
+          const int i = tab2[task - NLT], q0 = tab2[task] * CG;
+          abt_task<M>(Lo[nxt], Lo[nxt], i, q0, acc);
+#pragma unroll
+          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) W[i * LDT + q0 + c2] = Sdd[nxt][i * LDT + q0 + c2] - acc[c2];
+        } else {
+          const int t2 = task - 2 * NLT;
+          const int i = t2 / NG, q0 = (t2 - i * NG) * CG;
+          abt_task<M>(Lo[nxt], LiT, i, q0, acc);
+#pragma unroll
+          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) gV[i * GLD + q0 + c2] = acc[c2];
+        }
+      }
+      G_PAR_FOR(it, NX * NX) { const int i = it / NX, m = it - i * NX; Wr[i * LDT + m] = (i == m) ? 1.0 : 0.0; }
+    }
+    G_SYNC();
   }
+  if (G_TID == 0) c.prof[1] += g_clock() - tc0;
   bad = block_max(bad, c.red);
   return bad == 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------ KKT solves
-// cp.async ring over the R tiles of the factor (global -> shared, RING_STAGES deep), used by warp 0 only.
-template <int M> GDEV void ring_fetch(const IpmCtx<M>& c, int j) {
+// cp.async ring over the V tiles of the factor (global -> shared, RING_STAGES deep, 16-byte copies), warp 0 only.
+template <int M> GDEV void ring_fetch(const double* fac, double* ring, int N, int j) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NN = L::NN;
-  if (j >= 1 && j <= c.N) {
-    const double* src = c.fac + (size_t)(2 * j + 1) * NN;
-    double* dst = c.ring + (j % RING_STAGES) * L::TILE;
-    G_W0_FOR(it, NN) { const int i = it / NX, m = it - i * NX; g_cp_async8(dst + i * L::LDR + m, src + it); }
+  constexpr int NX = L::NX, GLD = L::GLD, HC = GLD / 2;
+  if (j >= 1 && j <= N) {
+    const double* src = fac + (size_t)(2 * j + 1) * L::GT;
+    double* dst = ring + (j % RING_STAGES) * L::TILE;
+    G_W0_FOR(it, NX * HC) { const int i = it / HC, m = 2 * (it - i * HC); g_cp_async16(dst + i * L::LDT + m, src + i * GLD + m); }
   }
   g_cp_async_commit();
 }
 
 // Block-tridiagonal solve  S nu = b  (sy holds b on entry, nu on exit):
-//   forward  w_j = b_j - R_j w_{j-1};   middle  v_j = D_j^-1 w_j (all threads);   backward  nu_j = v_j - R_{j+1}' nu_{j+1}.
+//   forward  w_j = b_j - V_j w_{j-1};   middle  v_j = D_j^-1 w_j (all threads);   backward  nu_j = v_j - V_{j+1}' nu_{j+1}.
 template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NN = L::NN, LDR = L::LDR, S = RING_STAGES;
+  constexpr int NX = L::NX, LDT = L::LDT, GLD = L::GLD, S = RING_STAGES;
   const int N = c.N;
-  double* y = c.sy;
+  double* const y = c.sy;
+  double* const ring = c.ring;
+  const double* const fac = c.fac;
+  G_ASSUME_SHARED(y);
+  G_ASSUME_SHARED(ring);
+  long long tc0 = g_clock();
   if (G_TID < G_WARP) {
-    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(c, jj);
+    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(fac, ring, N, jj);
     for (int j = 1; j <= N; ++j) {
       g_cp_async_wait_group<S - 2>();             // tile j has landed (at most S-2 younger groups in flight)
       G_SYNCWARP();                               // ... for every lane; everyone is done with tile j-1
-      ring_fetch<M>(c, j + S - 1);                // reuses the slot of tile j-1
-      const double* R = c.ring + (j % S) * L::TILE;
+      ring_fetch<M>(fac, ring, N, j + S - 1);                // reuses the slot of tile j-1
+      const double* R = ring + (j % S) * L::TILE;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
 #pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[i * LDR + m] * y[(j - 1) * NX + m]; a1 -= R[i * LDR + m + 1] * y[(j - 1) * NX + m + 1]; }
-        if (NX & 1) a0 -= R[i * LDR + NX - 1] * y[(j - 1) * NX + NX - 1];
+        for (int m = 0; m < GLD; m += 2) {
+          const g_d2 rv = g_ld2(R + i * LDT + m);
+          a0 -= rv.x * y[(j - 1) * NX + m];
+          if (m + 1 < NX) a1 -= rv.y * y[(j - 1) * NX + m + 1];
+        }
         y[j * NX + i] = a0 + a1;
       }
     }
     g_cp_async_wait();
   }
   G_SYNC();
-  // middle: v = D^-1 w, staged through the (idle) ring so that no row is overwritten while still being read
-  double* v = c.ring;
-  G_PAR_FOR(it, (N + 1) * NX) {
-    const int j = it / NX, i = it - j * NX;
-    const double* Di = c.fac + (size_t)(2 * j) * NN + i * NX;
-    double a0 = 0.0, a1 = 0.0;
+  if (G_TID == 0) c.prof[2] += g_clock() - tc0;
+  tc0 = g_clock();
+  // middle: v = D^-1 w, staged through the (idle) ring so that no row is overwritten while still being read.
+  // Two rows per thread and round, all loads issued before the arithmetic (the factor streams from L2 / HBM).
+  double* v = ring;
+  const int ne = (N + 1) * NX;
+  for (int it0 = G_TID; it0 < ne; it0 += 2 * G_NTHR) {
+    const int it1 = it0 + G_NTHR;
+    const bool two = it1 < ne;
+    const int j0 = it0 / NX, i0 = it0 - j0 * NX;
+    const int j1 = two ? it1 / NX : j0, i1 = two ? it1 - j1 * NX : i0;
+    const double* D0 = fac + (size_t)(2 * j0) * L::GT + i0 * GLD;
+    const double* D1 = fac + (size_t)(2 * j1) * L::GT + i1 * GLD;
+    g_d2 d0[GLD / 2], d1[GLD / 2];
 #pragma unroll
-    for (int m = 0; m + 1 < NX; m += 2) { a0 += Di[m] * y[j * NX + m]; a1 += Di[m + 1] * y[j * NX + m + 1]; }
-    if (NX & 1) a0 += Di[NX - 1] * y[j * NX + NX - 1];
-    v[it] = a0 + a1;
+    for (int m = 0; m < GLD / 2; ++m) { d0[m] = g_ld2(D0 + 2 * m); d1[m] = g_ld2(D1 + 2 * m); }
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < GLD / 2; ++m) {
+      a0 += d0[m].x * y[j0 * NX + 2 * m]; b0 += d1[m].x * y[j1 * NX + 2 * m];
+      if (2 * m + 1 < NX) { a1 += d0[m].y * y[j0 * NX + 2 * m + 1]; b1 += d1[m].y * y[j1 * NX + 2 * m + 1]; }
+    }
+    v[it0] = a0 + a1;
+    if (two) v[it1] = b0 + b1;
   }
   G_SYNC();
-  G_PAR_FOR(it, (N + 1) * NX) y[it] = v[it];
+  G_PAR_FOR(it, ne) y[it] = v[it];
   G_SYNC();
+  if (G_TID == 0) c.prof[3] += g_clock() - tc0;
+  tc0 = g_clock();
   if (G_TID < G_WARP) {
     // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
-    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(c, N - jj);
+    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(fac, ring, N, N - jj);
     for (int j = N - 1; j >= 0; --j) {
       g_cp_async_wait_group<S - 2>();
       G_SYNCWARP();
-      ring_fetch<M>(c, j + 1 - (S - 1));          // reuses the slot of tile j+2
-      const double* R = c.ring + ((j + 1) % S) * L::TILE;
+      ring_fetch<M>(fac, ring, N, j + 1 - (S - 1));          // reuses the slot of tile j+2
+      const double* R = ring + ((j + 1) % S) * L::TILE;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
 #pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * LDR + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * LDR + i] * y[(j + 1) * NX + m + 1]; }
-        if (NX & 1) a0 -= R[(NX - 1) * LDR + i] * y[(j + 1) * NX + NX - 1];
+        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * LDT + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * LDT + i] * y[(j + 1) * NX + m + 1]; }
+        if (NX & 1) a0 -= R[(NX - 1) * LDT + i] * y[(j + 1) * NX + NX - 1];
         y[j * NX + i] = a0 + a1;
       }
     }
     g_cp_async_wait();
   }
   G_SYNC();
+  if (G_TID == 0) c.prof[4] += g_clock() - tc0;
 }
 
 // [dz; dnu] (+)= Ktilde^-1 [rin; rnuin]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]] via the Schur complement.
@@ -970,20 +1071,20 @@ template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* 
     double v[NX];
     aeq_row<M>(c, c.t1, j, v);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) c.sy[j * NX + i] = v[i] - rnuin[j * NX + i];
+    for (int i = 0; i < NX; ++i) sh_sy<M>(c)[j * NX + i] = v[i] - rnuin[j * NX + i];
   }
   G_SYNC();
   schur_solve<M>(c);
   G_PAR_FOR(k, N) {
     double in[NV], out[NV];
-    aeqT_knot<M>(c, c.sy, k, in);
+    aeqT_knot<M>(c, sh_sy<M>(c), k, in);
 #pragma unroll
     for (int i = 0; i < NV; ++i) in[i] = rin[k * NV + i] - in[i];
     apply_phi<M>(c, k, in, out);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) c.dz[k * NV + i] = accumulate ? c.dz[k * NV + i] + out[i] : out[i];
+    for (int i = 0; i < NV; ++i) sh_dz<M>(c)[k * NV + i] = accumulate ? sh_dz<M>(c)[k * NV + i] + out[i] : out[i];
   }
-  G_PAR_FOR(it, (N + 1) * NX) c.dnu[it] = accumulate ? c.dnu[it] + c.sy[it] : c.sy[it];
+  G_PAR_FOR(it, (N + 1) * NX) c.dnu[it] = accumulate ? c.dnu[it] + sh_sy<M>(c)[it] : sh_sy<M>(c)[it];
   G_SYNC();
 }
 
@@ -998,14 +1099,14 @@ template <int M> GDEV void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
       double at[NV], hd[NV], dk[NV];
       aeqT_knot<M>(c, c.dnu, k, at);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) dk[i] = c.dz[k * NV + i];
+      for (int i = 0; i < NV; ++i) dk[i] = sh_dz<M>(c)[k * NV + i];
       apply_H<M>(c, k, dk, hd);
 #pragma unroll
       for (int i = 0; i < NV; ++i) c.res[k * NV + i] = c.r[k * NV + i] - hd[i] - at[i];
     }
     G_PAR_FOR(j, N + 1) {
       double v[NX];
-      aeq_row<M>(c, c.dz, j, v);
+      aeq_row<M>(c, sh_dz<M>(c), j, v);
 #pragma unroll
       for (int i = 0; i < NX; ++i) c.resnu[j * NX + i] = c.rnu[j * NX + i] - v[i];
     }
@@ -1024,26 +1125,26 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
   const int N = c.N;
   G_PAR_FOR(it, N * L::SP) {
     const int k = it / L::SP, s = it - k * L::SP;
-    const double* x = c.z + k * NV;
+    const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)it * SLOT_W;
     if (T::HAS_TR && s == L::S_TR) {
       double v = -c.Delta / c.omega, gdz = 0.0;
-      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; gdz += 2.0 * dxi * c.dz[k * NV + i]; }
+      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
       fn(st, true, v, gdz);
     } else {
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
       if (!o.valid) continue;
       double gdz = 0.0;
-      if (want_gdz) { const double* dv = c.dz + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[a]; }
+      if (want_gdz) { const double* dv = sh_dz<M>(c) + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[a]; }
       fn(st, o.has_t, o.c0, gdz);
     }
   }
   if (c.bmask != 0) {
     G_PAR_FOR(j, L::NBOX) {
       if (!((c.bmask >> (j >> 1)) & 1)) continue;
-      const double* x = c.z + (N - 1) * NV;
-      const double gdz = ((j & 1) == 0 ? 1.0 : -1.0) * c.dz[(N - 1) * NV + (j >> 1)];
+      const double* x = sh_z<M>(c) + (N - 1) * NV;
+      const double gdz = ((j & 1) == 0 ? 1.0 : -1.0) * sh_dz<M>(c)[(N - 1) * NV + (j >> 1)];
       fn(c.bslot + (size_t)j * SLOT_W, false, box_c0<M>(c, j, x), gdz);
     }
   }
@@ -1052,8 +1153,8 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     G_PAR_FOR(p, c.nact) {
       const double* row = c.orow + (size_t)p * OROW_W;
       const int k = (int)row[4];
-      const double* x = c.z + k * NV;
-      const double* dv = c.dz + k * NV;
+      const double* x = sh_z<M>(c) + k * NV;
+      const double* dv = sh_dz<M>(c) + k * NV;
       double v = row[3], gdz = 0.0;
 #pragma unroll
       for (int a = 0; a < WS; ++a) { v -= row[a] * x[a]; gdz -= row[a] * dv[a]; }
@@ -1104,7 +1205,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
   const int N = c.N;
   // start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); multipliers 0
-  G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; c.z[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
+  G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; sh_z<M>(c)[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
   G_PAR_FOR(it, (N + 1) * NX) c.nu[it] = 0.0;
   // A_k on its sparsity pattern
   G_PAR_FOR(it, N * ANZ) { const int k = it / ANZ, e = it - k * ANZ; c.Ac[it] = c.A[(size_t)k * NX * NX + T::a_row(e) * NX + T::a_col(e)]; }
@@ -1113,20 +1214,20 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     G_PAR_FOR(k, N) {
       int cnt = 0;
       for (int i = 0; i < c.n_obs; ++i) cnt += (c.rows[((size_t)k * c.n_obs + i) * 5 + 4] < c.toggle) ? 1 : 0;
-      c.seg[k + 1] = cnt;
+      sh_seg<M>(c)[k + 1] = cnt;
     }
     G_SYNC();
-    if (G_TID == 0) { c.seg[0] = 0; for (int k = 0; k < N; ++k) c.seg[k + 1] += c.seg[k]; }
+    if (G_TID == 0) { sh_seg<M>(c)[0] = 0; for (int k = 0; k < N; ++k) sh_seg<M>(c)[k + 1] += sh_seg<M>(c)[k]; c.nact = sh_seg<M>(c)[N]; }
     G_SYNC();
   } else {
-    G_PAR_FOR(k, N + 1) c.seg[k] = 0;
+    G_PAR_FOR(k, N + 1) sh_seg<M>(c)[k] = 0;
+    if (G_TID == 0) c.nact = 0;
     G_SYNC();
   }
-  c.nact = c.seg[N];
   if (T::WS > 0) {
     G_PAR_FOR(k, N) {
-      int p = c.seg[k];
-      const double* x = c.z + k * NV;
+      int p = sh_seg<M>(c)[k];
+      const double* x = sh_z<M>(c) + k * NV;
       for (int i = 0; i < c.n_obs; ++i) {
         const double* row = c.rows + ((size_t)k * c.n_obs + i) * 5;
         if (!(row[4] < c.toggle)) continue;
@@ -1142,14 +1243,14 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   // special rows: slacks one unit inside
   G_PAR_FOR(it, N * L::SP) {
     const int k = it / L::SP, s = it - k * L::SP;
-    const double* x = c.z + k * NV;
+    const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)it * SLOT_W;
     if (T::HAS_TR && s == L::S_TR) slot_init(st, true, true, tr_c0<M>(c, k, x), c.omega);
     else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, o.valid, o.has_t, o.c0, c.omega); }
   }
   G_PAR_FOR(j, L::NBOX) {
     const bool valid = (c.bmask >> (j >> 1)) & 1;
-    slot_init(c.bslot + (size_t)j * SLOT_W, valid, false, valid ? box_c0<M>(c, j, c.z + (N - 1) * NV) : 0.0, c.omega);
+    slot_init(c.bslot + (size_t)j * SLOT_W, valid, false, valid ? box_c0<M>(c, j, sh_z<M>(c) + (N - 1) * NV) : 0.0, c.omega);
   }
   G_SYNC();
 }
@@ -1165,38 +1266,48 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   using T = Traits<M>;
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV, NN = L::NN;
   const int N = d.N;
-  IpmCtx<M> c;
-  c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
-  c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
-  c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS]; c.dp = prm.delta_p; c.dd = prm.delta_d;
-  c.pmask = 0; c.bmask = 0;
-  for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
-  c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
-  c.A = p.A + (size_t)b * N * NX * NX; c.g = p.g + (size_t)b * N * NX;
-  c.rows = p.rows + (size_t)b * N * d.n_obs * 5;
-  c.x_init = p.x_init + (size_t)b * NX; c.goal_lo = p.goal_lo + (size_t)b * NX; c.goal_hi = p.goal_hi + (size_t)b * NX;
-  {
-    double Bm[NX * NU];
-    for (int i = 0; i < NX * NU; ++i) Bm[i] = 0.0;
-    dyn_B<M>(d.rp, Bm);
-#pragma unroll
-    for (int a = 0; a < NU; ++a) c.bv[a] = Bm[T::b_row(a) * NU + a];
+  // The context is ONE struct per instance in shared memory (filled by thread 0): phase functions read it with
+  // shared loads instead of per-thread local-memory copies.
+  static_assert(sizeof(IpmCtx<M>) <= (size_t)L::CTX_DOUBLES * sizeof(double), "IpmCtx does not fit its shared-memory slot");
+  IpmCtx<M>& c = *reinterpret_cast<IpmCtx<M>*>(smem);
+  smem += L::CTX_DOUBLES;
+  if (G_TID == 0) {
+    c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
+    c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
+    c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS]; c.dp = prm.delta_p; c.dd = prm.delta_d;
+    c.pmask = 0; c.bmask = 0;
+    for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
+    c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
+    c.A = p.A + (size_t)b * N * NX * NX; c.g = p.g + (size_t)b * N * NX;
+    c.rows = p.rows + (size_t)b * N * d.n_obs * 5;
+    c.x_init = p.x_init + (size_t)b * NX; c.goal_lo = p.goal_lo + (size_t)b * NX; c.goal_hi = p.goal_hi + (size_t)b * NX;
+    {
+      double Bm[NX * NU];
+      for (int i = 0; i < NX * NU; ++i) Bm[i] = 0.0;
+      dyn_B<M>(d.rp, Bm);
+      for (int a = 0; a < NU; ++a) c.bv[a] = Bm[T::b_row(a) * NU + a];
+    }
+    const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs;
+    double* q = scratch;
+    c.r = q; q += nz; c.t1 = q; q += nz; c.res = q; q += nz;
+    c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne; c.resnu = q; q += ne;
+    c.Ac = q; q += L::rnd((size_t)N * L::ANZ);
+    c.sslot = q; q += L::rnd((size_t)N * L::SP * SLOT_W);
+    c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
+    c.ost = q; q += L::rnd((size_t)N * no * SLOT_W);
+    c.orow = q; q += L::rnd((size_t)N * no * OROW_W);
+    c.kd = q; q += L::rnd((size_t)N * L::KDW);
+    c.fac = q; q += (size_t)(N + 1) * 2 * L::GT;
+    c.z = smem; c.dz = c.z + L::rnd((size_t)N * NV); c.sy = c.dz + L::rnd((size_t)N * NV); c.ring = c.sy + L::rnd((size_t)(N + 1) * NX);
+    c.red = c.dz + L::work_doubles(N);
+    c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
+    c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
+    for (int i = 0; i < 5; ++i) c.prof[i] = 0;
+    unsigned char* t2 = c.tab + NX * (NX + 1);
+    int n = 0;
+    for (int i = 0; i < NX; ++i) for (int g = 0; g < L::NG; ++g) if (g * L::CG <= i) { t2[n] = (unsigned char)i; t2[L::NLT + n] = (unsigned char)g; ++n; }
   }
-  const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs;
-  double* q = scratch;
-  c.r = q; q += nz; c.t1 = q; q += nz; c.res = q; q += nz;
-  c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne; c.resnu = q; q += ne;
-  c.Ac = q; q += L::rnd((size_t)N * L::ANZ);
-  c.sslot = q; q += L::rnd((size_t)N * L::SP * SLOT_W);
-  c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
-  c.ost = q; q += L::rnd((size_t)N * no * SLOT_W);
-  c.orow = q; q += L::rnd((size_t)N * no * OROW_W);
-  c.kd = q; q += L::rnd((size_t)N * L::KDW);
-  c.fac = q; q += (size_t)(N + 1) * 2 * NN;
-  c.z = smem; c.dz = c.z + N * NV; c.sy = c.dz + N * NV; c.ring = c.sy + (N + 1) * NX;
-  c.red = c.z + N * NV + L::work_doubles(N);
-  c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
-  c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
+  G_SYNC();
   G_PAR_FOR(t, NX * (NX + 1) / 2) {
     int i = 0;
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
@@ -1262,7 +1373,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     double ap = tau * am[0], ad = tau * am[1];
     ap = ap < 1.0 ? ap : 1.0; ad = ad < 1.0 ? ad : 1.0;
     slot_steps<M>(c, 1, smu, 2, ap, ad, am, &mu_aff);
-    G_PAR_FOR(it, N * NV) c.z[it] += ap * c.dz[it];
+    G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
     G_PAR_FOR(it, (N + 1) * NX) c.nu[it] += ad * c.dnu[it];
     G_SYNC();
     recenter<M>(c);
@@ -1271,15 +1382,15 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   if (status == IPM_ITERATION_LIMIT && res <= 1e3 * prm.tol) status = IPM_OPTIMAL;
   {   // a NaN/Inf anywhere in the iterate is a numerical failure, never an answer
     double badz = 0.0;
-    G_PAR_FOR(it, N * NV) { const double v = c.z[it]; if (!(v == v) || fabs(v) > 1e100) badz = 1.0; }
+    G_PAR_FOR(it, N * NV) { const double v = sh_z<M>(c)[it]; if (!(v == v) || fabs(v) > 1e100) badz = 1.0; }
     if (block_max(badz, c.red) > 0.0) status = IPM_NUMERICAL;
   }
   // ---- write the candidate trajectory and the objective (cost + omega * sum t)
   double obj = 0;
   G_PAR_FOR(k, N) {
     const double wk = (k == 0 || k == N - 1) ? 0.5 * c.h : c.h;
-    for (int i = 0; i < NX; ++i) p.Xn[((size_t)b * N + k) * NX + i] = c.z[k * NV + i];
-    for (int i = 0; i < NU; ++i) { const double uv = c.z[k * NV + NX + i]; p.Un[((size_t)b * N + k) * NU + i] = uv; obj += wk * uv * uv; }
+    for (int i = 0; i < NX; ++i) p.Xn[((size_t)b * N + k) * NX + i] = sh_z<M>(c)[k * NV + i];
+    for (int i = 0; i < NU; ++i) { const double uv = sh_z<M>(c)[k * NV + NX + i]; p.Un[((size_t)b * N + k) * NU + i] = uv; obj += wk * uv * uv; }
   }
   {
     const double omega = c.omega;
@@ -1288,7 +1399,13 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   obj = block_sum(obj, c.red);
   if (G_TID == 0) {
     info[0] = (double)status; info[1] = (double)it_done; info[2] = res; info[3] = mu; info[4] = obj;
+#if !defined(GUSTO_PROF_MODE) || GUSTO_PROF_MODE == 0
     info[5] = (double)(cyc_asm + cyc_slot); info[6] = (double)cyc_fac; info[7] = (double)cyc_sol;   // SM cycles per phase
+#elif GUSTO_PROF_MODE == 1      // developer builds: finer split of the factorisation
+    info[5] = (double)c.prof[0]; info[6] = (double)c.prof[1]; info[7] = (double)cyc_asm;
+#else                           // ... and of the solves
+    info[5] = (double)c.prof[2]; info[6] = (double)c.prof[3]; info[7] = (double)c.prof[4];
+#endif
   }
 }
 
