@@ -45,6 +45,12 @@ GDEV long long g_clock() { return 0; }
 GDEV long long g_clock() { return clock64(); }
 #endif
 
+#if defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3
+#define GUSTO_PROF_SOLVE 0
+#else
+#define GUSTO_PROF_SOLVE 1
+#endif
+
 struct IpmParams {
   int max_iter;      // Newton iterations cap
   int nref;          // refinement steps on the corrector solve
@@ -82,8 +88,8 @@ template <int M> struct IpmLayout {
   static constexpr int SP = S_BALL + T::NBALL;
   static constexpr int NBOX = 2 * NX;                      // goal-box rows (upper, lower per coordinate), knot N-1 only
   static constexpr int XPK = T::XB_pk(T::XB_CNT), UPK = T::UB_pk(T::UB_CNT);
-  // per-knot record: Hb[XPK] P[XPK] w[NX] aw[NX] Hub[UPK] Th[UPK] kap coef
-  static constexpr int KD_HB = 0, KD_P = XPK, KD_W = 2 * XPK, KD_AW = KD_W + NX, KD_HU = KD_AW + NX, KD_TH = KD_HU + UPK,
+  // per-knot record: Hb[XPK] P[XPK] w[NX] Hub[UPK] Th[UPK] kap coef
+  static constexpr int KD_HB = 0, KD_P = XPK, KD_W = 2 * XPK, KD_HU = KD_W + NX, KD_TH = KD_HU + UPK,
                        KD_KAP = KD_TH + UPK, KD_COEF = KD_KAP + 1, KDW = KD_COEF + 1;
   GHD static size_t rnd(size_t v) { return (v + 1) & ~(size_t)1; }   // keep every array 16-byte aligned
   // doubles of global scratch per instance
@@ -95,11 +101,16 @@ template <int M> struct IpmLayout {
   GHD static int work_doubles(int N) {      // dz | sy | ring, also the 8 factorisation tiles
     const int ne = (int)rnd((size_t)(N + 1) * NX);
     const int ring = RING_STAGES * TILE > ne ? RING_STAGES * TILE : ne;
-    const int w = (int)rnd((size_t)N * NV) + ne + ring, f = 10 * TILE + 2 * NX + 4;
+    const int w = (int)rnd((size_t)N * NV) + ne + ring, f = FAC_TILES * TILE + 2 * KS + 2 * NX + 4;
     return (w > f ? w : f) + 2;
   }
-  // byte tables: (row, col) of the packed lower triangle, then (row, group) of the lower-triangular product tasks
-  static constexpr int TAB_DOUBLES = (NX * (NX + 1) + 2 * NLT + 7) / 8;
+  // byte tables: (row, col) of the packed lower triangle, (row, group) of the lower-triangular product tasks, then the
+  // model tables used with run-time indices: a_row[ANZ], a_col[ANZ], blk_of[NX], ctrl_of[NX]
+  static constexpr int TAB_MODEL = NX * (NX + 1) + 2 * NLT;
+  static constexpr int TAB_DOUBLES = (TAB_MODEL + 2 * ANZ + 2 * NX + 7) / 8;
+  // factor sweep: 10 sweep tiles + Phi, Ah, Y, Z, RR of the Schur-block producer; staged knot record
+  static constexpr int FAC_TILES = 15;
+  static constexpr int KS_P = 0, KS_W = XPK, KS_TH = XPK + NX, KS_COEF = KS_TH + UPK, KS_A = KS_COEF + 1, KS = (KS_A + ANZ + 1) & ~1;
   GHD static int seg_doubles(int N) { return (N + 4) / 2 + 2; }
   static constexpr int CTX_DOUBLES = 80;                   // the per-instance context struct (IpmCtx) lives in shared memory too
   GHD static int smem_doubles(int N, int nthr) { return CTX_DOUBLES + (int)rnd((size_t)N * NV) + work_doubles(N) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES; }
@@ -505,9 +516,11 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
     if (T::WS > 0 && B0 == T::XB_of(0)) {
       constexpr int WS = T::WS > 0 ? T::WS : 1;
       const int s0 = sh_seg<M>(c)[k], s1 = sh_seg<M>(c)[k + 1];
+      const double* __restrict__ orow = c.orow;
+      const double* __restrict__ ost = c.ost;
       for (int p = s0; p < s1; ++p) {
-        const double* row = c.orow + (size_t)p * OROW_W;
-        const double* st = c.ost + (size_t)p * SLOT_W;
+        const double* row = orow + (size_t)p * OROW_W;
+        const double* st = ost + (size_t)p * SLOT_W;
         double gv[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
         double v = row[3];
 #pragma unroll
@@ -631,16 +644,6 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       double* kd = c.kd + (size_t)k * L::KDW;
       kd[L::KD_KAP] = ka.kap_tr;
       kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr / (1.0 + ka.kap_tr * ka.gw) : 0.0;
-      if (T::HAS_TR) {       // aw = A_k w  (sparse)
-        const double* Ak = c.Ac + (size_t)k * ANZ;
-        double aw[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) aw[i] = 0.0;
-#pragma unroll
-        for (int e = 0; e < ANZ; ++e) aw[T::a_row(e)] += Ak[e] * kd[L::KD_W + T::a_col(e)];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) kd[L::KD_AW + i] = aw[i];
-      }
     }
   }
   if (phase == 0) {
@@ -675,123 +678,119 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 }
 
 // ------------------------------------------------------------------------------------------ Schur complement
-// Row I of (Phi, A Phi, Phi A', A Phi A') of knot k, Phi = blockdiag(P_b) - coef w w'.  I is a compile-time index so
-// that the sparse products collapse to the handful of entries that exist.
-template <int M, int I> GHD constexpr int ymask() {       // coordinates where row I of A*blockdiag() can be non-zero
-  using T = Traits<M>;
-  int m = 0;
-  for (int e = 0; e < T::ANZ; ++e)
-    if (T::a_row(e) == I) { const int b = T::XB_of(T::a_col(e)); for (int j = 0; j < T::XB_n(b); ++j) m |= 1 << (T::XB_off(b) + j); }
-  return m;
-}
-template <int M, int I>
-GDEV void knot_rows(const IpmCtx<M>& c, int k, double* phi, double* y, double* yt, double* zz) {
+// S = Aeq (H + dp I)^-1 Aeq' is never stored: its block rows are produced one per sweep step, in shared memory, by the
+// threads that do not run the elimination.  Knot k appears in row k as "current" (coefficient Lk = aL A_k + bL I;
+// row 0 is x_0 itself) and in row k+1 as "previous" (Rk = aR A_k + diag(dR); row N is the masked goal row):
+//   S_kk += Lk Phi Lk' + Xi,   S_{k+1,k} = Rk Phi Lk' + Xi,   S_{k+1,k+1} += Rk Phi Rk' + Xi,   Xi = G Theta_k G',
+// with Phi = blockdiag(P_b) - coef w w'.  With Y = (h/2 A) Phi and Z = Y (h/2 A)' (two small tile products) all three
+// are element-wise combinations of Z, Y, Y' and Phi.
+template <int M> GHD constexpr int ctrl_of_row(int I) { int r = -1; for (int a = 0; a < Traits<M>::NU; ++a) if (Traits<M>::b_row(a) == I) r = a; return r; }
+
+struct SchurTiles { double *Phi, *Ah, *Y, *Z, *RR; };
+
+// Threads [t0, t0 + nt) build the dense Phi of the staged knot record `ks`, and refresh Ah (the pattern of A is static,
+// so the tile is zeroed once by the caller).  Barrier-free: followed by the caller's barrier.
+template <int M> GDEV void schur_build(const IpmCtx<M>& c, const double* ks, const SchurTiles& t, int t0, int nt) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, ANZ = L::ANZ;
-  constexpr int bI = T::XB_of(I), offI = T::XB_off(bI), nI = T::XB_n(bI);
-  constexpr int YM = ymask<M, I>();
-  const double* kd = c.kd + (size_t)k * L::KDW;
-  const double* P = kd + L::KD_P;
-  const double* Ak = c.Ac + (size_t)k * ANZ;
-#pragma unroll
-  for (int j = 0; j < NX; ++j) { phi[j] = 0.0; y[j] = 0.0; yt[j] = 0.0; zz[j] = 0.0; }
-#pragma unroll
-  for (int j = 0; j < nI; ++j) phi[offI + j] = P[T::XB_pk(bI) + tri(I - offI, j)];
-#pragma unroll
-  for (int e = 0; e < ANZ; ++e) {
-    if (T::a_row(e) != I) continue;
-    const int cc = T::a_col(e), bb = T::XB_of(cc), ob = T::XB_off(bb);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) if (j < T::XB_n(bb)) y[ob + j] += Ak[e] * P[T::XB_pk(bb) + tri(cc - ob, j)];
+  constexpr int NX = L::NX, LDT = L::LDT;
+  const unsigned char* mt = c.tab + L::TAB_MODEL;           // a_row | a_col | blk_of | ctrl_of
+  G_ASSUME_SHARED(mt);
+  const double coef = ks[L::KS_COEF];
+  for (int it = G_TID - t0; it < NX * NX; it += nt) {
+    const int i = it / NX, q = it - i * NX;
+    const int bi = mt[2 * L::ANZ + i];
+    double v = 0.0;
+    if (bi == mt[2 * L::ANZ + q]) { const int off = T::XB_off(bi); v = ks[L::KS_P + T::XB_pk(bi) + tri(i - off, q - off)]; }
+    if (T::HAS_TR) v -= coef * ks[L::KS_W + i] * ks[L::KS_W + q];
+    t.Phi[i * LDT + q] = v;
   }
+  for (int e = G_TID - t0; e < L::ANZ; e += nt) t.Ah[mt[e] * LDT + mt[L::ANZ + e]] = c.hh * ks[L::KS_A + e];
+}
+
+// out(i, q) = sum_m X[i][m] * Yt[q][m]  for all (i, q), by threads [t0, t0 + nt)
+template <int M> GDEV void abt_task(const double* X, const double* Y, int i, int q0, double* acc);
+template <int M> GDEV void schur_product(const double* X, const double* Yt, double* out, int t0, int nt) {
+  using L = IpmLayout<M>;
+  for (int task = G_TID - t0; task < L::NTASK; task += nt) {
+    const int i = task / L::NG, q0 = (task - i * L::NG) * L::CG;
+    double acc[L::CG];
+    abt_task<M>(X, Yt, i, q0, acc);
 #pragma unroll
-  for (int e = 0; e < ANZ; ++e) if (T::XB_of(T::a_col(e)) == bI) yt[T::a_row(e)] += phi[T::a_col(e)] * Ak[e];
-#pragma unroll
-  for (int e = 0; e < ANZ; ++e) if ((YM >> T::a_col(e)) & 1) zz[T::a_row(e)] += y[T::a_col(e)] * Ak[e];
-  if (T::HAS_TR) {
-    const double* w = kd + L::KD_W;
-    const double* aw = kd + L::KD_AW;
-    const double cw = kd[L::KD_COEF] * w[I], ca = kd[L::KD_COEF] * aw[I];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) { phi[j] -= cw * w[j]; y[j] -= ca * w[j]; yt[j] -= cw * aw[j]; zz[j] -= ca * aw[j]; }
+    for (int c2 = 0; c2 < L::CG; ++c2) if (q0 + c2 < L::NX) out[i * L::LDT + q0 + c2] = acc[c2];
   }
 }
 
-// Row I of S_jj and of S_{j+1,j}.  Knot k appears in row k as "current" (coefficient Lk = aL A_k + bL I; row 0 is
-// x_0 itself) and in row k+1 as "previous" (Rk = aR A_k + diag(dR); row N is the masked goal row).
-template <int M> GHD constexpr int ctrl_of_row(int I) { int r = -1; for (int a = 0; a < Traits<M>::NU; ++a) if (Traits<M>::b_row(a) == I) r = a; return r; }
-template <int M, int I> GDEV void schur_rows(const IpmCtx<M>& c, int j) {
+// Element-wise emission for knot k (k < N):  Sdd (= S_kk) = RR + Lk Phi Lk' [+ Xi] (+ regularisation),
+// Sod (= S_{k+1,k}) = Rk Phi Lk' [+ Xi],  RR = Rk Phi Rk' [+ Xi]  (carried to S_{k+1,k+1}).
+template <int M> GDEV void schur_emit(const IpmCtx<M>& c, const double* ks, const SchurTiles& t, int k, double* Sdd, double* Sod,
+                                      int t0, int nt) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, NU = L::NU, NN = L::NN;
+  constexpr int NX = L::NX, LDT = L::LDT;
+  const unsigned char* mt = c.tab + L::TAB_MODEL;
+  G_ASSUME_SHARED(mt);
   const int N = c.N;
-  double dd[NX], od[NX], phi[NX], y[NX], yt[NX], zz[NX];
-#pragma unroll
-  for (int q = 0; q < NX; ++q) { dd[q] = 0.0; od[q] = 0.0; }
-  // control coupling Xi = G Theta G' touches only rows b_row(a)
-  constexpr int aI = ctrl_of_row<M>(I);
-  if (j < N) {
-    knot_rows<M, I>(c, j, phi, y, yt, zz);
-    const double aL = j == 0 ? 0.0 : c.hh, bL = j == 0 ? 1.0 : -1.0;
-    const bool last = (j == N - 1);
-    const double aR = last ? 0.0 : c.hh;
-    const double dRI = last ? (double)((c.pmask >> I) & 1) : 1.0;
-#pragma unroll
-    for (int q = 0; q < NX; ++q) {
-      dd[q] = aL * aL * zz[q] + aL * bL * (y[q] + yt[q]) + bL * bL * phi[q];
-      od[q] = aR * aL * zz[q] + aR * bL * y[q] + aL * dRI * yt[q] + bL * dRI * phi[q];
+  // Y and Z already carry the h/2 factors, so the A-coefficients of Lk and Rk are 0 or 1 here
+  const double hh = c.hh, aL = k == 0 ? 0.0 : 1.0, bL = k == 0 ? 1.0 : -1.0;
+  const bool last = (k == N - 1);
+  const double aR = last ? 0.0 : 1.0;
+  const int pmask = c.pmask;
+  for (int it = G_TID - t0; it < NX * NX; it += nt) {
+    const int i = it / NX, q = it - i * NX;
+    const double z = t.Z[i * LDT + q], y = t.Y[i * LDT + q], yt = t.Y[q * LDT + i], ph = t.Phi[i * LDT + q];
+    const double dRi = last ? (double)((pmask >> i) & 1) : 1.0, dRq = last ? (double)((pmask >> q) & 1) : 1.0;
+    double xi = 0.0;
+    const int a = (signed char)mt[2 * L::ANZ + NX + i], b2 = (signed char)mt[2 * L::ANZ + NX + q];
+    if (a >= 0 && b2 >= 0 && T::UB_of(a) == T::UB_of(b2)) {
+      const int ub = T::UB_of(a), uo = T::UB_off(ub);
+      xi = hh * hh * c.bv[a] * c.bv[b2] * ks[L::KS_TH + T::UB_pk(ub) + tri(a - uo, b2 - uo)];
     }
-    if constexpr (aI >= 0) {
-      if (j >= 1) {
-        const double* Th = c.kd + (size_t)j * L::KDW + L::KD_TH;
-        constexpr int ub = T::UB_of(aI), uo = T::UB_off(ub);
-#pragma unroll
-        for (int b2 = 0; b2 < T::UB_n(ub); ++b2) {
-          const double xi = c.hh * c.hh * c.bv[aI] * c.bv[uo + b2] * Th[T::UB_pk(ub) + tri(aI - uo, b2)];
-          dd[T::b_row(uo + b2)] += xi;
-          if (j <= N - 2) od[T::b_row(uo + b2)] += xi;
-        }
-      }
-    }
-  }
-  if (j >= 1) {
-    const int k = j - 1;
-    knot_rows<M, I>(c, k, phi, y, yt, zz);
-    const bool last = (k == N - 1);
-    const double aR = last ? 0.0 : c.hh;
-    const double dRI = last ? (double)((c.pmask >> I) & 1) : 1.0;
-#pragma unroll
-    for (int q = 0; q < NX; ++q) {
-      const double dRq = last ? (double)((c.pmask >> q) & 1) : 1.0;
-      dd[q] += aR * aR * zz[q] + aR * (y[q] * dRq + dRI * yt[q]) + dRI * phi[q] * dRq;
-    }
-    if constexpr (aI >= 0) {
-      if (k <= N - 2) {
-        const double* Th = c.kd + (size_t)k * L::KDW + L::KD_TH;
-        constexpr int ub = T::UB_of(aI), uo = T::UB_off(ub);
-#pragma unroll
-        for (int b2 = 0; b2 < T::UB_n(ub); ++b2)
-          dd[T::b_row(uo + b2)] += c.hh * c.hh * c.bv[aI] * c.bv[uo + b2] * Th[T::UB_pk(ub) + tri(aI - uo, b2)];
-      }
-    }
-  }
-  if (j == N && !((c.pmask >> I) & 1)) dd[I] += 1.0;        // free goal coordinates: keep the block non-singular
-  dd[I] += c.dd * dd[I] + 1e-300;
-  double* Sd = c.fac + (size_t)(2 * j) * L::GT + I * L::GLD;
-#pragma unroll
-  for (int q = 0; q < L::GLD; q += 2) g_st2(Sd + q, dd[q], q + 1 < NX ? dd[q + 1 < NX ? q + 1 : q] : 0.0);
-  if (j < N) {
-    double* So = c.fac + (size_t)(2 * (j + 1) + 1) * L::GT + I * L::GLD;
-#pragma unroll
-    for (int q = 0; q < L::GLD; q += 2) g_st2(So + q, od[q], q + 1 < NX ? od[q + 1 < NX ? q + 1 : q] : 0.0);
+    double dd = t.RR[i * LDT + q] + aL * aL * z + aL * bL * (y + yt) + bL * bL * ph + (k >= 1 ? xi : 0.0);
+    if (i == q) dd += c.dd * dd + 1e-300;
+    Sdd[i * LDT + q] = dd;
+    Sod[i * LDT + q] = aR * aL * z + aR * bL * y + aL * dRi * yt + bL * dRi * ph + ((k >= 1 && k <= N - 2) ? xi : 0.0);
+    t.RR[i * LDT + q] = aR * aR * z + aR * (y * dRq + dRi * yt) + dRi * ph * dRq + (k <= N - 2 ? xi : 0.0);
   }
 }
-template <int M, int I = 0> GDEV void schur_rows_dispatch(const IpmCtx<M>& c, int j, int i) {
-  if constexpr (I < Traits<M>::NX) {
-    if (i == I) schur_rows<M, I>(c, j);
-    else schur_rows_dispatch<M, I + 1>(c, j, i);
+// Last block row: S_NN = RR (+ identity on the free goal coordinates so that the block stays non-singular)
+template <int M> GDEV void schur_emit_last(const IpmCtx<M>& c, const SchurTiles& t, double* Sdd, int t0, int nt) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, LDT = L::LDT;
+  for (int it = G_TID - t0; it < NX * NX; it += nt) {
+    const int i = it / NX, q = it - i * NX;
+    double dd = t.RR[i * LDT + q];
+    if (i == q) { if (!((c.pmask >> i) & 1)) dd += 1.0; dd += c.dd * dd + 1e-300; }
+    Sdd[i * LDT + q] = dd;
   }
+}
+// Stage the record of knot k (P, w, Theta, coef, A entries) from global memory: the loads are issued into registers first
+// (schur_stage_load) and stored after the producer's arithmetic (schur_stage_store), which hides their latency.
+template <int M> GDEV double schur_stage_src(const double* kd, const double* Ak, int t) {
+  using L = IpmLayout<M>;
+  if (t < L::KS_TH) return kd[L::KD_P + t];                       // P | w are contiguous in the record
+  if (t < L::KS_COEF) return kd[L::KD_TH + t - L::KS_TH];
+  if (t == L::KS_COEF) return kd[L::KD_COEF];
+  if (t < L::KS_A + L::ANZ) return Ak[t - L::KS_A];
+  return 0.0;
+}
+template <int M> GDEV void schur_stage_load(const IpmCtx<M>& c, int k, double* pre, int t0, int nt) {
+#ifndef GUSTO_HOSTSIM
+  using L = IpmLayout<M>;
+  const double* kd = c.kd + (size_t)k * L::KDW;
+  const double* Ak = c.Ac + (size_t)k * L::ANZ;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { const int t = G_TID - t0 + r * nt; pre[r] = t < L::KS ? schur_stage_src<M>(kd, Ak, t) : 0.0; }
+#endif
+}
+template <int M> GDEV void schur_stage_store(const IpmCtx<M>& c, int k, double* ks, const double* pre, int t0, int nt) {
+  using L = IpmLayout<M>;
+#ifdef GUSTO_HOSTSIM
+  for (int t = 0; t < L::KS; ++t) ks[t] = schur_stage_src<M>(c.kd + (size_t)k * L::KDW, c.Ac + (size_t)k * L::ANZ, t);
+#else
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { const int t = G_TID - t0 + r * nt; if (t < L::KS) ks[t] = pre[r]; }
+#endif
 }
 
 // acc[c] = sum_m X[i][m] * Y[q0 + c][m]  over one shared-memory tile row pair (rows are LDT apart, MLEN = GLD terms)
@@ -826,31 +825,48 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
   constexpr int CG = L::CG, NG = L::NG, NTASK = L::NTASK, NLT = L::NLT;
   const int N = c.N;
   long long tc0 = g_clock();
-  // (1) Schur blocks.  Items ordered row-index-major so that a warp shares the compile-time row index.
-  G_PAR_FOR(it, (N + 1) * NX) {
-    const int i = it / (N + 1), j = it - i * (N + 1);
-    schur_rows_dispatch<M>(c, j, i);
-  }
-  // (2) sweep over block rows.  dz | sy | ring are dead here: 10 tiles + pivots.
+  // dz | sy | ring are dead here: 15 tiles + pivots + two staged knot records
   double* tile = sh_dz<M>(c);
   double* W = tile;                          // D_j, eliminated in place (lower triangle)
   double* Wr = tile + TILE;                  // I -> unit-lower elimination history (L~^-1)
   double* Li = tile + 2 * TILE;              // L_j^-1 (lower, explicit zeros) and its transpose
   double* LiT = tile + 3 * TILE;
-  double* Sdd[2] = {tile + 4 * TILE, tile + 5 * TILE};
-  double* Sod[2] = {tile + 6 * TILE, tile + 7 * TILE};
-  double* Lo[2] = {tile + 8 * TILE, tile + 9 * TILE};
-  double* ipv = tile + 10 * TILE;            // 1 / pivot, then 1 / sqrt(pivot)
+  // ping-pong tiles are addressed arithmetically (an indexed pointer array would live in local memory)
+#define GUSTO_SDD(w) (tile + (4 + (w)) * TILE)
+#define GUSTO_SOD(w) (tile + (6 + (w)) * TILE)
+#define GUSTO_LO(w) (tile + (8 + (w)) * TILE)
+  SchurTiles st;
+  st.Phi = tile + 10 * TILE; st.Ah = tile + 11 * TILE; st.Y = tile + 12 * TILE; st.Z = tile + 13 * TILE; st.RR = tile + 14 * TILE;
+  double* ipv = tile + L::FAC_TILES * TILE;  // 1 / pivot, then 1 / sqrt(pivot)
+  double* ksb = ipv + ((NX + 1) & ~1);       // two staged knot records
   const unsigned char* const tab = c.tab;
   G_ASSUME_SHARED(tab);
   const unsigned char* const tab2 = tab + 2 * NT;
   double* const fac = c.fac;
-  const int pf0 = G_NTHR > G_WARP ? G_WARP : 0;            // threads [pf0, NTHR) prefetch while warp 0 eliminates
-  const int npf = G_NTHR - pf0;
+  // producer threads: the second warp (or the only one)
+  const int pf0 = G_NTHR > G_WARP ? G_WARP : 0;
+  const int npf = G_NTHR > G_WARP ? G_WARP : G_NTHR;
+  const bool producer = G_TID >= pf0 && G_TID < pf0 + npf;
   double bad = 0.0;
-  G_PAR_FOR(it, 10 * TILE) tile[it] = 0.0;
+  G_PAR_FOR(it, L::FAC_TILES * TILE) tile[it] = 0.0;
+  // knot 0 (all threads): S_00 -> W, S_10 -> Sod[1], RR <- R0 Phi R0'; stage knot 1
+  for (int t = G_TID; t < 2 * L::KS; t += G_NTHR) {
+    const int k = t / L::KS, tt = t - k * L::KS;
+    if (k < N) ksb[t] = schur_stage_src<M>(c.kd + (size_t)k * L::KDW, c.Ac + (size_t)k * L::ANZ, tt);
+  }
   G_SYNC();
+  schur_build<M>(c, ksb, st, 0, G_NTHR);
+  G_PAR_FOR(i, NX) Wr[i * LDT + i] = 1.0;
+  G_SYNC();
+  schur_product<M>(st.Ah, st.Phi, st.Y, 0, G_NTHR);
+  G_SYNC();
+  schur_product<M>(st.Y, st.Ah, st.Z, 0, G_NTHR);
+  G_SYNC();
+  schur_emit<M>(c, ksb, st, 0, W, GUSTO_SOD(1), 0, G_NTHR);
+  G_SYNC();
+#if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
   if (G_TID == 0) c.prof[0] += g_clock() - tc0;
+#endif
   tc0 = g_clock();
   // my entries of the packed lower triangle during the elimination (warp 0)
   int ei[3], ee[3];
@@ -859,49 +875,90 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
     const int t = G_TID + r * G_WARP;
     ei[r] = t < NT ? tab[t] : 0; ee[r] = t < NT ? tab[NT + t] : 0;
   }
-  G_PAR_FOR(it, NX * GLD / 2) {
-    const int i = it / (GLD / 2), m = 2 * (it - i * (GLD / 2));
-    const g_d2 v = g_ld2(fac + i * GLD + m);
-    g_st2(W + i * LDT + m, v.x, v.y);
-  }
-  G_PAR_FOR(i, NX) Wr[i * LDT + i] = 1.0;
-  G_SYNC();
   for (int j = 0; j <= N; ++j) {
     const int cur = j & 1, nxt = cur ^ 1;
     // (E) warp 0: eliminate column q from the rows below it, in W (columns > q) and in Wr (columns <= q)
+#if defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3
+    long long tp = g_clock();
+#define GUSTO_PROF_TICK(slot) do { if (G_TID == 0) { const long long tn = g_clock(); c.prof[slot] += tn - tp; tp = tn; } } while (0)
+#else
+#define GUSTO_PROF_TICK(slot) ((void)0)
+#endif
     if (G_TID < G_WARP) {
+#ifdef GUSTO_HOSTSIM
       for (int q = 0; q < NX; ++q) {
         double piv = W[q * LDT + q];
         if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
         const double ip = g_rcp(piv);
-        if (G_LANE == 0) ipv[q] = ip;
-#ifdef GUSTO_HOSTSIM
+        ipv[q] = ip;
         for (int t = 0; t < NT; ++t) {
           const int i = tab[t], e = tab[NT + t];
-#else
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int i = ei[r], e = ee[r];
-#endif
           if (i <= q) continue;
           const double mult = W[i * LDT + q] * ip;
           if (e <= q) Wr[i * LDT + e] -= mult * Wr[q * LDT + e];
           else W[i * LDT + e] -= mult * W[e * LDT + q];
         }
+      }
+#else
+      // Branch-free: every lane owns <= 3 entries (i, e) of the packed lower triangle; entry (i, e) lives in W while
+      // e > q and in Wr afterwards.  All operands of a step are loaded before any arithmetic, and the reciprocal of
+      // the NEXT pivot is started from pre-update values so that it overlaps the rank-1 update (it is the longest
+      // dependent operation of the step).
+      double piv = W[0];
+      if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
+      double ip = g_rcp(piv);
+      for (int q = 0; q < NX; ++q) {
+        const int qn = q + 1 < NX ? q + 1 : q;
+        const double wq1 = W[qn * LDT + q], d1 = W[qn * LDT + qn];
+        double av[3], sv[3], ov[3];
+        int to[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int i = ei[r], e = ee[r];
+          const bool right = e <= q;
+          to[r] = (right ? TILE : 0) + i * LDT + e;
+          av[r] = W[i * LDT + q];
+          sv[r] = tile[right ? TILE + q * LDT + e : e * LDT + q];
+          ov[r] = tile[to[r]];
+        }
+        G_SYNCWARP();                                // the look-ahead read W[q+1][q+1] before its owner updates it
+        double pn = fma(-(wq1 * ip), wq1, d1);
+        if (q + 1 < NX && !(pn > 0.0)) { bad = 1.0; pn = 1e-300; }
+        const double ipn = g_rcp(pn);
+        if (G_LANE == 0) ipv[q] = ip;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double nv = fma(-(av[r] * ip), sv[r], ov[r]);
+          if (ei[r] > q) tile[to[r]] = nv;
+        }
+        ip = ipn;
         G_SYNCWARP();
       }
+#endif
       G_W0_FOR(q, NX) ipv[q] = sqrt(ipv[q]);
     }
-    if (j < N && G_TID >= pf0) {
-      const double* gd = fac + (size_t)(2 * (j + 1)) * GT;
-      for (int it = G_TID - pf0; it < NX * GLD; it += npf) {      // two tiles, 16 bytes at a time
-        const int tl = it / (NX * GLD / 2), rem = it - tl * (NX * GLD / 2);
-        const int i = rem / (GLD / 2), m = 2 * (rem - i * (GLD / 2));
-        const g_d2 v = g_ld2(gd + tl * GT + i * GLD + m);
-        g_st2((tl == 0 ? Sdd[nxt] : Sod[nxt]) + i * LDT + m, v.x, v.y);
+    GUSTO_PROF_TICK(0);
+    // producer: block row j+1 of S from knot j+1 (and the record of knot j+2 staged for the next step)
+    if (producer) {
+      const int kn = j + 1;
+      if (kn <= N - 1) {
+        double pre[4];
+        const double* ks = ksb + (kn & 1) * L::KS;
+        if (kn + 1 <= N - 1) schur_stage_load<M>(c, kn + 1, pre, pf0, npf);
+        schur_build<M>(c, ks, st, pf0, npf);
+        G_SYNCWARP();
+        schur_product<M>(st.Ah, st.Phi, st.Y, pf0, npf);
+        G_SYNCWARP();
+        schur_product<M>(st.Y, st.Ah, st.Z, pf0, npf);
+        G_SYNCWARP();
+        schur_emit<M>(c, ks, st, kn, GUSTO_SDD(nxt), GUSTO_SOD(cur), pf0, npf);
+        if (kn + 1 <= N - 1) schur_stage_store<M>(c, kn + 1, ksb + ((kn + 1) & 1) * L::KS, pre, pf0, npf);
+      } else if (kn == N) {
+        schur_emit_last<M>(c, st, GUSTO_SDD(nxt), pf0, npf);
       }
     }
     G_SYNC();
+    GUSTO_PROF_TICK(1);
     // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose
     G_PAR_FOR(it, NX * NX) {
       const int i = it / NX, m = it - i * NX;
@@ -910,17 +967,19 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
       LiT[m * LDT + i] = v;
     }
     G_SYNC();
+    GUSTO_PROF_TICK(2);
     // (C2) Lo_{j+1} = S_{j+1,j} Li'
     if (j < N) {
       G_PAR_FOR(task, NTASK) {
         const int i = task / NG, q0 = (task - i * NG) * CG;
         double acc[CG];
-        abt_task<M>(Sod[nxt], Li, i, q0, acc);
+        abt_task<M>(GUSTO_SOD(nxt), Li, i, q0, acc);
 #pragma unroll
-        for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) Lo[nxt][i * LDT + q0 + c2] = acc[c2];
+        for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) GUSTO_LO(nxt)[i * LDT + q0 + c2] = acc[c2];
       }
     }
     G_SYNC();
+    GUSTO_PROF_TICK(3);
     // (X) V_{j+1} = Lo_{j+1} Li -> global;  D_j^-1 = Li' Li -> global;  D_{j+1} = S_{j+1,j+1} - Lo_{j+1} Lo_{j+1}' -> W;  Wr = I
     {
       double* gD = fac + (size_t)(2 * j) * GT;
@@ -935,13 +994,13 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
           for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 <= i) { gD[i * GLD + q0 + c2] = acc[c2]; gD[(q0 + c2) * GLD + i] = acc[c2]; }
         } else if (task < 2 * NLT) {                        // D_{j+1}, lower tasks (the strict upper triangle of W is never read)
           const int i = tab2[task - NLT], q0 = tab2[task] * CG;
-          abt_task<M>(Lo[nxt], Lo[nxt], i, q0, acc);
+          abt_task<M>(GUSTO_LO(nxt), GUSTO_LO(nxt), i, q0, acc);
 #pragma unroll
-          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) W[i * LDT + q0 + c2] = Sdd[nxt][i * LDT + q0 + c2] - acc[c2];
+          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) W[i * LDT + q0 + c2] = GUSTO_SDD(nxt)[i * LDT + q0 + c2] - acc[c2];
         } else {
           const int t2 = task - 2 * NLT;
           const int i = t2 / NG, q0 = (t2 - i * NG) * CG;
-          abt_task<M>(Lo[nxt], LiT, i, q0, acc);
+          abt_task<M>(GUSTO_LO(nxt), LiT, i, q0, acc);
 #pragma unroll
           for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) gV[i * GLD + q0 + c2] = acc[c2];
         }
@@ -949,8 +1008,14 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
       G_PAR_FOR(it, NX * NX) { const int i = it / NX, m = it - i * NX; Wr[i * LDT + m] = (i == m) ? 1.0 : 0.0; }
     }
     G_SYNC();
+    GUSTO_PROF_TICK(4);
   }
+#if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
   if (G_TID == 0) c.prof[1] += g_clock() - tc0;
+#endif
+#undef GUSTO_SDD
+#undef GUSTO_SOD
+#undef GUSTO_LO
   bad = block_max(bad, c.red);
   return bad == 0.0;
 }
@@ -1001,7 +1066,7 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
     g_cp_async_wait();
   }
   G_SYNC();
-  if (G_TID == 0) c.prof[2] += g_clock() - tc0;
+  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[2] += g_clock() - tc0;
   tc0 = g_clock();
   // middle: v = D^-1 w, staged through the (idle) ring so that no row is overwritten while still being read.
   // Two rows per thread and round, all loads issued before the arithmetic (the factor streams from L2 / HBM).
@@ -1029,7 +1094,7 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   G_SYNC();
   G_PAR_FOR(it, ne) y[it] = v[it];
   G_SYNC();
-  if (G_TID == 0) c.prof[3] += g_clock() - tc0;
+  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[3] += g_clock() - tc0;
   tc0 = g_clock();
   if (G_TID < G_WARP) {
     // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
@@ -1050,7 +1115,7 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
     g_cp_async_wait();
   }
   G_SYNC();
-  if (G_TID == 0) c.prof[4] += g_clock() - tc0;
+  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[4] += g_clock() - tc0;
 }
 
 // [dz; dnu] (+)= Ktilde^-1 [rin; rnuin]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]] via the Schur complement.
@@ -1084,7 +1149,18 @@ template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* 
 #pragma unroll
     for (int i = 0; i < NV; ++i) sh_dz<M>(c)[k * NV + i] = accumulate ? sh_dz<M>(c)[k * NV + i] + out[i] : out[i];
   }
-  G_PAR_FOR(it, (N + 1) * NX) c.dnu[it] = accumulate ? c.dnu[it] + sh_sy<M>(c)[it] : sh_sy<M>(c)[it];
+  {
+    double* __restrict__ dnu = c.dnu;
+    const double* sy = sh_sy<M>(c);
+    const int ne = (N + 1) * NX;
+    if (accumulate) {
+#pragma unroll 4
+      for (int it = G_TID; it < ne; it += G_NTHR) dnu[it] += sy[it];
+    } else {
+#pragma unroll 4
+      for (int it = G_TID; it < ne; it += G_NTHR) dnu[it] = sy[it];
+    }
+  }
   G_SYNC();
 }
 
@@ -1150,15 +1226,20 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
   }
   if (T::WS > 0) {
     constexpr int WS = T::WS > 0 ? T::WS : 1;
-    G_PAR_FOR(p, c.nact) {
-      const double* row = c.orow + (size_t)p * OROW_W;
+    const double* __restrict__ orow = c.orow;
+    double* __restrict__ ost = c.ost;
+    const double* zs = sh_z<M>(c);
+    const double* dzs = sh_dz<M>(c);
+    const int nact = c.nact;
+    for (int p = G_TID; p < nact; p += G_NTHR) {
+      const double* row = orow + (size_t)p * OROW_W;
       const int k = (int)row[4];
-      const double* x = sh_z<M>(c) + k * NV;
-      const double* dv = sh_dz<M>(c) + k * NV;
+      const double* x = zs + k * NV;
+      const double* dv = dzs + k * NV;
       double v = row[3], gdz = 0.0;
 #pragma unroll
       for (int a = 0; a < WS; ++a) { v -= row[a] * x[a]; gdz -= row[a] * dv[a]; }
-      fn(c.ost + (size_t)p * SLOT_W, true, v, gdz);
+      fn(ost + (size_t)p * SLOT_W, true, v, gdz);
     }
   }
 }
@@ -1306,6 +1387,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     unsigned char* t2 = c.tab + NX * (NX + 1);
     int n = 0;
     for (int i = 0; i < NX; ++i) for (int g = 0; g < L::NG; ++g) if (g * L::CG <= i) { t2[n] = (unsigned char)i; t2[L::NLT + n] = (unsigned char)g; ++n; }
+    unsigned char* mt = c.tab + L::TAB_MODEL;                 // a_row | a_col | blk_of | ctrl_of (0xff: no control drives the row)
+    for (int e = 0; e < L::ANZ; ++e) { mt[e] = (unsigned char)T::a_row(e); mt[L::ANZ + e] = (unsigned char)T::a_col(e); }
+    for (int i = 0; i < NX; ++i) { mt[2 * L::ANZ + i] = (unsigned char)T::XB_of(i); mt[2 * L::ANZ + NX + i] = (unsigned char)ctrl_of_row<M>(i); }
   }
   G_SYNC();
   G_PAR_FOR(t, NX * (NX + 1) / 2) {
@@ -1374,7 +1458,13 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     ap = ap < 1.0 ? ap : 1.0; ad = ad < 1.0 ? ad : 1.0;
     slot_steps<M>(c, 1, smu, 2, ap, ad, am, &mu_aff);
     G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
-    G_PAR_FOR(it, (N + 1) * NX) c.nu[it] += ad * c.dnu[it];
+    {
+      double* __restrict__ nu = c.nu;
+      const double* __restrict__ dnu = c.dnu;
+      const int ne = (N + 1) * NX;
+#pragma unroll 4
+      for (int it = G_TID; it < ne; it += G_NTHR) nu[it] += ad * dnu[it];
+    }
     G_SYNC();
     recenter<M>(c);
     cyc_slot += g_clock() - tc0;
@@ -1403,8 +1493,10 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     info[5] = (double)(cyc_asm + cyc_slot); info[6] = (double)cyc_fac; info[7] = (double)cyc_sol;   // SM cycles per phase
 #elif GUSTO_PROF_MODE == 1      // developer builds: finer split of the factorisation
     info[5] = (double)c.prof[0]; info[6] = (double)c.prof[1]; info[7] = (double)cyc_asm;
-#else                           // ... and of the solves
+#elif GUSTO_PROF_MODE == 2      // ... and of the solves
     info[5] = (double)c.prof[2]; info[6] = (double)c.prof[3]; info[7] = (double)c.prof[4];
+#else                           // ... and of one sweep step: elimination | wait for the stager + C1 | C2 (packed: X + loop barrier in info[3])
+    info[5] = (double)c.prof[0]; info[6] = (double)(c.prof[1] + c.prof[2]); info[7] = (double)c.prof[3]; info[3] = (double)c.prof[4];
 #endif
   }
 }

@@ -25,5 +25,5 @@ for rep in range(reps):
     it = info[:, 1]
     cyc = info[:, 5:8]
     print(f"{name} B={B} rep{rep}: ms lin {ms['linearize']:.3f} solve {ms['solve']:.3f} eval {ms['evaluate']:.3f} | newton mean {it.mean():.2f} max {it.max():.0f} | "
-          f"ok {int((info[:,0]==0).sum())}/{B} | cycles/newton-iter c5 {np.mean(cyc[:,0]/it):.0f} c6 {np.mean(cyc[:,1]/it):.0f} c7 {np.mean(cyc[:,2]/it):.0f}")
+          f"ok {int((info[:,0]==0).sum())}/{B} | info3/iter {np.mean(info[:,3]/it):.3g} | cycles/newton-iter c5 {np.mean(cyc[:,0]/it):.0f} c6 {np.mean(cyc[:,1]/it):.0f} c7 {np.mean(cyc[:,2]/it):.0f}")
 eng.close()
