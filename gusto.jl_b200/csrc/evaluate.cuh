@@ -15,24 +15,38 @@ namespace gusto {
 
 constexpr int EVAL_NOUT = 8;   // conv, tr_ok, ineq_ok, rho, J_true, J_full, max_k |dX_k|^2, max soft row value
 
-GDEV double block_sum(double v, double* red) {
+// CTA-wide reductions.  GPU: warp shuffles, then one shared-memory slot per warp (deterministic order; not inlined --
+// they are called from dozens of places and the kernel is instruction-cache bound).  Host simulation: identity.
+#ifdef GUSTO_HOSTSIM
+inline double block_sum(double v, double* red) { (void)red; return v; }
+inline double block_max(double v, double* red) { (void)red; return (v == v) ? v : 1e300; }   // NaN-propagating
+#else
+__device__ __noinline__ double block_sum(double v, double* red) {
   G_ASSUME_SHARED(red);
-  red[G_TID] = v;
-  G_SYNC();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
   double s = 0.0;
-  for (int i = 0; i < G_NTHR; ++i) s += red[i];
-  G_SYNC();
+  for (int i = 0; i < nw; ++i) s += red[i];
+  __syncthreads();
   return s;
 }
-GDEV double block_max(double v, double* red) {   // NaN-propagating: a NaN anywhere yields +huge
+__device__ __noinline__ double block_max(double v, double* red) {   // NaN-propagating: a NaN anywhere yields +huge
   G_ASSUME_SHARED(red);
-  red[G_TID] = (v == v) ? v : 1e300;
-  G_SYNC();
+  v = (v == v) ? v : 1e300;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, o); v = u > v ? u : v; }
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
   double s = red[0];
-  for (int i = 1; i < G_NTHR; ++i) s = red[i] > s ? red[i] : s;
-  G_SYNC();
+  for (int i = 1; i < nw; ++i) s = red[i] > s ? red[i] : s;
+  __syncthreads();
   return s;
 }
+#endif
 
 // X,U: candidate trajectory of instance b; Xp: previous.  red: G_NTHR doubles of shared memory.
 template <int M>

@@ -123,6 +123,7 @@ template <int M> struct IpmCtx {
   const double* rp;
   int N, n_obs, b, nact, pmask, bmask;
   double h, hh, omega, Delta, toggle, eps, dp, dd;
+  mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
   // global scratch
@@ -177,9 +178,12 @@ GDEV void pair_stat(const double* st, bool has_t, const Pair& q, Stat& S) {
   if (has_t) { S.rz = fabs(q.rt) > S.rz ? fabs(q.rt) : S.rz; S.mus += st[2] * st[3]; S.np += 1.0; }
 }
 
-// Step of one row given gdz = gv . dz.   mode 0: largest steps to the boundary; mode 1: same + store the predictor
-// products and the complementarity at step ap; mode 2: apply (ap, ad).
-struct StepAcc { double amp, amd, mus; };
+// Step of one row given gdz = gv . dz.
+//   mode 0: largest steps to the boundary;
+//   mode 1: same + store the predictor products ds*dlam and the coefficients of  sum (s + a ds)(lam + a dlam) = c0 + a c1 + a^2 c2
+//           (Mehrotra's mu_aff for any step a, so the predictor needs ONE pass over the rows);
+//   mode 2: apply (ap, ad) and accumulate the new complementarity sum / pair count (for the central-path floor).
+struct StepAcc { double amp, amd, c0, c1, c2, np; };
 GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a) {
   const double sa = st[0], la = st[1];
   if (has_t) {
@@ -187,23 +191,37 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
     const double dt = (q.wa * gdz + q.ba + q.bb - q.rt) * q.iw;
     const double dla = q.wa * (gdz - dt) + q.ba, dlb = -q.wb * dt + q.bb, ds = -q.rc - (gdz - dt);
     if (mode == 2) {
-      st[0] = sa + ap * ds; st[2] = t + ap * dt; st[1] = la + ad * dla; st[3] = lb + ad * dlb;
+      const double s1 = sa + ap * ds, t1 = t + ap * dt, l1 = la + ad * dla, b1 = lb + ad * dlb;
+      st[0] = s1; st[2] = t1; st[1] = l1; st[3] = b1;
+      a.c0 += s1 * l1 + t1 * b1; a.np += 2.0;
     } else {
       if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
       if (dt < 0) { const double v = -t / dt; a.amp = v < a.amp ? v : a.amp; }
       if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
       if (dlb < 0) { const double v = -lb / dlb; a.amd = v < a.amd ? v : a.amd; }
-      if (mode == 1) { st[4] = ds * dla; st[5] = dt * dlb; a.mus += (sa + ap * ds) * (la + ap * dla) + (t + ap * dt) * (lb + ap * dlb); }
+      if (mode == 1) {
+        st[4] = ds * dla; st[5] = dt * dlb;
+        a.c0 += sa * la + t * lb; a.c1 += sa * dla + la * ds + t * dlb + lb * dt; a.c2 += ds * dla + dt * dlb;
+      }
     }
   } else {
     const double dla = q.wa * gdz + q.ba, ds = -q.rc - gdz;
-    if (mode == 2) { st[0] = sa + ap * ds; st[1] = la + ad * dla; }
-    else {
+    if (mode == 2) {
+      const double s1 = sa + ap * ds, l1 = la + ad * dla;
+      st[0] = s1; st[1] = l1;
+      a.c0 += s1 * l1; a.np += 1.0;
+    } else {
       if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
       if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
-      if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; a.mus += (sa + ap * ds) * (la + ap * dla); }
+      if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; a.c0 += sa * la; a.c1 += sa * dla + la * ds; a.c2 += ds * dla; }
     }
   }
+}
+// Keep a complementarity pair above floor = 1e-4 * mu (wide neighbourhood of the central path, as the oracle does).
+// Applied lazily by the first reader of the row in the next Newton iteration (assemble, phase 0).
+GDEV void pair_floor(double* st, bool has_t, double floor_) {
+  if (st[0] * st[1] < floor_) st[1] = floor_ / st[0];
+  if (has_t && st[2] * st[3] < floor_) st[3] = floor_ / st[2];
 }
 
 GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega) {
@@ -506,8 +524,9 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       if (spec_block<M>(s) != B0) continue;
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
-      const double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
       Pair q;
+      if (phase == 0) pair_floor(st, o.has_t, c.floor_);
       pair_eval(st, o.has_t, o.c0, c.omega, smu, phase, q);
       if (phase == 0) pair_stat(st, o.has_t, q, ka.st);
       block_add<n>(Hb, gz + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
@@ -517,15 +536,16 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       constexpr int WS = T::WS > 0 ? T::WS : 1;
       const int s0 = sh_seg<M>(c)[k], s1 = sh_seg<M>(c)[k + 1];
       const double* __restrict__ orow = c.orow;
-      const double* __restrict__ ost = c.ost;
+      double* __restrict__ ost = c.ost;
       for (int p = s0; p < s1; ++p) {
         const double* row = orow + (size_t)p * OROW_W;
-        const double* st = ost + (size_t)p * SLOT_W;
+        double* st = ost + (size_t)p * SLOT_W;
         double gv[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
         double v = row[3];
 #pragma unroll
         for (int a = 0; a < WS; ++a) { gv[a] = -row[a]; v -= row[a] * x[a]; }
         Pair q;
+        if (phase == 0) pair_floor(st, true, c.floor_);
         pair_eval(st, true, v, c.omega, smu, phase, q);
         if (phase == 0) pair_stat(st, true, q, ka.st);
         block_add<n>(Hb, gz + off, rr, 0, WS, gv, hq, q, phase);
@@ -539,9 +559,10 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
           const int j = 2 * (off + i) + side;
-          const double* st = c.bslot + (size_t)j * SLOT_W;
+          double* st = c.bslot + (size_t)j * SLOT_W;
           double gv[4] = {side == 0 ? 1.0 : -1.0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
           Pair q;
+          if (phase == 0) pair_floor(st, false, c.floor_);
           pair_eval(st, false, box_c0<M>(c, j, x), c.omega, smu, phase, q);
           if (phase == 0) pair_stat(st, false, q, ka.st);
           block_add<n>(Hb, gz + off, rr, i, 1, gv, hq, q, phase);
@@ -588,8 +609,9 @@ GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
       if (!o.valid) continue;
-      const double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
       Pair q;
+      if (phase == 0) pair_floor(st, false, c.floor_);
       pair_eval(st, false, o.c0, c.omega, smu, phase, q);
       if (phase == 0) pair_stat(st, false, q, ka.st);
       block_add<n>(Hb, gz + NX + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
@@ -631,8 +653,9 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
     KnotAcc<M> ka;
     ka.la_tr = 0; ka.bt_tr = 0; ka.kap_tr = 0; ka.gw = 0; ka.st = S;
     if (T::HAS_TR) {
-      const double* st = c.sslot + ((size_t)k * L::SP + L::S_TR) * SLOT_W;
+      double* st = c.sslot + ((size_t)k * L::SP + L::S_TR) * SLOT_W;
       Pair q;
+      if (phase == 0) pair_floor(st, true, c.floor_);
       pair_eval(st, true, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
       if (phase == 0) pair_stat(st, true, q, ka.st);
       ka.la_tr = q.la; ka.bt_tr = q.bt; ka.kap_tr = q.kap;
@@ -936,6 +959,15 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
       }
 #endif
       G_W0_FOR(q, NX) ipv[q] = sqrt(ipv[q]);
+      G_SYNCWARP();
+      // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose -- still on the eliminating warp, which would
+      // otherwise wait for the producer
+      G_W0_FOR(it, NX * NX) {
+        const int i = it / NX, m = it - i * NX;
+        const double v = m <= i ? Wr[i * LDT + m] * ipv[i] : 0.0;
+        Li[i * LDT + m] = v;
+        LiT[m * LDT + i] = v;
+      }
     }
     GUSTO_PROF_TICK(0);
     // producer: block row j+1 of S from knot j+1 (and the record of knot j+2 staged for the next step)
@@ -950,21 +982,8 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
         schur_product<M>(st.Ah, st.Phi, st.Y, pf0, npf);
         G_SYNCWARP();
         schur_product<M>(st.Y, st.Ah, st.Z, pf0, npf);
-        G_SYNCWARP();
-        schur_emit<M>(c, ks, st, kn, GUSTO_SDD(nxt), GUSTO_SOD(cur), pf0, npf);
         if (kn + 1 <= N - 1) schur_stage_store<M>(c, kn + 1, ksb + ((kn + 1) & 1) * L::KS, pre, pf0, npf);
-      } else if (kn == N) {
-        schur_emit_last<M>(c, st, GUSTO_SDD(nxt), pf0, npf);
       }
-    }
-    G_SYNC();
-    GUSTO_PROF_TICK(1);
-    // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose
-    G_PAR_FOR(it, NX * NX) {
-      const int i = it / NX, m = it - i * NX;
-      const double v = m <= i ? Wr[i * LDT + m] * ipv[i] : 0.0;
-      Li[i * LDT + m] = v;
-      LiT[m * LDT + i] = v;
     }
     G_SYNC();
     GUSTO_PROF_TICK(2);
@@ -977,6 +996,9 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
 #pragma unroll
         for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) GUSTO_LO(nxt)[i * LDT + q0 + c2] = acc[c2];
       }
+      // ... and the producer's element-wise emission of block row j+1 (S_{j+1,j+1} -> Sdd, S_{j+2,j+1} -> Sod, carry RR)
+      if (j + 1 <= N - 1) schur_emit<M>(c, ksb + ((j + 1) & 1) * L::KS, st, j + 1, GUSTO_SDD(nxt), GUSTO_SOD(cur), 0, G_NTHR);
+      else schur_emit_last<M>(c, st, GUSTO_SDD(nxt), 0, G_NTHR);
     }
     G_SYNC();
     GUSTO_PROF_TICK(3);
@@ -1244,10 +1266,10 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
   }
 }
 
-// mode 0: step lengths of the current direction; mode 1: + predictor products and mu at step ap; mode 2: apply.
-template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* amax,
-                                               double* mu_aff) {
-  StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.mus = 0.0;
+// One pass over the rows (see pair_step).  out[0..1]: largest primal / dual step to the boundary (modes 0, 1);
+// out[2..4]: c0, c1, c2 (mode 1);  mode 2: installs the central-path floor for the next iteration.
+template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* out) {
+  StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.c0 = 0.0; acc.c1 = 0.0; acc.c2 = 0.0; acc.np = 0.0;
   const double omega = c.omega;
   for_each_row<M>(c, true, [&](double* st, bool has_t, double c0, double gdz) {
     Pair q;
@@ -1255,28 +1277,14 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
     pair_step(st, has_t, q, gdz, mode, ap, ad, acc);
   });
   if (mode != 2) {
-    amax[0] = -block_max(-acc.amp, c.red);
-    amax[1] = -block_max(-acc.amd, c.red);
-    if (mode == 1) *mu_aff = block_sum(acc.mus, c.red);
+    out[0] = -block_max(-acc.amp, c.red);
+    out[1] = -block_max(-acc.amd, c.red);
+    if (mode == 1) { out[2] = block_sum(acc.c0, c.red); out[3] = block_sum(acc.c1, c.red); out[4] = block_sum(acc.c2, c.red); }
   } else {
+    const double ms = block_sum(acc.c0, c.red), np = block_sum(acc.np, c.red);
+    if (G_TID == 0) c.floor_ = np > 0 ? 1e-4 * ms / np : 0.0;
     G_SYNC();
   }
-}
-
-// Keep every complementarity pair above 1e-4 * mu (wide neighbourhood of the central path), as the oracle does.
-template <int M> GDEV_NOINLINE void recenter(const IpmCtx<M>& c) {
-  double musum = 0, npair = 0;
-  for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) {
-    musum += st[0] * st[1]; npair += 1;
-    if (has_t) { musum += st[2] * st[3]; npair += 1; }
-  });
-  const double ms = block_sum(musum, c.red), np = block_sum(npair, c.red);
-  const double floor_ = np > 0 ? 1e-4 * ms / np : 0.0;
-  for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) {
-    if (st[0] * st[1] < floor_) st[1] = floor_ / st[0];
-    if (has_t && st[2] * st[3] < floor_) st[3] = floor_ / st[2];
-  });
-  G_SYNC();
 }
 
 // --------------------------------------------------------------------------------------------------- setup
@@ -1384,6 +1392,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
     c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
     for (int i = 0; i < 5; ++i) c.prof[i] = 0;
+    c.floor_ = 0.0;
     unsigned char* t2 = c.tab + NX * (NX + 1);
     int n = 0;
     for (int i = 0; i < NX; ++i) for (int g = 0; g < L::NG; ++g) if (g * L::CG <= i) { t2[n] = (unsigned char)i; t2[L::NLT + n] = (unsigned char)g; ++n; }
@@ -1431,13 +1440,13 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     tc0 = g_clock();
     kkt_solve_refined<M>(c, 0);
     cyc_sol += g_clock() - tc0;
-    double am[2], mu_aff = 0;
+    double am[5];
     tc0 = g_clock();
-    slot_steps<M>(c, 0, 0.0, 0, 0, 0, am, &mu_aff);
+    slot_steps<M>(c, 0, 0.0, 1, 0, 0, am);
     double a_aff = am[0] < am[1] ? am[0] : am[1];
     a_aff = a_aff < 1.0 ? a_aff : 1.0;
-    slot_steps<M>(c, 0, 0.0, 1, a_aff, a_aff, am, &mu_aff);
     cyc_slot += g_clock() - tc0;
+    double mu_aff = am[2] + a_aff * (am[3] + a_aff * am[4]);
     mu_aff = R.npair > 0 ? mu_aff / R.npair : 0.0;
     double sigma = mu > 0 ? (mu_aff / mu) : 0.0;
     sigma = sigma * sigma * sigma;
@@ -1451,12 +1460,12 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     kkt_solve_refined<M>(c, prm.nref);
     cyc_sol += g_clock() - tc0;
     tc0 = g_clock();
-    slot_steps<M>(c, 1, smu, 0, 0, 0, am, &mu_aff);
+    slot_steps<M>(c, 1, smu, 0, 0, 0, am);
     double tau = 0.995;
     if (mu < 1.0) { tau = 1.0 - mu; tau = tau > 0.995 ? tau : 0.995; tau = tau < 0.999999 ? tau : 0.999999; }
     double ap = tau * am[0], ad = tau * am[1];
     ap = ap < 1.0 ? ap : 1.0; ad = ad < 1.0 ? ad : 1.0;
-    slot_steps<M>(c, 1, smu, 2, ap, ad, am, &mu_aff);
+    slot_steps<M>(c, 1, smu, 2, ap, ad, am);
     G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
     {
       double* __restrict__ nu = c.nu;
@@ -1466,7 +1475,6 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
       for (int it = G_TID; it < ne; it += G_NTHR) nu[it] += ad * dnu[it];
     }
     G_SYNC();
-    recenter<M>(c);
     cyc_slot += g_clock() - tc0;
   }
   if (status == IPM_ITERATION_LIMIT && res <= 1e3 * prm.tol) status = IPM_OPTIMAL;
