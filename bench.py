@@ -146,7 +146,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or max(8, min(2 * cores, 64))
+    n_sample = args.cpu_sample or max(64, 16 * cores)
     Btot = args.batch * args.gpus
     N = args.knots
     # one "step" = one forced SCP iteration over the bounded sample
@@ -362,10 +362,10 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n_sample = args.cpu_sample or max(8, min(2 * cores, 64))
-            v, done, wall_c = cpu_baseline(args.config, args.knots, Btot, Btot, n_sample, 2, cores)
+            n_sample = args.cpu_sample or max(64, 16 * cores)
+            v, done, wall_c = cpu_baseline(args.config, args.knots, Btot, Btot, n_sample, 4, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_sample} instances x 2 forced SCP iterations of the same workload "
+                                    "sample": f"{n_sample} instances x 4 forced SCP iterations of the same workload "
                                               f"({done} instance-iterations in {wall_c:.1f} s, NumPy/SciPy oracle, one process per core)"}
         print(json.dumps(line))
     eng.close()

@@ -69,11 +69,13 @@ struct g_d2 { double x, y; };
 inline g_d2 g_ld2(const double* p) { g_d2 v; v.x = p[0]; v.y = p[1]; return v; }
 inline void g_st2(double* p, double a, double b) { p[0] = a; p[1] = b; }
 inline double g_rcp(double x) { return 1.0 / x; }
+inline double g_rsqrt(double x) { return 1.0 / sqrt(x); }
 #else
 typedef double2 g_d2;
 __device__ __forceinline__ g_d2 g_ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void g_st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 __device__ __forceinline__ double g_rcp(double x) { return __drcp_rn(x); }
+__device__ __forceinline__ double g_rsqrt(double x) { return rsqrt(x); }
 #endif
 
 // Address-space hint: pointers that travel through the per-instance context struct come back as generic pointers;

@@ -123,6 +123,7 @@ template <int M> struct IpmCtx {
   const double* rp;
   int N, n_obs, b, nact, pmask, bmask;
   double h, hh, omega, Delta, toggle, eps, dp, dd;
+  double dow, eow;         // Delta / omega, eps / omega
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
@@ -148,17 +149,17 @@ struct Pair { double rc, rt, wa, wb, ba, bb, iw, kap, bt, la; };
 
 GDEV void pair_eval(const double* st, bool has_t, double c0, double omega, double smu, int phase, Pair& q) {
   const double sa = st[0], la = st[1];
-  const double isa = 1.0 / sa;
+  const double isa = g_rcp(sa);
   q.la = la;
   q.wa = la * isa;
   if (has_t) {
     const double t = st[2], lb = st[3];
-    const double it = 1.0 / t;
+    const double it = g_rcp(t);
     q.rc = c0 - t + sa; q.rt = omega - la - lb;
     q.wb = lb * it;
     const double rsa = sa * la - smu + (phase ? st[4] : 0.0), rsb = t * lb - smu + (phase ? st[5] : 0.0);
     q.ba = (la * q.rc - rsa) * isa; q.bb = -rsb * it;
-    q.iw = 1.0 / (q.wa + q.wb);
+    q.iw = g_rcp(q.wa + q.wb);
     q.kap = q.wa * q.wb * q.iw;
     q.bt = q.ba - q.wa * (q.ba + q.bb - q.rt) * q.iw;
   } else {
@@ -195,10 +196,10 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
       st[0] = s1; st[2] = t1; st[1] = l1; st[3] = b1;
       a.c0 += s1 * l1 + t1 * b1; a.np += 2.0;
     } else {
-      if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
-      if (dt < 0) { const double v = -t / dt; a.amp = v < a.amp ? v : a.amp; }
-      if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
-      if (dlb < 0) { const double v = -lb / dlb; a.amd = v < a.amd ? v : a.amd; }
+      if (ds < 0) { const double v = -sa * g_rcp(ds); a.amp = v < a.amp ? v : a.amp; }
+      if (dt < 0) { const double v = -t * g_rcp(dt); a.amp = v < a.amp ? v : a.amp; }
+      if (dla < 0) { const double v = -la * g_rcp(dla); a.amd = v < a.amd ? v : a.amd; }
+      if (dlb < 0) { const double v = -lb * g_rcp(dlb); a.amd = v < a.amd ? v : a.amd; }
       if (mode == 1) {
         st[4] = ds * dla; st[5] = dt * dlb;
         a.c0 += sa * la + t * lb; a.c1 += sa * dla + la * ds + t * dlb + lb * dt; a.c2 += ds * dla + dt * dlb;
@@ -211,8 +212,8 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
       st[0] = s1; st[1] = l1;
       a.c0 += s1 * l1; a.np += 1.0;
     } else {
-      if (ds < 0) { const double v = -sa / ds; a.amp = v < a.amp ? v : a.amp; }
-      if (dla < 0) { const double v = -la / dla; a.amd = v < a.amd ? v : a.amd; }
+      if (ds < 0) { const double v = -sa * g_rcp(ds); a.amp = v < a.amp ? v : a.amp; }
+      if (dla < 0) { const double v = -la * g_rcp(dla); a.amd = v < a.amd ? v : a.amd; }
       if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; a.c0 += sa * la; a.c1 += sa * dla + la * ds; a.c2 += ds * dla; }
     }
   }
@@ -220,8 +221,8 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
 // Keep a complementarity pair above floor = 1e-4 * mu (wide neighbourhood of the central path, as the oracle does).
 // Applied lazily by the first reader of the row in the next Newton iteration (assemble, phase 0).
 GDEV void pair_floor(double* st, bool has_t, double floor_) {
-  if (st[0] * st[1] < floor_) st[1] = floor_ / st[0];
-  if (has_t && st[2] * st[3] < floor_) st[3] = floor_ / st[2];
+  if (st[0] * st[1] < floor_) st[1] = floor_ * g_rcp(st[0]);
+  if (has_t && st[2] * st[3] < floor_) st[3] = floor_ * g_rcp(st[2]);
 }
 
 GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega) {
@@ -284,7 +285,7 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
     const bool hinge = (s == L::S_QUAT);
     o.i0 = 6; o.n = 4; o.has_t = hinge;
     for (int i = 0; i < 4; ++i) o.gv[i] = (hinge ? 1.0 : -1.0) * qp[i] / nq;
-    o.c0 = (hinge ? ev : -ev) - c.eps / c.omega;
+    o.c0 = (hinge ? ev : -ev) - c.eow;
   } else {
     // control balls cover k = 1..N-1 only (astrobee_se3.jl:370-371, quirk q3)
     o.is_u = true; o.has_t = false;
@@ -304,7 +305,7 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
 // stri_state_trust_region (astrobee_se3.jl:308-311) in slack-scaled form: |x - xp|^2 - Delta/omega - t <= 0
 template <int M> GDEV double tr_c0(const IpmCtx<M>& c, int k, const double* x) {
   constexpr int NX = IpmCtx<M>::NX;
-  double v = -c.Delta / c.omega;
+  double v = -c.dow;
   for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; }
   return v;
 }
@@ -325,7 +326,7 @@ template <int n> GDEV bool spd_inv_packed(const double* H, double dp, double* P)
 #pragma unroll
     for (int m = 0; m < j; ++m) dj -= Lc[tri(j, m)] * Lc[tri(j, m)];
     if (!(dj > 0.0)) { ok = false; dj = 1e-300; }
-    const double il = 1.0 / sqrt(dj);
+    const double il = g_rsqrt(dj);
     Lc[tri(j, j)] = il;                       // the diagonal holds 1 / l_jj
 #pragma unroll
     for (int i = j + 1; i < n; ++i) {
@@ -552,11 +553,11 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       }
     }
     // goal box rows (last knot only)
-    if (k == c.N - 1 && c.bmask != 0) {
+    if (k == c.N - 1 && c.bmask != 0) {       // rare path: sides kept rolled (the kernel is instruction-cache bound)
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         if (!((c.bmask >> (off + i)) & 1)) continue;
-#pragma unroll
+#pragma unroll 1
         for (int side = 0; side < 2; ++side) {
           const int j = 2 * (off + i) + side;
           double* st = c.bslot + (size_t)j * SLOT_W;
@@ -1044,13 +1045,30 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
 
 // ------------------------------------------------------------------------------------------------ KKT solves
 // cp.async ring over the V tiles of the factor (global -> shared, RING_STAGES deep, 16-byte copies), warp 0 only.
-template <int M> GDEV void ring_fetch(const double* fac, double* ring, int N, int j) {
+struct RingLane { int so[3], dof[3]; };       // per-lane source / destination offsets of its <= 3 16-byte chunks of a tile
+template <int M> GDEV void ring_lane_init(RingLane& rl) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, GLD = L::GLD, HC = GLD / 2;
+  constexpr int HC = L::GLD / 2;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int it = G_LANE + r * G_NLANE;
+    const int i = it / HC, m = 2 * (it - i * HC);
+    rl.so[r] = it < L::NX * HC ? i * L::GLD + m : -1;
+    rl.dof[r] = i * L::LDT + m;
+  }
+}
+template <int M> GDEV void ring_fetch(const double* fac, double* ring, int N, int j, const RingLane& rl) {
+  using L = IpmLayout<M>;
   if (j >= 1 && j <= N) {
     const double* src = fac + (size_t)(2 * j + 1) * L::GT;
     double* dst = ring + (j % RING_STAGES) * L::TILE;
-    G_W0_FOR(it, NX * HC) { const int i = it / HC, m = 2 * (it - i * HC); g_cp_async16(dst + i * L::LDT + m, src + i * GLD + m); }
+#ifdef GUSTO_HOSTSIM
+    constexpr int HC = L::GLD / 2;
+    for (int it = 0; it < L::NX * HC; ++it) { const int i = it / HC, m = 2 * (it - i * HC); g_cp_async16(dst + i * L::LDT + m, src + i * L::GLD + m); }
+#else
+#pragma unroll
+    for (int r = 0; r < 3; ++r) if (rl.so[r] >= 0) g_cp_async16(dst + rl.dof[r], src + rl.so[r]);
+#endif
   }
   g_cp_async_commit();
 }
@@ -1066,13 +1084,15 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   const double* const fac = c.fac;
   G_ASSUME_SHARED(y);
   G_ASSUME_SHARED(ring);
+  RingLane rl;
+  ring_lane_init<M>(rl);
   long long tc0 = g_clock();
   if (G_TID < G_WARP) {
-    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(fac, ring, N, jj);
+    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(fac, ring, N, jj, rl);
     for (int j = 1; j <= N; ++j) {
       g_cp_async_wait_group<S - 2>();             // tile j has landed (at most S-2 younger groups in flight)
       G_SYNCWARP();                               // ... for every lane; everyone is done with tile j-1
-      ring_fetch<M>(fac, ring, N, j + S - 1);                // reuses the slot of tile j-1
+      ring_fetch<M>(fac, ring, N, j + S - 1, rl);                // reuses the slot of tile j-1
       const double* R = ring + (j % S) * L::TILE;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
@@ -1120,11 +1140,11 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   tc0 = g_clock();
   if (G_TID < G_WARP) {
     // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
-    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(fac, ring, N, N - jj);
+    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(fac, ring, N, N - jj, rl);
     for (int j = N - 1; j >= 0; --j) {
       g_cp_async_wait_group<S - 2>();
       G_SYNCWARP();
-      ring_fetch<M>(fac, ring, N, j + 1 - (S - 1));          // reuses the slot of tile j+2
+      ring_fetch<M>(fac, ring, N, j + 1 - (S - 1), rl);          // reuses the slot of tile j+2
       const double* R = ring + ((j + 1) % S) * L::TILE;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
@@ -1187,7 +1207,7 @@ template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* 
 }
 
 // Solve, then `nref` refinement steps against the exact KKT matrix [[H, Aeq'], [Aeq, 0]].
-template <int M> GDEV void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
+template <int M> GDEV_NOINLINE void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
@@ -1226,7 +1246,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)it * SLOT_W;
     if (T::HAS_TR && s == L::S_TR) {
-      double v = -c.Delta / c.omega, gdz = 0.0;
+      double v = -c.dow, gdz = 0.0;
       for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
       fn(st, true, v, gdz);
     } else {
@@ -1364,6 +1384,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
     c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
     c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS]; c.dp = prm.delta_p; c.dd = prm.delta_d;
+    c.dow = c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
     for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
     c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;

@@ -65,7 +65,8 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal                                                                */
   /* convex-solver controls (0 selects the default) */
   int32_t ipm_max_iter;    /* default 60   */
-  int32_t ipm_nref;        /* default 2    */
+  int32_t ipm_nref;        /* refinement steps of the corrector solve; default 1 (as the oracle) for the models with a
+                              state trust region, 2 for dubins / astrobeeSE3manifold */
   double ipm_tol;          /* default 1e-8 */
   double ipm_delta_p;      /* default 1e-6 */
   double ipm_delta_d;      /* default 1e-10 */
