@@ -669,6 +669,14 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       kd[L::KD_KAP] = ka.kap_tr;
       kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr / (1.0 + ka.kap_tr * ka.gw) : 0.0;
     }
+    {   // first pass of the KKT solve that follows: t1 = (H + dp I)^-1 r  (kkt_solve)
+      double rv[NV], tv[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) rv[i] = c.r[k * NV + i];
+      apply_phi<M>(c, k, rv, tv);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = tv[i];
+    }
   }
   if (phase == 0) {
     // equality residual r_p = Aeq z - b  ;  rnu = -r_p
@@ -1161,35 +1169,42 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
 }
 
 // [dz; dnu] (+)= Ktilde^-1 [rin; rnuin]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]] via the Schur complement.
-template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* rin, const double* rnuin, bool accumulate) {
+// One Schur-complement solve of  Ktilde [d; dnu] = [rin; rnu - Aeq dz]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]],
+// added to (or installed in) dz / dnu.  On entry c.t1 holds  Phi rin (+ dz when accumulating)  -- written by assemble()
+// for the first solve of a direction and by the previous call for a refinement solve -- so the Schur right-hand side
+// is simply  Aeq t1 - rnu.  When `more` refinement follows, the same per-knot pass that recovers d also leaves the
+// next residual  res = rin - Aeq' dnu - H d  (unregularised H, i.e. the exact KKT matrix) in c.res and its Phi-image
+// plus the updated dz in c.t1: a refinement step costs two passes and two chains, nothing else.
+template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* rin, bool accumulate, bool more) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
-  G_PAR_FOR(k, N) {
-    double in[NV], out[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) in[i] = rin[k * NV + i];
-    apply_phi<M>(c, k, in, out);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = out[i];
-  }
-  G_SYNC();
   G_PAR_FOR(j, N + 1) {
     double v[NX];
     aeq_row<M>(c, c.t1, j, v);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) sh_sy<M>(c)[j * NX + i] = v[i] - rnuin[j * NX + i];
+    for (int i = 0; i < NX; ++i) sh_sy<M>(c)[j * NX + i] = v[i] - c.rnu[j * NX + i];
   }
   G_SYNC();
   schur_solve<M>(c);
   G_PAR_FOR(k, N) {
-    double in[NV], out[NV];
-    aeqT_knot<M>(c, sh_sy<M>(c), k, in);
+    double t[NV], d[NV];
+    aeqT_knot<M>(c, sh_sy<M>(c), k, t);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) in[i] = rin[k * NV + i] - in[i];
-    apply_phi<M>(c, k, in, out);
+    for (int i = 0; i < NV; ++i) t[i] = rin[k * NV + i] - t[i];
+    apply_phi<M>(c, k, t, d);
+    double dzn[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sh_dz<M>(c)[k * NV + i] = accumulate ? sh_dz<M>(c)[k * NV + i] + out[i] : out[i];
+    for (int i = 0; i < NV; ++i) { dzn[i] = accumulate ? sh_dz<M>(c)[k * NV + i] + d[i] : d[i]; sh_dz<M>(c)[k * NV + i] = dzn[i]; }
+    if (more) {
+      double hd[NV], pr[NV];
+      apply_H<M>(c, k, d, hd);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { t[i] -= hd[i]; c.res[k * NV + i] = t[i]; }
+      apply_phi<M>(c, k, t, pr);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = pr[i] + dzn[i];
+    }
   }
   {
     double* __restrict__ dnu = c.dnu;
@@ -1208,29 +1223,8 @@ template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* 
 
 // Solve, then `nref` refinement steps against the exact KKT matrix [[H, Aeq'], [Aeq, 0]].
 template <int M> GDEV_NOINLINE void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NV = L::NV;
-  const int N = c.N;
-  kkt_solve<M>(c, c.r, c.rnu, false);
-  for (int it_ref = 0; it_ref < nref; ++it_ref) {
-    G_PAR_FOR(k, N) {
-      double at[NV], hd[NV], dk[NV];
-      aeqT_knot<M>(c, c.dnu, k, at);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) dk[i] = sh_dz<M>(c)[k * NV + i];
-      apply_H<M>(c, k, dk, hd);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) c.res[k * NV + i] = c.r[k * NV + i] - hd[i] - at[i];
-    }
-    G_PAR_FOR(j, N + 1) {
-      double v[NX];
-      aeq_row<M>(c, sh_dz<M>(c), j, v);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) c.resnu[j * NX + i] = c.rnu[j * NX + i] - v[i];
-    }
-    G_SYNC();
-    kkt_solve<M>(c, c.res, c.resnu, true);
-  }
+  kkt_solve<M>(c, c.r, false, nref > 0);
+  for (int it_ref = 1; it_ref <= nref; ++it_ref) kkt_solve<M>(c, c.res, true, it_ref < nref);
 }
 
 // --------------------------------------------------------------------------------------------- slot passes
