@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   __shared__ alignas(16) double su[KPC * NU];
   __shared__ double ws[KPC][NX * NX + NX];
   __shared__ alignas(8) unsigned long long mbar;
+  __shared__ double sbv[NU > 0 ? NU : 1];
   const BatchDesc& d = *dp;
+  if (threadIdx.x == 0) dyn_B_columns<M>(d.rp, sbv);     // visible after the barrier / mbarrier wait below
   const int total = d.B * d.N;
   const int k0 = blockIdx.x * KPC;
   const int nk = (total - k0) < KPC ? (total - k0) : KPC;
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   const int warp = threadIdx.x >> 5;
   if (warp < nk) {
     const int gk = k0 + warp;
-    linearize_knot<M>(d, p, gk / d.N, gk % d.N, sx + warp * NX, su + warp * NU, ws[warp]);
+    linearize_knot<M>(d, p, gk / d.N, gk % d.N, sx + warp * NX, su + warp * NU, ws[warp], sbv);
   }
 }
 

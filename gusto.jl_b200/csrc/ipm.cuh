@@ -718,7 +718,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 // are element-wise combinations of Z, Y, Y' and Phi.
 template <int M> GHD constexpr int ctrl_of_row(int I) { int r = -1; for (int a = 0; a < Traits<M>::NU; ++a) if (Traits<M>::b_row(a) == I) r = a; return r; }
 
-struct SchurTiles { double *Phi, *Ah, *Y, *Z, *RR; };
+struct SchurTiles { double *Phi, *Ah, *Y, *Z, *RR, *Xi; };
 
 // Threads [t0, t0 + nt) build the dense Phi of the staged knot record `ks`, and refresh Ah (the pattern of A is static,
 // so the tile is zeroed once by the caller).  Barrier-free: followed by the caller's barrier.
@@ -738,6 +738,14 @@ template <int M> GDEV void schur_build(const IpmCtx<M>& c, const double* ks, con
     t.Phi[i * LDT + q] = v;
   }
   for (int e = G_TID - t0; e < L::ANZ; e += nt) t.Ah[mt[e] * LDT + mt[L::ANZ + e]] = c.hh * ks[L::KS_A + e];
+  // control coupling Xi = G Theta G' (G = h/2 B): one entry per pair of controls of the same block (static pattern too)
+  for (int pr = G_TID - t0; pr < L::NU * L::NU; pr += nt) {
+    const int a = pr / L::NU, b2 = pr - a * L::NU;
+    const int ub = T::UB_of(a);
+    if (ub != T::UB_of(b2)) continue;
+    const int uo = T::UB_off(ub);
+    t.Xi[T::b_row(a) * LDT + T::b_row(b2)] = c.hh * c.hh * c.bv[a] * c.bv[b2] * ks[L::KS_TH + T::UB_pk(ub) + tri(a - uo, b2 - uo)];
+  }
 }
 
 // out(i, q) = sum_m X[i][m] * Yt[q][m]  for all (i, q), by threads [t0, t0 + nt)
@@ -755,16 +763,14 @@ template <int M> GDEV void schur_product(const double* X, const double* Yt, doub
 
 // Element-wise emission for knot k (k < N):  Sdd (= S_kk) = RR + Lk Phi Lk' [+ Xi] (+ regularisation),
 // Sod (= S_{k+1,k}) = Rk Phi Lk' [+ Xi],  RR = Rk Phi Rk' [+ Xi]  (carried to S_{k+1,k+1}).
-template <int M> GDEV void schur_emit(const IpmCtx<M>& c, const double* ks, const SchurTiles& t, int k, double* Sdd, double* Sod,
+template <int M> GDEV void schur_emit(const IpmCtx<M>& c, const SchurTiles& t, int k, double* Sdd, double* Sod,
                                       int t0, int nt) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX, LDT = L::LDT;
-  const unsigned char* mt = c.tab + L::TAB_MODEL;
-  G_ASSUME_SHARED(mt);
   const int N = c.N;
   // Y and Z already carry the h/2 factors, so the A-coefficients of Lk and Rk are 0 or 1 here
-  const double hh = c.hh, aL = k == 0 ? 0.0 : 1.0, bL = k == 0 ? 1.0 : -1.0;
+  const double aL = k == 0 ? 0.0 : 1.0, bL = k == 0 ? 1.0 : -1.0;
   const bool last = (k == N - 1);
   const double aR = last ? 0.0 : 1.0;
   const int pmask = c.pmask;
@@ -772,12 +778,7 @@ template <int M> GDEV void schur_emit(const IpmCtx<M>& c, const double* ks, cons
     const int i = it / NX, q = it - i * NX;
     const double z = t.Z[i * LDT + q], y = t.Y[i * LDT + q], yt = t.Y[q * LDT + i], ph = t.Phi[i * LDT + q];
     const double dRi = last ? (double)((pmask >> i) & 1) : 1.0, dRq = last ? (double)((pmask >> q) & 1) : 1.0;
-    double xi = 0.0;
-    const int a = (signed char)mt[2 * L::ANZ + NX + i], b2 = (signed char)mt[2 * L::ANZ + NX + q];
-    if (a >= 0 && b2 >= 0 && T::UB_of(a) == T::UB_of(b2)) {
-      const int ub = T::UB_of(a), uo = T::UB_off(ub);
-      xi = hh * hh * c.bv[a] * c.bv[b2] * ks[L::KS_TH + T::UB_pk(ub) + tri(a - uo, b2 - uo)];
-    }
+    const double xi = t.Xi[i * LDT + q];
     double dd = t.RR[i * LDT + q] + aL * aL * z + aL * bL * (y + yt) + bL * bL * ph + (k >= 1 ? xi : 0.0);
     if (i == q) dd += c.dd * dd + 1e-300;
     Sdd[i * LDT + q] = dd;
@@ -864,11 +865,12 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
   double* Li = tile + 2 * TILE;              // L_j^-1 (lower, explicit zeros) and its transpose
   double* LiT = tile + 3 * TILE;
   // ping-pong tiles are addressed arithmetically (an indexed pointer array would live in local memory)
-#define GUSTO_SDD(w) (tile + (4 + (w)) * TILE)
+#define GUSTO_SDD(w) (tile + 4 * TILE)                 /* one tile: emitted and consumed within a step */
 #define GUSTO_SOD(w) (tile + (6 + (w)) * TILE)
 #define GUSTO_LO(w) (tile + (8 + (w)) * TILE)
   SchurTiles st;
   st.Phi = tile + 10 * TILE; st.Ah = tile + 11 * TILE; st.Y = tile + 12 * TILE; st.Z = tile + 13 * TILE; st.RR = tile + 14 * TILE;
+  st.Xi = tile + 5 * TILE;
   double* ipv = tile + L::FAC_TILES * TILE;  // 1 / pivot, then 1 / sqrt(pivot)
   double* ksb = ipv + ((NX + 1) & ~1);       // two staged knot records
   const unsigned char* const tab = c.tab;
@@ -888,13 +890,12 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
   }
   G_SYNC();
   schur_build<M>(c, ksb, st, 0, G_NTHR);
-  G_PAR_FOR(i, NX) Wr[i * LDT + i] = 1.0;
   G_SYNC();
   schur_product<M>(st.Ah, st.Phi, st.Y, 0, G_NTHR);
   G_SYNC();
   schur_product<M>(st.Y, st.Ah, st.Z, 0, G_NTHR);
   G_SYNC();
-  schur_emit<M>(c, ksb, st, 0, W, GUSTO_SOD(1), 0, G_NTHR);
+  schur_emit<M>(c, st, 0, W, GUSTO_SOD(1), 0, G_NTHR);
   G_SYNC();
 #if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
   if (G_TID == 0) c.prof[0] += g_clock() - tc0;
@@ -927,7 +928,8 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
           const int i = tab[t], e = tab[NT + t];
           if (i <= q) continue;
           const double mult = W[i * LDT + q] * ip;
-          if (e <= q) Wr[i * LDT + e] -= mult * Wr[q * LDT + e];
+          if (e < q) Wr[i * LDT + e] -= mult * Wr[q * LDT + e];
+          else if (e == q) Wr[i * LDT + e] = -mult;            // Wr starts as the identity, kept implicit
           else W[i * LDT + e] -= mult * W[e * LDT + q];
         }
       }
@@ -952,6 +954,7 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
           av[r] = W[i * LDT + q];
           sv[r] = tile[right ? TILE + q * LDT + e : e * LDT + q];
           ov[r] = tile[to[r]];
+          if (e == q) { sv[r] = 1.0; ov[r] = 0.0; }            // Wr starts as the identity, kept implicit
         }
         G_SYNCWARP();                                // the look-ahead read W[q+1][q+1] before its owner updates it
         double pn = fma(-(wq1 * ip), wq1, d1);
@@ -973,7 +976,7 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
       // otherwise wait for the producer
       G_W0_FOR(it, NX * NX) {
         const int i = it / NX, m = it - i * NX;
-        const double v = m <= i ? Wr[i * LDT + m] * ipv[i] : 0.0;
+        const double v = m < i ? Wr[i * LDT + m] * ipv[i] : (m == i ? ipv[i] : 0.0);
         Li[i * LDT + m] = v;
         LiT[m * LDT + i] = v;
       }
@@ -1006,12 +1009,12 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
         for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) GUSTO_LO(nxt)[i * LDT + q0 + c2] = acc[c2];
       }
       // ... and the producer's element-wise emission of block row j+1 (S_{j+1,j+1} -> Sdd, S_{j+2,j+1} -> Sod, carry RR)
-      if (j + 1 <= N - 1) schur_emit<M>(c, ksb + ((j + 1) & 1) * L::KS, st, j + 1, GUSTO_SDD(nxt), GUSTO_SOD(cur), 0, G_NTHR);
+      if (j + 1 <= N - 1) schur_emit<M>(c, st, j + 1, GUSTO_SDD(nxt), GUSTO_SOD(cur), 0, G_NTHR);
       else schur_emit_last<M>(c, st, GUSTO_SDD(nxt), 0, G_NTHR);
     }
     G_SYNC();
     GUSTO_PROF_TICK(3);
-    // (X) V_{j+1} = Lo_{j+1} Li -> global;  D_j^-1 = Li' Li -> global;  D_{j+1} = S_{j+1,j+1} - Lo_{j+1} Lo_{j+1}' -> W;  Wr = I
+    // (X) V_{j+1} = Lo_{j+1} Li -> global;  D_j^-1 = Li' Li -> global;  D_{j+1} = S_{j+1,j+1} - Lo_{j+1} Lo_{j+1}' -> W
     {
       double* gD = fac + (size_t)(2 * j) * GT;
       double* gV = fac + (size_t)(2 * (j + 1) + 1) * GT;
@@ -1036,7 +1039,6 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
           for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) gV[i * GLD + q0 + c2] = acc[c2];
         }
       }
-      G_PAR_FOR(it, NX * NX) { const int i = it / NX, m = it - i * NX; Wr[i * LDT + m] = (i == m) ? 1.0 : 0.0; }
     }
     G_SYNC();
     GUSTO_PROF_TICK(4);

@@ -13,10 +13,17 @@
 
 namespace gusto {
 
-// ws: per-warp scratch of NX*NX + NX doubles (shared memory on the GPU).
+// ws: per-warp scratch of NX*NX + NX doubles (shared memory on the GPU).  bv[NU]: the non-zero entry of each column of B.
+template <int M> GDEV void dyn_B_columns(const double* rp, double* bv) {
+  using T = Traits<M>;
+  double Bm[T::NX * T::NU];
+  for (int i = 0; i < T::NX * T::NU; ++i) Bm[i] = 0.0;
+  dyn_B<M>(rp, Bm);
+  for (int a = 0; a < T::NU; ++a) bv[a] = Bm[T::b_row(a) * T::NU + a];
+}
 template <int M>
 GDEV void linearize_knot(const BatchDesc& d, const BatchPtrs& p, int b, int k, const double* x, const double* u,
-                         double* ws) {
+                         double* ws, const double* bv) {
   using T = Traits<M>;
   constexpr int NX = T::NX, NU = T::NU;
   double* sA = ws;             // [NX*NX]
@@ -37,14 +44,11 @@ GDEV void linearize_knot(const BatchDesc& d, const BatchPtrs& p, int b, int k, c
   double* gf = p.f + gk * NX;
   double* gg = p.g + gk * NX;
   for (int i = lane; i < NX; i += G_NLANE) {
-    double Bm_row[NU > 0 ? NU : 1];
     double acc = sf[i];
     for (int j = 0; j < NX; ++j) acc -= sA[i * NX + j] * x[j];
-    // B is constant and sparse; rebuild the row on the fly (dyn_B fills a zeroed NX x NU matrix)
-    double Bfull[NX * NU];
-    for (int j = 0; j < NX * NU; ++j) Bfull[j] = 0.0;
-    dyn_B<M>(d.rp, Bfull);
-    for (int j = 0; j < NU; ++j) { Bm_row[j] = Bfull[i * NU + j]; acc -= Bm_row[j] * u[j]; }
+    // B is constant with one entry per column (B[b_row(a)][a] = bv[a], Traits<M>::b_row): no matrix is rebuilt
+#pragma unroll
+    for (int a = 0; a < NU; ++a) if (T::b_row(a) == i) acc -= bv[a] * u[a];
     gf[i] = sf[i];
     gg[i] = acc;
   }

@@ -23,9 +23,11 @@ static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stag
   const int N = d.N, B = d.B;
   if (stages & 1) {
     std::vector<double> ws(T::NX * T::NX + T::NX);
+    double bv[T::NU > 0 ? T::NU : 1];
+    dyn_B_columns<M>(d.rp, bv);
     for (int b = 0; b < B; ++b)
       for (int k = 0; k < N; ++k)
-        linearize_knot<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data());
+        linearize_knot<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data(), bv);
   }
   if (stages & 2) {
     std::vector<double> scratch(L::scratch_doubles(N, d.n_obs)), smem(L::smem_doubles(N, 1));
