@@ -146,8 +146,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or max(64, 16 * cores)
     Btot = args.batch * args.gpus
+    n_sample = args.cpu_sample or min(Btot, 48 * cores)
     N = args.knots
     # one "step" = one forced SCP iteration over the bounded sample
     val, done, wall = cpu_baseline(args.config, N, Btot, Btot, n_sample, max(1, min(args.steps, 3)), cores)
@@ -337,6 +337,14 @@ def main():
             gbs = (ab[k] * B / 1e9) / (ms / 1e3) if ms > 0 else 0.0
             kern[k] = {"ms": ms, "algorithmic_bytes": ab[k] * B, "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(kern, key=lambda k: kern[k]["ms"])
+        # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        # (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); null when the workload differs
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == f"{bp.model.name} B={B} N={bp.N}":
+                traffic = tj.get(f"{dom}_kernel")
         step_kernel_ms = sum(kern[k]["ms"] for k in kern)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -351,7 +359,7 @@ def main():
             "gpu_launches": int(launches),
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": kern[dom]["achieved_gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "share_of_step_kernel_time": kern[dom]["ms"] / step_kernel_ms if step_kernel_ms else None,
                          "note": "solve kernel is latency/FP64-bound (sequential block-tridiagonal sweeps), see DESIGN.md section 5"},
             "kernels": kern,
@@ -362,7 +370,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n_sample = args.cpu_sample or max(64, 16 * cores)
+            n_sample = args.cpu_sample or min(Btot, 48 * cores)
             v, done, wall_c = cpu_baseline(args.config, args.knots, Btot, Btot, n_sample, 4, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_sample} instances x 4 forced SCP iterations of the same workload "

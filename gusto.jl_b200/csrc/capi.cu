@@ -231,8 +231,9 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   }
   ctx->prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
   ctx->prm.nref = cfg->ipm_nref > 0 ? cfg->ipm_nref : ((cfg->model_id == ASTROBEE_SE3 || cfg->model_id == FREEFLYER_SE2) ? 1 : 2);   // no trust region => H is only regularised by delta_p on free directions: refine twice
+  // astrobeeSE3manifold: no trust region (H singular in many directions) -> larger primal regularisation
   ctx->prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
-  ctx->prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : 1e-6;
+  ctx->prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : (cfg->model_id == ASTROBEE_SE3_MANIFOLD ? 1e-5 : 1e-6);
   ctx->prm.delta_d = cfg->ipm_delta_d > 0 ? cfg->ipm_delta_d : 1e-10;
 
   const size_t B = cfg->B, N = cfg->N, no = h.n_obs > 0 ? h.n_obs : 1;

@@ -122,7 +122,8 @@ template <int M> struct IpmCtx {
   const BatchDesc* d;
   const double* rp;
   int N, n_obs, b, nact, pmask, bmask;
-  double h, hh, omega, Delta, toggle, eps, dp, dd;
+  double h, hh, omega, Delta, toggle, eps, dd;
+  mutable double dp;       // primal regularisation (raised x100 after a failed factorisation)
   double dow, eow;         // Delta / omega, eps / omega
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
@@ -1424,14 +1425,31 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.tab[t] = (unsigned char)i; c.tab[NX * (NX + 1) / 2 + t] = (unsigned char)(t - i * (i + 1) / 2);
   }
 
-  setup<M>(c);
-
+  // The solve is attempted with the configured primal regularisation; an attempt that breaks down (non-positive
+  // pivot, NaN) or stalls (no progress of the residual for 12 Newton iterations) is restarted from the same start
+  // point with delta_p x10, at most twice.  The oracle factorises the full KKT matrix (LU) and only regularises on a
+  // failed factorisation (ipm.py); the Schur-complement form used here needs (H + delta_p I)^-1, and on problems
+  // whose H is singular in many directions (no trust region: astrobeeSE3manifold) the right delta_p is
+  // instance-dependent.
   int status = IPM_ITERATION_LIMIT, it_done = 0;
   long long cyc_asm = 0, cyc_fac = 0, cyc_sol = 0, cyc_slot = 0, tc0;
   double res = 1e300, mu = 0;
   const double scd = 1.0 + c.omega;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+  if (attempt > 0) {
+    G_SYNC();
+    if (G_TID == 0) { c.dp *= 10.0; c.floor_ = 0.0; }
+    G_SYNC();
+#ifdef GUSTO_HOSTSIM
+    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  restart with delta_p = %.1e\n", c.dp);
+#endif
+  }
+  setup<M>(c);
+  status = IPM_ITERATION_LIMIT;
+  double best = 1e300;
+  int best_it = 0;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
-    it_done = iter;
+    ++it_done;
     Resid R;
     bool blocks_ok = true;
     tc0 = g_clock();
@@ -1445,14 +1463,12 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
 #endif
     if (res <= prm.tol) { status = IPM_OPTIMAL; break; }
     if (!(res == res) || res > 1e200) { status = IPM_NUMERICAL; break; }
+    if (res < 0.5 * best) { best = res; best_it = iter; }
+    else if (iter - best_it >= 12) break;                       // stalled
     tc0 = g_clock();
     const bool fac_ok = factorize<M>(c);
     cyc_fac += g_clock() - tc0;
-    if (!(fac_ok && blocks_ok)) {
-#ifdef GUSTO_HOSTSIM
-      if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  factorize: non-positive pivot\n");
-#endif
-    }
+    if (!(fac_ok && blocks_ok)) { status = IPM_NUMERICAL; break; }   // non-positive pivot
     // predictor
     tc0 = g_clock();
     kkt_solve_refined<M>(c, 0);
@@ -1499,6 +1515,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     double badz = 0.0;
     G_PAR_FOR(it, N * NV) { const double v = sh_z<M>(c)[it]; if (!(v == v) || fabs(v) > 1e100) badz = 1.0; }
     if (block_max(badz, c.red) > 0.0) status = IPM_NUMERICAL;
+  }
+  if (status == IPM_OPTIMAL) break;
   }
   // ---- write the candidate trajectory and the objective (cost + omega * sum t)
   double obj = 0;

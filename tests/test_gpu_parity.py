@@ -143,3 +143,63 @@ def test_errors_are_reported_not_thrown(host):
     ctx = ctypes.c_void_p()
     rc = host.load_library().gusto_create(ctypes.byref(cfg), None, None, None, ctypes.byref(ctx))
     assert rc < 0 and b"N >= 3" in host.load_library().gusto_last_error(None)
+
+
+def test_full_size_batch_properties(host):
+    """BASELINE.json configs[2] at full size (astrobeeSE3 B=1024 N=50): size-independent properties of one SCP
+    iteration -- every solve OPTIMAL, hard rows of the candidate satisfied (init, goal, linearised trapezoid defect,
+    control balls), the penalised objective is never below the true cost, and the full SCP converges everywhere."""
+    from gusto_oracle.models import B_dyn
+    bp = gb.problems.CONFIGS["astrobeeSE3"](B=1024)
+    X0, U0 = bp.init_traj_straightline()
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0)
+    out, info = e.iterate()
+    Xn, Un = e.get_candidate()
+    f, A, g, rows = e.get_blocks()
+    assert np.all(info[:, 0] == 0) and np.all(info[:, 1] <= 25)
+    assert np.max(np.abs(Xn[:, 0] - bp.x_init)) < 1e-7
+    sel = bp.goal_type == 1
+    assert np.max(np.abs(Xn[:, -1][:, sel] - bp.goal_lo[:, sel])) < 1e-7
+    Bm = B_dyn(orc.get_model(bp.model.name))
+    h = (bp.tf / (bp.N - 1))[:, None, None]
+    lin = np.einsum("bkij,bkj->bki", A, Xn) + Un @ Bm.T + g            # f + A (X - Xp) + B (U - Up) at every knot
+    defect = Xn[:, :-1] - Xn[:, 1:] + 0.5 * h * (lin[:, :-1] + lin[:, 1:])
+    assert np.max(np.abs(defect)) < 1e-7
+    rp = bp.robot_params()
+    acc = np.linalg.norm(Un[:, :-1, :3], axis=-1) / rp[0]                # cci_translational_accel_bound, k = 1..N-1
+    alp = np.linalg.norm(Un[:, :-1, 3:] / rp[1:4], axis=-1)              # cci_angular_accel_bound
+    assert acc.max() <= rp[6] * (1 + 1e-6) and alp.max() <= rp[8] * (1 + 1e-6)
+    assert np.all(out[:, 5] >= out[:, 4] - 1e-9)                        # J_full >= J_true
+    assert np.all(np.abs(info[:, 4] - out[:, 5]) <= 1e-5 * np.maximum(1.0, np.abs(out[:, 5])))   # solver objective == evaluated J_full
+    S = host.solve_gusto_batch(e, X0, U0, max_iter=30)
+    assert int(S.converged.sum()) == bp.B and int(S.successful.sum()) == bp.B
+    e.close()
+
+
+def test_solver_restarts_instead_of_failing(host):
+    """astrobeeSE3manifold past the first SCP iteration: the default primal regularisation breaks down on some
+    instances (H is singular without a trust region); the kernel restarts with a larger one instead of returning
+    ITERATION_LIMIT / NUMERICAL.  KNOWN GAP: on these later iterations the attitude is only
+    determined inside the quaternion dead-band and the regularised Schur solver may stop at the "almost solved"
+    threshold (1e3 * tol), so the objective is only required to agree with the oracle to 2e-3 relative here (1e-6 on
+    the first iteration, test_subproblem_and_evaluation_match_oracle)."""
+    bp = gb.problems.CONFIGS["astrobeeSE3manifold"](B=2, N=60)
+    sp = bp.model.scp_params
+    p = to_oracle(bp, 0)
+    trace = []
+
+    def sub(p_, X, U, omega, Delta, toggle, eps):
+        res = solve_subproblem(p_, X, U, omega, Delta, toggle, eps)
+        trace.append((X.copy(), U.copy(), omega, Delta, res[2]))
+        return res
+
+    solve_gusto(p, max_iter=4, subproblem=sub)
+    e = host.Engine(bp, device=0)
+    for X, U, omega, Delta, obj in trace:
+        e.set_trajectory(np.stack([X, X]), np.stack([U, U]))
+        e.set_penalties(np.full(2, omega), np.full(2, Delta))
+        out, info = e.iterate()
+        assert info[0, 0] == 0
+        assert abs(info[0, 4] - obj) <= 2e-3 * abs(obj)
+    e.close()
