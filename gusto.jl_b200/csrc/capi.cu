@@ -12,6 +12,7 @@
 #include "linearize.cuh"
 #include "ipm.cuh"
 #include "evaluate.cuh"
+#include "postprocess.cuh"
 
 using namespace gusto;
 
@@ -115,6 +116,28 @@ __global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const BatchDesc*
   if (p.active && !p.active[b]) return;
   evaluate_instance<M>(*dp, p, b, p.Xn + (size_t)b * dp->N * T::NX, p.Un + (size_t)b * dp->N * T::NU,
                        out + (size_t)b * EVAL_NOUT, red);
+}
+
+// K5.  Grid: B CTAs: post-processing scalars of the ACCEPTED trajectory.
+template <int M>
+__global__ void __launch_bounds__(EVAL_THREADS) check_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
+  using T = Traits<M>;
+  __shared__ double red[EVAL_THREADS];
+  const int b = blockIdx.x;
+  check_instance<M>(*dp, p, b, p.Xp + (size_t)b * dp->N * T::NX, p.Up + (size_t)b * dp->N * T::NU, out + (size_t)b * CHECK_NOUT, red);
+}
+
+// K6.  One thread per (instance, knot interval): RK4 upsampling of the accepted trajectory.
+template <int M>
+__global__ void __launch_bounds__(128) interp_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, int nstep, double* Xfull, double* Ufull) {
+  using T = Traits<M>;
+  const int N = dp->N, nseg = N - 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= dp->B * nseg) return;
+  const int b = t / nseg, k = t - b * nseg;
+  const size_t nf = (size_t)nstep * nseg;
+  interpolate_interval<M>(*dp, p, b, k, nstep, p.Xp + (size_t)b * N * T::NX, p.Up + (size_t)b * N * T::NU,
+                          Xfull + (size_t)b * (nf + 1) * T::NX, Ufull + (size_t)b * nf * T::NU);
 }
 
 // accept: candidate -> accepted trajectory for flagged instances; install next omega / Delta.
@@ -505,6 +528,55 @@ int32_t gusto_timer_stop(gusto_ctx* ctx, float* ms) {
   CK(cudaEventRecord(ctx->tev[1], ctx->stream));
   CK(cudaEventSynchronize(ctx->tev[1]));
   CK(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
+  return GUSTO_OK;
+}
+
+int32_t gusto_check_trajectory(gusto_ctx* ctx, double* out) {
+  NEED(out);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int grid = ctx->cfg.B;
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, (size_t)grid * CHECK_NOUT * sizeof(double)));
+  switch (ctx->cfg.model_id) {
+    case DUBINS: check_kernel<DUBINS><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
+    case FREEFLYER_SE2: check_kernel<FREEFLYER_SE2><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
+    case ASTROBEE_SE3: check_kernel<ASTROBEE_SE3><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
+    default: check_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)grid * CHECK_NOUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { ctx->err = std::string("gusto_check_trajectory: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
+  ctx->launches++;
+  return GUSTO_OK;
+}
+
+int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xfull, double* Ufull) {
+  NEED(Xfull && Ufull);
+  if (nstep < 1) { ctx->err = "gusto_interpolate_trajectory: nstep must be >= 1"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B, nseg = ctx->cfg.N - 1, nf = (size_t)nstep * nseg;
+  const size_t nX = B * (nf + 1) * ctx->nx, nU = B * nf * ctx->nu;
+  double *dX = nullptr, *dU = nullptr;
+  if (cudaMalloc((void**)&dX, nX * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&dU, nU * sizeof(double)) != cudaSuccess) {
+    if (dX) cudaFree(dX);
+    ctx->err = "gusto_interpolate_trajectory: cudaMalloc failed"; return GUSTO_E_ALLOC;
+  }
+  const int total = (int)(B * nseg), grid = (total + 127) / 128;
+  switch (ctx->cfg.model_id) {
+    case DUBINS: interp_kernel<DUBINS><<<grid, 128, 0, ctx->stream>>>(ctx->ddesc, ctx->p, nstep, dX, dU); break;
+    case FREEFLYER_SE2: interp_kernel<FREEFLYER_SE2><<<grid, 128, 0, ctx->stream>>>(ctx->ddesc, ctx->p, nstep, dX, dU); break;
+    case ASTROBEE_SE3: interp_kernel<ASTROBEE_SE3><<<grid, 128, 0, ctx->stream>>>(ctx->ddesc, ctx->p, nstep, dX, dU); break;
+    default: interp_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, 128, 0, ctx->stream>>>(ctx->ddesc, ctx->p, nstep, dX, dU); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Xfull, dX, nX * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Ufull, dU, nU * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dX); cudaFree(dU);
+  if (e != cudaSuccess) { ctx->err = std::string("gusto_interpolate_trajectory: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
+  ctx->launches++;
   return GUSTO_OK;
 }
 

@@ -19,6 +19,7 @@ from .problems import BatchProblem
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GUSTO_B200_LIB", os.path.join(_HERE, "libgusto_b200.so"))
 EVAL_NOUT = 8
+CHECK_NOUT = 8
 SOLVE_NINFO = 8
 EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)
 SCP_STATUS = ("NA", "OK", "InaccurateModel", "ViolatesConstraints", "TrustRegionViolated", "SolverFailed", "Inactive")
@@ -86,6 +87,8 @@ def load_library(path=LIB_PATH):
     lib.gusto_accept.argtypes = [vp, _BP, _DP, _DP]
     lib.gusto_set_active.argtypes = [vp, _BP]
     lib.gusto_iterate.argtypes = [vp, _DP, _DP]
+    lib.gusto_check_trajectory.argtypes = [vp, _DP]
+    lib.gusto_interpolate_trajectory.argtypes = [vp, i32, _DP, _DP]
     lib.gusto_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.gusto_timer_start.argtypes = [vp]
     lib.gusto_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
@@ -212,6 +215,19 @@ class Engine:
         p, n = ctypes.c_void_p(), ctypes.c_int64()
         self._chk(self.lib.gusto_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
+
+    def check_trajectory(self):
+        """Post-processing scalars of the accepted trajectory, [B, CHECK_NOUT] (see include/gusto_b200.h)."""
+        out = np.empty((self.B, CHECK_NOUT))
+        self._chk(self.lib.gusto_check_trajectory(self._ctx, _dp(out)))
+        return out
+
+    def interpolate(self, nstep):
+        """interpolate_traj: RK4 upsampling of the accepted trajectory, nstep sub-steps per knot interval."""
+        nf = int(nstep) * (self.N - 1)
+        Xf = np.empty((self.B, nf + 1, self.nx)); Uf = np.empty((self.B, nf, self.nu))
+        self._chk(self.lib.gusto_interpolate_trajectory(self._ctx, int(nstep), _dp(Xf), _dp(Uf)))
+        return Xf, Uf
 
     def kernel_ms(self):
         ms = (ctypes.c_float * 4)()

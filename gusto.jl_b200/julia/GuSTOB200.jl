@@ -155,6 +155,12 @@ linearize!(ctx) = check(ctx, ccall((:gusto_linearize, LIB), Int32, (Ptr{Cvoid},)
 evaluate!(ctx, out) = GC.@preserve out check(ctx, ccall((:gusto_evaluate, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, out))
 iterate!(ctx, out, info) = GC.@preserve out info check(ctx, ccall((:gusto_iterate, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, out, info))
+# post-processing of the accepted trajectory (dynamics_constraint_satisfaction, verify_collision_free, interpolate_traj:
+# dynamics/astrobee_se3.jl:495-562).  out is B x 8 (see GUSTO_CHECK_NOUT in the header); Xfull / Ufull are
+# (x_dim, nstep*(N-1)+1, B) and (u_dim, nstep*(N-1), B).
+check_trajectory!(ctx, out) = GC.@preserve out check(ctx, ccall((:gusto_check_trajectory, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, out))
+interpolate_trajectory!(ctx, nstep::Integer, Xfull, Ufull) = GC.@preserve Xfull Ufull check(ctx, ccall((:gusto_interpolate_trajectory, LIB), Int32,
+  (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), ctx.ptr, Int32(nstep), Xfull, Ufull))
 accept!(ctx, acc::Vector{UInt8}, ω, Δ) = GC.@preserve acc ω Δ check(ctx, ccall((:gusto_accept, LIB), Int32,
     (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, acc, ω, Δ))
 

@@ -115,6 +115,18 @@ int32_t gusto_set_active(gusto_ctx* ctx, const uint8_t* active);
  * linearize -> solve -> evaluate, a single D2H copy of out[B*GUSTO_EVAL_NOUT] and info[B*GUSTO_SOLVE_NINFO]. */
 int32_t gusto_iterate(gusto_ctx* ctx, double* out, double* info);
 
+/* Post-processing of the ACCEPTED trajectory (SCPS.traj), SURVEY.md section 8(f):
+ * out[B*GUSTO_CHECK_NOUT] = { dynamics_constraint_satisfaction (dynamics/astrobee_se3.jl:529-540: sum_k |(X_{k+1}-X_k)/dt -
+ * f(X_k,U_k)|_1), max |X_{k+1} - X_k - h/2 (f_k + f_{k+1})| (nonlinear trapezoid defect), verify_collision_free (:542-562)
+ * as collision_free (0/1), first violating knot k (0-based, -1), its obstacle index (-1), its signed distance, the
+ * minimum signed distance over all (knot, obstacle) pairs, max_k |scale .* U_k| / bound over the control balls }. */
+#define GUSTO_CHECK_NOUT 8
+int32_t gusto_check_trajectory(gusto_ctx* ctx, double* out);
+/* interpolate_traj (dynamics/astrobee_se3.jl:495-527): RK4 upsampling of the accepted trajectory with nstep sub-steps per
+ * knot interval (the reference uses nstep = ceil(dt/dt_min), dt_min = 0.1) under the held control U_k.
+ * Xfull[B*(nstep*(N-1)+1)*n_x], Ufull[B*nstep*(N-1)*n_u]. */
+int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xfull, double* Ufull);
+
 /* Timing of the last call of each kernel on this context, in milliseconds (CUDA events on the context's stream):
  * ms[0] linearize, ms[1] solve, ms[2] evaluate, ms[3] accept. */
 int32_t gusto_last_kernel_ms(gusto_ctx* ctx, float* ms);

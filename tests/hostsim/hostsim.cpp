@@ -13,6 +13,7 @@
 #include "../../gusto.jl_b200/csrc/linearize.cuh"
 #include "../../gusto.jl_b200/csrc/ipm.cuh"
 #include "../../gusto.jl_b200/csrc/evaluate.cuh"
+#include "../../gusto.jl_b200/csrc/postprocess.cuh"
 
 using namespace gusto;
 
@@ -70,6 +71,46 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
     case FREEFLYER_SE2: run<FREEFLYER_SE2>(d, p, prm, stages, info, eval); break;
     case ASTROBEE_SE3: run<ASTROBEE_SE3>(d, p, prm, stages, info, eval); break;
     case ASTROBEE_SE3_MANIFOLD: run<ASTROBEE_SE3_MANIFOLD>(d, p, prm, stages, info, eval); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+// post-processing bodies (check_instance / interpolate_interval) on the trajectory (X, U)
+template <int M>
+static void run_post(const BatchDesc& d, BatchPtrs& p, const double* X, const double* U, int nstep, double* chk, double* Xfull, double* Ufull) {
+  using T = Traits<M>;
+  const int N = d.N;
+  double red[4];
+  for (int b = 0; b < d.B; ++b) {
+    const double* Xb = X + (size_t)b * N * T::NX;
+    const double* Ub = U + (size_t)b * N * T::NU;
+    check_instance<M>(d, p, b, Xb, Ub, chk + (size_t)b * CHECK_NOUT, red);
+    const size_t nf = (size_t)nstep * (N - 1);
+    for (int k = 0; k < N - 1; ++k)
+      interpolate_interval<M>(d, p, b, k, nstep, Xb, Ub, Xfull + (size_t)b * (nf + 1) * T::NX, Ufull + (size_t)b * nf * T::NU);
+  }
+}
+
+extern "C" int hostsim_postprocess(const gusto_config* cfg, const int32_t* obs_kind, const double* obs_a, const double* obs_b,
+                                   const double* tf, const double* X, const double* U, int nstep, double* chk, double* Xfull, double* Ufull) {
+  BatchDesc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = cfg->model_id; d.N = cfg->N; d.B = cfg->B; d.n_obs = cfg->model_id == DUBINS ? 0 : cfg->n_obs;
+  for (int i = 0; i < 16; ++i) d.rp[i] = cfg->robot_params[i];
+  for (int i = 0; i < 10; ++i) d.sp[i] = cfg->scp_params[i];
+  for (int i = 0; i < d.n_obs; ++i) {
+    d.obs_kind[i] = obs_kind[i];
+    for (int a = 0; a < 3; ++a) { d.obs_a[i][a] = obs_a[i * 3 + a]; d.obs_b[i][a] = obs_b[i * 3 + a]; }
+  }
+  BatchPtrs p;
+  memset(&p, 0, sizeof(p));
+  p.tf = tf;
+  switch (cfg->model_id) {
+    case DUBINS: run_post<DUBINS>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
+    case FREEFLYER_SE2: run_post<FREEFLYER_SE2>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
+    case ASTROBEE_SE3: run_post<ASTROBEE_SE3>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
+    case ASTROBEE_SE3_MANIFOLD: run_post<ASTROBEE_SE3_MANIFOLD>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
     default: return -1;
   }
   return 0;

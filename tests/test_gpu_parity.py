@@ -203,3 +203,40 @@ def test_solver_restarts_instead_of_failing(host):
         assert info[0, 0] == 0
         assert abs(info[0, 4] - obj) <= 2e-3 * abs(obj)
     e.close()
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES])
+def test_postprocessing_matches_oracle(engines, name):
+    """dynamics_constraint_satisfaction, verify_collision_free, interpolate_traj through the C ABI."""
+    from gusto_oracle import postprocess as pp
+    bp, eng = engines[name]
+    X0, U0 = bp.init_traj_straightline()
+    rng = np.random.default_rng(11)
+    X = X0 + 0.3 * rng.normal(size=X0.shape); U = U0 + 0.05 * rng.normal(size=U0.shape)
+    eng.set_trajectory(X, U)
+    chk = eng.check_trajectory()
+    nstep = pp.nstep_of(to_oracle(bp, 0), 0.5)
+    Xf, Uf = eng.interpolate(nstep)
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        assert abs(chk[b, 0] - pp.dynamics_constraint_satisfaction(p, X[b], U[b])) <= 1e-10 * max(1.0, chk[b, 0])
+        assert abs(chk[b, 1] - pp.trapezoid_defect(p, X[b], U[b])) <= 1e-12 * max(1.0, chk[b, 1])
+        ok, k, i, dist = pp.verify_collision_free(p, X[b])
+        assert bool(chk[b, 2]) == ok and int(chk[b, 3]) == k and int(chk[b, 4]) == i and abs(chk[b, 5] - dist) < 1e-12
+        assert abs(chk[b, 6] - pp.min_distance(p, X[b])) < 1e-12
+        Xo, Uo = pp.interpolate_traj(p, X[b], U[b], nstep)
+        assert np.max(np.abs(Xf[b] - Xo)) < 1e-11 and np.array_equal(Uf[b], Uo)
+
+
+def test_converged_trajectories_are_dynamically_consistent_and_collision_free(host):
+    """End of the pipeline at full size: after the batched SCP every astrobeeSE3 trajectory satisfies the nonlinear
+    trapezoid dynamics to the convergence threshold, respects the control bounds and keeps the ISS keep-out zones."""
+    bp = gb.problems.CONFIGS["astrobeeSE3"](B=1024)
+    e = host.Engine(bp, device=0)
+    S = host.solve_gusto_batch(e, max_iter=30)
+    chk = e.check_trajectory()
+    assert int(S.converged.sum()) == bp.B
+    assert chk[:, 1].max() < 1e-3            # nonlinear trapezoid defect of the accepted trajectory
+    assert np.all(chk[:, 2] == 1.0) and chk[:, 6].min() >= 0.0
+    assert chk[:, 7].max() <= 1.0 + 1e-6
+    e.close()

@@ -5,7 +5,7 @@ are covered by the -m gpu tests.  The host simulation is test infrastructure (te
 import numpy as np
 import pytest
 
-from util import gb, orc, to_oracle, hostsim_iterate
+from util import gb, orc, to_oracle, hostsim_iterate, hostsim_postprocess
 from gusto_oracle.scp import solve_subproblem, evaluate, solve_gusto
 from gusto_oracle.subproblem import linearize, obstacle_rows
 
@@ -78,3 +78,24 @@ def test_numerical_failure_is_reported_as_status_not_as_an_answer():
     X0[0, 3, 0] = np.nan
     hs = hostsim_iterate(bp, X0, U0, 1.0, 10.0, stages=3)
     assert hs["info"][0, 0] == 2
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_postprocessing_bodies_match_oracle(name, kw):
+    """dynamics_constraint_satisfaction / verify_collision_free / interpolate_traj kernel bodies."""
+    from gusto_oracle import postprocess as pp
+    bp = gb.problems.CONFIGS[name](**kw)
+    X0, U0 = bp.init_traj_straightline()
+    rng = np.random.default_rng(3)
+    X = X0 + 0.3 * rng.normal(size=X0.shape); U = U0 + 0.05 * rng.normal(size=U0.shape)   # pushed into obstacles on purpose
+    nstep = 4
+    chk, Xf, Uf = hostsim_postprocess(bp, X, U, nstep)
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        assert abs(chk[b, 0] - pp.dynamics_constraint_satisfaction(p, X[b], U[b])) <= 1e-10 * max(1.0, chk[b, 0])
+        assert abs(chk[b, 1] - pp.trapezoid_defect(p, X[b], U[b])) <= 1e-12 * max(1.0, chk[b, 1])
+        ok, k, i, dist = pp.verify_collision_free(p, X[b])
+        assert bool(chk[b, 2]) == ok and int(chk[b, 3]) == k and int(chk[b, 4]) == i and abs(chk[b, 5] - dist) < 1e-12
+        assert abs(chk[b, 6] - pp.min_distance(p, X[b])) < 1e-12
+        Xo, Uo = pp.interpolate_traj(p, X[b], U[b], nstep)
+        assert err(Xf[b], Xo) < 1e-12 and err(Uf[b], Uo) == 0.0

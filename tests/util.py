@@ -76,3 +76,19 @@ def hostsim_iterate(bp, Xp, Up, omega, delta, stages=7, Xn=None, Un=None, **ipm_
                                        dp(delta), dp(f), dp(A), dp(g), dp(rows), ctypes.c_int(stages), dp(info), dp(ev))
     assert rc == 0
     return dict(f=f, A=A, g=g, rows=rows[:, :, :no], Xn=Xn, Un=Un, info=info, eval=ev)
+
+
+def hostsim_postprocess(bp, X, U, nstep):
+    """check_instance / interpolate_interval kernel bodies on the host.  Returns (chk[B,8], Xfull, Ufull)."""
+    host = gb.engine()
+    cfg, (kind, a, b) = host.make_config(bp, 0)
+    B, N, nx, nu = bp.B, bp.N, bp.model.x_dim, bp.model.u_dim
+    dp = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    X = np.ascontiguousarray(X, dtype=np.float64); U = np.ascontiguousarray(U, dtype=np.float64)
+    tf = np.ascontiguousarray(bp.tf)
+    nf = nstep * (N - 1)
+    chk = np.zeros((B, 8)); Xf = np.zeros((B, nf + 1, nx)); Uf = np.zeros((B, nf, nu))
+    rc = hostsim_lib().hostsim_postprocess(ctypes.byref(cfg), kind.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), dp(a), dp(b),
+                                           dp(tf), dp(X), dp(U), ctypes.c_int(nstep), dp(chk), dp(Xf), dp(Uf))
+    assert rc == 0
+    return chk, Xf, Uf
