@@ -270,6 +270,7 @@ def main():
         Xh = torch.empty((B, N, nx), dtype=torch.float64).pin_memory(); Uh = torch.empty((B, N, nu), dtype=torch.float64).pin_memory()
         Xc = torch.empty((B, N, nx), dtype=torch.float64).pin_memory(); Uc = torch.empty((B, N, nu), dtype=torch.float64).pin_memory()
         Xh.numpy()[...] = X0; Uh.numpy()[...] = U0
+        hb = {"Xh": Xh, "Uh": Uh, "Xc": Xc, "Uc": Uc}
         om = torch.empty(B, dtype=torch.float64).pin_memory(); de = torch.empty(B, dtype=torch.float64).pin_memory()
         oute = torch.empty((B, host.EVAL_NOUT), dtype=torch.float64).pin_memory()
         infoe = torch.empty((B, host.SOLVE_NINFO), dtype=torch.float64).pin_memory()
@@ -277,17 +278,21 @@ def main():
 
         def e2e_step():
             if st8["k"] >= MAX_ITER:
-                Xh.numpy()[...] = X0; Uh.numpy()[...] = U0
+                hb["Xh"].numpy()[...] = X0; hb["Uh"].numpy()[...] = U0
                 st8.update(Delta=np.full(B, sp[0]), omega=np.full(B, sp[1]), iters=np.zeros(B, np.int64), conv=np.zeros(B), k=0)
             om.numpy()[...] = st8["omega"]; de.numpy()[...] = st8["Delta"]
-            eng.set_trajectory(Xh.numpy(), Uh.numpy())                 # H2D: this step's accepted trajectory
+            eng.set_trajectory(hb["Xh"].numpy(), hb["Uh"].numpy())     # H2D: this step's accepted trajectory
             eng.set_penalties(om.numpy(), de.numpy())                   # H2D
             eng.iterate(oute.numpy(), infoe.numpy())                    # kernels + D2H of the scalars
-            eng.get_candidate(Xc.numpy(), Uc.numpy())                   # D2H: the step's result
+            eng.get_candidate(hb["Xc"].numpy(), hb["Uc"].numpy())       # D2H: the step's result
             o = oute.numpy()
             s = host.gusto_update(o, infoe.numpy()[:, 0] == 0, active, st8["Delta"], st8["omega"], st8["iters"], st8["conv"], sp, force=True)
             acc = s["accept"]
-            Xh.numpy()[acc] = Xc.numpy()[acc]; Uh.numpy()[acc] = Uc.numpy()[acc]
+            if acc.all():                                               # every candidate accepted: swap the pinned buffers
+                hb["Xh"], hb["Xc"] = hb["Xc"], hb["Xh"]; hb["Uh"], hb["Uc"] = hb["Uc"], hb["Uh"]
+            elif acc.any():
+                np.copyto(hb["Xh"].numpy(), hb["Xc"].numpy(), where=acc[:, None, None])
+                np.copyto(hb["Uh"].numpy(), hb["Uc"].numpy(), where=acc[:, None, None])
             st8.update(Delta=s["Delta"], omega=s["omega"], iters=s["iterations"], conv=o[:, 0].copy(), k=st8["k"] + 1)
             allgather_status(~active)
 

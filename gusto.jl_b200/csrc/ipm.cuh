@@ -234,7 +234,9 @@ GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega)
     const double sa = t - c0;
     st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = 0.5 * omega; st[2] = t; st[3] = 0.5 * omega;
   } else {
-    st[0] = -c0 > 1e-2 ? -c0 : 1e-2; st[1] = 1e-2;
+    // hard rows: the oracle's s = max(-c, 1e-2), except that a strictly feasible row keeps its exact slack -- a BoxGoal of
+    // width 2e-4 (astrobeeSE3manifold notebook) would otherwise start 100x outside its own width on both sides
+    st[0] = -c0 > 1e-2 ? -c0 : (-c0 > 1e-6 ? -c0 : 1e-2); st[1] = 1e-2;
   }
 }
 
