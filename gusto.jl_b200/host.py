@@ -34,14 +34,34 @@ class GustoConfig(ctypes.Structure):
                 ("ipm_tol", ctypes.c_double), ("ipm_delta_p", ctypes.c_double), ("ipm_delta_d", ctypes.c_double)]
 
 
-def make_config(bp: BatchProblem, device=0, ipm_max_iter=0, ipm_nref=0, ipm_tol=0.0, ipm_delta_p=0.0, ipm_delta_d=0.0):
+NARROW_BOX_TOL = 1e-3
+
+
+def presolve_goals(goal_type, goal_lo, goal_hi, tol=NARROW_BOX_TOL):
+    """Host-side presolve: a BoxGoal coordinate whose width is below `tol` on every instance is handed to the solver as
+    a PointGoal at the box centre (|change| <= tol/2; the astrobeeSE3manifold notebook's BoxGoal(q +- 1e-4) moves by
+    <= 1e-4 and the subproblem objective by < 1e-9).  An interior-point method cannot centre a pair of inequalities
+    2e-4 apart while the other rows are O(1); with the pair as an equality the solves take the oracle's iteration
+    counts.  tol = 0 disables it.  Returns new (goal_type, goal_lo, goal_hi) arrays."""
+    goal_type = np.array(goal_type, copy=True); goal_lo = np.array(goal_lo, dtype=np.float64, copy=True)
+    goal_hi = np.array(goal_hi, dtype=np.float64, copy=True)
+    if tol > 0:
+        narrow = (goal_type == M.GOAL_BOX) & np.all(goal_hi - goal_lo < tol, axis=0)
+        mid = 0.5 * (goal_lo + goal_hi)
+        goal_type[narrow] = M.GOAL_POINT
+        goal_lo[:, narrow] = mid[:, narrow]; goal_hi[:, narrow] = mid[:, narrow]
+    return goal_type, goal_lo, goal_hi
+
+
+def make_config(bp: BatchProblem, device=0, ipm_max_iter=0, ipm_nref=0, ipm_tol=0.0, ipm_delta_p=0.0, ipm_delta_d=0.0,
+                narrow_box_tol=NARROW_BOX_TOL):
     kind, a, b = bp.obstacle_table()
     cfg = GustoConfig()
     cfg.model_id, cfg.N, cfg.B, cfg.n_obs = bp.model.model_id, bp.N, bp.B, int(kind.shape[0])
     cfg.robot_params[:] = list(bp.robot_params())
     cfg.scp_params[:] = list(bp.model.scp_params)
     gt = np.zeros(16, dtype=np.int32)
-    gt[:bp.model.x_dim] = bp.goal_type
+    gt[:bp.model.x_dim] = presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi, narrow_box_tol)[0]
     cfg.goal_type[:] = list(gt)
     cfg.device = device
     cfg.ipm_max_iter, cfg.ipm_nref = ipm_max_iter, ipm_nref
@@ -126,8 +146,9 @@ class Engine:
         rc = self.lib.gusto_create(ctypes.byref(cfg), kind.ctypes.data_as(_IP), _dp(a), _dp(b), ctypes.byref(self._ctx))
         if rc != 0:
             raise GustoError(f"gusto_create failed ({rc}): {self.lib.gusto_last_error(None).decode()}")
+        _, glo, ghi = presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi, ipm_opts.get("narrow_box_tol", NARROW_BOX_TOL))
         self._chk(self.lib.gusto_set_problems(self._ctx, _dp(np.ascontiguousarray(bp.x_init)),
-                                              _dp(np.ascontiguousarray(bp.goal_lo)), _dp(np.ascontiguousarray(bp.goal_hi)),
+                                              _dp(np.ascontiguousarray(glo)), _dp(np.ascontiguousarray(ghi)),
                                               _dp(np.ascontiguousarray(bp.tf))))
 
     def _chk(self, rc):

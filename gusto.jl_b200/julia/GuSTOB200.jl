@@ -107,6 +107,8 @@ function obstacle_table(env, model)
   return kinds, a, b
 end
 
+const NARROW_BOX_TOL = 1e-3
+
 # Final-time goals -> per-coordinate (type, lo, hi)   (goals.jl; registries e.g. astrobee_se3.jl:339-345)
 function flatten_goals(goal_set, x_dim, tf_guess)
   gtype = zeros(Int32, 16); lo = zeros(x_dim); hi = zeros(x_dim)
@@ -117,6 +119,13 @@ function flatten_goals(goal_set, x_dim, tf_guess)
       gtype[ind] .= GOAL_POINT; lo[ind] = goal.params.point; hi[ind] = goal.params.point
     else
       gtype[ind] .= GOAL_BOX; lo[ind] = goal.params.lower_bound; hi[ind] = goal.params.upper_bound
+    end
+  end
+  # presolve (host.py::presolve_goals): a BoxGoal coordinate narrower than NARROW_BOX_TOL is handed to the solver as a
+  # PointGoal at its centre (the astrobeeSE3manifold notebook's BoxGoal(q +- 1e-4) moves by <= 1e-4)
+  for i in 1:x_dim
+    if gtype[i] == GOAL_BOX && hi[i] - lo[i] < NARROW_BOX_TOL
+      gtype[i] = GOAL_POINT; lo[i] = hi[i] = 0.5 * (lo[i] + hi[i])
     end
   end
   return gtype, lo, hi

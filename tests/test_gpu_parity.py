@@ -72,8 +72,9 @@ def test_subproblem_and_evaluation_match_oracle(engines, name, omega):
         Xs, Us, obj, st, lin, rows, _ = solve_subproblem(p, X0[b], U0[b], omega, sp[0], toggle, sp[3])
         assert st == "OPTIMAL"
         assert abs(info[b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
-        xtol = 1e-3 if name == "astrobeeSE3manifold" else 1e-4     # manifold: attitude is weakly determined by the cost
-        assert np.max(np.abs(Xn[b] - Xs)) < xtol and np.max(np.abs(Un[b] - Us)) < 1e-5
+        # manifold: attitude weakly determined by the cost; BoxGoal(q +- 1e-4) presolved to a PointGoal (host.presolve_goals)
+        xtol, utol = (1e-3, 3e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
+        assert np.max(np.abs(Xn[b] - Xs)) < xtol and np.max(np.abs(Un[b] - Us)) < utol
         # evaluation scalars on the GPU's own candidate
         ev = evaluate(p, Xn[b], Un[b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
         assert abs(out[b, 0] - ev["conv"]) <= 1e-12 * max(1.0, ev["conv"])

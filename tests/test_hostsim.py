@@ -49,8 +49,10 @@ def test_solve_and_evaluate_bodies_match_oracle(name, kw, omega):
         assert st == "OPTIMAL" and hs["info"][b, 0] == 0
         assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
         assert abs(hs["info"][b, 1] - r.iters) <= 3          # same algorithm: Newton iteration counts agree
-        xtol = 1e-3 if name == "astrobeeSE3manifold" else 1e-4
-        assert err(hs["Xn"][b], Xs) < xtol and err(hs["Un"][b], Us) < 1e-5
+        # manifold: the attitude is weakly determined by the cost, and the host presolve hands the BoxGoal(q +- 1e-4) to
+        # the solver as a PointGoal at its centre (host.presolve_goals) while the oracle keeps the box: |dU| <= 3e-5
+        xtol, utol = (1e-3, 3e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
+        assert err(hs["Xn"][b], Xs) < xtol and err(hs["Un"][b], Us) < utol
         ev = evaluate(p, hs["Xn"][b], hs["Un"][b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
         o = hs["eval"][b]
         assert abs(o[0] - ev["conv"]) < 1e-12 and bool(o[1]) == ev["tr_ok"] and bool(o[2]) == ev["ineq_ok"]

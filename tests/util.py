@@ -69,7 +69,8 @@ def hostsim_iterate(bp, Xp, Up, omega, delta, stages=7, Xn=None, Un=None, **ipm_
     delta = np.ascontiguousarray(np.broadcast_to(delta, (B,)), dtype=np.float64).copy()
     f = np.zeros((B, N, nx)); A = np.zeros((B, N, nx, nx)); g = np.zeros((B, N, nx)); rows = np.zeros((B, N, max(no, 1), 5))
     info = np.zeros((B, 8)); ev = np.zeros((B, 8))
-    x_init = np.ascontiguousarray(bp.x_init); glo = np.ascontiguousarray(bp.goal_lo); ghi = np.ascontiguousarray(bp.goal_hi)
+    _, glo, ghi = host.presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi)     # what Engine hands to the solver
+    x_init = np.ascontiguousarray(bp.x_init); glo = np.ascontiguousarray(glo); ghi = np.ascontiguousarray(ghi)
     tf = np.ascontiguousarray(bp.tf)
     rc = hostsim_lib().hostsim_iterate(ctypes.byref(cfg), kind.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), dp(a), dp(b),
                                        dp(x_init), dp(glo), dp(ghi), dp(tf), dp(Xp), dp(Up), dp(Xn), dp(Un), dp(omega),

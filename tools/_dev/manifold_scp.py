@@ -7,6 +7,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "astrobeeSE3manifold"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 bp = pkg.problems.CONFIGS[name](B=B)
 opts = {}
+if os.environ.get('NARROW_BOX_AS_POINT'):
+    w = bp.goal_hi - bp.goal_lo
+    narrow = (bp.goal_type == 2) & np.all(w < 1e-3, axis=0)
+    mid = 0.5 * (bp.goal_lo + bp.goal_hi)
+    bp.goal_type = np.where(narrow, 1, bp.goal_type).astype(bp.goal_type.dtype)
+    bp.goal_lo = np.where(narrow[None, :], mid, bp.goal_lo); bp.goal_hi = np.where(narrow[None, :], mid, bp.goal_hi)
+    print('narrow boxes -> point goals:', narrow)
 if len(sys.argv) > 3: opts['ipm_delta_p'] = float(sys.argv[3])
 if len(sys.argv) > 4: opts['ipm_nref'] = int(sys.argv[4])
 if len(sys.argv) > 5: opts['ipm_tol'] = float(sys.argv[5])
