@@ -230,6 +230,8 @@ GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega)
   for (int i = 0; i < SLOT_W; ++i) st[i] = 0.0;
   if (!valid) return;
   if (has_t) {
+    // interior start of the penalty slack: one unit inside, as the oracle.  (0.3 - 0.5 would save one Newton iteration
+    // of nine on the headline workload but costs restarts on freeflyerSE2 at omega = 25: measured, rejected.)
     const double t = (c0 > 0 ? c0 : 0.0) + 1.0;
     const double sa = t - c0;
     st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = 0.5 * omega; st[2] = t; st[3] = 0.5 * omega;
