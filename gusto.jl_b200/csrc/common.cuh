@@ -78,6 +78,41 @@ __device__ __forceinline__ double g_rcp(double x) { return __drcp_rn(x); }
 __device__ __forceinline__ double g_rsqrt(double x) { return rsqrt(x); }
 #endif
 
+// TMA (cp.async.bulk) 1-D global -> shared copies completing on an mbarrier, and the mbarrier primitives they need.
+// Host simulation: the copy is immediate and the barrier calls are no-ops.
+#ifdef GUSTO_HOSTSIM
+inline void g_mbar_init(unsigned long long*, unsigned) {}
+inline void g_mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void g_tma_bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { for (unsigned i = 0; i < bytes / 8; ++i) dst[i] = src[i]; }
+inline void g_mbar_wait(unsigned long long*, unsigned) {}
+inline void g_fence_proxy_async() {}
+#else
+__device__ __forceinline__ void g_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void g_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_tma_bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(unsigned long long* bar, unsigned parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+#endif
+
 // Address-space hint: pointers that travel through the per-instance context struct come back as generic pointers;
 // telling the compiler they are shared turns LD.E/ST.E (64-bit generic path) back into LDS/STS.
 #ifdef GUSTO_HOSTSIM

@@ -16,8 +16,8 @@
 //   * the equality rows (init, trapezoid dynamics, point goal) are block-bidiagonal, so the Schur complement
 //     S = Aeq (H + dp I)^-1 Aeq' is block-tridiagonal with N+1 blocks of NX x NX.  It is factorised as a block
 //     L D L' with explicit D_j^-1 (Gauss-Jordan in shared memory on one warp while the other warp prefetches the
-//     next block row), so each solve is two chains of N dependent NX x NX mat-vecs streamed through a cp.async
-//     ring plus one fully parallel D^-1 pass;
+//     next block row), so each solve is two chains of N dependent NX x NX mat-vecs streamed through a TMA
+//     (cp.async.bulk + mbarrier) ring plus one fully parallel D^-1 pass;
 //   * Newton directions are recovered with `nref` steps of iterative refinement against the unregularised KKT
 //     matrix (H alone is only positive SEMI-definite: the cost has no state term).
 // A first-order splitting (ADMM, prototyped in tools/admm_proto.py) was rejected: GuSTO's accept test compares
@@ -100,7 +100,7 @@ template <int M> struct IpmLayout {
   }
   GHD static int work_doubles(int N) {      // dz | sy | ring, also the 8 factorisation tiles
     const int ne = (int)rnd((size_t)(N + 1) * NX);
-    const int ring = RING_STAGES * TILE > ne ? RING_STAGES * TILE : ne;
+    const int ring = RING_STAGES * GT > ne ? RING_STAGES * GT : ne;      // ring stages are plain copies of the global tiles
     const int w = (int)rnd((size_t)N * NV) + ne + ring, f = FAC_TILES * TILE + 2 * KS + 2 * NX + 4;
     return (w > f ? w : f) + 2;
   }
@@ -133,6 +133,8 @@ template <int M> struct IpmCtx {
   // shared
   double *z, *dz, *sy, *ring, *red;
   int* seg;
+  mutable unsigned long long ring_bar[RING_STAGES];   // one mbarrier per ring stage (TMA completion)
+  mutable unsigned ring_o;                             // tiles fetched so far (stage = o % S, wait parity = (o / S) & 1)
   mutable long long prof[5];      // thread-0 cycle counters: schur rows, factor sweep, forward chain, middle pass, backward chain
   unsigned char* tab;     // [2][NX(NX+1)/2]: row / column of packed-lower entry t; then [2][NLT]: row / group of lower task
 };
@@ -1060,32 +1062,17 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
 
 // ------------------------------------------------------------------------------------------------ KKT solves
 // cp.async ring over the V tiles of the factor (global -> shared, RING_STAGES deep, 16-byte copies), warp 0 only.
-struct RingLane { int so[3], dof[3]; };       // per-lane source / destination offsets of its <= 3 16-byte chunks of a tile
-template <int M> GDEV void ring_lane_init(RingLane& rl) {
+// TMA ring over the V tiles of the factor: one elected lane issues ONE bulk copy (cp.async.bulk, 1-D, GT*8 bytes) per
+// tile into stage o % S and the copy completes on that stage's mbarrier; the consumers spin on the barrier's phase
+// parity (o / S) & 1.  `o` counts tiles over the whole kernel (fetch order == consume order), so the barriers are
+// initialised once.
+template <int M> GDEV void ring_fetch(const IpmCtx<M>& c, const double* fac, double* ring, int N, int j, unsigned o) {
   using L = IpmLayout<M>;
-  constexpr int HC = L::GLD / 2;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int it = G_LANE + r * G_NLANE;
-    const int i = it / HC, m = 2 * (it - i * HC);
-    rl.so[r] = it < L::NX * HC ? i * L::GLD + m : -1;
-    rl.dof[r] = i * L::LDT + m;
+  if (j >= 1 && j <= N && G_LANE == 0) {
+    unsigned long long* bar = &c.ring_bar[o % RING_STAGES];
+    g_mbar_expect_tx(bar, (unsigned)(L::GT * sizeof(double)));
+    g_tma_bulk_g2s(ring + (o % RING_STAGES) * L::GT, fac + (size_t)(2 * j + 1) * L::GT, (unsigned)(L::GT * sizeof(double)), bar);
   }
-}
-template <int M> GDEV void ring_fetch(const double* fac, double* ring, int N, int j, const RingLane& rl) {
-  using L = IpmLayout<M>;
-  if (j >= 1 && j <= N) {
-    const double* src = fac + (size_t)(2 * j + 1) * L::GT;
-    double* dst = ring + (j % RING_STAGES) * L::TILE;
-#ifdef GUSTO_HOSTSIM
-    constexpr int HC = L::GLD / 2;
-    for (int it = 0; it < L::NX * HC; ++it) { const int i = it / HC, m = 2 * (it - i * HC); g_cp_async16(dst + i * L::LDT + m, src + i * L::GLD + m); }
-#else
-#pragma unroll
-    for (int r = 0; r < 3; ++r) if (rl.so[r] >= 0) g_cp_async16(dst + rl.dof[r], src + rl.so[r]);
-#endif
-  }
-  g_cp_async_commit();
 }
 
 // Block-tridiagonal solve  S nu = b  (sy holds b on entry, nu on exit):
@@ -1099,28 +1086,30 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   const double* const fac = c.fac;
   G_ASSUME_SHARED(y);
   G_ASSUME_SHARED(ring);
-  RingLane rl;
-  ring_lane_init<M>(rl);
+  unsigned o = c.ring_o;                          // next tile to consume; of = next tile to fetch
   long long tc0 = g_clock();
   if (G_TID < G_WARP) {
-    for (int jj = 1; jj < S; ++jj) ring_fetch<M>(fac, ring, N, jj, rl);
+    unsigned of = o;
+    g_fence_proxy_async();                        // the ring region was last written by ordinary stores (sweep tiles)
+    for (int jj = 1; jj < S; ++jj) if (jj <= N) ring_fetch<M>(c, fac, ring, N, jj, of++);
     for (int j = 1; j <= N; ++j) {
-      g_cp_async_wait_group<S - 2>();             // tile j has landed (at most S-2 younger groups in flight)
-      G_SYNCWARP();                               // ... for every lane; everyone is done with tile j-1
-      ring_fetch<M>(fac, ring, N, j + S - 1, rl);                // reuses the slot of tile j-1
-      const double* R = ring + (j % S) * L::TILE;
+      g_mbar_wait(&c.ring_bar[o % S], (o / S) & 1);               // tile j has landed
+      G_SYNCWARP();                               // everyone is done with tile j-1: its stage can be refilled
+      if (j + S - 1 <= N) ring_fetch<M>(c, fac, ring, N, j + S - 1, of++);
+      const double* R = ring + (o % S) * L::GT;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
 #pragma unroll
         for (int m = 0; m < GLD; m += 2) {
-          const g_d2 rv = g_ld2(R + i * LDT + m);
+          const g_d2 rv = g_ld2(R + i * GLD + m);
           a0 -= rv.x * y[(j - 1) * NX + m];
           if (m + 1 < NX) a1 -= rv.y * y[(j - 1) * NX + m + 1];
         }
         y[j * NX + i] = a0 + a1;
       }
+      ++o;
     }
-    g_cp_async_wait();
+    G_SYNCWARP();
   }
   G_SYNC();
   if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[2] += g_clock() - tc0;
@@ -1155,21 +1144,25 @@ template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
   tc0 = g_clock();
   if (G_TID < G_WARP) {
     // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
-    for (int jj = 0; jj < S - 1; ++jj) ring_fetch<M>(fac, ring, N, N - jj, rl);
+    unsigned of = o;
+    g_fence_proxy_async();                        // the middle pass wrote the ring region with ordinary stores
+    for (int jj = 0; jj < S - 1; ++jj) if (N - jj >= 1) ring_fetch<M>(c, fac, ring, N, N - jj, of++);
     for (int j = N - 1; j >= 0; --j) {
-      g_cp_async_wait_group<S - 2>();
+      g_mbar_wait(&c.ring_bar[o % S], (o / S) & 1);
       G_SYNCWARP();
-      ring_fetch<M>(fac, ring, N, j + 1 - (S - 1), rl);          // reuses the slot of tile j+2
-      const double* R = ring + ((j + 1) % S) * L::TILE;
+      if (j + 1 - (S - 1) >= 1) ring_fetch<M>(c, fac, ring, N, j + 1 - (S - 1), of++);
+      const double* R = ring + (o % S) * L::GT;
       G_W0_FOR(i, NX) {
         double a0 = y[j * NX + i], a1 = 0.0;
 #pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * LDT + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * LDT + i] * y[(j + 1) * NX + m + 1]; }
-        if (NX & 1) a0 -= R[(NX - 1) * LDT + i] * y[(j + 1) * NX + NX - 1];
+        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * GLD + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * GLD + i] * y[(j + 1) * NX + m + 1]; }
+        if (NX & 1) a0 -= R[(NX - 1) * GLD + i] * y[(j + 1) * NX + NX - 1];
         y[j * NX + i] = a0 + a1;
       }
+      ++o;
     }
-    g_cp_async_wait();
+    G_SYNCWARP();
+    if (G_TID == 0) c.ring_o = o;
   }
   G_SYNC();
   if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[4] += g_clock() - tc0;
@@ -1414,6 +1407,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
     c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
     for (int i = 0; i < 5; ++i) c.prof[i] = 0;
+    for (int i = 0; i < RING_STAGES; ++i) g_mbar_init(&c.ring_bar[i], 1);
+    c.ring_o = 0;
     c.floor_ = 0.0;
     unsigned char* t2 = c.tab + NX * (NX + 1);
     int n = 0;
