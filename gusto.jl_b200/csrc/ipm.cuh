@@ -63,7 +63,10 @@ enum : int { IPM_OPTIMAL = 0, IPM_ITERATION_LIMIT = 1, IPM_NUMERICAL = 2 };
 constexpr int SLOT_W = 6;     // s, lam, t, lamb, pa (ds*dlam of the predictor), pb (dt*dlamb of the predictor)
 constexpr int OROW_W = 5;     // compacted obstacle row: nhat[3], off, knot
 constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cycles: assemble+slots, factorize, kkt solves
-constexpr int RING_STAGES = 8;
+#ifndef GUSTO_RING_STAGES
+#define GUSTO_RING_STAGES 8
+#endif
+constexpr int RING_STAGES = GUSTO_RING_STAGES;
 
 GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
@@ -1061,7 +1064,6 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
 }
 
 // ------------------------------------------------------------------------------------------------ KKT solves
-// cp.async ring over the V tiles of the factor (global -> shared, RING_STAGES deep, 16-byte copies), warp 0 only.
 // TMA ring over the V tiles of the factor: one elected lane issues ONE bulk copy (cp.async.bulk, 1-D, GT*8 bytes) per
 // tile into stage o % S and the copy completes on that stage's mbarrier; the consumers spin on the barrier's phase
 // parity (o / S) & 1.  `o` counts tiles over the whole kernel (fetch order == consume order), so the barriers are
