@@ -114,3 +114,20 @@ def test_two_rank_gloo_run_equals_single_rank_run(tmp_path):
         subprocess.check_call(cmd, env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=600)
         outs[world] = np.concatenate([np.load(d / f"rank{r}_of{world}.npy") for r in range(world)])
     assert np.array_equal(outs[1], outs[2])
+
+
+def test_narrow_box_goals_are_presolved_to_point_goals(host):
+    """host.presolve_goals: BoxGoal(q +- 1e-4) of the astrobeeSE3manifold notebook -> PointGoal at the centre; wide
+    boxes, point goals and free coordinates are untouched; tol = 0 disables it."""
+    gt = np.array([1, 2, 2, 0], np.int32)
+    lo = np.array([[1.0, 0.5 - 1e-4, -1.0, 0.0], [2.0, 0.7 - 1e-4, -2.0, 0.0]])
+    hi = np.array([[1.0, 0.5 + 1e-4, 1.0, 0.0], [2.0, 0.7 + 1e-4, 2.0, 0.0]])
+    t2, l2, h2 = host.presolve_goals(gt, lo, hi)
+    assert list(t2) == [1, 1, 2, 0]
+    assert np.allclose(l2[:, 1], [0.5, 0.7]) and np.array_equal(l2[:, 1], h2[:, 1])
+    assert np.array_equal(l2[:, [0, 2, 3]], lo[:, [0, 2, 3]]) and np.array_equal(h2[:, [0, 2, 3]], hi[:, [0, 2, 3]])
+    t3, l3, h3 = host.presolve_goals(gt, lo, hi, tol=0.0)
+    assert np.array_equal(t3, gt) and np.array_equal(l3, lo) and np.array_equal(h3, hi)
+    # a box that is narrow on one instance only stays a box (the goal type is shared by the batch)
+    hi2 = hi.copy(); hi2[1, 1] = 0.9
+    assert list(host.presolve_goals(gt, lo, hi2)[0]) == [1, 2, 2, 0]
