@@ -1227,6 +1227,26 @@ template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* 
 template <int M> GDEV_NOINLINE void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
   kkt_solve<M>(c, c.r, false, nref > 0);
   for (int it_ref = 1; it_ref <= nref; ++it_ref) kkt_solve<M>(c, c.res, true, it_ref < nref);
+#if defined(GUSTO_HOSTSIM) && defined(GUSTO_DEBUG_KKT)
+  {   // true residuals of the direction against the exact KKT matrix
+    using L = IpmLayout<M>;
+    constexpr int NX = L::NX, NV = L::NV;
+    double rp = 0, rd = 0, np_ = 0, nd = 0;
+    for (int k = 0; k < c.N; ++k) {
+      double at[NV], hd[NV], dk[NV];
+      aeqT_knot<M>(c, c.dnu, k, at);
+      for (int i = 0; i < NV; ++i) dk[i] = c.dz[k * NV + i];
+      apply_H<M>(c, k, dk, hd);
+      for (int i = 0; i < NV; ++i) { rp = fmax(rp, fabs(c.r[k * NV + i] - hd[i] - at[i])); np_ = fmax(np_, fabs(c.r[k * NV + i])); }
+    }
+    for (int j = 0; j <= c.N; ++j) {
+      double v[NX];
+      aeq_row<M>(c, c.dz, j, v);
+      for (int i = 0; i < NX; ++i) { rd = fmax(rd, fabs(c.rnu[j * NX + i] - v[i])); nd = fmax(nd, fabs(c.rnu[j * NX + i])); }
+    }
+    printf("    kkt(nref=%d): |r - H dz - A'dnu| = %.2e (|r| %.2e)   |rnu - A dz| = %.2e (|rnu| %.2e)\n", nref, rp, np_, rd, nd);
+  }
+#endif
 }
 
 // --------------------------------------------------------------------------------------------- slot passes
