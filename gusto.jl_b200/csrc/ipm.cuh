@@ -807,34 +807,28 @@ template <int M> GDEV void schur_emit_last(const IpmCtx<M>& c, const SchurTiles&
     Sdd[i * LDT + q] = dd;
   }
 }
-// Stage the record of knot k (P, w, Theta, coef, A entries) from global memory: the loads are issued into registers first
-// (schur_stage_load) and stored after the producer's arithmetic (schur_stage_store), which hides their latency.
+// Stage the record of knot k (P, w, Theta, coef, A entries) from global memory into the idle half of the double-buffered
+// staging area with 8-byte asynchronous copies (LDGSTS): nothing passes through registers (a register-staged version
+// was spilled to local memory by ptxas and serialised three DRAM latencies on the producer warp), and the producer only
+// waits for the copies (schur_stage_wait) after its arithmetic, right before the step's barrier.
+template <int M> GDEV const double* schur_stage_ptr(const double* kd, const double* Ak, int t) {
+  using L = IpmLayout<M>;
+  if (t < L::KS_TH) return kd + L::KD_P + t;                      // P | w are contiguous in the record
+  if (t < L::KS_COEF) return kd + L::KD_TH + t - L::KS_TH;
+  if (t == L::KS_COEF) return kd + L::KD_COEF;
+  return Ak + (t - L::KS_A);
+}
 template <int M> GDEV double schur_stage_src(const double* kd, const double* Ak, int t) {
   using L = IpmLayout<M>;
-  if (t < L::KS_TH) return kd[L::KD_P + t];                       // P | w are contiguous in the record
-  if (t < L::KS_COEF) return kd[L::KD_TH + t - L::KS_TH];
-  if (t == L::KS_COEF) return kd[L::KD_COEF];
-  if (t < L::KS_A + L::ANZ) return Ak[t - L::KS_A];
-  return 0.0;
+  return t < L::KS_A + L::ANZ ? *schur_stage_ptr<M>(kd, Ak, t) : 0.0;
 }
-template <int M> GDEV void schur_stage_load(const IpmCtx<M>& c, int k, double* pre, int t0, int nt) {
-#ifndef GUSTO_HOSTSIM
+template <int M> GDEV void schur_stage_async(const IpmCtx<M>& c, int k, double* ks, int t0, int nt) {
   using L = IpmLayout<M>;
   const double* kd = c.kd + (size_t)k * L::KDW;
   const double* Ak = c.Ac + (size_t)k * L::ANZ;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) { const int t = G_TID - t0 + r * nt; pre[r] = t < L::KS ? schur_stage_src<M>(kd, Ak, t) : 0.0; }
-#endif
+  for (int t = G_TID - t0; t < L::KS_A + L::ANZ; t += nt) g_cp_async8(ks + t, schur_stage_ptr<M>(kd, Ak, t));   // the padding stays 0
 }
-template <int M> GDEV void schur_stage_store(const IpmCtx<M>& c, int k, double* ks, const double* pre, int t0, int nt) {
-  using L = IpmLayout<M>;
-#ifdef GUSTO_HOSTSIM
-  for (int t = 0; t < L::KS; ++t) ks[t] = schur_stage_src<M>(c.kd + (size_t)k * L::KDW, c.Ac + (size_t)k * L::ANZ, t);
-#else
-#pragma unroll
-  for (int r = 0; r < 4; ++r) { const int t = G_TID - t0 + r * nt; if (t < L::KS) ks[t] = pre[r]; }
-#endif
-}
+GDEV void schur_stage_wait() { g_cp_async_wait(); }
 
 // acc[c] = sum_m X[i][m] * Y[q0 + c][m]  over one shared-memory tile row pair (rows are LDT apart, MLEN = GLD terms)
 template <int M> GDEV void abt_task(const double* X, const double* Y, int i, int q0, double* acc) {
@@ -996,15 +990,14 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
     if (producer) {
       const int kn = j + 1;
       if (kn <= N - 1) {
-        double pre[4];
         const double* ks = ksb + (kn & 1) * L::KS;
-        if (kn + 1 <= N - 1) schur_stage_load<M>(c, kn + 1, pre, pf0, npf);
+        if (kn + 1 <= N - 1) schur_stage_async<M>(c, kn + 1, ksb + ((kn + 1) & 1) * L::KS, pf0, npf);
         schur_build<M>(c, ks, st, pf0, npf);
         G_SYNCWARP();
         schur_product<M>(st.Ah, st.Phi, st.Y, pf0, npf);
         G_SYNCWARP();
         schur_product<M>(st.Y, st.Ah, st.Z, pf0, npf);
-        if (kn + 1 <= N - 1) schur_stage_store<M>(c, kn + 1, ksb + ((kn + 1) & 1) * L::KS, pre, pf0, npf);
+        schur_stage_wait();
       }
     }
     G_SYNC();
