@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/gusto_b200.h"
 #include "common.cuh"
@@ -13,6 +14,7 @@
 #include "ipm.cuh"
 #include "evaluate.cuh"
 #include "postprocess.cuh"
+#include "shooting.cuh"
 
 using namespace gusto;
 
@@ -140,6 +142,18 @@ __global__ void __launch_bounds__(128) interp_kernel(const BatchDesc* __restrict
                           Xfull + (size_t)b * (nf + 1) * T::NX, Ufull + (size_t)b * nf * T::NU);
 }
 
+// K7.  Grid: B CTAs of ONE warp: indirect shooting (Levenberg-Marquardt on the initial costate), lanes = Jacobian columns.
+template <int M>
+__global__ void __launch_bounds__(32) shoot_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, const double* p0, const double* x_goal,
+                                                   int nsub, int max_iter, double ftol, double* Xs, double* Us, double* Ps, double* out) {
+  using T = Traits<M>;
+  __shared__ double sm[ShootLayout<M>::TOTAL];
+  const int b = blockIdx.x;
+  const size_t N = dp->N;
+  shoot_instance<M>(*dp, p, b, p0 + (size_t)b * T::NX, x_goal + (size_t)b * T::NX, nsub, max_iter, ftol, sm,
+                    Xs + (size_t)b * N * T::NX, Us + (size_t)b * N * T::NU, Ps + (size_t)b * N * T::NX, out + (size_t)b * SHOOT_NOUT);
+}
+
 // accept: candidate -> accepted trajectory for flagged instances; install next omega / Delta.
 __global__ void accept_kernel(BatchPtrs p, int N, int nx, int nu, const uint8_t* accept, const double* omega,
                               const double* delta) {
@@ -164,6 +178,7 @@ struct gusto_ctx {
   BatchPtrs p;
   double *d_tf = nullptr, *d_xinit = nullptr, *d_glo = nullptr, *d_ghi = nullptr;
   double *d_scratch = nullptr, *d_info = nullptr, *d_eval = nullptr, *d_omega_in = nullptr, *d_delta_in = nullptr;
+  double *d_dual = nullptr, *d_Xs = nullptr, *d_Us = nullptr, *d_Ps = nullptr, *d_p0 = nullptr, *d_xgoal = nullptr, *d_shoot = nullptr;
   uint8_t* d_accept = nullptr;
   uint8_t* d_active = nullptr;
   size_t scratch_stride = 0;
@@ -278,11 +293,12 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   ok = ok && alloc(&p.f, B * N * nx) && alloc(&p.A, B * N * nx * nx) && alloc(&p.g, B * N * nx) && alloc(&p.rows, B * N * no * 5);
   ctx->scratch_stride = scratch_doubles_of(cfg->model_id, (int)N, h.n_obs);
   ok = ok && alloc(&ctx->d_scratch, B * ctx->scratch_stride);
-  ok = ok && alloc(&ctx->d_info, B * IPM_NINFO) && alloc(&ctx->d_eval, B * EVAL_NOUT);
+  ok = ok && alloc(&ctx->d_info, B * IPM_NINFO) && alloc(&ctx->d_eval, B * EVAL_NOUT) && alloc(&ctx->d_dual, B * nx);
   ok = ok && cudaMalloc((void**)&ctx->d_accept, B) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&ctx->d_active, B) == cudaSuccess && cudaMemset(ctx->d_active, 1, B) == cudaSuccess;
   if (!ok) { if (ctx->err.empty()) ctx->err = std::string("gusto_create: ") + cudaGetErrorString(cudaGetLastError()); return fail(GUSTO_E_ALLOC); }
   p.active = ctx->d_active;
+  p.dual = ctx->d_dual;
   p.tf = ctx->d_tf; p.x_init = ctx->d_xinit; p.goal_lo = ctx->d_glo; p.goal_hi = ctx->d_ghi;
   // initial penalties: omega0, Delta0
   {
@@ -312,7 +328,8 @@ int32_t gusto_destroy(gusto_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   BatchPtrs& p = ctx->p;
   void* ptrs[] = {ctx->ddesc, ctx->d_tf, ctx->d_xinit, ctx->d_glo, ctx->d_ghi, p.Xp, p.Up, p.Xn, p.Un, p.omega, p.delta,
-                  ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active};
+                  ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active,
+                  ctx->d_dual, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_p0, ctx->d_xgoal, ctx->d_shoot};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; ++i) if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
@@ -577,6 +594,71 @@ int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xful
   cudaFree(dX); cudaFree(dU);
   if (e != cudaSuccess) { ctx->err = std::string("gusto_interpolate_trajectory: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
   ctx->launches++;
+  return GUSTO_OK;
+}
+
+int32_t gusto_get_duals(gusto_ctx* ctx, double* dual) {
+  NEED(dual);
+  CK(cudaSetDevice(ctx->cfg.device));
+  D2H(dual, ctx->d_dual, (size_t)ctx->cfg.B * ctx->nx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int32_t nsub, int32_t max_iter, double ftol, double* out) {
+  NEED(out);
+  const int model = ctx->cfg.model_id;
+  if (model != DUBINS && model != ASTROBEE_SE3_MANIFOLD) {
+    ctx->err = "gusto_shoot: the reference defines shooting_ode! only for DubinsCar and AstrobeeSE3Manifold"; return GUSTO_E_ARG;
+  }
+  if (nsub < 1 || max_iter < 0 || !(ftol > 0.0)) { ctx->err = "gusto_shoot: need nsub >= 1, max_iter >= 0, ftol > 0"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B, N = ctx->cfg.N, nx = ctx->nx, nu = ctx->nu;
+  if (!ctx->d_Xs) {    // SS.traj starts as the trajectory held by the context at the first attempt (traj_opt.jl:18)
+    bool ok = cudaMalloc((void**)&ctx->d_Xs, B * N * nx * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_Us, B * N * nu * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_Ps, B * N * nx * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_p0, B * nx * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_xgoal, B * nx * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_shoot, B * SHOOT_NOUT * sizeof(double)) == cudaSuccess;
+    if (!ok) { ctx->err = "gusto_shoot: cudaMalloc failed"; return GUSTO_E_ALLOC; }
+    CK(cudaMemcpyAsync(ctx->d_Xs, ctx->p.Xp, B * N * nx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_Us, ctx->p.Up, B * N * nu * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_Ps, 0, B * N * nx * sizeof(double), ctx->stream));
+  }
+  if (p0) H2D(ctx->d_p0, p0, B * nx);
+  else CK(cudaMemcpyAsync(ctx->d_p0, ctx->d_dual, B * nx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (x_goal) H2D(ctx->d_xgoal, x_goal, B * nx);
+  else {               // ShootingProblem (types.jl:219-226): centre of the goal sets
+    std::vector<double> lo(B * nx), hi(B * nx);
+    D2H(lo.data(), ctx->d_glo, B * nx);
+    D2H(hi.data(), ctx->d_ghi, B * nx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < B * nx; ++i) lo[i] = 0.5 * (lo[i] + hi[i]);
+    H2D(ctx->d_xgoal, lo.data(), B * nx);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  const int grid = (int)B;
+  if (model == DUBINS)
+    shoot_kernel<DUBINS><<<grid, 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
+  else
+    shoot_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  D2H(out, ctx->d_shoot, B * SHOOT_NOUT);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_get_shooting_trajectory(gusto_ctx* ctx, double* X, double* U, double* P) {
+  NEED(X || U || P);
+  if (!ctx->d_Xs) { ctx->err = "gusto_get_shooting_trajectory: gusto_shoot has not been called"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B, N = ctx->cfg.N;
+  if (X) D2H(X, ctx->d_Xs, B * N * ctx->nx);
+  if (U) D2H(U, ctx->d_Us, B * N * ctx->nu);
+  if (P) D2H(P, ctx->d_Ps, B * N * ctx->nx);
+  CK(cudaStreamSynchronize(ctx->stream));
   return GUSTO_OK;
 }
 

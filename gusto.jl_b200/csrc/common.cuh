@@ -237,6 +237,7 @@ struct BatchPtrs {
   double* g;       // [B][N][NX]      f - A Xp - B Up  (affine part of the trapezoid row, halves summed by the consumer)
   const uint8_t* active;  // [B] instances still iterating (solve/evaluate skip the others); may be null
   double* rows;    // [B][N][n_obs][5] (nhat_x, nhat_y, nhat_z, off, dist0): row value = off - nhat.r, active iff dist0 < toggle
+  double* dual;    // [B][NX] multiplier of the init rows X[:,1] = x_init of the last solve (= -JuMP.dual, get_dual_jump); may be null
 };
 
 GHD double sq(double a) { return a * a; }

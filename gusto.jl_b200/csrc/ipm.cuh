@@ -1545,6 +1545,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     const double omega = c.omega;
     for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) { if (has_t) obj += omega * st[2]; });
   }
+  // SCPS.dual (scp_gusto.jl:116, get_dual_jump): row 0 of Aeq is  x_0 = x_init  and the Lagrangian is f + nu'(Aeq z - b)
+  if (p.dual) G_PAR_FOR(i, NX) p.dual[(size_t)b * NX + i] = c.nu[i];
   obj = block_sum(obj, c.red);
   if (G_TID == 0) {
     info[0] = (double)status; info[1] = (double)it_done; info[2] = res; info[3] = mu; info[4] = obj;

@@ -20,6 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GUSTO_B200_LIB", os.path.join(_HERE, "libgusto_b200.so"))
 EVAL_NOUT = 8
 CHECK_NOUT = 8
+SHOOT_NOUT = 8
+SH_STATUS, SH_ITERS, SH_FNORM, SH_JTRUE, SH_CONV, SH_LAMBDA = range(6)
 SOLVE_NINFO = 8
 EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)
 SCP_STATUS = ("NA", "OK", "InaccurateModel", "ViolatesConstraints", "TrustRegionViolated", "SolverFailed", "Inactive")
@@ -109,6 +111,9 @@ def load_library(path=LIB_PATH):
     lib.gusto_iterate.argtypes = [vp, _DP, _DP]
     lib.gusto_check_trajectory.argtypes = [vp, _DP]
     lib.gusto_interpolate_trajectory.argtypes = [vp, i32, _DP, _DP]
+    lib.gusto_get_duals.argtypes = [vp, _DP]
+    lib.gusto_shoot.argtypes = [vp, _DP, _DP, i32, i32, ctypes.c_double, _DP]
+    lib.gusto_get_shooting_trajectory.argtypes = [vp, _DP, _DP, _DP]
     lib.gusto_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.gusto_timer_start.argtypes = [vp]
     lib.gusto_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
@@ -123,7 +128,8 @@ def load_library(path=LIB_PATH):
                  "gusto_get_candidate", "gusto_set_candidate", "gusto_set_penalties", "gusto_linearize",
                  "gusto_get_blocks", "gusto_solve_subproblem", "gusto_evaluate", "gusto_accept", "gusto_set_active",
                  "gusto_iterate", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
-                 "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop"):
+                 "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop", "gusto_check_trajectory",
+                 "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -249,6 +255,25 @@ class Engine:
         Xf = np.empty((self.B, nf + 1, self.nx)); Uf = np.empty((self.B, nf, self.nu))
         self._chk(self.lib.gusto_interpolate_trajectory(self._ctx, int(nstep), _dp(Xf), _dp(Uf)))
         return Xf, Uf
+
+    def get_duals(self):
+        """SCPS.dual of the last solve: minus the JuMP dual of the init constraints (scp_gusto.jl:116), [B, n_x]."""
+        d = np.empty((self.B, self.nx))
+        self._chk(self.lib.gusto_get_duals(self._ctx, _dp(d)))
+        return d
+
+    def shoot(self, p0=None, x_goal=None, nsub=4, max_iter=100, ftol=1e-3):
+        """One shooting attempt per instance (solve!(SS, SP), shooting.jl:4-49).  Returns out[B, SHOOT_NOUT]."""
+        out = np.empty((self.B, SHOOT_NOUT))
+        p0 = None if p0 is None else np.ascontiguousarray(p0, dtype=np.float64)
+        x_goal = None if x_goal is None else np.ascontiguousarray(x_goal, dtype=np.float64)
+        self._chk(self.lib.gusto_shoot(self._ctx, _dp(p0), _dp(x_goal), int(nsub), int(max_iter), float(ftol), _dp(out)))
+        return out
+
+    def get_shooting_trajectory(self):
+        X = np.empty((self.B, self.N, self.nx)); U = np.empty((self.B, self.N, self.nu)); P = np.empty((self.B, self.N, self.nx))
+        self._chk(self.lib.gusto_get_shooting_trajectory(self._ctx, _dp(X), _dp(U), _dp(P)))
+        return X, U, P
 
     def kernel_ms(self):
         ms = (ctypes.c_float * 4)()
@@ -385,3 +410,103 @@ def solve_gusto_batch(engine: Engine, X0=None, U0=None, max_iter=30, force=False
     S.X, S.U = engine.get_trajectory()
     S.total_time = time.perf_counter() - t0
     return S
+
+
+# ------------------------------------------------------------------------------------- SCP + shooting
+@dataclass
+class BatchShootingSolution:
+    """Per-instance ShootingSolution histories (types.jl:197-208) next to the SCP solution (TrajectoryOptimizationSolution)."""
+    SCPS: BatchSCPSolution
+    X: np.ndarray                       # TOS.traj: the shooting trajectory where shooting converged, else SCPS.traj
+    U: np.ndarray
+    converged: np.ndarray               # SS.converged
+    prob_status: list = field(default_factory=list)          # per attempt [B]: 0 :Optimal, 1 :Diverged, -1 not attempted
+    J_true: list = field(default_factory=list)
+    convergence_measure: list = field(default_factory=list)
+    newton_iters: list = field(default_factory=list)
+    attempts: int = 0
+
+
+def solve_scp_shooting_batch(engine: Engine, X0=None, U0=None, max_iter=30, nsub=4, shoot_max_iter=100, ftol=1e-3, verbose=False):
+    """Batched solve_SCPshooting! (traj_opt.jl:4-45): one GuSTO iteration, then alternate {shooting attempt started from the
+    init-constraint duals of the last convex solve, one more GuSTO iteration} until the last two successful shooting runs
+    of an instance moved less than the convergence threshold (SS.converged) or its SCP converged / ran out of iterations.
+    Host logic only; every number comes from the kernels behind the C ABI."""
+    bp = engine.bp
+    B = bp.B
+    thr = bp.model.scp_params[M.SP_CONVTHR]
+    # solve_method!(SCPS, SCPP, solver, 1): the batched loop below is solve_gusto_batch unrolled one iteration at a time
+    st = _ScpStepper(engine, X0, U0)
+    st.step(np.ones(B, bool))
+    S = st.S
+    SS = BatchShootingSolution(S, S.X, S.U, np.zeros(B, bool))
+    SS.J_true.append(S.J_true[1].copy())
+    conv_hist = [np.full(B, np.nan)]                                     # SS.convergence_measure starts as [NaN]
+    x_goal = 0.5 * (bp.goal_lo + bp.goal_hi)                             # types.jl:219-224
+    while True:
+        run = ~S.converged & (S.iterations < max_iter) & ~SS.converged & ~st.dead
+        if not run.any():
+            break
+        out = engine.shoot(None, x_goal, nsub, shoot_max_iter, ftol)     # SP = ShootingProblem(TOP, SCPS); solve!(SS, SP)
+        ok = run & (out[:, SH_STATUS] == 0)
+        SS.prob_status.append(np.where(run, out[:, SH_STATUS], -1).astype(np.int32))
+        SS.J_true.append(np.where(ok, out[:, SH_JTRUE], np.nan))
+        conv_hist.append(np.where(run, np.where(ok, out[:, SH_CONV], np.nan), conv_hist[-1]))
+        SS.newton_iters.append(np.where(run, out[:, SH_ITERS], 0))
+        SS.attempts += 1
+        with np.errstate(invalid="ignore"):
+            two = conv_hist[-1] + conv_hist[-2]
+            done = run & (S.iterations > 2) & (two <= thr)               # traj_opt.jl:32-38 (NaN compares false)
+        SS.converged |= done
+        if verbose:
+            print(f"[shooting] attempt {SS.attempts}: optimal {int(ok.sum())}/{int(run.sum())} converged {int(SS.converged.sum())}")
+        cont = run & ~done
+        if not cont.any():
+            break
+        st.step(cont)                                                    # solve_method!(SCPS, SCPP, solver, 1)
+    SS.convergence_measure = conv_hist
+    Xs, Us, _ = engine.get_shooting_trajectory() if SS.attempts else (None, None, None)
+    S.X, S.U = engine.get_trajectory()
+    SS.X, SS.U = S.X.copy(), S.U.copy()
+    if SS.attempts:
+        SS.X[SS.converged] = Xs[SS.converged]; SS.U[SS.converged] = Us[SS.converged]
+    return SS
+
+
+class _ScpStepper:
+    """solve_gusto_batch one outer iteration at a time (the reference calls solve_method! with max_iter = 1 repeatedly and
+    keeps Delta / omega / histories in SCPS between the calls -- here they live in this object)."""
+
+    def __init__(self, engine, X0=None, U0=None):
+        bp = engine.bp
+        self.engine, self.B, self.sp = engine, bp.B, bp.model.scp_params
+        if X0 is None:
+            X0, U0 = bp.init_traj_straightline()
+        B, sp = self.B, self.sp
+        engine.set_trajectory(X0, U0)
+        self.Delta = np.full(B, sp[M.SP_DELTA0]); self.omega = np.full(B, sp[M.SP_OMEGA0])
+        engine.set_penalties(self.omega, self.Delta)
+        engine.set_candidate(X0, U0)
+        engine.linearize()
+        ev0 = engine.evaluate()
+        S = BatchSCPSolution(X0, U0, np.zeros(B, bool), np.zeros(B, bool), np.zeros(B, np.int64))
+        S.J_true.append(ev0[:, EV_JTRUE].copy()); S.convergence_measure.append(np.zeros(B))
+        self.S = S
+        self.dead = np.zeros(B, bool)          # solver failure or omega > omega_max: the reference's loop would spin; we stop
+
+    def step(self, active):
+        e, S = self.engine, self.S
+        e.set_active(active)
+        out, info = e.iterate()
+        st = gusto_update(out, info[:, 0] == 0, active, self.Delta, self.omega, S.iterations, S.convergence_measure[-1], self.sp)
+        e.accept(st["accept"], st["omega"], st["Delta"])
+        S.J_true.append(np.where(st["accept"], out[:, EV_JTRUE], S.J_true[-1]))
+        S.convergence_measure.append(np.where(st["run"], out[:, EV_CONV], S.convergence_measure[-1]))
+        S.scp_status.append(st["status"]); S.accept_solution.append(st["accept"])
+        self.Delta, self.omega = st["Delta"], st["omega"]
+        S.iterations = st["iterations"]
+        S.converged |= st["converged_now"]; S.successful |= st["successful_now"]
+        self.dead |= st["done"] & ~st["converged_now"]
+        S.batch_iterations += 1
+        S.X, S.U = e.get_trajectory()
+        return st

@@ -127,6 +127,24 @@ int32_t gusto_check_trajectory(gusto_ctx* ctx, double* out);
  * Xfull[B*(nstep*(N-1)+1)*n_x], Ufull[B*nstep*(N-1)*n_u]. */
 int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xfull, double* Ufull);
 
+/* Indirect shooting refinement (reference shooting.jl:4-66, solve_SCPshooting! traj_opt.jl:4-45).
+ * gusto_get_duals: dual[B*n_x] = SCPS.dual of the last gusto_solve_subproblem / gusto_iterate, i.e. minus the JuMP dual of
+ * the init constraints X[:,1] = x_init (scp_gusto.jl:116, get_dual_jump dynamics/dubins_car.jl:254-257).
+ * gusto_shoot: one shooting attempt per instance (solve!(SS, SP)): find the initial costate p0 with
+ * x(tf; x_init, p0) = x_goal under shooting_ode! (dynamics/dubins_car.jl:259-280, astrobee_se3_manifold.jl:831-895; only
+ * these two models -- GUSTO_E_ARG otherwise).  p0[B*n_x] start (NULL: the duals of the last solve, types.jl:225),
+ * x_goal[B*n_x] (NULL: centres of the goal sets, types.jl:219-224), RK4 with nsub sub-steps per knot interval,
+ * Levenberg-Marquardt with at most max_iter iterations (reference: 100) until |F|_inf <= ftol (reference: 1e-3).
+ * out[B*GUSTO_SHOOT_NOUT] = { status (0 :Optimal, 1 :Diverged), LM iterations, |x_goal - x(tf)|_inf, J_true (cost_true of the
+ * new trajectory), convergence_metric(new, SS.traj) (traj_opt.jl:74-85), final damping, 0, 0 }; J_true and the metric are NaN
+ * for a diverged attempt (shooting.jl:16-22,41-47).  A converged attempt replaces the shooting trajectory SS.traj kept on
+ * the device (initially the context's trajectory at the first call); gusto_get_shooting_trajectory downloads it
+ * (X[B*N*n_x], U[B*N*n_u] = get_control, costates P[B*N*n_x]; any pointer may be NULL). */
+#define GUSTO_SHOOT_NOUT 8
+int32_t gusto_get_duals(gusto_ctx* ctx, double* dual);
+int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int32_t nsub, int32_t max_iter, double ftol, double* out);
+int32_t gusto_get_shooting_trajectory(gusto_ctx* ctx, double* X, double* U, double* P);
+
 /* Timing of the last call of each kernel on this context, in milliseconds (CUDA events on the context's stream):
  * ms[0] linearize, ms[1] solve, ms[2] evaluate, ms[3] accept. */
 int32_t gusto_last_kernel_ms(gusto_ctx* ctx, float* ms);

@@ -136,6 +136,7 @@ class SCPResult:
     rho_vec: list = field(default_factory=lambda: [0.0])
     tr_ok_vec: list = field(default_factory=lambda: [False])
     ineq_ok_vec: list = field(default_factory=lambda: [False])
+    dual: np.ndarray = None          # -JuMP.dual of the init constraints of the last solve (scp_gusto.jl:116, get_dual_jump)
 
 
 def solve_gusto(p: Problem, X0=None, U0=None, max_iter=30, force=False, subproblem=solve_subproblem, verbose=False):
@@ -153,10 +154,12 @@ def solve_gusto(p: Problem, X0=None, U0=None, max_iter=30, force=False, subprobl
     iter_cap = S.iterations + max_iter
     while S.iterations < iter_cap:
         Delta, omega = S.Delta_vec[-1], S.omega_vec[-1]
-        Xn, Un, obj, status, lin, rows, _ = subproblem(p, S.X, S.U, omega, Delta, toggle, eps)
+        Xn, Un, obj, status, lin, rows, r = subproblem(p, S.X, S.U, omega, Delta, toggle, eps)
         S.solver_status.append(status)
         if status != "OPTIMAL":                                       # :107-111
             return S
+        if getattr(r, "nu", None) is not None:                        # :116; init rows follow the (N-1) n_x dynamics rows
+            S.dual = np.array(r.nu[(p.N - 1) * m.n_x:p.N * m.n_x])
         S.convergence_measure.append(convergence_metric(Xn, S.X))     # :115
         S.J_full.append(obj)
         S.tr_ok_vec.append(trust_region_satisfied(Xn, S.X, Delta))    # :120

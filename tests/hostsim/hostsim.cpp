@@ -14,8 +14,13 @@
 #include "../../gusto.jl_b200/csrc/ipm.cuh"
 #include "../../gusto.jl_b200/csrc/evaluate.cuh"
 #include "../../gusto.jl_b200/csrc/postprocess.cuh"
+#include "../../gusto.jl_b200/csrc/shooting.cuh"
 
 using namespace gusto;
+
+// optional [B][n_x] buffer that receives SCPS.dual (the init-row multipliers) of the next hostsim_iterate call
+static double* g_dual = nullptr;
+extern "C" void hostsim_set_dual_buffer(double* dual) { g_dual = dual; }
 
 template <int M>
 static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stages, double* info, double* eval) {
@@ -57,6 +62,7 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
   }
   BatchPtrs p;
   p.active = nullptr;
+  p.dual = g_dual;
   p.tf = tf; p.x_init = x_init; p.goal_lo = goal_lo; p.goal_hi = goal_hi;
   p.Xp = Xp; p.Up = Up; p.Xn = Xn; p.Un = Un; p.omega = omega; p.delta = delta; p.f = f; p.A = A; p.g = g; p.rows = rows;
   IpmParams prm;
@@ -111,6 +117,35 @@ extern "C" int hostsim_postprocess(const gusto_config* cfg, const int32_t* obs_k
     case FREEFLYER_SE2: run_post<FREEFLYER_SE2>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
     case ASTROBEE_SE3: run_post<ASTROBEE_SE3>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
     case ASTROBEE_SE3_MANIFOLD: run_post<ASTROBEE_SE3_MANIFOLD>(d, p, X, U, nstep, chk, Xfull, Ufull); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+// shooting body (shoot_instance), lanes run one after the other
+template <int M>
+static void run_shoot(const BatchDesc& d, BatchPtrs& p, const double* p0, const double* x_goal, int nsub, int max_iter, double ftol,
+                      double* Xs, double* Us, double* Ps, double* out) {
+  using T = Traits<M>;
+  std::vector<double> sm(ShootLayout<M>::TOTAL);
+  const size_t N = d.N;
+  for (int b = 0; b < d.B; ++b)
+    shoot_instance<M>(d, p, b, p0 + (size_t)b * T::NX, x_goal + (size_t)b * T::NX, nsub, max_iter, ftol, sm.data(),
+                      Xs + (size_t)b * N * T::NX, Us + (size_t)b * N * T::NU, Ps + (size_t)b * N * T::NX, out + (size_t)b * SHOOT_NOUT);
+}
+
+extern "C" int hostsim_shoot(const gusto_config* cfg, const double* x_init, const double* tf, const double* p0, const double* x_goal,
+                             int nsub, int max_iter, double ftol, double* Xs, double* Us, double* Ps, double* out) {
+  BatchDesc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = cfg->model_id; d.N = cfg->N; d.B = cfg->B; d.n_obs = 0;
+  for (int i = 0; i < 16; ++i) d.rp[i] = cfg->robot_params[i];
+  BatchPtrs p;
+  memset(&p, 0, sizeof(p));
+  p.tf = tf; p.x_init = x_init;
+  switch (cfg->model_id) {
+    case DUBINS: run_shoot<DUBINS>(d, p, p0, x_goal, nsub, max_iter, ftol, Xs, Us, Ps, out); break;
+    case ASTROBEE_SE3_MANIFOLD: run_shoot<ASTROBEE_SE3_MANIFOLD>(d, p, p0, x_goal, nsub, max_iter, ftol, Xs, Us, Ps, out); break;
     default: return -1;
   }
   return 0;

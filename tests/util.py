@@ -93,3 +93,32 @@ def hostsim_postprocess(bp, X, U, nstep):
                                            dp(tf), dp(X), dp(U), ctypes.c_int(nstep), dp(chk), dp(Xf), dp(Uf))
     assert rc == 0
     return chk, Xf, Uf
+
+
+def hostsim_iterate_with_duals(bp, Xp, Up, omega, delta, **kw):
+    """hostsim_iterate that also returns SCPS.dual (the init-row multipliers written by the IPM body), [B, n_x]."""
+    dual = np.zeros((bp.B, bp.model.x_dim))
+    lib = hostsim_lib()
+    lib.hostsim_set_dual_buffer(dual.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    try:
+        hs = hostsim_iterate(bp, Xp, Up, omega, delta, **kw)
+    finally:
+        lib.hostsim_set_dual_buffer(None)
+    hs["dual"] = dual
+    return hs
+
+
+def hostsim_shoot(bp, p0, x_goal, Xs_prev, nsub=4, max_iter=100, ftol=1e-3):
+    """shoot_instance kernel body on the host.  Returns (out[B,8], Xs, Us, Ps)."""
+    host = gb.engine()
+    cfg, _ = host.make_config(bp, 0)
+    B, N, nx, nu = bp.B, bp.N, bp.model.x_dim, bp.model.u_dim
+    dp = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    p0 = np.ascontiguousarray(p0, dtype=np.float64); x_goal = np.ascontiguousarray(x_goal, dtype=np.float64)
+    x_init = np.ascontiguousarray(bp.x_init); tf = np.ascontiguousarray(bp.tf)
+    Xs = np.ascontiguousarray(Xs_prev, dtype=np.float64).copy(); Us = np.zeros((B, N, nu)); Ps = np.zeros((B, N, nx))
+    out = np.zeros((B, 8))
+    rc = hostsim_lib().hostsim_shoot(ctypes.byref(cfg), dp(x_init), dp(tf), dp(p0), dp(x_goal), ctypes.c_int(nsub), ctypes.c_int(max_iter),
+                                     ctypes.c_double(ftol), dp(Xs), dp(Us), dp(Ps), dp(out))
+    assert rc == 0
+    return out, Xs, Us, Ps
