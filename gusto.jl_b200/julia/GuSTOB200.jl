@@ -170,8 +170,52 @@ iterate!(ctx, out, info) = GC.@preserve out info check(ctx, ccall((:gusto_iterat
 check_trajectory!(ctx, out) = GC.@preserve out check(ctx, ccall((:gusto_check_trajectory, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, out))
 interpolate_trajectory!(ctx, nstep::Integer, Xfull, Ufull) = GC.@preserve Xfull Ufull check(ctx, ccall((:gusto_interpolate_trajectory, LIB), Int32,
   (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), ctx.ptr, Int32(nstep), Xfull, Ufull))
+# shooting refinement (shooting.jl:4-66): duals is x_dim x B, out is 8 x B (GUSTO_SHOOT_NOUT), p0 / x_goal may be `nothing`
+get_duals!(ctx, duals) = GC.@preserve duals check(ctx, ccall((:gusto_get_duals, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, duals))
+function shoot!(ctx, p0, x_goal, out; nsub::Integer=4, max_iter::Integer=100, ftol::Float64=1e-3)
+  pp = p0 === nothing ? Ptr{Float64}(C_NULL) : pointer(p0)
+  pg = x_goal === nothing ? Ptr{Float64}(C_NULL) : pointer(x_goal)
+  GC.@preserve p0 x_goal out check(ctx, ccall((:gusto_shoot, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Ptr{Float64}), ctx.ptr, pp, pg, Int32(nsub), Int32(max_iter), ftol, out))
+end
+get_shooting_trajectory!(ctx, X, U, P) = GC.@preserve X U P check(ctx, ccall((:gusto_get_shooting_trajectory, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, X, U, P))
 accept!(ctx, acc::Vector{UInt8}, ω, Δ) = GC.@preserve acc ω Δ check(ctx, ccall((:gusto_accept, LIB), Int32,
     (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, acc, ω, Δ))
+
+# ------------------------------------------------------------------------------------- shooting plug-in
+"""
+    solve_shooting_b200!(SS, SP; device=0, nsub=4)
+
+Same contract as `solve!(SS::ShootingSolution, SP::ShootingProblem)` (shooting.jl:4-49): one shooting attempt started
+from `SP.p0` (= `SCPS.dual`); pushes `:Optimal` / `:Diverged`, `J_true`, `convergence_measure`, `iter_elapsed_times` and, on
+success, replaces `SS.traj`.  DubinsCar and AstrobeeSE3Manifold only (the models for which the reference defines
+`shooting_ode!`).
+"""
+function solve_shooting_b200!(SS, SP; device::Int=0, nsub::Int=4)
+  model, robot, env = SP.PD.model, SP.PD.robot, SP.PD.env
+  x_dim, u_dim, N = model.x_dim, model.u_dim, SP.N
+  gtype = fill(GOAL_POINT, x_dim)
+  ctx = GustoContext(robot, model, env, N, 1, gtype, Main.SCPParam_GuSTO(model), nothing; device=device)
+  xg = Float64.(SP.x_goal)
+  set_problems!(ctx, Float64.(SP.PD.x_init), xg, xg, Float64[SP.tf])
+  set_trajectory!(ctx, Matrix{Float64}(SS.traj.X), Matrix{Float64}(SS.traj.U))     # convergence_metric is taken against SS.traj
+  out = zeros(8)
+  time_start = time_ns()
+  shoot!(ctx, Float64.(SP.p0), xg, out; nsub=nsub)
+  iter_elapsed_time = (time_ns() - time_start)/10^9
+  if out[1] == 0
+    X = zeros(x_dim, N); U = zeros(u_dim, N); P = zeros(x_dim, N)
+    get_shooting_trajectory!(ctx, X, U, P)
+    push!(SS.prob_status, :Optimal); push!(SS.J_true, out[4]); push!(SS.convergence_measure, out[5])
+    push!(SS.iter_elapsed_times, iter_elapsed_time)
+    SS.traj.X = X; SS.traj.U = U; SS.traj.Tf = SP.tf; SS.traj.dt = SP.tf/(N-1)
+  else
+    push!(SS.prob_status, :Diverged); push!(SS.J_true, NaN); push!(SS.convergence_measure, NaN)
+    push!(SS.iter_elapsed_times, iter_elapsed_time)
+  end
+  return
+end
 
 # ------------------------------------------------------------------------------------- single-instance plug-in
 """
@@ -257,7 +301,7 @@ function solve_gusto_b200!(SCPS, SCPP, solver="B200", max_iter=30, force=false; 
   end
   get_trajectory!(ctx, X, U)
   SCPS.traj.X = X; SCPS.traj.U = U
-  SCPS.dual = fill(NaN, x_dim)            # init-constraint duals are only needed by the shooting refinement (out of scope)
+  SCPS.dual = zeros(x_dim); get_duals!(ctx, SCPS.dual)     # -JuMP.dual of the init constraints (:116, get_dual_jump): p0 of the shooting refinement
   return
 end
 
