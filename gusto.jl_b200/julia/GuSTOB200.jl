@@ -196,7 +196,7 @@ function solve_shooting_b200!(SS, SP; device::Int=0, nsub::Int=4)
   model, robot, env = SP.PD.model, SP.PD.robot, SP.PD.env
   x_dim, u_dim, N = model.x_dim, model.u_dim, SP.N
   gtype = fill(GOAL_POINT, x_dim)
-  ctx = GustoContext(robot, model, env, N, 1, gtype, Main.SCPParam_GuSTO(model), nothing; device=device)
+  ctx = GustoContext(robot, model, env, N, 1, gtype, Main.SCPParam_GuSTO(model), (convergence_threshold = 0.0,); device=device)   # SCP parameters unused by K7
   xg = Float64.(SP.x_goal)
   set_problems!(ctx, Float64.(SP.PD.x_init), xg, xg, Float64[SP.tf])
   set_trajectory!(ctx, Matrix{Float64}(SS.traj.X), Matrix{Float64}(SS.traj.U))     # convergence_metric is taken against SS.traj
