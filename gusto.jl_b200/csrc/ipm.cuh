@@ -231,13 +231,14 @@ GDEV void pair_floor(double* st, bool has_t, double floor_) {
   if (has_t && st[2] * st[3] < floor_) st[3] = floor_ * g_rcp(st[2]);
 }
 
-GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega) {
+GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega, double t_in = 1.0) {
   for (int i = 0; i < SLOT_W; ++i) st[i] = 0.0;
   if (!valid) return;
   if (has_t) {
-    // interior start of the penalty slack: one unit inside, as the oracle.  (0.3 - 0.5 would save one Newton iteration
-    // of nine on the headline workload but costs restarts on freeflyerSE2 at omega = 25: measured, rejected.)
-    const double t = (c0 > 0 ? c0 : 0.0) + 1.0;
+    // interior start of the penalty slack: t_in inside (the oracle uses one unit).  0.25 saves 0.85 Newton iterations of 8.85 on
+    // astrobeeSE3 but costs restarts on freeflyerSE2 at omega = 25 (measured), so it is a per-model setting
+    // (slack_start<M>()), like the refinement count; the optimum reached is the same to the solver tolerance.
+    const double t = (c0 > 0 ? c0 : 0.0) + t_in;
     const double sa = t - c0;
     st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = 0.5 * omega; st[2] = t; st[3] = 0.5 * omega;
   } else {
@@ -1317,6 +1318,10 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
 }
 
 // --------------------------------------------------------------------------------------------------- setup
+#ifndef GUSTO_SLACK_START_SE3
+#define GUSTO_SLACK_START_SE3 0.25
+#endif
+template <int M> GHD constexpr double slack_start() { return M == ASTROBEE_SE3 ? GUSTO_SLACK_START_SE3 : 1.0; }
 template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
@@ -1353,7 +1358,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
         double v = row[3];
         for (int a = 0; a < 3; ++a) { o[a] = row[a]; if (a < T::WS) v -= row[a] * x[a]; }
         o[3] = row[3]; o[4] = (double)k;
-        slot_init(c.ost + (size_t)p * SLOT_W, true, true, v, c.omega);
+        slot_init(c.ost + (size_t)p * SLOT_W, true, true, v, c.omega, slack_start<M>());
         ++p;
       }
     }
@@ -1363,8 +1368,8 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     const int k = it / L::SP, s = it - k * L::SP;
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)it * SLOT_W;
-    if (T::HAS_TR && s == L::S_TR) slot_init(st, true, true, tr_c0<M>(c, k, x), c.omega);
-    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, o.valid, o.has_t, o.c0, c.omega); }
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, true, true, tr_c0<M>(c, k, x), c.omega, slack_start<M>());
+    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, o.valid, o.has_t, o.c0, c.omega, slack_start<M>()); }
   }
   G_PAR_FOR(j, L::NBOX) {
     const bool valid = (c.bmask >> (j >> 1)) & 1;
