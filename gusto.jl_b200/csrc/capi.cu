@@ -3,6 +3,7 @@
 // no B200 is usable.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -56,6 +57,8 @@ constexpr int LIN_KNOTS_PER_CTA = 8;      // one warp per knot
 #define GUSTO_IPM_MINBLOCKS 7
 #endif
 constexpr int IPM_THREADS = GUSTO_IPM_THREADS;
+constexpr int IPM_MAX_PACK = 8;            // 8 groups x 64 threads x 128 registers = the register file of an SM
+static_assert(GUSTO_IPM_THREADS == GUSTO_IPM_GROUP, "ipm.cuh's group size and the launch configuration must agree");
 constexpr int EVAL_THREADS = 128;
 
 // K1+K2.  Grid: ceil(B*N/8) CTAs of 8 warps.  The 8 knots' states and controls are contiguous in HBM
@@ -99,14 +102,17 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   }
 }
 
-// K3.  Grid: B CTAs (one problem instance each).
+// K3.  One instance per GROUP of IPM_THREADS threads; a CTA packs blockDim.x / IPM_THREADS groups (ipm_pack(), chosen so that
+// B instances fill the SMs in one wave), each with its own slice of the dynamic shared memory.
 template <int M>
-__global__ void __launch_bounds__(IPM_THREADS, GUSTO_IPM_MINBLOCKS) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
-                                                          double* scratch, size_t stride, double* info) {
+__global__ void __launch_bounds__(IPM_THREADS * IPM_MAX_PACK, 1) ipm_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
+                                                          double* scratch, size_t stride, double* info, int smem_doubles) {
   extern __shared__ __align__(16) double smem[];
-  const int b = blockIdx.x;
-  if (p.active && !p.active[b]) return;      // converged / failed instance: frozen (CTA-uniform exit)
-  ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem, info + (size_t)b * IPM_NINFO);
+  const int sub = threadIdx.x / IPM_THREADS;
+  const int b = blockIdx.x * (blockDim.x / IPM_THREADS) + sub;
+  if (b >= dp->B) return;                    // group-uniform exits: an exited group no longer counts in the CTA barrier
+  if (p.active && !p.active[b]) return;      // converged / failed instance: frozen
+  ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem + (size_t)sub * smem_doubles, info + (size_t)b * IPM_NINFO);
 }
 
 // K4.  Grid: B CTAs.
@@ -182,7 +188,10 @@ struct gusto_ctx {
   uint8_t* d_accept = nullptr;
   uint8_t* d_active = nullptr;
   size_t scratch_stride = 0;
-  int ipm_smem = 0;
+  int ipm_smem = 0;          // dynamic shared memory of ONE instance group (bytes)
+  int ipm_pack_max = 1;      // groups per CTA allowed by shared memory / registers
+  int ipm_pack_force = 0;    // test hook (GUSTO_IPM_FORCE_PACK): use exactly this many groups per CTA
+  int nsm = 1;
   IpmParams prm;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
@@ -220,7 +229,7 @@ static size_t scratch_doubles_of(int model, int N, int n_obs) {
     default: return IpmLayout<ASTROBEE_SE3_MANIFOLD>::scratch_doubles(N, n_obs);
   }
 }
-static int ipm_smem_doubles_of(int model, int N) {
+static int ipm_smem_doubles_raw(int model, int N) {
   switch (model) {
     case DUBINS: return IpmLayout<DUBINS>::smem_doubles(N, IPM_THREADS);
     case FREEFLYER_SE2: return IpmLayout<FREEFLYER_SE2>::smem_doubles(N, IPM_THREADS);
@@ -228,6 +237,9 @@ static int ipm_smem_doubles_of(int model, int N) {
     default: return IpmLayout<ASTROBEE_SE3_MANIFOLD>::smem_doubles(N, IPM_THREADS);
   }
 }
+// per-group slice of the CTA's dynamic shared memory: a multiple of 128 bytes, so that every group's tiles keep the
+// 16-byte alignment LDS.128 and the TMA ring need
+static int ipm_smem_doubles_of(int model, int N) { return (ipm_smem_doubles_raw(model, N) + 15) & ~15; }
 
 extern "C" {
 
@@ -310,11 +322,23 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   }
   ctx->ipm_smem = ipm_smem_doubles_of(cfg->model_id, (int)N) * (int)sizeof(double);
   cudaError_t e = cudaSuccess;
+  {
+    int max_optin = 0, nsm = 1;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
+    ctx->nsm = nsm > 0 ? nsm : 1;
+    int pm = ctx->ipm_smem > 0 ? max_optin / ctx->ipm_smem : 1;
+    pm = pm < 1 ? 1 : (pm > IPM_MAX_PACK ? IPM_MAX_PACK : pm);
+    if (const char* ev = getenv("GUSTO_IPM_PACK")) { const int v = atoi(ev); if (v >= 1 && v <= pm) pm = v; }
+    ctx->ipm_pack_max = pm;
+    if (const char* ev = getenv("GUSTO_IPM_FORCE_PACK")) { const int v = atoi(ev); if (v >= 1) ctx->ipm_pack_force = v > pm ? pm : v; }
+  }
+  const int smem_attr = ctx->ipm_smem * ctx->ipm_pack_max;
   switch (cfg->model_id) {
-    case DUBINS: e = cudaFuncSetAttribute(ipm_kernel<DUBINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
-    case FREEFLYER_SE2: e = cudaFuncSetAttribute(ipm_kernel<FREEFLYER_SE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
-    case ASTROBEE_SE3: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
-    default: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3_MANIFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->ipm_smem); break;
+    case DUBINS: e = cudaFuncSetAttribute(ipm_kernel<DUBINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr); break;
+    case FREEFLYER_SE2: e = cudaFuncSetAttribute(ipm_kernel<FREEFLYER_SE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr); break;
+    case ASTROBEE_SE3: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr); break;
+    default: e = cudaFuncSetAttribute(ipm_kernel<ASTROBEE_SE3_MANIFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr); break;
   }
   if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GUSTO_E_CUDA); }
   if (cudaDeviceSynchronize() != cudaSuccess) { ctx->err = "gusto_create: device sync failed"; return fail(GUSTO_E_CUDA); }
@@ -389,13 +413,18 @@ static int32_t launch_linearize(gusto_ctx* ctx) {
   return GUSTO_OK;
 }
 static int32_t launch_solve(gusto_ctx* ctx) {
-  const int grid = ctx->cfg.B;
+  // groups per CTA: as many as it takes to hold the batch in ONE wave (B / #SM, rounded up), within the shared-memory /
+  // register limit; small batches stay spread over the SMs
+  int pack = (ctx->cfg.B + ctx->nsm - 1) / ctx->nsm;
+  pack = pack < 1 ? 1 : (pack > ctx->ipm_pack_max ? ctx->ipm_pack_max : pack);
+  if (ctx->ipm_pack_force > 0) pack = ctx->ipm_pack_force;
+  const int grid = (ctx->cfg.B + pack - 1) / pack, block = IPM_THREADS * pack, smem = ctx->ipm_smem * pack, sd = ctx->ipm_smem / (int)sizeof(double);
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   switch (ctx->cfg.model_id) {
-    case DUBINS: ipm_kernel<DUBINS><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
-    case FREEFLYER_SE2: ipm_kernel<FREEFLYER_SE2><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
-    case ASTROBEE_SE3: ipm_kernel<ASTROBEE_SE3><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
-    default: ipm_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, IPM_THREADS, ctx->ipm_smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info); break;
+    case DUBINS: ipm_kernel<DUBINS><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
+    case FREEFLYER_SE2: ipm_kernel<FREEFLYER_SE2><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
+    case ASTROBEE_SE3: ipm_kernel<ASTROBEE_SE3><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
+    default: ipm_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev[3], ctx->stream));

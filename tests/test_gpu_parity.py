@@ -122,6 +122,29 @@ def test_shard_equivalence_and_ragged_batch(host):
         assert np.array_equal(o2, out[lo:lo + bs.B])
 
 
+@pytest.mark.parametrize("name", ["astrobeeSE3", "freeflyerSE2", "astrobeeSE3manifold", "dubins"])
+def test_instance_groups_packed_into_one_cta_give_identical_results(name, host, monkeypatch):
+    """The solve kernel packs several instance groups (64 threads each) into one CTA for large batches; forcing 3 groups
+    per CTA on a batch of 5 (ragged last CTA, one inactive instance) must reproduce the one-group-per-CTA result bit for bit."""
+    bp = gb.problems.CONFIGS[name](B=5, N=20)
+    X0, U0 = bp.init_traj_straightline()
+    res = []
+    for force in ("1", "3"):
+        monkeypatch.setenv("GUSTO_IPM_FORCE_PACK", force)
+        e = host.Engine(bp, device=0)
+        e.set_trajectory(X0, U0); e.set_candidate(X0, U0)
+        e.set_active(np.array([1, 1, 0, 1, 1], np.uint8))
+        out, info = e.iterate()
+        res.append((e.get_candidate(), out.copy(), info[:, :5].copy(), e.get_duals()))
+        e.close()
+    (Xa, Ua), oa, ia, da = res[0]
+    (Xb, Ub), ob, ib, db = res[1]
+    act = [0, 1, 3, 4]
+    assert np.all(ia[act, 0] == 0)
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub) and np.array_equal(oa[act], ob[act]) and np.array_equal(ia[act], ib[act])
+    assert np.array_equal(da[act], db[act]) and np.array_equal(Xa[2], X0[2])
+
+
 def test_inactive_instances_are_frozen(host):
     bp = gb.problems.config_freeflyer_se2(B=4, N=20, seed=5)
     X0, U0 = bp.init_traj_straightline()
