@@ -86,7 +86,9 @@ inline void g_mbar_expect_tx(unsigned long long*, unsigned) {}
 inline void g_tma_bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { for (unsigned i = 0; i < bytes / 8; ++i) dst[i] = src[i]; }
 inline void g_mbar_wait(unsigned long long*, unsigned) {}
 inline void g_fence_proxy_async() {}
+inline void g_prefetch_l1(const void*) {}
 #else
+__device__ __forceinline__ void g_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void g_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void g_mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");

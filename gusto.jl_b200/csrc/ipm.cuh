@@ -614,6 +614,7 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       const double* __restrict__ orow = c.orow;
       double* __restrict__ ost = c.ost;
       for (int p = s0; p < s1; ++p) {
+        if (p + 2 < s1) { g_prefetch_l1(orow + (size_t)(p + 2) * OROW_W); g_prefetch_l1(ost + (size_t)(p + 2) * SLOT_W); }
         const double* row = orow + (size_t)p * OROW_W;
         double* st = ost + (size_t)p * SLOT_W;
         double gv[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
@@ -1316,6 +1317,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
   G_PAR_FOR(it, N * L::SP) {
+    if (it + G_NTHR < N * L::SP) g_prefetch_l1(c.sslot + (size_t)(it + G_NTHR) * SLOT_W);
     const int k = it / L::SP, s = it - k * L::SP;
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)it * SLOT_W;
@@ -1348,6 +1350,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     const double* dzs = sh_dz<M>(c);
     const int nact = c.nact;
     for (int p = G_TID; p < nact; p += G_NTHR) {
+      if (p + G_NTHR < nact) { g_prefetch_l1(orow + (size_t)(p + G_NTHR) * OROW_W); g_prefetch_l1(ost + (size_t)(p + G_NTHR) * SLOT_W); }
       const double* row = orow + (size_t)p * OROW_W;
       const int k = (int)row[4];
       const double* x = zs + k * NV;
