@@ -148,15 +148,19 @@ __global__ void __launch_bounds__(128) interp_kernel(const BatchDesc* __restrict
                           Xfull + (size_t)b * (nf + 1) * T::NX, Ufull + (size_t)b * nf * T::NU);
 }
 
-// K7.  Grid: B CTAs of ONE warp: indirect shooting (Levenberg-Marquardt on the initial costate), lanes = Jacobian columns.
+// K7.  One WARP per instance, SHOOT_WARPS instances per CTA (the warps of a CTA share instruction fetches: the kernel is
+// ~150 KB of SASS for the quaternion model): indirect shooting, lanes = Jacobian columns.
+constexpr int SHOOT_WARPS = 4;
 template <int M>
-__global__ void __launch_bounds__(32) shoot_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, const double* p0, const double* x_goal,
+__global__ void __launch_bounds__(32 * SHOOT_WARPS) shoot_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, const double* p0, const double* x_goal,
                                                    int nsub, int max_iter, double ftol, double* Xs, double* Us, double* Ps, double* out) {
   using T = Traits<M>;
-  __shared__ double sm[ShootLayout<M>::TOTAL];
-  const int b = blockIdx.x;
+  __shared__ double sm[SHOOT_WARPS][ShootLayout<M>::TOTAL];
+  const int w = threadIdx.x >> 5;
+  const int b = blockIdx.x * SHOOT_WARPS + w;
+  if (b >= dp->B) return;
   const size_t N = dp->N;
-  shoot_instance<M>(*dp, p, b, p0 + (size_t)b * T::NX, x_goal + (size_t)b * T::NX, nsub, max_iter, ftol, sm,
+  shoot_instance<M>(*dp, p, b, p0 + (size_t)b * T::NX, x_goal + (size_t)b * T::NX, nsub, max_iter, ftol, sm[w],
                     Xs + (size_t)b * N * T::NX, Us + (size_t)b * N * T::NU, Ps + (size_t)b * N * T::NX, out + (size_t)b * SHOOT_NOUT);
 }
 
@@ -667,11 +671,11 @@ int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int3
     H2D(ctx->d_xgoal, lo.data(), B * nx);
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  const int grid = (int)B;
+  const int grid = (int)((B + SHOOT_WARPS - 1) / SHOOT_WARPS);
   if (model == DUBINS)
-    shoot_kernel<DUBINS><<<grid, 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
+    shoot_kernel<DUBINS><<<grid, 32 * SHOOT_WARPS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
   else
-    shoot_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
+    shoot_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, 32 * SHOOT_WARPS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_p0, ctx->d_xgoal, nsub, max_iter, ftol, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_shoot);
   CK(cudaGetLastError());
   ctx->launches++;
   D2H(out, ctx->d_shoot, B * SHOOT_NOUT);
