@@ -145,6 +145,26 @@ def test_instance_groups_packed_into_one_cta_give_identical_results(name, host, 
     assert np.array_equal(da[act], db[act]) and np.array_equal(Xa[2], X0[2])
 
 
+def test_two_waves_of_packed_ctas_match_a_small_batch(host):
+    """B = 1500 instances: 7 groups per CTA, 215 CTAs (more than one wave of 148 SMs, ragged last CTA); the first shard of
+    15 instances solved alone (one group per CTA) must give bit-identical candidates."""
+    bp = gb.problems.config_astrobee_se3(B=1500, N=20, seed=11)
+    X0, U0 = bp.init_traj_straightline()
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0)
+    out, info = e.iterate()
+    Xn, Un = e.get_candidate()
+    e.close()
+    assert np.all(info[:, 0] == 0)
+    bs = bp.shard(0, 100)
+    es = host.Engine(bs, device=0)
+    es.set_trajectory(X0[:bs.B], U0[:bs.B])
+    o2, i2 = es.iterate()
+    X2, U2 = es.get_candidate()
+    es.close()
+    assert bs.B == 15 and np.array_equal(X2, Xn[:15]) and np.array_equal(U2, Un[:15]) and np.array_equal(o2, out[:15])
+
+
 def test_inactive_instances_are_frozen(host):
     bp = gb.problems.config_freeflyer_se2(B=4, N=20, seed=5)
     X0, U0 = bp.init_traj_straightline()
