@@ -743,7 +743,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
     if (phase == 0) {
       double* kd = c.kd + (size_t)k * L::KDW;
       kd[L::KD_KAP] = ka.kap_tr;
-      kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr / (1.0 + ka.kap_tr * ka.gw) : 0.0;
+      kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr * g_rcp(1.0 + ka.kap_tr * ka.gw) : 0.0;
     }
     {   // first pass of the KKT solve that follows: t1 = (H + dp I)^-1 r  (kkt_solve)
       double rv[NV], tv[NV];
@@ -1040,7 +1040,7 @@ template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
         G_SYNCWARP();
       }
 #endif
-      G_W0_FOR(q, NX) ipv[q] = sqrt(ipv[q]);
+      G_W0_FOR(q, NX) { const double v = ipv[q]; ipv[q] = v * g_rsqrt(v); }     // sqrt(1/pivot) without the IEEE sqrt sequence
       G_SYNCWARP();
       // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose -- still on the eliminating warp, which would
       // otherwise wait for the producer
