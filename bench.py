@@ -221,7 +221,7 @@ def main():
         if state["k"] >= MAX_ITER:
             reset()
         eng.iterate(out, info)
-        st = host.gusto_update(out, info[:, 0] == 0, active, state["Delta"], state["omega"], state["iters"],
+        st = host.gusto_update(out, host.solver_status_ok(info[:, 0]), active, state["Delta"], state["omega"], state["iters"],
                                state["conv_prev"], sp, force=True)
         eng.accept(st["accept"], st["omega"], st["Delta"])
         state["Delta"], state["omega"], state["iters"] = st["Delta"], st["omega"], st["iterations"]
@@ -286,7 +286,7 @@ def main():
             eng.iterate(oute.numpy(), infoe.numpy())                    # kernels + D2H of the scalars
             eng.get_candidate(hb["Xc"].numpy(), hb["Uc"].numpy())       # D2H: the step's result
             o = oute.numpy()
-            s = host.gusto_update(o, infoe.numpy()[:, 0] == 0, active, st8["Delta"], st8["omega"], st8["iters"], st8["conv"], sp, force=True)
+            s = host.gusto_update(o, host.solver_status_ok(infoe.numpy()[:, 0]), active, st8["Delta"], st8["omega"], st8["iters"], st8["conv"], sp, force=True)
             acc = s["accept"]
             if acc.all():                                               # every candidate accepted: swap the pinned buffers
                 hb["Xh"], hb["Xc"] = hb["Xc"], hb["Xh"]; hb["Uh"], hb["Uc"] = hb["Uc"], hb["Uh"]

@@ -57,7 +57,10 @@ constexpr int LIN_KNOTS_PER_CTA = 8;      // one warp per knot
 #define GUSTO_IPM_MINBLOCKS 7
 #endif
 constexpr int IPM_THREADS = GUSTO_IPM_THREADS;
-constexpr int IPM_MAX_PACK = 8;            // 8 groups x 64 threads x 128 registers = the register file of an SM
+#ifndef GUSTO_IPM_MAX_PACK
+#define GUSTO_IPM_MAX_PACK 7
+#endif
+constexpr int IPM_MAX_PACK = GUSTO_IPM_MAX_PACK;   // 7 groups x 64 threads x 144 registers fit the register file of an SM (8 x 128 spilled more)
 static_assert(GUSTO_IPM_THREADS == GUSTO_IPM_GROUP, "ipm.cuh's group size and the launch configuration must agree");
 constexpr int EVAL_THREADS = 128;
 
@@ -284,11 +287,10 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
     for (int a = 0; a < 3; ++a) { h.obs_a[i][a] = obs_a[i * 3 + a]; h.obs_b[i][a] = obs_b[i * 3 + a]; }
   }
   ctx->prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
-  ctx->prm.nref = cfg->ipm_nref > 0 ? cfg->ipm_nref : ((cfg->model_id == ASTROBEE_SE3 || cfg->model_id == FREEFLYER_SE2) ? 1 : 2);   // no trust region => H is only regularised by delta_p on free directions: refine twice
-  // astrobeeSE3manifold: no trust region (H singular in many directions) -> larger primal regularisation
   ctx->prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
-  ctx->prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : (cfg->model_id == ASTROBEE_SE3_MANIFOLD ? 1e-5 : 1e-6);
-  ctx->prm.delta_d = cfg->ipm_delta_d > 0 ? cfg->ipm_delta_d : 1e-10;
+  // PointGoal rows: penalty weight w_N = wn_base + wn_omega * omega (ipm.cuh); ipm_nref / ipm_delta_p / ipm_delta_d of the
+  // configuration are accepted and ignored since round 2 (the Riccati solve has no regularisation and no refinement)
+  ctx->prm.wn_base = 1e8; ctx->prm.wn_omega = 1e4;
 
   const size_t B = cfg->B, N = cfg->N, no = h.n_obs > 0 ? h.n_obs : 1;
   auto alloc = [&](double** ptr, size_t n) {

@@ -42,6 +42,8 @@
 #define G_WARP 32
 #endif
 #define G_W0_FOR(i, n) for (int i = G_TID; i < (n); i += G_WARP)
+// loop over the lanes of the executing warp (any warp)
+#define G_LANE_FOR(i, n) for (int i = G_LANE; i < (n); i += G_NLANE)
 
 // Asynchronous global->shared copies (LDGSTS): the block-tridiagonal sweeps prefetch the next block's factor while the
 // current one is applied.  16-byte form needs 16-byte aligned source and destination.  Host simulation: plain copies.
@@ -99,10 +101,13 @@ inline void g_mbar_expect_tx(unsigned long long*, unsigned) {}
 inline void g_tma_bulk_g2s(double* dst, const double* src, unsigned bytes, unsigned long long*) { for (unsigned i = 0; i < bytes / 8; ++i) dst[i] = src[i]; }
 inline void g_mbar_wait(unsigned long long*, unsigned) {}
 inline void g_fence_proxy_async() {}
+inline void g_fence_proxy_async_global() {}
 inline void g_prefetch_l1(const void*) {}
 #else
 __device__ __forceinline__ void g_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void g_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy GLOBAL writes that a later cp.async.bulk (async proxy) reads back need the unqualified cross-proxy fence
+__device__ __forceinline__ void g_fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void g_mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -127,6 +132,123 @@ __device__ __forceinline__ void g_mbar_wait(unsigned long long* bar, unsigned pa
   }
 }
 #endif
+
+// Warp-level FP64 tensor-core tile product (DMMA, mma.sync.m8n8k4.f64): one warp produces an 8 x 8 output tile
+//   D[i0 + r][q0 + c] = sum_{m < 4 KS} X(i0 + r, m) * Y(q0 + c, m)          ("A B'" form; both operands are read the same way)
+// with X(r, m) = X[r*ldx + m] (or X[m*ldx + r] when TA), likewise Y / TB.  Fragments come straight from shared memory, one
+// 8-byte load per operand and k-step: lane l reads row (l >> 2), k-offset (l & 3) -- conflict-free when ld mod 16 is 4 or 12 --
+// and ends up holding D[i0 + (l >> 2)][q0 + 2 (l & 3) + {0, 1}], handed to the epilogue `epi(row, col, value)`.
+// One DMMA issues 256 multiply-adds in ONE instruction slot (8 DFMA slots otherwise): the solve kernel is issue-bound.
+//   -DGUSTO_NO_DMMA : same thread -> element mapping with scalar DFMA (the measured comparison, profiles/r02_history.md)
+//   host simulation : plain loops over the 64 elements.
+#ifdef GUSTO_HOSTSIM
+#define G_WARPID 0
+#define G_NWARP 1
+#else
+#define G_WARPID ((int)(G_TID >> 5))
+#define G_NWARP ((int)(G_NTHR >> 5))
+__device__ __forceinline__ void g_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+template <bool T> GDEV double g_tile_at(const double* X, int ld, int row, int m) { return T ? X[m * ld + row] : X[row * ld + m]; }
+#ifndef GUSTO_HOSTSIM
+template <int KS, bool TA, bool TB>
+__device__ __forceinline__ void g_tile_acc(double& c0, double& c1, const double* X, int ldx, int i0, const double* Y, int ldy, int q0) {
+  const int g = G_LANE >> 2, t = G_LANE & 3;
+#ifndef GUSTO_NO_DMMA
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) g_dmma(c0, c1, g_tile_at<TA>(X, ldx, i0 + g, 4 * ks + t), g_tile_at<TB>(Y, ldy, q0 + g, 4 * ks + t));
+#else
+#pragma unroll
+  for (int m = 0; m < 4 * KS; ++m) {
+    const double xa = g_tile_at<TA>(X, ldx, i0 + g, m);
+    c0 = fma(xa, g_tile_at<TB>(Y, ldy, q0 + 2 * t, m), c0);
+    c1 = fma(xa, g_tile_at<TB>(Y, ldy, q0 + 2 * t + 1, m), c1);
+  }
+#endif
+}
+#endif
+template <int KS, bool TA, bool TB, typename EPI>
+GDEV void g_tile_job(const double* X, int ldx, int i0, const double* Y, int ldy, int q0, EPI&& epi) {
+#ifdef GUSTO_HOSTSIM
+  for (int r = 0; r < 8; ++r)
+    for (int c2 = 0; c2 < 8; ++c2) {
+      double s = 0.0;
+      for (int m = 0; m < 4 * KS; ++m) s += g_tile_at<TA>(X, ldx, i0 + r, m) * g_tile_at<TB>(Y, ldy, q0 + c2, m);
+      epi(i0 + r, q0 + c2, s);
+    }
+#else
+  double c0 = 0.0, c1 = 0.0;
+  g_tile_acc<KS, TA, TB>(c0, c1, X, ldx, i0, Y, ldy, q0);
+  const int g = G_LANE >> 2, t = G_LANE & 3;
+  epi(i0 + g, q0 + 2 * t, c0);
+  epi(i0 + g, q0 + 2 * t + 1, c1);
+#endif
+}
+// MT x NT tiles at once (rows i0 + 8 mi, columns q0 + 8 ni): the k-steps of the tiles are interleaved, so MT * NT independent
+// DMMA chains are in flight (one DMMA has ~150 cycles of latency here) and every fragment is loaded once per k-step.
+template <int KS, int MT, int NT, bool TA, bool TB, typename EPI>
+GDEV void g_tile_grid(const double* X, int ldx, int i0, const double* Y, int ldy, int q0, EPI&& epi) {
+#ifdef GUSTO_HOSTSIM
+  for (int mi = 0; mi < MT; ++mi)
+    for (int ni = 0; ni < NT; ++ni) g_tile_job<KS, TA, TB>(X, ldx, i0 + 8 * mi, Y, ldy, q0 + 8 * ni, epi);
+#else
+  const int g = G_LANE >> 2, t = G_LANE & 3;
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+#ifndef GUSTO_NO_DMMA
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    double a[MT], b[NT];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) a[mi] = g_tile_at<TA>(X, ldx, i0 + 8 * mi + g, 4 * ks + t);
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) b[ni] = g_tile_at<TB>(Y, ldy, q0 + 8 * ni + g, 4 * ks + t);
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) g_dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+#else
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) g_tile_acc<KS, TA, TB>(acc[mi][ni][0], acc[mi][ni][1], X, ldx, i0 + 8 * mi, Y, ldy, q0 + 8 * ni);
+#endif
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+      epi(i0 + 8 * mi + g, q0 + 8 * ni + 2 * t, acc[mi][ni][0]);
+      epi(i0 + 8 * mi + g, q0 + 8 * ni + 2 * t + 1, acc[mi][ni][1]);
+    }
+#endif
+}
+// ... the sum of two such products (second operand pair X2 / Y2 with its own k-length and orientation)
+template <int KS, bool TA, bool TB, int KS2, bool TA2, bool TB2, typename EPI>
+GDEV void g_tile_job2(const double* X, int ldx, const double* Y, int ldy, const double* X2, int ldx2, const double* Y2, int ldy2,
+                      int i0, int q0, EPI&& epi) {
+#ifdef GUSTO_HOSTSIM
+  for (int r = 0; r < 8; ++r)
+    for (int c2 = 0; c2 < 8; ++c2) {
+      double s = 0.0;
+      for (int m = 0; m < 4 * KS; ++m) s += g_tile_at<TA>(X, ldx, i0 + r, m) * g_tile_at<TB>(Y, ldy, q0 + c2, m);
+      for (int m = 0; m < 4 * KS2; ++m) s += g_tile_at<TA2>(X2, ldx2, i0 + r, m) * g_tile_at<TB2>(Y2, ldy2, q0 + c2, m);
+      epi(i0 + r, q0 + c2, s);
+    }
+#else
+  double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;               // two independent chains
+  g_tile_acc<KS, TA, TB>(c0, c1, X, ldx, i0, Y, ldy, q0);
+  g_tile_acc<KS2, TA2, TB2>(d0, d1, X2, ldx2, i0, Y2, ldy2, q0);
+  const int g = G_LANE >> 2, t = G_LANE & 3;
+  epi(i0 + g, q0 + 2 * t, c0 + d0);
+  epi(i0 + g, q0 + 2 * t + 1, c1 + d1);
+#endif
+}
 
 // Address-space hint: pointers that travel through the per-instance context struct come back as generic pointers;
 // telling the compiler they are shared turns LD.E/ST.E (64-bit generic path) back into LDS/STS.
@@ -161,6 +283,8 @@ constexpr int MAX_OBS = 64;
 //     Hessian of a knot is then  dg*I + blockdiag(blocks) + kappa_tr * g g'  (Sherman-Morrison invertible).
 //   * a_row/a_col: the static sparsity pattern of A = df/dx (entries that can be non-zero), ANZ entries.
 //   * b_row(a): the single state row driven by control a (B = df/du has one entry per column).
+//   * DSPLIT: the dynamics decouple into the coordinates [0, DSPLIT) and [DSPLIT, NX) (translation | rotation of the Astrobee
+//     models; 0 = no split): A, B and hence F^-1, Ah, Bh, Gam of the Riccati solve are block diagonal in that partition.
 #define GUSTO_BLOCKS(NAME, CNT, O0, N0, O1, N1, O2, N2, O3, N3)                                            \
   static constexpr int NAME##_CNT = CNT;                                                                    \
   GHD static constexpr int NAME##_off(int b) { return b == 0 ? O0 : b == 1 ? O1 : b == 2 ? O2 : O3; }      \
@@ -178,7 +302,7 @@ constexpr int MAX_OBS = 64;
 
 template <int M> struct Traits;
 template <> struct Traits<DUBINS> {
-  static constexpr int NX = 3, NU = 1, WS = 0, HAS_TR = 0, NNORM = 0, NLIN = 6, HAS_QUAT = 0, NBALL = 1;
+  static constexpr int NX = 3, NU = 1, WS = 0, HAS_TR = 0, NNORM = 0, NLIN = 6, HAS_QUAT = 0, NBALL = 1, DSPLIT = 0;
   GUSTO_BLOCKS(XB, 3, 0, 1, 1, 1, 2, 1, 0, 0)
   GUSTO_BLOCKS(UB, 1, 0, 1, 0, 0, 0, 0, 0, 0)
   static constexpr int ANZ = 2;
@@ -187,7 +311,7 @@ template <> struct Traits<DUBINS> {
   GHD static constexpr int b_row(int) { return 2; }
 };
 template <> struct Traits<FREEFLYER_SE2> {
-  static constexpr int NX = 6, NU = 3, WS = 2, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2;
+  static constexpr int NX = 6, NU = 3, WS = 2, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2, DSPLIT = 0;
   GUSTO_BLOCKS(XB, 4, 0, 2, 2, 1, 3, 2, 5, 1)
   GUSTO_BLOCKS(UB, 2, 0, 2, 2, 1, 0, 0, 0, 0)
   static constexpr int ANZ = 3;
@@ -196,7 +320,7 @@ template <> struct Traits<FREEFLYER_SE2> {
   GHD static constexpr int b_row(int a) { return 3 + a; }
 };
 template <> struct Traits<ASTROBEE_SE3> {
-  static constexpr int NX = 12, NU = 6, WS = 3, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2;
+  static constexpr int NX = 12, NU = 6, WS = 3, HAS_TR = 1, NNORM = 2, NLIN = 0, HAS_QUAT = 0, NBALL = 2, DSPLIT = 6;
   GUSTO_BLOCKS(XB, 4, 0, 3, 3, 3, 6, 3, 9, 3)
   GUSTO_BLOCKS(UB, 2, 0, 3, 3, 3, 0, 0, 0, 0)
   // rows 0-2: identity on v | rows 6-8: MRP kinematics wrt (p, w) | rows 9-11: gyroscopic wrt w (off-diagonal)
@@ -211,7 +335,7 @@ template <> struct Traits<ASTROBEE_SE3> {
   GHD static constexpr int b_row(int a) { return a < 3 ? 3 + a : 6 + a; }
 };
 template <> struct Traits<ASTROBEE_SE3_MANIFOLD> {
-  static constexpr int NX = 13, NU = 6, WS = 3, HAS_TR = 0, NNORM = 2, NLIN = 1, HAS_QUAT = 1, NBALL = 2;
+  static constexpr int NX = 13, NU = 6, WS = 3, HAS_TR = 0, NNORM = 2, NLIN = 1, HAS_QUAT = 1, NBALL = 2, DSPLIT = 6;
   GUSTO_BLOCKS(XB, 4, 0, 3, 3, 3, 6, 4, 10, 3)
   GUSTO_BLOCKS(UB, 2, 0, 3, 3, 3, 0, 0, 0, 0)
   // rows 0-2: identity on v | rows 6-9: quaternion kinematics wrt (q, w) minus the zero diagonal | rows 10-12: gyroscopic

@@ -1,4 +1,4 @@
-// K3: batched convex-subproblem solve, one CTA per problem instance.
+// K3: batched convex-subproblem solve, one group of threads per problem instance.
 //
 // Solves the GuSTO penalized QCQP assembled by add_constraints_gusto_jump! / add_objective_gusto_jump!
 // (/root/reference/src/scp/scp_gusto.jl:192-314; exact form in SURVEY.md App. A) directly from the blocks the
@@ -10,23 +10,33 @@
 //   * every inequality touches one knot only; its slack t and both multipliers are eliminated analytically,
 //     leaving a block-diagonal reduced Hessian  H = blkdiag(Hx_k, Hu_k);
 //   * inside a knot every row except the state trust region lives in ONE coordinate block (position | velocity |
-//     attitude | rate, Traits<M>::XB_*), so  Hx_k = blockdiag(<=4x4 blocks) + kappa_tr g g'  and its inverse is
-//     blockdiag(P_b) - coef w w'  (Sherman-Morrison); nothing larger than 4x4 is ever factorised per knot;
+//     attitude | rate, Traits<M>::XB_*), so  Hx_k = blockdiag(<=4x4 blocks) + kappa_tr g g';
 //   * A_k = df/dx is used through its static sparsity pattern (Traits<M>::a_row/a_col, 27 of 144 entries for SE3);
-//   * the equality rows (init, trapezoid dynamics, point goal) are block-bidiagonal, so the Schur complement
-//     S = Aeq (H + dp I)^-1 Aeq' is block-tridiagonal with N+1 blocks of NX x NX.  It is factorised as a block
-//     L D L' with explicit D_j^-1 (Gauss-Jordan in shared memory on one warp while the other warp prefetches the
-//     next block row), so each solve is two chains of N dependent NX x NX mat-vecs streamed through a TMA
-//     (cp.async.bulk + mbarrier) ring plus one fully parallel D^-1 pass;
-//   * Newton directions are recovered with `nref` steps of iterative refinement against the unregularised KKT
-//     matrix (H alone is only positive SEMI-definite: the cost has no state term).
+//   * the Newton system  [[H, Aeq'], [Aeq, 0]] [dz; dnu] = [r; rnu]  is solved by a PRIMAL RICCATI RECURSION over the
+//     knots (round 2; round 1 factorised the Schur complement Aeq (H + dp I)^-1 Aeq', which needs a regularised inverse
+//     of Hx -- Hx is singular wherever no soft row is active, on astrobeeSE3manifold in most directions).  The
+//     trapezoid row  E_j x_{j-1} + G u_{j-1} - F_j x_j + G u_j = rho_j  (E_j = I + h/2 A_{j-1}, F_j = I - h/2 A_j,
+//     G = h/2 B) is implicit in x_j and couples u_{j-1} AND u_j; with the shifted state  s_j = x_j - Gam_j u_j,
+//     Gam_j = F_j^-1 G (Gam_0 = 0) it becomes  s_{j+1} = Ah_j s_j + Bh_j u_j + ch_j  with  Ah_j = F_{j+1}^-1 E_{j+1},
+//     Bh_j = Ah_j Gam_j + Gam_{j+1},  ch_j = -F_{j+1}^-1 rho_{j+1},  and the stage cost picks up the cross term
+//     S = Gam'Hx, R = Hu + Gam'Hx Gam.  Ah, Bh, Gam are computed once per solve (setup_dynamics); per Newton iteration
+//       Lam_k = R_k + Bh_k'P_{k+1}Bh_k (n_u x n_u, >= Hu_k > 0: the ONLY matrix ever factorised, Cholesky in registers),
+//       M_k = S_k + Bh_k'P_{k+1}Ah_k,  K_k = Lam_k^-1 M_k,  P_k = Hx_k + Ah_k'P_{k+1}Ah_k - M_k'K_k,
+//     4 group barriers per knot; the backward vector pass of the predictor is fused into the same sweep.  A solve with a
+//     new right-hand side is a backward and a forward chain of ONE n_x x n_x mat-vec per knot with the closed-loop
+//     tiles  Acl_k = Ah_k - Bh_k K_k  prefetched into registers three knots ahead, plus parallel per-knot passes.  No primal or dynamics regularisation and no iterative refinement; the PointGoal rows  M x_{N-1} = goal
+//     are a quadratic penalty  w_N |.|^2 / 2  = dual regularisation 1/w_N of THOSE rows only (w_N = 1e8 + 1e4 omega;
+//     the row error after a step is dnu_N / w_N and contracts by ~1e-6 per Newton iteration);
+//   * equality multipliers of the original rows are recovered from the Riccati costates:  dnu_j = F_j^-T (P_j s_j - p_j).
+// tools/riccati_proto.py is the NumPy prototype of this arithmetic inside the oracle's IPM (same Newton counts on all
+// four models, omega = 1 .. 1e10).
 // A first-order splitting (ADMM, prototyped in tools/admm_proto.py) was rejected: GuSTO's accept test compares
 // soft rows against eps = 1e-6 (astrobee_se3.jl:31, scp_gusto.jl:318-327), and with a trapezoid double
 // integrator over 70 s ADMM needs >2000 iterations for 1e-6 residuals while this method needs 8-25 for 1e-8.
 //
-// Memory: the iterate z, the direction dz and the Schur right-hand side live in shared memory; multipliers, slack
-// records (compacted to the obstacle rows inside the toggle distance), per-knot block inverses and the
-// block-tridiagonal factor live in a per-instance global scratch that stays L2-resident.
+// Memory: the iterate z, the direction dz and the costate chain live in shared memory; multipliers, slack records
+// (compacted to the obstacle rows inside the toggle distance), per-knot Hessian blocks, the per-solve dynamics records
+// and the per-iteration Riccati factors (Acl, K, chol(Lam), P) live in a per-instance global scratch.
 // All arithmetic is FP64 (the reference is Float64 throughout).
 #pragma once
 #include "common.cuh"
@@ -36,7 +46,6 @@
 #include <cstdio>
 #include <cstdlib>
 #endif
-
 // ---- instance groups.  One instance is solved by a GROUP of GUSTO_IPM_GROUP threads (2 warps).  A CTA packs several groups
 // (one per instance, capi.cu chooses how many): inside this file the SPMD macros address the group, not the CTA --
 // G_TID / G_NTHR are the thread's index in / the size of its group, G_SYNC is the group's own named barrier
@@ -110,42 +119,47 @@ __device__ __noinline__ double ipm_group_max(double v, double* red) {   // NaN-p
 #endif
 
 #if defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3
-#define GUSTO_PROF_SOLVE 0
+#define GUSTO_PROF_CHAINS 0
 #else
-#define GUSTO_PROF_SOLVE 1
+#define GUSTO_PROF_CHAINS 1
 #endif
 
 struct IpmParams {
   int max_iter;      // Newton iterations cap
-  int nref;          // refinement steps on the corrector solve
   double tol;        // max(|r_dual|/(1+omega), |r_eq|, |r_ineq|, mu) <= tol
-  double delta_p;    // primal regularisation added to Hx, Hu in the factorisation only
-  double delta_d;    // relative regularisation of the Schur diagonal
+  double wn_base;    // terminal (PointGoal) penalty  w_N = wn_base + wn_omega * omega
+  double wn_omega;
 };
 
-enum : int { IPM_OPTIMAL = 0, IPM_ITERATION_LIMIT = 1, IPM_NUMERICAL = 2 };
+// IPM_ALMOST_OPTIMAL: stalled within 1e3*tol of the tolerance AND far below the SCP's own soft-row threshold eps -- the
+// MOI.ALMOST_LOCALLY_SOLVED the reference accepts next to OPTIMAL (scp_gusto.jl:107); the host records it as such.
+enum : int { IPM_OPTIMAL = 0, IPM_ITERATION_LIMIT = 1, IPM_NUMERICAL = 2, IPM_ALMOST_OPTIMAL = 3 };
 constexpr int SLOT_W = 6;     // s, lam, t, lamb, pa (ds*dlam of the predictor), pb (dt*dlamb of the predictor)
 constexpr int OROW_W = 5;     // compacted obstacle row: nhat[3], off, knot
 constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cycles: assemble+slots, factorize, kkt solves
-#ifndef GUSTO_RING_STAGES
-#define GUSTO_RING_STAGES 8
-#endif
-constexpr int RING_STAGES = GUSTO_RING_STAGES;
 
 GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
 template <int M> struct IpmLayout {
   using T = Traits<M>;
   static constexpr int NX = T::NX, NU = T::NU, NV = NX + NU, NN = NX * NX, ANZ = T::ANZ;
-  static constexpr int GLD = (NX + 1) & ~1;               // row stride of a factor tile in global memory (16-byte rows)
-  static constexpr int GT = NX * GLD;
-  static constexpr int LDT = 2 * (((NX + 1) / 2) | 1);     // row stride of a shared-memory tile: even, LDT/2 odd -> LDS.128 conflict-free
-  static constexpr int TILE = NX * LDT;
-  static constexpr int CG = NX <= 12 ? 3 : 4;              // output columns per thread task in the tile products
-  static constexpr int NG = (NX + CG - 1) / CG;
-  static constexpr int NTASK = NX * NG;                    // tasks of a full product
-  GHD static constexpr int nlt() { int n = 0; for (int i = 0; i < NX; ++i) for (int g = 0; g < NG; ++g) if (g * CG <= i) ++n; return n; }
-  static constexpr int NLT = nlt();                        // tasks touching the lower triangle
+  // Tiles of the Riccati sweep are operands of 8x8x4 FP64 tensor-core products (g_tile_job, common.cuh): contraction lengths
+  // are padded to a multiple of 4 (KP, KU), row counts to a multiple of 8 (NXP, NUP, RXS), and the row stride is the smallest
+  // value >= the padded length with stride mod 16 in {4, 12} (conflict-free fragment loads).
+  static constexpr int KP = (NX + 3) & ~3, KU = (NU + 3) & ~3;
+  GHD static constexpr int ld_of(int kp) { int ld = kp; while ((ld & 15) != 4 && (ld & 15) != 12) ++ld; return ld; }
+  static constexpr int LDT = ld_of(KP);                    // 12 (SE3), 20 (manifold), 12 (freeflyer), 4 (dubins)
+  static constexpr int LDU = ld_of(KU);                    // row stride of the n_x x n_u tiles (K', Y', M', S')
+  static constexpr int NXP = (NX + 7) & ~7, NUP = 8, RXS = (NX + NU + 1 + 7) & ~7;
+  static constexpr int TILE = NXP * LDT;
+  static constexpr int GT = NX * LDT;                      // closed-loop tile in global memory (one bulk copy per chain step)
+  static constexpr int NTX = NX * (NX + 1) / 2, NTU = NU * (NU + 1) / 2;
+  // decoupled dynamics blocks (Traits<M>::DSPLIT): state range [dlo(i), dhi(i)) of the block holding coordinate i
+  GHD static constexpr int dlo(int i) { return (T::DSPLIT > 0 && i >= T::DSPLIT) ? T::DSPLIT : 0; }
+  GHD static constexpr int dhi(int i) { return (T::DSPLIT > 0 && i < T::DSPLIT) ? T::DSPLIT : NX; }
+  GHD static constexpr bool dsame(int i, int j) { return dlo(i) == dlo(j); }
+  GHD static constexpr bool dcheck() { for (int e = 0; e < ANZ; ++e) if (!dsame(T::a_row(e), T::a_col(e))) return false; return true; }
+  static constexpr int DMAX = T::DSPLIT > 0 ? (T::DSPLIT > NX - T::DSPLIT ? T::DSPLIT : NX - T::DSPLIT) : NX;
   // special (non-obstacle) slots of a knot
   static constexpr int S_TR = 0;
   static constexpr int S_NORM = T::HAS_TR;
@@ -155,32 +169,50 @@ template <int M> struct IpmLayout {
   static constexpr int SP = S_BALL + T::NBALL;
   static constexpr int NBOX = 2 * NX;                      // goal-box rows (upper, lower per coordinate), knot N-1 only
   static constexpr int XPK = T::XB_pk(T::XB_CNT), UPK = T::UB_pk(T::UB_CNT);
-  // per-knot record: Hb[XPK] P[XPK] w[NX] Hub[UPK] Th[UPK] kap coef
-  static constexpr int KD_HB = 0, KD_P = XPK, KD_W = 2 * XPK, KD_HU = KD_W + NX, KD_TH = KD_HU + UPK,
-                       KD_KAP = KD_TH + UPK, KD_COEF = KD_KAP + 1, KDW = KD_COEF + 1;
+  // per-knot Hessian record: Hb[XPK] (packed x-blocks) | Hub[UPK] (packed u-blocks) | w[NX] = sqrt(kap_tr) * 2 (x - xp)
+  static constexpr int KD_HB = 0, KD_HU = XPK, KD_W = XPK + UPK, KDW = (KD_W + NX + 1) & ~1;
+  // per-knot dynamics record, constant over a solve (setup_dynamics): rows of Ah' (NX), Bh' (NU), Gam' (NU), each LDT long
+  static constexpr int CR_AT = 0, CR_BT = NX, CR_GT = NX + NU, CRR = NX + 2 * NU, CRW = CRR * LDT;
+  // per-knot Riccati factor of one Newton iteration: K' [NX][LDU], packed P
+  static constexpr int KTW = NX * LDU, LPW = (NTU + 1) & ~1, PKW = (NTX + 1) & ~1;   // lp: packed lower L^-1 of Lam = L L'
   GHD static size_t rnd(size_t v) { return (v + 1) & ~(size_t)1; }   // keep every array 16-byte aligned
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
-    const size_t nz = rnd((size_t)N * NV), ne = rnd((size_t)(N + 1) * NX), no = T::WS > 0 ? n_obs : 0;
-    return 3 * nz + 4 * ne + rnd((size_t)N * ANZ) + rnd((size_t)N * SP * SLOT_W) + (size_t)NBOX * SLOT_W +
-           rnd((size_t)N * no * SLOT_W) + rnd((size_t)N * no * OROW_W) + rnd((size_t)N * KDW) + (size_t)(N + 1) * 2 * GT;
+    const size_t nz = rnd((size_t)N * NV), ne = rnd((size_t)(N + 1) * NX), no = T::WS > 0 ? n_obs : 0, nn = (size_t)N;
+    return nz /* r */ + 3 * ne /* nu dnu rnu */ + rnd(nn * ANZ) + rnd(nn * SP * SLOT_W) + (size_t)NBOX * SLOT_W +
+           rnd(nn * no * SLOT_W) + rnd(nn * no * OROW_W) + nn * KDW +
+           rnd(nn * NN) /* Fi */ + nn * CRW + nn * GT /* Acl */ + nn * KTW + nn * LPW + nn * PKW + 2 * rnd(nn * NX) /* psi ch */ + nn * LDU /* kap */;
   }
-  GHD static int work_doubles(int N) {      // dz | sy | ring, also the 8 factorisation tiles
-    const int ne = (int)rnd((size_t)(N + 1) * NX);
-    const int ring = RING_STAGES * GT > ne ? RING_STAGES * GT : ne;      // ring stages are plain copies of the global tiles
-    const int w = (int)rnd((size_t)N * NV) + ne + ring, f = FAC_TILES * TILE + 2 * KS + 2 * NX + 4;
-    return (w > f ? w : f) + 2;
+  // shared-memory tiles of the Riccati sweep (doubles); they alias the direction dz
+  static constexpr int XSR = RXS + NUP;                     // staged dynamics record: Ah' | Bh' | ch | 0.. | Gam' (row RXS) | 0..
+  static constexpr int F_XS = 0;                            // two of them
+  static constexpr int F_PA = F_XS + 2 * XSR * LDT;         // P_{k+1} and the W / P_k under construction, alternating
+  static constexpr int F_PB = F_PA + TILE;
+  static constexpr int F_Z1 = F_PB + TILE;                  // (P Ah)' rows | (P Bh)' rows | (P ch)' ; later Y' = (L^-1 [M | rt])'
+  static constexpr int F_QD = F_Z1 + RXS * LDT;             // dense Hx
+  static constexpr int F_SM = F_QD + TILE;                  // S' = Hx Gam, then M' (row NX: rt), then K' (row NX: kap)
+  static constexpr int F_LM = F_SM + NXP * LDU;             // Lam
+  static constexpr int F_LI = F_LM + NUP * LDU;             // L^-1 (lower triangular)
+  static constexpr int F_HU = F_LI + NUP * LDU;             // dense Hu
+  static constexpr int SBW = (KDW + NV + NX + 1) & ~1;      // staged inputs of a knot: Hessian record | rhs | ch
+  static constexpr int F_SB = F_HU + NUP * LDU;             // two of them
+  static constexpr int F_VEC = F_SB + 2 * SBW;              // q[2][KP] | ru[2][KU] | pit[KP]
+  static constexpr int V_Q = 0, V_RU = 2 * KP, V_PIT = V_RU + 2 * KU, VECW = V_PIT + KP;
+  static constexpr int FAC_DOUBLES = F_VEC + VECW;
+  static constexpr int GJ_ROWS = (64 / NX) * NX;            // setup_dynamics: (knot, row) pairs of one Gauss-Jordan batch
+  static constexpr int GJ_DOUBLES = GJ_ROWS * 2 * NX;
+  static_assert(NXP * LDU <= RXS * LDT && GJ_DOUBLES <= FAC_DOUBLES, "aliased tiles do not fit");
+  GHD static int work_doubles(int N) {      // dz, also the tiles of the sweep
+    const int w = (int)rnd((size_t)N * NV);
+    return (w > FAC_DOUBLES ? w : FAC_DOUBLES) + 2;
   }
-  // byte tables: (row, col) of the packed lower triangle, (row, group) of the lower-triangular product tasks, then the
-  // model tables used with run-time indices: a_row[ANZ], a_col[ANZ], blk_of[NX], ctrl_of[NX]
-  static constexpr int TAB_MODEL = NX * (NX + 1) + 2 * NLT;
-  static constexpr int TAB_DOUBLES = (TAB_MODEL + 2 * ANZ + 2 * NX + 7) / 8;
-  // factor sweep: 10 sweep tiles + Phi, Ah, Y, Z, RR of the Schur-block producer; staged knot record
-  static constexpr int FAC_TILES = 15;
-  static constexpr int KS_P = 0, KS_W = XPK, KS_TH = XPK + NX, KS_COEF = KS_TH + UPK, KS_A = KS_COEF + 1, KS = (KS_A + ANZ + 1) & ~1;
+  // byte tables with run-time indices: a_row[ANZ], a_col[ANZ], blk_of[NX]
+  static constexpr int TAB_DOUBLES = (2 * ANZ + NX + 7) / 8;
   GHD static int seg_doubles(int N) { return (N + 4) / 2 + 2; }
   static constexpr int CTX_DOUBLES = 80;                   // the per-instance context struct (IpmCtx) lives in shared memory too
-  GHD static int smem_doubles(int N, int nthr) { return CTX_DOUBLES + (int)rnd((size_t)N * NV) + work_doubles(N) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES; }
+  GHD static int smem_doubles(int N, int nthr) {
+    return CTX_DOUBLES + (int)rnd((size_t)N * NV) + work_doubles(N) + (int)rnd((size_t)(N + 1) * NX) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES;
+  }
 };
 
 template <int M> struct IpmCtx {
@@ -189,27 +221,25 @@ template <int M> struct IpmCtx {
   const BatchDesc* d;
   const double* rp;
   int N, n_obs, b, nact, pmask, bmask;
-  double h, hh, omega, Delta, toggle, eps, dd;
-  mutable double dp;       // primal regularisation (raised x100 after a failed factorisation)
+  double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
   // global scratch
-  double *nu, *dnu, *r, *rnu, *t1, *res, *resnu, *Ac, *sslot, *bslot, *ost, *orow, *kd, *fac;
+  double *nu, *dnu, *r, *rnu, *Ac, *sslot, *bslot, *ost, *orow, *kd;
+  double *fi, *cr, *acl, *kt, *lp, *pk, *psi, *ch, *kap;
   // shared
-  double *z, *dz, *sy, *ring, *red;
+  double *z, *dz, *vp, *red;
   int* seg;
-  mutable unsigned long long ring_bar[RING_STAGES];   // one mbarrier per ring stage (TMA completion)
-  mutable unsigned ring_o;                             // tiles fetched so far (stage = o % S, wait parity = (o / S) & 1)
-  mutable long long prof[5];      // thread-0 cycle counters: schur rows, factor sweep, forward chain, middle pass, backward chain
-  unsigned char* tab;     // [2][NX(NX+1)/2]: row / column of packed-lower entry t; then [2][NLT]: row / group of lower task
+  mutable long long prof[4];      // thread-0 cycle counters: Riccati sweep, chains, per-knot passes, (spare)
+  unsigned char* tab;     // a_row[ANZ] | a_col[ANZ] | blk_of[NX]
 };
 
 // shared-memory members, with the address space made known to the compiler
 template <int M> GDEV double* sh_z(const IpmCtx<M>& c) { double* p = c.z; G_ASSUME_SHARED(p); return p; }
 template <int M> GDEV double* sh_dz(const IpmCtx<M>& c) { double* p = c.dz; G_ASSUME_SHARED(p); return p; }
-template <int M> GDEV double* sh_sy(const IpmCtx<M>& c) { double* p = c.sy; G_ASSUME_SHARED(p); return p; }
+template <int M> GDEV double* sh_vp(const IpmCtx<M>& c) { double* p = c.vp; G_ASSUME_SHARED(p); return p; }
 template <int M> GDEV int* sh_seg(const IpmCtx<M>& c) { return c.seg; }   // (an address-space assumption on this one miscompiles with nvcc 12.9)
 
 // ------------------------------------------------------------------------------------------- slot algebra
@@ -390,19 +420,29 @@ template <int M> GDEV double box_c0(const IpmCtx<M>& c, int j, const double* x) 
   return (j & 1) == 0 ? x[i] - c.goal_hi[i] : c.goal_lo[i] - x[i];
 }
 
-// ------------------------------------------------------------------------------------- small SPD blocks
-// P = (H + dp I)^-1 for a packed-lower SPD block of order n <= 4 (Cholesky, triangular inverse, Li' Li).
-template <int n> GDEV bool spd_inv_packed(const double* H, double dp, double* P) {
-  double Lc[n * (n + 1) / 2], Li[n * (n + 1) / 2];
+
+// ------------------------------------------------------------------------------------- small dense helpers
+// out[0:n) = Sym(packed) * v[0:n)
+template <int n> GDEV void sym_mv(const double* Pk, const double* v, double* out) {
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) s += Pk[tri(i, j)] * v[j];
+    out[i] = s;
+  }
+}
+// In-register Cholesky of a packed-lower SPD matrix of order n <= 6; the diagonal of Lc holds 1 / l_jj.
+template <int n> GDEV bool chol_packed(const double* H, double* Lc) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < n; ++j) {
-    double dj = H[tri(j, j)] + dp;
+    double dj = H[tri(j, j)];
 #pragma unroll
     for (int m = 0; m < j; ++m) dj -= Lc[tri(j, m)] * Lc[tri(j, m)];
     if (!(dj > 0.0)) { ok = false; dj = 1e-300; }
     const double il = g_rsqrt(dj);
-    Lc[tri(j, j)] = il;                       // the diagonal holds 1 / l_jj
+    Lc[tri(j, j)] = il;
 #pragma unroll
     for (int i = j + 1; i < n; ++i) {
       double v = H[tri(i, j)];
@@ -411,36 +451,24 @@ template <int n> GDEV bool spd_inv_packed(const double* H, double dp, double* P)
       Lc[tri(i, j)] = v * il;
     }
   }
-#pragma unroll
-  for (int j = 0; j < n; ++j) {
-    Li[tri(j, j)] = Lc[tri(j, j)];
-#pragma unroll
-    for (int i = j + 1; i < n; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int m = j; m < i; ++m) s += Lc[tri(i, m)] * Li[tri(m, j)];
-      Li[tri(i, j)] = -s * Lc[tri(i, i)];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < n; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int m = i; m < n; ++m) s += Li[tri(m, i)] * Li[tri(m, j)];
-      P[tri(i, j)] = s;
-    }
   return ok;
 }
-
-// out[0:n) = Sym(packed) * v[0:n)
-template <int n> GDEV void sym_mv(const double* Pk, const double* v, double* out) {
+// out = Lv in  /  out = Lv' in  for a packed lower-triangular Lv (the stored L^-1 of a Lam_k)
+template <int n> GDEV void tri_lower_mv(const double* Lv, const double* in, double* out) {
 #pragma unroll
   for (int i = 0; i < n; ++i) {
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < n; ++j) s += Pk[tri(i, j)] * v[j];
+    for (int m = 0; m <= i; ++m) s += Lv[tri(i, m)] * in[m];
+    out[i] = s;
+  }
+}
+template <int n> GDEV void tri_lower_tmv(const double* Lv, const double* in, double* out) {
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int m = i; m < n; ++m) s += Lv[tri(m, i)] * in[m];
     out[i] = s;
   }
 }
@@ -500,54 +528,35 @@ template <int M> GDEV void aeqT_knot(const IpmCtx<M>& c, const double* nu, int k
   for (int a = 0; a < NU; ++a) out[NX + a] = c.hh * c.bv[a] * wv[T::b_row(a)];
 }
 
-// out = (H_k + dp I)^-1 in  for knot k:  state part blockdiag(P_b) - coef w w', control part blockdiag(Th_b)
-template <int M, int B0 = 0> GDEV void phi_x_blocks(const double* P, const double* in, double* out) {
+// out = blockdiag(packed blocks) * in  over the x-blocks / u-blocks
+template <int M, int B0 = 0> GDEV void xblocks_mv(const double* P, const double* in, double* out) {
   using T = Traits<M>;
   if constexpr (B0 < T::XB_CNT) {
     sym_mv<T::XB_n(B0)>(P + T::XB_pk(B0), in + T::XB_off(B0), out + T::XB_off(B0));
-    phi_x_blocks<M, B0 + 1>(P, in, out);
+    xblocks_mv<M, B0 + 1>(P, in, out);
   }
 }
-template <int M, int B0 = 0> GDEV void phi_u_blocks(const double* P, const double* in, double* out) {
+template <int M, int B0 = 0> GDEV void ublocks_mv(const double* P, const double* in, double* out) {
   using T = Traits<M>;
   if constexpr (B0 < T::UB_CNT) {
     sym_mv<T::UB_n(B0)>(P + T::UB_pk(B0), in + T::UB_off(B0), out + T::UB_off(B0));
-    phi_u_blocks<M, B0 + 1>(P, in, out);
+    ublocks_mv<M, B0 + 1>(P, in, out);
   }
 }
-template <int M> GDEV void apply_phi(const IpmCtx<M>& c, int k, const double* in, double* out) {
+// out[0:NX) = Hx_k in   (Hx_k = blockdiag(Hb) + w w',  w = sqrt(kap_tr) 2 (x_k - xp_k))
+template <int M> GDEV void apply_Hx(const IpmCtx<M>& c, int k, const double* in, double* out) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX;
   const double* kd = c.kd + (size_t)k * L::KDW;
-  phi_x_blocks<M>(kd + L::KD_P, in, out);
+  xblocks_mv<M>(kd + L::KD_HB, in, out);
   if (T::HAS_TR) {
-    const double* w = kd + L::KD_W;
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) s += w[i] * in[i];
-    s *= kd[L::KD_COEF];
+    for (int i = 0; i < NX; ++i) s += kd[L::KD_W + i] * in[i];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) out[i] -= s * w[i];
+    for (int i = 0; i < NX; ++i) out[i] += s * kd[L::KD_W + i];
   }
-  phi_u_blocks<M>(kd + L::KD_TH, in + NX, out + NX);
-}
-// out = H_k in  (unregularised)
-template <int M> GDEV void apply_H(const IpmCtx<M>& c, int k, const double* in, double* out) {
-  using L = IpmLayout<M>;
-  using T = Traits<M>;
-  constexpr int NX = L::NX, NV = L::NV;
-  const double* kd = c.kd + (size_t)k * L::KDW;
-  phi_x_blocks<M>(kd + L::KD_HB, in, out);
-  if (T::HAS_TR) {
-    double gvec[NX], s = 0.0;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) { gvec[i] = 2.0 * (sh_z<M>(c)[k * NV + i] - c.Xp[k * NX + i]); s += gvec[i] * in[i]; }
-    s *= kd[L::KD_KAP];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) out[i] += s * gvec[i];
-  }
-  phi_u_blocks<M>(kd + L::KD_HU, in + NX, out + NX);
 }
 
 // ------------------------------------------------------------------------- assembly of H, rhs, residuals
@@ -569,12 +578,12 @@ template <int n> GDEV void block_add(double* Hb, double* gzb, double* rrb, int i
 }
 
 template <int M> struct KnotAcc {       // what the state blocks of a knot share
-  double la_tr, bt_tr, kap_tr, gw;
+  double la_tr, bt_tr, kap_tr;
   Stat st;
 };
 
 template <int M, int B0>
-GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double* gz, KnotAcc<M>& ka, bool& ok) {
+GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double* gz, KnotAcc<M>& ka) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX, NV = L::NV;
@@ -653,23 +662,15 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
     }
     if (phase == 0) {
       double* kd = c.kd + (size_t)k * L::KDW;
-      double P[npk];
-      if (!spd_inv_packed<n>(Hb, c.dp, P)) ok = false;
 #pragma unroll
-      for (int i = 0; i < npk; ++i) { kd[L::KD_HB + T::XB_pk(B0) + i] = Hb[i]; kd[L::KD_P + T::XB_pk(B0) + i] = P[i]; }
-      if (T::HAS_TR) {
-        double w[n];
-        sym_mv<n>(P, gtr, w);
-#pragma unroll
-        for (int i = 0; i < n; ++i) { kd[L::KD_W + off + i] = w[i]; ka.gw += w[i] * gtr[i]; }
-      }
+      for (int i = 0; i < npk; ++i) kd[L::KD_HB + T::XB_pk(B0) + i] = Hb[i];
     }
-    assemble_xblock<M, B0 + 1>(c, k, phase, smu, x, gz, ka, ok);
+    assemble_xblock<M, B0 + 1>(c, k, phase, smu, x, gz, ka);
   }
 }
 
 template <int M, int B0>
-GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double wk, double* gz, KnotAcc<M>& ka, bool& ok) {
+GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, const double* x, double wk, double* gz, KnotAcc<M>& ka) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX, NV = L::NV;
@@ -700,25 +701,22 @@ GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, cons
     }
     if (phase == 0) {
       double* kd = c.kd + (size_t)k * L::KDW;
-      double P[npk];
-      if (!spd_inv_packed<n>(Hb, c.dp, P)) ok = false;
 #pragma unroll
-      for (int i = 0; i < npk; ++i) { kd[L::KD_HU + T::UB_pk(B0) + i] = Hb[i]; kd[L::KD_TH + T::UB_pk(B0) + i] = P[i]; }
+      for (int i = 0; i < npk; ++i) kd[L::KD_HU + T::UB_pk(B0) + i] = Hb[i];
     }
-    assemble_ublock<M, B0 + 1>(c, k, phase, smu, x, wk, gz, ka, ok);
+    assemble_ublock<M, B0 + 1>(c, k, phase, smu, x, wk, gz, ka);
   }
 }
 
-// phase 0: build the per-knot Hessian blocks, their inverses and the predictor rhs (sigma*mu = 0, no second-order
-//          term); also the residual norms.  Returns false through *ok_out when a block is not positive definite.
+// phase 0: build the per-knot Hessian blocks and the predictor rhs (sigma*mu = 0, no second-order term); also the
+//          residual norms and the equality residual rnu = b - Aeq z.
 // phase 1: corrector rhs with centering target `smu` and the stored predictor products.
-template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out, bool* ok_out) {
+template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, double smu, Resid* out) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const int N = c.N;
   Stat S; S.rz = 0; S.rc = 0; S.mus = 0; S.np = 0;
-  bool ok = true;
   G_PAR_FOR(k, N) {
     const double* x = sh_z<M>(c) + k * NV;
     const double* u = x + NX;
@@ -728,7 +726,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 #pragma unroll
     for (int i = 0; i < NU; ++i) gz[NX + i] += 2.0 * wk * u[i];
     KnotAcc<M> ka;
-    ka.la_tr = 0; ka.bt_tr = 0; ka.kap_tr = 0; ka.gw = 0; ka.st = S;
+    ka.la_tr = 0; ka.bt_tr = 0; ka.kap_tr = 0; ka.st = S;
     if (T::HAS_TR) {
       double* st = c.sslot + ((size_t)k * L::SP + L::S_TR) * SLOT_W;
       Pair q;
@@ -737,21 +735,14 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       if (phase == 0) pair_stat(st, true, q, ka.st);
       ka.la_tr = q.la; ka.bt_tr = q.bt; ka.kap_tr = q.kap;
     }
-    assemble_xblock<M, 0>(c, k, phase, smu, x, gz, ka, ok);
-    assemble_ublock<M, 0>(c, k, phase, smu, x, wk, gz, ka, ok);
+    assemble_xblock<M, 0>(c, k, phase, smu, x, gz, ka);
+    assemble_ublock<M, 0>(c, k, phase, smu, x, wk, gz, ka);
     S = ka.st;
-    if (phase == 0) {
+    if (phase == 0 && T::HAS_TR) {
       double* kd = c.kd + (size_t)k * L::KDW;
-      kd[L::KD_KAP] = ka.kap_tr;
-      kd[L::KD_COEF] = T::HAS_TR ? ka.kap_tr * g_rcp(1.0 + ka.kap_tr * ka.gw) : 0.0;
-    }
-    {   // first pass of the KKT solve that follows: t1 = (H + dp I)^-1 r  (kkt_solve)
-      double rv[NV], tv[NV];
+      const double sk = sqrt(ka.kap_tr);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) rv[i] = c.r[k * NV + i];
-      apply_phi<M>(c, k, rv, tv);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = tv[i];
+      for (int i = 0; i < NX; ++i) kd[L::KD_W + i] = sk * (2.0 * (x[i] - c.Xp[k * NX + i]));
     }
   }
   if (phase == 0) {
@@ -779,533 +770,659 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
     out->npair = np;
     out->mu = np > 0 ? ms / np : 0.0;
     if (!(out->mu == out->mu)) out->mu = 1e300;
-    *ok_out = block_max(ok ? 0.0 : 1.0, c.red) == 0.0;
   } else {
     G_SYNC();
   }
 }
 
-// ------------------------------------------------------------------------------------------ Schur complement
-// S = Aeq (H + dp I)^-1 Aeq' is never stored: its block rows are produced one per sweep step, in shared memory, by the
-// threads that do not run the elimination.  Knot k appears in row k as "current" (coefficient Lk = aL A_k + bL I;
-// row 0 is x_0 itself) and in row k+1 as "previous" (Rk = aR A_k + diag(dR); row N is the masked goal row):
-//   S_kk += Lk Phi Lk' + Xi,   S_{k+1,k} = Rk Phi Lk' + Xi,   S_{k+1,k+1} += Rk Phi Rk' + Xi,   Xi = G Theta_k G',
-// with Phi = blockdiag(P_b) - coef w w'.  With Y = (h/2 A) Phi and Z = Y (h/2 A)' (two small tile products) all three
-// are element-wise combinations of Z, Y, Y' and Phi.
-template <int M> GHD constexpr int ctrl_of_row(int I) { int r = -1; for (int a = 0; a < Traits<M>::NU; ++a) if (Traits<M>::b_row(a) == I) r = a; return r; }
-
-struct SchurTiles { double *Phi, *Ah, *Y, *Z, *RR, *Xi; };
-
-// Threads [t0, t0 + nt) build the dense Phi of the staged knot record `ks`, and refresh Ah (the pattern of A is static,
-// so the tile is zeroed once by the caller).  Barrier-free: followed by the caller's barrier.
-template <int M> GDEV void schur_build(const IpmCtx<M>& c, const double* ks, const SchurTiles& t, int t0, int nt) {
+// --------------------------------------------------------------------------------- per-solve dynamics records
+// Fi_k = F_k^-1 = (I - h/2 A_k)^-1  and, per knot, the rows of  Ah_k' | Bh_k' | Gam_k'  (see the file header).  Constant
+// over the Newton iterations of a solve: only the Hessian blocks change.  Gauss-Jordan on [F | I] with one thread per
+// (knot, row) pair, 64 / NX knots at a time, rows in shared memory (the pivot row is read by the other rows of its knot);
+// F is a small perturbation of the identity (h/2 |A_ii| << 1), so there is no pivoting (a breakdown surfaces as NaN ->
+// IPM_NUMERICAL).
+template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, LDT = L::LDT;
-  const unsigned char* mt = c.tab + L::TAB_MODEL;           // a_row | a_col | blk_of | ctrl_of
-  G_ASSUME_SHARED(mt);
-  const double coef = ks[L::KS_COEF];
-  for (int it = G_TID - t0; it < NX * NX; it += nt) {
-    const int i = it / NX, q = it - i * NX;
-    const int bi = mt[2 * L::ANZ + i];
-    double v = 0.0;
-    if (bi == mt[2 * L::ANZ + q]) { const int off = T::XB_off(bi); v = ks[L::KS_P + T::XB_pk(bi) + tri(i - off, q - off)]; }
-    if (T::HAS_TR) v -= coef * ks[L::KS_W + i] * ks[L::KS_W + q];
-    t.Phi[i * LDT + q] = v;
-  }
-  for (int e = G_TID - t0; e < L::ANZ; e += nt) t.Ah[mt[e] * LDT + mt[L::ANZ + e]] = c.hh * ks[L::KS_A + e];
-  // control coupling Xi = G Theta G' (G = h/2 B): one entry per pair of controls of the same block (static pattern too)
-  for (int pr = G_TID - t0; pr < L::NU * L::NU; pr += nt) {
-    const int a = pr / L::NU, b2 = pr - a * L::NU;
-    const int ub = T::UB_of(a);
-    if (ub != T::UB_of(b2)) continue;
-    const int uo = T::UB_off(ub);
-    t.Xi[T::b_row(a) * LDT + T::b_row(b2)] = c.hh * c.hh * c.bv[a] * c.bv[b2] * ks[L::KS_TH + T::UB_pk(ub) + tri(a - uo, b2 - uo)];
-  }
-}
-
-// out(i, q) = sum_m X[i][m] * Yt[q][m]  for all (i, q), by threads [t0, t0 + nt)
-template <int M> GDEV void abt_task(const double* X, const double* Y, int i, int q0, double* acc);
-template <int M> GDEV void schur_product(const double* X, const double* Yt, double* out, int t0, int nt) {
-  using L = IpmLayout<M>;
-  for (int task = G_TID - t0; task < L::NTASK; task += nt) {
-    const int i = task / L::NG, q0 = (task - i * L::NG) * L::CG;
-    double acc[L::CG];
-    abt_task<M>(X, Yt, i, q0, acc);
-#pragma unroll
-    for (int c2 = 0; c2 < L::CG; ++c2) if (q0 + c2 < L::NX) out[i * L::LDT + q0 + c2] = acc[c2];
-  }
-}
-
-// Element-wise emission for knot k (k < N):  Sdd (= S_kk) = RR + Lk Phi Lk' [+ Xi] (+ regularisation),
-// Sod (= S_{k+1,k}) = Rk Phi Lk' [+ Xi],  RR = Rk Phi Rk' [+ Xi]  (carried to S_{k+1,k+1}).
-template <int M> GDEV void schur_emit(const IpmCtx<M>& c, const SchurTiles& t, int k, double* Sdd, double* Sod,
-                                      int t0, int nt) {
-  using L = IpmLayout<M>;
-  using T = Traits<M>;
-  constexpr int NX = L::NX, LDT = L::LDT;
+  constexpr int NX = L::NX, NU = L::NU, NN = L::NN, ANZ = L::ANZ, LDT = L::LDT, KB = 64 / NX, W2 = 2 * NX;
+  static_assert(L::dcheck(), "Traits<M>::DSPLIT does not decouple the pattern of A");
   const int N = c.N;
-  // Y and Z already carry the h/2 factors, so the A-coefficients of Lk and Rk are 0 or 1 here
-  const double aL = k == 0 ? 0.0 : 1.0, bL = k == 0 ? 1.0 : -1.0;
-  const bool last = (k == N - 1);
-  const double aR = last ? 0.0 : 1.0;
-  const int pmask = c.pmask;
-  for (int it = G_TID - t0; it < NX * NX; it += nt) {
-    const int i = it / NX, q = it - i * NX;
-    const double z = t.Z[i * LDT + q], y = t.Y[i * LDT + q], yt = t.Y[q * LDT + i], ph = t.Phi[i * LDT + q];
-    const double dRi = last ? (double)((pmask >> i) & 1) : 1.0, dRq = last ? (double)((pmask >> q) & 1) : 1.0;
-    const double xi = t.Xi[i * LDT + q];
-    double dd = t.RR[i * LDT + q] + aL * aL * z + aL * bL * (y + yt) + bL * bL * ph + (k >= 1 ? xi : 0.0);
-    if (i == q) dd += c.dd * dd + 1e-300;
-    Sdd[i * LDT + q] = dd;
-    Sod[i * LDT + q] = aR * aL * z + aR * bL * y + aL * dRi * yt + bL * dRi * ph + ((k >= 1 && k <= N - 2) ? xi : 0.0);
-    t.RR[i * LDT + q] = aR * aR * z + aR * (y * dRq + dRi * yt) + dRi * ph * dRq + (k <= N - 2 ? xi : 0.0);
-  }
-}
-// Last block row: S_NN = RR (+ identity on the free goal coordinates so that the block stays non-singular)
-template <int M> GDEV void schur_emit_last(const IpmCtx<M>& c, const SchurTiles& t, double* Sdd, int t0, int nt) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, LDT = L::LDT;
-  for (int it = G_TID - t0; it < NX * NX; it += nt) {
-    const int i = it / NX, q = it - i * NX;
-    double dd = t.RR[i * LDT + q];
-    if (i == q) { if (!((c.pmask >> i) & 1)) dd += 1.0; dd += c.dd * dd + 1e-300; }
-    Sdd[i * LDT + q] = dd;
-  }
-}
-// Stage the record of knot k (P, w, Theta, coef, A entries) from global memory into the idle half of the double-buffered
-// staging area with 8-byte asynchronous copies (LDGSTS): nothing passes through registers (a register-staged version
-// was spilled to local memory by ptxas and serialised three DRAM latencies on the producer warp), and the producer only
-// waits for the copies (schur_stage_wait) after its arithmetic, right before the step's barrier.
-template <int M> GDEV const double* schur_stage_ptr(const double* kd, const double* Ak, int t) {
-  using L = IpmLayout<M>;
-  if (t < L::KS_TH) return kd + L::KD_P + t;                      // P | w are contiguous in the record
-  if (t < L::KS_COEF) return kd + L::KD_TH + t - L::KS_TH;
-  if (t == L::KS_COEF) return kd + L::KD_COEF;
-  return Ak + (t - L::KS_A);
-}
-template <int M> GDEV double schur_stage_src(const double* kd, const double* Ak, int t) {
-  using L = IpmLayout<M>;
-  return t < L::KS_A + L::ANZ ? *schur_stage_ptr<M>(kd, Ak, t) : 0.0;
-}
-template <int M> GDEV void schur_stage_async(const IpmCtx<M>& c, int k, double* ks, int t0, int nt) {
-  using L = IpmLayout<M>;
-  const double* kd = c.kd + (size_t)k * L::KDW;
-  const double* Ak = c.Ac + (size_t)k * L::ANZ;
-  for (int t = G_TID - t0; t < L::KS_A + L::ANZ; t += nt) g_cp_async8(ks + t, schur_stage_ptr<M>(kd, Ak, t));   // the padding stays 0
-}
-GDEV void schur_stage_wait() { g_cp_async_wait(); }
-
-// acc[c] = sum_m X[i][m] * Y[q0 + c][m]  over one shared-memory tile row pair (rows are LDT apart, MLEN = GLD terms)
-template <int M> GDEV void abt_task(const double* X, const double* Y, int i, int q0, double* acc) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, LDT = L::LDT, CG = L::CG;
-#pragma unroll
-  for (int c2 = 0; c2 < CG; ++c2) acc[c2] = 0.0;
-#pragma unroll
-  for (int m = 0; m < L::GLD; m += 2) {
-    const g_d2 xv = g_ld2(X + i * LDT + m);
-#pragma unroll
-    for (int c2 = 0; c2 < CG; ++c2) {
-      const int q = q0 + c2 < NX ? q0 + c2 : NX - 1;      // clamped: the caller drops columns >= NX
-      const g_d2 yv = g_ld2(Y + q * LDT + m);
-      acc[c2] += xv.x * yv.x;
-      acc[c2] += xv.y * yv.y;
+  const double hh = c.hh;
+  double* const rows = sh_dz<M>(c);            // [KB * NX][2 NX]: row i of [F | W] of knot kb
+  for (int k0 = 0; k0 < N; k0 += KB) {
+    G_PAR_FOR(t, KB * NX) {
+      const int kb = t / NX, i = t - kb * NX, k = k0 + kb;
+      double* row = rows + t * W2;
+      for (int j = 0; j < W2; ++j) row[j] = 0.0;
+      row[i] = 1.0; row[NX + i] = 1.0;
+      if (k < N) for (int e = 0; e < ANZ; ++e) if (T::a_row(e) == i) row[T::a_col(e)] -= hh * c.Ac[(size_t)k * ANZ + e];
     }
+    G_SYNC();
+    // the decoupled blocks are eliminated side by side: step t uses pivot dlo + t of every block
+    for (int tp = 0; tp < L::DMAX; ++tp) {
+      G_PAR_FOR(t, KB * NX) {
+        const int kb = t / NX, i = t - kb * NX;
+        const int lo = L::dlo(i), hi = L::dhi(i), p = lo + tp;
+        if (i != p) continue;
+        double* row = rows + t * W2;
+        const double ip = 1.0 / row[p];
+        for (int j = lo; j < hi; ++j) { row[j] *= ip; row[NX + j] *= ip; }
+      }
+      G_SYNC();
+      G_PAR_FOR(t, KB * NX) {
+        const int kb = t / NX, i = t - kb * NX;
+        const int lo = L::dlo(i), hi = L::dhi(i), p = lo + tp;
+        if (p >= hi || i == p) continue;
+        double* row = rows + t * W2;
+        const double* piv = rows + (kb * NX + p) * W2;
+        const double f = row[p];
+        if (f != 0.0) for (int j = lo; j < hi; ++j) { row[j] -= f * piv[j]; row[NX + j] -= f * piv[NX + j]; }
+      }
+      G_SYNC();
+    }
+    // row i of Fi_k: the inverse itself, column i of Gam_k' and of Ah_{k-1}' = (Fi_k E_k)',  E_k = I + h/2 A_{k-1}
+    G_PAR_FOR(t, KB * NX) {
+      const int kb = t / NX, i = t - kb * NX, k = k0 + kb;
+      if (k >= N) continue;
+      const double* w = rows + t * W2 + NX;
+      double* fo = c.fi + (size_t)k * NN + i * NX;
+      for (int j = 0; j < NX; ++j) fo[j] = w[j];
+      double* cr = c.cr + (size_t)k * L::CRW;
+      for (int a = 0; a < NU; ++a) cr[(L::CR_GT + a) * LDT + i] = k == 0 ? 0.0 : hh * c.bv[a] * w[T::b_row(a)];
+      if (k >= 1) {
+        double ah[NX];
+        for (int j = 0; j < NX; ++j) ah[j] = w[j];
+        for (int e = 0; e < ANZ; ++e) ah[T::a_col(e)] += hh * c.Ac[(size_t)(k - 1) * ANZ + e] * w[T::a_row(e)];
+        double* crp = c.cr + (size_t)(k - 1) * L::CRW;
+        for (int j = 0; j < NX; ++j) crp[(L::CR_AT + j) * LDT + i] = ah[j];
+      }
+      if (k == N - 1) for (int j = 0; j < NX + NU; ++j) cr[j * LDT + i] = 0.0;      // no dynamics after the last knot
+    }
+    G_SYNC();
+  }
+  // Bh_k = Ah_k Gam_k + Gam_{k+1}
+  G_PAR_FOR(it, (N - 1) * NU * NX) {
+    const int k = it / (NU * NX), r = it - k * (NU * NX), a = r / NX, i = r - a * NX;
+    const double* cr = c.cr + (size_t)k * L::CRW;
+    const double* gk = cr + (L::CR_GT + a) * LDT;
+    double v = c.cr[(size_t)(k + 1) * L::CRW + (L::CR_GT + a) * LDT + i];
+    for (int m = L::dlo(i); m < L::dhi(i); ++m) v += cr[(L::CR_AT + m) * LDT + i] * gk[m];
+    c.cr[(size_t)k * L::CRW + (L::CR_BT + a) * LDT + i] = v;
+  }
+  G_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------- Riccati sweep
+// Inputs of knot k that change per Newton iteration (Hessian record, right-hand side, ch_k) are gathered into a staging
+// buffer with asynchronous 8-byte copies one knot ahead; the dynamics record goes straight into its tile rows.
+template <int M> GDEV void ric_stage_async(const IpmCtx<M>& c, int k, double* tile, int buf) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, LDT = L::LDT;
+  double* XS = tile + L::F_XS + buf * L::XSR * LDT;
+  const double* cr = c.cr + (size_t)k * L::CRW;
+  G_PAR_FOR(t, (NX + NU) * LDT / 2) g_cp_async16(XS + 2 * t, cr + 2 * t);
+  G_PAR_FOR(t, NU * LDT / 2) g_cp_async16(XS + L::RXS * LDT + 2 * t, cr + L::CR_GT * LDT + 2 * t);
+  double* SB = tile + L::F_SB + buf * L::SBW;
+  const double* kd = c.kd + (size_t)k * L::KDW;
+  G_PAR_FOR(t, L::KDW) g_cp_async8(SB + t, kd + t);
+  G_PAR_FOR(t, NV) g_cp_async8(SB + L::KDW + t, c.r + (size_t)k * NV + t);
+  if (k < c.N - 1) G_PAR_FOR(t, NX) g_cp_async8(SB + L::KDW + NV + t, c.ch + (size_t)k * NX + t);
+}
+// Dense stage inputs of knot k from its staging buffer, by the lanes of ONE warp (no barrier): lane i builds row i of Hx_k
+// (+ w_N on the PointGoal coordinates of the last knot) and of Hu_k, q = rx (+ w_N rho_N), ru, and ch_k into its row of the
+// dynamics tile.
+template <int M, int B0 = 0> GDEV void ric_hx_row(const double* Hb, int i, double* rowv) {
+  using T = Traits<M>;
+  if constexpr (B0 < T::XB_CNT) {
+    constexpr int off = T::XB_off(B0), n = T::XB_n(B0);
+    if (i >= off && i < off + n) {
+#pragma unroll
+      for (int q = 0; q < n; ++q) rowv[off + q] = Hb[T::XB_pk(B0) + tri(i - off, q)];
+    }
+    ric_hx_row<M, B0 + 1>(Hb, i, rowv);
+  }
+}
+template <int M, int B0 = 0> GDEV void ric_hu_row(const double* Hb, int a, double* rowv) {
+  using T = Traits<M>;
+  if constexpr (B0 < T::UB_CNT) {
+    constexpr int off = T::UB_off(B0), n = T::UB_n(B0);
+    if (a >= off && a < off + n) {
+#pragma unroll
+      for (int q = 0; q < n; ++q) rowv[off + q] = Hb[T::UB_pk(B0) + tri(a - off, q)];
+    }
+    ric_hu_row<M, B0 + 1>(Hb, a, rowv);
+  }
+}
+template <int M> GDEV void ric_stage_build(const IpmCtx<M>& c, int k, double* tile, int buf) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, LDT = L::LDT, LDU = L::LDU;
+  const int N = c.N;
+  double* Qd = tile + L::F_QD;
+  double* Hud = tile + L::F_HU;
+  double* vec = tile + L::F_VEC;
+  double* XS = tile + L::F_XS + buf * L::XSR * LDT;
+  const double* SB = tile + L::F_SB + buf * L::SBW;
+  const bool last = (k == N - 1);
+  G_LANE_FOR(i, NX) {
+    double rowv[NX];
+#pragma unroll
+    for (int q = 0; q < NX; ++q) rowv[q] = 0.0;
+    ric_hx_row<M>(SB + L::KD_HB, i, rowv);
+    const bool pin = last && ((c.pmask >> i) & 1);
+    const double wi = T::HAS_TR ? SB[L::KD_W + i] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) {
+      double v = rowv[q];
+      if (T::HAS_TR) v += wi * SB[L::KD_W + q];
+      if (pin && q == i) v += c.wN;
+      Qd[i * LDT + q] = v;
+    }
+    double qv = SB[L::KDW + i];
+    if (pin) qv += c.wN * c.rnu[N * NX + i];
+    vec[L::V_Q + buf * L::KP + i] = qv;
+    XS[(NX + NU) * LDT + i] = last ? 0.0 : SB[L::KDW + NV + i];
+  }
+  G_LANE_FOR(a, NU) {
+    double rowu[NU];
+#pragma unroll
+    for (int q = 0; q < NU; ++q) rowu[q] = 0.0;
+    ric_hu_row<M>(SB + L::KD_HU, a, rowu);
+#pragma unroll
+    for (int q = 0; q < NU; ++q) Hud[a * LDU + q] = rowu[q];
+    vec[L::V_RU + buf * L::KU + a] = SB[L::KDW + NX + a];
   }
 }
 
-// Factorisation of the block-tridiagonal S.  Block Cholesky recurrence (numerically the stable form: every update is a
-// symmetric  D_j = S_jj - Lo_j Lo_j'  with Lo_j = S_{j,j-1} L_{j-1}^-T), but what is STORED is the block L D L' form the
-// solves want:  slot (j,0) S_jj -> D_j^-1 = Li_j' Li_j,  slot (j,1) S_{j,j-1} -> V_j = Lo_j Li_{j-1} (= S_{j,j-1} D_{j-1}^-1),
-// so that a solve is two chains of single mat-vecs plus one parallel D^-1 pass.  Li_j = L_j^-1 comes out of one
-// Gaussian elimination of [D_j | I] in shared memory (NX dependent pivot steps on warp 0 -- the critical path of the
-// whole kernel) while the other warp stages block row j+1.  All tile products are row-by-row dot products over
-// zero-padded tiles (LDS.128, a 1 x CG register tile per thread).  Returns false on a non-positive pivot.
-template <int M> GDEV_NOINLINE bool factorize(const IpmCtx<M>& c) {
+// Backward sweep k = N-1 .. 0 (see the file header).  Every dense product is a grid of 8x8x4 FP64 tensor-core tiles
+// (g_tile_grid, common.cuh) issued by one warp; the two warps of the group split the products of a phase.  Five phases per knot:
+//   A   Z1 = [Ah'; Bh'; ch'] P   (= (P Ah)', (P Bh)', (P ch)'),   S' = Hx Gam
+//   B   Lam = Hu + Gam'S' + Bh'(P Bh),  rt = ru + Gam'q + Bh'pit,  pit = p_{k+1} - P ch  |  M' = S' + (P Ah)'Bh
+//   C   warp 0: Lam = L L' in registers, Li = L^-1  |  warp 1: W = Hx + Ah'(P Ah), dense inputs of knot k-1
+//   C2  Y' = [M'; rt'] Li'  (= (L^-1 [M | rt])')  |  BL = Bh Li'
+//   D   P_k = W - Y'Y (in place),  K' = Y' Li (row NX: kap)  |  Acl = Ah - BL Y,  p_k = q + Ah'pit - Y' yr
+// Leaves, per knot, Acl_k, K_k', L_k^-1, P_k, psi_k = P_{k+1} ch_k in global scratch, and for the right-hand side held in
+// c.r / c.rnu (the predictor's): kap_k in c.kap and the costate chain in vp:  vp[0] = p_0,  vp[k+1] = pit_k.  Returns false
+// on a non-positive pivot of a Lam_k.
+template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NT = NX * (NX + 1) / 2, LDT = L::LDT, TILE = L::TILE, GLD = L::GLD, GT = L::GT;
-  constexpr int CG = L::CG, NG = L::NG, NTASK = L::NTASK, NLT = L::NLT;
+  constexpr int NX = L::NX, NU = L::NU, LDT = L::LDT, LDU = L::LDU, NTU = L::NTU, KS = L::KP / 4, KSU = L::KU / 4;
+  constexpr int MT_X = L::NXP / 8, MT_Z = L::RXS / 8, MZ0 = (MT_Z + 1) / 2, MZ1 = MT_Z - MZ0;
   const int N = c.N;
-  long long tc0 = g_clock();
-  // dz | sy | ring are dead here: 15 tiles + pivots + two staged knot records
-  double* tile = sh_dz<M>(c);
-  double* W = tile;                          // D_j, eliminated in place (lower triangle)
-  double* Wr = tile + TILE;                  // I -> unit-lower elimination history (L~^-1)
-  double* Li = tile + 2 * TILE;              // L_j^-1 (lower, explicit zeros) and its transpose
-  double* LiT = tile + 3 * TILE;
-  // ping-pong tiles are addressed arithmetically (an indexed pointer array would live in local memory)
-#define GUSTO_SDD(w) (tile + 4 * TILE)                 /* one tile: emitted and consumed within a step */
-#define GUSTO_SOD(w) (tile + (6 + (w)) * TILE)
-#define GUSTO_LO(w) (tile + (8 + (w)) * TILE)
-  SchurTiles st;
-  st.Phi = tile + 10 * TILE; st.Ah = tile + 11 * TILE; st.Y = tile + 12 * TILE; st.Z = tile + 13 * TILE; st.RR = tile + 14 * TILE;
-  st.Xi = tile + 5 * TILE;
-  double* ipv = tile + L::FAC_TILES * TILE;  // 1 / pivot, then 1 / sqrt(pivot)
-  double* ksb = ipv + ((NX + 1) & ~1);       // two staged knot records
-  const unsigned char* const tab = c.tab;
-  G_ASSUME_SHARED(tab);
-  const unsigned char* const tab2 = tab + 2 * NT;
-  double* const fac = c.fac;
-  // producer threads: the second warp (or the only one)
-  const int pf0 = G_NTHR > G_WARP ? G_WARP : 0;
-  const int npf = G_NTHR > G_WARP ? G_WARP : G_NTHR;
-  const bool producer = G_TID >= pf0 && G_TID < pf0 + npf;
+  double* const tile = sh_dz<M>(c);
+  double* const vp = sh_vp<M>(c);
+  double* const Z1 = tile + L::F_Z1;
+  double* const Qd = tile + L::F_QD;
+  double* const Sm = tile + L::F_SM;
+  double* const Lm = tile + L::F_LM;
+  double* const Li = tile + L::F_LI;
+  double* const Hud = tile + L::F_HU;
+  double* const Yt = Z1;                                        // (Z1 is dead after phase B)
+  double* const vec = tile + L::F_VEC;
+  double* const pit = vec + L::V_PIT;
+  const bool w0 = G_NWARP == 1 || G_WARPID == 0, w1 = G_NWARP == 1 || G_WARPID == 1;
   double bad = 0.0;
-  G_PAR_FOR(it, L::FAC_TILES * TILE) tile[it] = 0.0;
-  // knot 0 (all threads): S_00 -> W, S_10 -> Sod[1], RR <- R0 Phi R0'; stage knot 1
-  for (int t = G_TID; t < 2 * L::KS; t += G_NTHR) {
-    const int k = t / L::KS, tt = t - k * L::KS;
-    if (k < N) ksb[t] = schur_stage_src<M>(c.kd + (size_t)k * L::KDW, c.Ac + (size_t)k * L::ANZ, tt);
-  }
+  const long long tc0 = g_clock();
+  G_PAR_FOR(it, L::FAC_DOUBLES) tile[it] = 0.0;
+  G_PAR_FOR(i, NX) vp[N * NX + i] = 0.0;
   G_SYNC();
-  schur_build<M>(c, ksb, st, 0, G_NTHR);
+  ric_stage_async<M>(c, N - 1, tile, (N - 1) & 1);
+  g_cp_async_wait();
   G_SYNC();
-  schur_product<M>(st.Ah, st.Phi, st.Y, 0, G_NTHR);
+  if (w0) ric_stage_build<M>(c, N - 1, tile, (N - 1) & 1);
   G_SYNC();
-  schur_product<M>(st.Y, st.Ah, st.Z, 0, G_NTHR);
-  G_SYNC();
-  schur_emit<M>(c, st, 0, W, GUSTO_SOD(1), 0, G_NTHR);
-  G_SYNC();
-#if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
-  if (G_TID == 0) c.prof[0] += g_clock() - tc0;
-#endif
-  tc0 = g_clock();
-  // my entries of the packed lower triangle during the elimination (warp 0)
-  int ei[3], ee[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int t = G_TID + r * G_WARP;
-    ei[r] = t < NT ? tab[t] : 0; ee[r] = t < NT ? tab[NT + t] : 0;
-  }
-  for (int j = 0; j <= N; ++j) {
-    const int cur = j & 1, nxt = cur ^ 1;
-    // (E) warp 0: eliminate column q from the rows below it, in W (columns > q) and in Wr (columns <= q)
 #if defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3
-    long long tp = g_clock();
+  long long tp = g_clock();
 #define GUSTO_PROF_TICK(slot) do { if (G_TID == 0) { const long long tn = g_clock(); c.prof[slot] += tn - tp; tp = tn; } } while (0)
 #else
 #define GUSTO_PROF_TICK(slot) ((void)0)
 #endif
-    if (G_TID < G_WARP) {
-#ifdef GUSTO_HOSTSIM
-      for (int q = 0; q < NX; ++q) {
-        double piv = W[q * LDT + q];
-        if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
-        const double ip = g_rcp(piv);
-        ipv[q] = ip;
-        for (int t = 0; t < NT; ++t) {
-          const int i = tab[t], e = tab[NT + t];
-          if (i <= q) continue;
-          const double mult = W[i * LDT + q] * ip;
-          if (e < q) Wr[i * LDT + e] -= mult * Wr[q * LDT + e];
-          else if (e == q) Wr[i * LDT + e] = -mult;            // Wr starts as the identity, kept implicit
-          else W[i * LDT + e] -= mult * W[e * LDT + q];
+  for (int k = N - 1; k >= 0; --k) {
+    const int cur = k & 1, nxt = cur ^ 1;
+    const double* XS = tile + L::F_XS + cur * L::XSR * LDT;        // rows: Ah' (NX) | Bh' (NU) | ch | 0.. | Gam' at row RXS
+    const double* Gt = XS + L::RXS * LDT;
+    const double* Bt = XS + NX * LDT;
+    double* const Pp = tile + (((N - 1 - k) & 1) ? L::F_PB : L::F_PA);   // P_{k+1}
+    double* const Wn = tile + (((N - 1 - k) & 1) ? L::F_PA : L::F_PB);   // W, then P_k
+    double* const Mt = Pp;                                                // M' (row NX: rt): P_{k+1} is dead after phase A
+    double* const BL = Sm;                                                // S' is dead after phase B
+    const double* qv = vec + L::V_Q + cur * L::KP;
+    const double* ruv = vec + L::V_RU + cur * L::KU;
+    const double* pn = vp + (k + 1) * NX;
+    // ---- phase A
+    if (k >= 1) ric_stage_async<M>(c, k - 1, tile, nxt);
+    auto z1_store = [&](int r, int q, double v) { if (r <= NX + NU && q < NX) Z1[r * LDT + q] = v; };
+    if (w0) g_tile_grid<KS, MZ0, MT_X, false, false>(XS, LDT, 0, Pp, LDT, 0, z1_store);
+    if (w1) {
+      if constexpr (MZ1 > 0) g_tile_grid<KS, (MZ1 > 0 ? MZ1 : 1), MT_X, false, false>(XS, LDT, 8 * MZ0, Pp, LDT, 0, z1_store);
+      g_tile_grid<KS, MT_X, 1, false, false>(Qd, LDT, 0, Gt, LDT, 0, [&](int r, int a, double v) {
+        if (r < NX && a < NU) Sm[r * LDU + a] = v;
+      });
+    }
+    G_SYNC();
+    GUSTO_PROF_TICK(0);
+    // ---- phase B
+    if (w0) {
+      g_tile_job2<KS, false, true, KS, false, false>(Gt, LDT, Sm, LDU, Bt, LDT, Z1 + NX * LDT, LDT, 0, 0, [&](int a, int b2, double v) {
+        if (a < NU && b2 < NU) Lm[a * LDU + b2] = v + Hud[a * LDU + b2];
+      });
+      G_LANE_FOR(i, NX + NU) {
+        if (i < NX) {
+          const double ps = Z1[(NX + NU) * LDT + i];             // psi_k = P_{k+1} ch_k  (Z1 is recycled after phase C)
+          pit[i] = pn[i] - ps;
+          c.psi[(size_t)k * NX + i] = ps;
+        } else {
+          const int a = i - NX;
+          double v = ruv[a];
+          for (int m = 0; m < NX; ++m) v += Gt[a * LDT + m] * qv[m] + Bt[a * LDT + m] * (pn[m] - Z1[(NX + NU) * LDT + m]);
+          Mt[NX * LDU + a] = v;
         }
-      }
-#else
-      // Branch-free: every lane owns <= 3 entries (i, e) of the packed lower triangle; entry (i, e) lives in W while
-      // e > q and in Wr afterwards.  All operands of a step are loaded before any arithmetic, and the reciprocal of
-      // the NEXT pivot is started from pre-update values so that it overlaps the rank-1 update (it is the longest
-      // dependent operation of the step).
-      double piv = W[0];
-      if (!(piv > 0.0)) { bad = 1.0; piv = 1e-300; }
-      double ip = g_rcp(piv);
-      for (int q = 0; q < NX; ++q) {
-        const int qn = q + 1 < NX ? q + 1 : q;
-        const double wq1 = W[qn * LDT + q], d1 = W[qn * LDT + qn];
-        double av[3], sv[3], ov[3];
-        int to[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int i = ei[r], e = ee[r];
-          const bool right = e <= q;
-          to[r] = (right ? TILE : 0) + i * LDT + e;
-          av[r] = W[i * LDT + q];
-          sv[r] = tile[right ? TILE + q * LDT + e : e * LDT + q];
-          ov[r] = tile[to[r]];
-          if (e == q) { sv[r] = 1.0; ov[r] = 0.0; }            // Wr starts as the identity, kept implicit
-        }
-        G_SYNCWARP();                                // the look-ahead read W[q+1][q+1] before its owner updates it
-        double pn = fma(-(wq1 * ip), wq1, d1);
-        if (q + 1 < NX && !(pn > 0.0)) { bad = 1.0; pn = 1e-300; }
-        const double ipn = g_rcp(pn);
-        if (G_LANE == 0) ipv[q] = ip;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const double nv = fma(-(av[r] * ip), sv[r], ov[r]);
-          if (ei[r] > q) tile[to[r]] = nv;
-        }
-        ip = ipn;
-        G_SYNCWARP();
-      }
-#endif
-      G_W0_FOR(q, NX) { const double v = ipv[q]; ipv[q] = v * g_rsqrt(v); }     // sqrt(1/pivot) without the IEEE sqrt sequence
-      G_SYNCWARP();
-      // (C1) Li = diag(rs) * Wr  (lower triangular) and its transpose -- still on the eliminating warp, which would
-      // otherwise wait for the producer
-      G_W0_FOR(it, NX * NX) {
-        const int i = it / NX, m = it - i * NX;
-        const double v = m < i ? Wr[i * LDT + m] * ipv[i] : (m == i ? ipv[i] : 0.0);
-        Li[i * LDT + m] = v;
-        LiT[m * LDT + i] = v;
       }
     }
-    GUSTO_PROF_TICK(0);
-    // producer: block row j+1 of S from knot j+1 (and the record of knot j+2 staged for the next step)
-    if (producer) {
-      const int kn = j + 1;
-      if (kn <= N - 1) {
-        const double* ks = ksb + (kn & 1) * L::KS;
-        if (kn + 1 <= N - 1) schur_stage_async<M>(c, kn + 1, ksb + ((kn + 1) & 1) * L::KS, pf0, npf);
-        schur_build<M>(c, ks, st, pf0, npf);
-        G_SYNCWARP();
-        schur_product<M>(st.Ah, st.Phi, st.Y, pf0, npf);
-        G_SYNCWARP();
-        schur_product<M>(st.Y, st.Ah, st.Z, pf0, npf);
-        schur_stage_wait();
+    if (w1) {
+      g_tile_grid<KS, MT_X, 1, false, false>(Z1, LDT, 0, Bt, LDT, 0, [&](int r, int a, double v) {
+        if (r < NX && a < L::KU) Mt[r * LDU + a] = a < NU ? v + Sm[r * LDU + a] : 0.0;
+      });
+    }
+    g_cp_async_wait();
+    G_SYNC();
+    GUSTO_PROF_TICK(1);
+    // ---- phase C
+    if (w0) {
+      double Hl[NTU], Lc[NTU], Lv[NTU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 <= a; ++b2) Hl[tri(a, b2)] = Lm[a * LDU + b2];
+      if (!chol_packed<NU>(Hl, Lc)) bad = 1.0;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        Lv[tri(j, j)] = Lc[tri(j, j)];
+#pragma unroll
+        for (int i = j + 1; i < NU; ++i) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int m = j; m < i; ++m) sacc += Lc[tri(i, m)] * Lv[tri(m, j)];
+          Lv[tri(i, j)] = -sacc * Lc[tri(i, i)];
+        }
       }
+      G_LANE_FOR(a, NU) {
+#pragma unroll
+        for (int b2 = 0; b2 < NU; ++b2) {
+          double v = 0.0;
+#pragma unroll
+          for (int a2 = 0; a2 < NU; ++a2) if (a2 == a && b2 <= a2) v = Lv[tri(a2, b2)];
+          Li[a * LDU + b2] = v;
+        }
+      }
+      if (G_LANE == 0) {
+        double* lp = c.lp + (size_t)k * L::LPW;
+#pragma unroll
+        for (int t = 0; t < NTU; ++t) lp[t] = Lv[t];
+      }
+    }
+    if (w1) {
+      // W does not depend on Lam: it runs beside the (serial) Cholesky of warp 0, then the dense inputs of knot k - 1
+      g_tile_grid<KS, MT_X, MT_X, false, false>(XS, LDT, 0, Z1, LDT, 0, [&](int r, int q, double v) {
+        if (r < NX && q < NX) Wn[r * LDT + q] = v + Qd[r * LDT + q];
+      });
+      G_SYNCWARP();
+      if (k >= 1) ric_stage_build<M>(c, k - 1, tile, nxt);
     }
     G_SYNC();
     GUSTO_PROF_TICK(2);
-    // (C2) Lo_{j+1} = S_{j+1,j} Li'
-    if (j < N) {
-      G_PAR_FOR(task, NTASK) {
-        const int i = task / NG, q0 = (task - i * NG) * CG;
-        double acc[CG];
-        abt_task<M>(GUSTO_SOD(nxt), Li, i, q0, acc);
+    // ---- phase C2
+    if (w0) g_tile_grid<KSU, MT_X, 1, false, false>(Mt, LDU, 0, Li, LDU, 0, [&](int r, int a, double v) {
+      if (r <= NX && a < L::KU) Yt[r * LDU + a] = v;            // columns NU .. KU-1 are exact zeros (rows of Li beyond NU are)
+    });
+    if (w1) g_tile_grid<KSU, MT_X, 1, true, false>(Bt, LDT, 0, Li, LDU, 0, [&](int r, int a, double v) {
+      if (r < NX && a < NU) BL[r * LDU + a] = v;
+    });
+    G_SYNC();
+    // ---- phase D
+    if (w0) {
+      g_tile_grid<KSU, MT_X, MT_X, false, false>(Yt, LDU, 0, Yt, LDU, 0, [&](int r, int q, double v) {
+        if (r < NX && q < NX) {
+          const double pv = Wn[r * LDT + q] - v;
+          Wn[r * LDT + q] = pv;
+          if (q <= r) c.pk[(size_t)k * L::PKW + tri(r, q)] = pv;
+        }
+      });
+      g_tile_grid<KSU, MT_X, 1, false, true>(Yt, LDU, 0, Li, LDU, 0, [&](int r, int a, double v) {
+        if (a < NU) {
+          if (r < NX) c.kt[(size_t)k * L::KTW + r * LDU + a] = v;
+          else if (r == NX) c.kap[(size_t)k * LDU + a] = v;
+        }
+      });
+    }
+    if (w1) {
+      g_tile_grid<KSU, MT_X, MT_X, false, false>(BL, LDU, 0, Yt, LDU, 0, [&](int r, int q, double v) {
+        if (r < NX && q < NX) c.acl[(size_t)k * L::GT + r * LDT + q] = XS[q * LDT + r] - v;
+      });
+      G_LANE_FOR(i, NX) {
+        double v = qv[i];
+        for (int m = 0; m < NX; ++m) v += XS[i * LDT + m] * pit[m];
 #pragma unroll
-        for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) GUSTO_LO(nxt)[i * LDT + q0 + c2] = acc[c2];
+        for (int a = 0; a < NU; ++a) v -= Yt[i * LDU + a] * Yt[NX * LDU + a];
+        vp[k * NX + i] = v;
+        if (k < N - 1) vp[(k + 1) * NX + i] = pit[i];
       }
-      // ... and the producer's element-wise emission of block row j+1 (S_{j+1,j+1} -> Sdd, S_{j+2,j+1} -> Sod, carry RR)
-      if (j + 1 <= N - 1) schur_emit<M>(c, st, j + 1, GUSTO_SDD(nxt), GUSTO_SOD(cur), 0, G_NTHR);
-      else schur_emit_last<M>(c, st, GUSTO_SDD(nxt), 0, G_NTHR);
     }
     G_SYNC();
     GUSTO_PROF_TICK(3);
-    // (X) V_{j+1} = Lo_{j+1} Li -> global;  D_j^-1 = Li' Li -> global;  D_{j+1} = S_{j+1,j+1} - Lo_{j+1} Lo_{j+1}' -> W
-    {
-      double* gD = fac + (size_t)(2 * j) * GT;
-      double* gV = fac + (size_t)(2 * (j + 1) + 1) * GT;
-      const int nt = j < N ? NTASK + 2 * NLT : NLT;
-      G_PAR_FOR(task, nt) {
-        double acc[CG];
-        if (task < NLT) {                                   // D_j^-1, lower tasks mirrored
-          const int i = tab2[task], q0 = tab2[NLT + task] * CG;
-          abt_task<M>(LiT, LiT, i, q0, acc);
-#pragma unroll
-          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 <= i) { gD[i * GLD + q0 + c2] = acc[c2]; gD[(q0 + c2) * GLD + i] = acc[c2]; }
-        } else if (task < 2 * NLT) {                        // D_{j+1}, lower tasks (the strict upper triangle of W is never read)
-          const int i = tab2[task - NLT], q0 = tab2[task] * CG;
-          abt_task<M>(GUSTO_LO(nxt), GUSTO_LO(nxt), i, q0, acc);
-#pragma unroll
-          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) W[i * LDT + q0 + c2] = GUSTO_SDD(nxt)[i * LDT + q0 + c2] - acc[c2];
-        } else {
-          const int t2 = task - 2 * NLT;
-          const int i = t2 / NG, q0 = (t2 - i * NG) * CG;
-          abt_task<M>(GUSTO_LO(nxt), LiT, i, q0, acc);
-#pragma unroll
-          for (int c2 = 0; c2 < CG; ++c2) if (q0 + c2 < NX) gV[i * GLD + q0 + c2] = acc[c2];
-        }
-      }
-    }
-    G_SYNC();
-    GUSTO_PROF_TICK(4);
   }
-#if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
-  if (G_TID == 0) c.prof[1] += g_clock() - tc0;
-#endif
-#undef GUSTO_SDD
-#undef GUSTO_SOD
-#undef GUSTO_LO
   bad = block_max(bad, c.red);
+#if !(defined(GUSTO_PROF_MODE) && GUSTO_PROF_MODE == 3)
+  if (G_TID == 0) c.prof[0] += g_clock() - tc0;
+#endif
   return bad == 0.0;
 }
 
-// ------------------------------------------------------------------------------------------------ KKT solves
-// TMA ring over the V tiles of the factor: one elected lane issues ONE bulk copy (cp.async.bulk, 1-D, GT*8 bytes) per
-// tile into stage o % S and the copy completes on that stage's mbarrier; the consumers spin on the barrier's phase
-// parity (o / S) & 1.  `o` counts tiles over the whole kernel (fetch order == consume order), so the barriers are
-// initialised once.
-template <int M> GDEV void ring_fetch(const IpmCtx<M>& c, const double* fac, double* ring, int N, int j, unsigned o) {
-  using L = IpmLayout<M>;
-  if (j >= 1 && j <= N && G_LANE == 0) {
-    unsigned long long* bar = &c.ring_bar[o % RING_STAGES];
-    g_mbar_expect_tx(bar, (unsigned)(L::GT * sizeof(double)));
-    g_tma_bulk_g2s(ring + (o % RING_STAGES) * L::GT, fac + (size_t)(2 * j + 1) * L::GT, (unsigned)(L::GT * sizeof(double)), bar);
-  }
-}
-
-// Block-tridiagonal solve  S nu = b  (sy holds b on entry, nu on exit):
-//   forward  w_j = b_j - V_j w_{j-1};   middle  v_j = D_j^-1 w_j (all threads);   backward  nu_j = v_j - V_{j+1}' nu_{j+1}.
-template <int M> GDEV_NOINLINE void schur_solve(const IpmCtx<M>& c) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, LDT = L::LDT, GLD = L::GLD, S = RING_STAGES;
-  const int N = c.N;
-  double* const y = c.sy;
-  double* const ring = c.ring;
-  const double* const fac = c.fac;
-  G_ASSUME_SHARED(y);
-  G_ASSUME_SHARED(ring);
-  unsigned o = c.ring_o;                          // next tile to consume; of = next tile to fetch
-  long long tc0 = g_clock();
-  if (G_TID < G_WARP) {
-    unsigned of = o;
-    g_fence_proxy_async();                        // the ring region was last written by ordinary stores (sweep tiles)
-    for (int jj = 1; jj < S; ++jj) if (jj <= N) ring_fetch<M>(c, fac, ring, N, jj, of++);
-    for (int j = 1; j <= N; ++j) {
-      g_mbar_wait(&c.ring_bar[o % S], (o / S) & 1);               // tile j has landed
-      G_SYNCWARP();                               // everyone is done with tile j-1: its stage can be refilled
-      if (j + S - 1 <= N) ring_fetch<M>(c, fac, ring, N, j + S - 1, of++);
-      const double* R = ring + (o % S) * L::GT;
-      G_W0_FOR(i, NX) {
-        double a0 = y[j * NX + i], a1 = 0.0;
-#pragma unroll
-        for (int m = 0; m < GLD; m += 2) {
-          const g_d2 rv = g_ld2(R + i * GLD + m);
-          a0 -= rv.x * y[(j - 1) * NX + m];
-          if (m + 1 < NX) a1 -= rv.y * y[(j - 1) * NX + m + 1];
-        }
-        y[j * NX + i] = a0 + a1;
-      }
-      ++o;
-    }
-    G_SYNCWARP();
-  }
-  G_SYNC();
-  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[2] += g_clock() - tc0;
-  tc0 = g_clock();
-  // middle: v = D^-1 w, staged through the (idle) ring so that no row is overwritten while still being read.
-  // Two rows per thread and round, all loads issued before the arithmetic (the factor streams from L2 / HBM).
-  double* v = ring;
-  const int ne = (N + 1) * NX;
-  for (int it0 = G_TID; it0 < ne; it0 += 2 * G_NTHR) {
-    const int it1 = it0 + G_NTHR;
-    const bool two = it1 < ne;
-    const int j0 = it0 / NX, i0 = it0 - j0 * NX;
-    const int j1 = two ? it1 / NX : j0, i1 = two ? it1 - j1 * NX : i0;
-    const double* D0 = fac + (size_t)(2 * j0) * L::GT + i0 * GLD;
-    const double* D1 = fac + (size_t)(2 * j1) * L::GT + i1 * GLD;
-    g_d2 d0[GLD / 2], d1[GLD / 2];
-#pragma unroll
-    for (int m = 0; m < GLD / 2; ++m) { d0[m] = g_ld2(D0 + 2 * m); d1[m] = g_ld2(D1 + 2 * m); }
-    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll
-    for (int m = 0; m < GLD / 2; ++m) {
-      a0 += d0[m].x * y[j0 * NX + 2 * m]; b0 += d1[m].x * y[j1 * NX + 2 * m];
-      if (2 * m + 1 < NX) { a1 += d0[m].y * y[j0 * NX + 2 * m + 1]; b1 += d1[m].y * y[j1 * NX + 2 * m + 1]; }
-    }
-    v[it0] = a0 + a1;
-    if (two) v[it1] = b0 + b1;
-  }
-  G_SYNC();
-  G_PAR_FOR(it, ne) y[it] = v[it];
-  G_SYNC();
-  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[3] += g_clock() - tc0;
-  tc0 = g_clock();
-  if (G_TID < G_WARP) {
-    // backward: tiles N, N-1, ..., 1 ; tile t is used at step j = t - 1
-    unsigned of = o;
-    g_fence_proxy_async();                        // the middle pass wrote the ring region with ordinary stores
-    for (int jj = 0; jj < S - 1; ++jj) if (N - jj >= 1) ring_fetch<M>(c, fac, ring, N, N - jj, of++);
-    for (int j = N - 1; j >= 0; --j) {
-      g_mbar_wait(&c.ring_bar[o % S], (o / S) & 1);
-      G_SYNCWARP();
-      if (j + 1 - (S - 1) >= 1) ring_fetch<M>(c, fac, ring, N, j + 1 - (S - 1), of++);
-      const double* R = ring + (o % S) * L::GT;
-      G_W0_FOR(i, NX) {
-        double a0 = y[j * NX + i], a1 = 0.0;
-#pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) { a0 -= R[m * GLD + i] * y[(j + 1) * NX + m]; a1 -= R[(m + 1) * GLD + i] * y[(j + 1) * NX + m + 1]; }
-        if (NX & 1) a0 -= R[(NX - 1) * GLD + i] * y[(j + 1) * NX + NX - 1];
-        y[j * NX + i] = a0 + a1;
-      }
-      ++o;
-    }
-    G_SYNCWARP();
-    if (G_TID == 0) c.ring_o = o;
-  }
-  G_SYNC();
-  if (G_TID == 0 && GUSTO_PROF_SOLVE) c.prof[4] += g_clock() - tc0;
-}
-
-// [dz; dnu] (+)= Ktilde^-1 [rin; rnuin]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]] via the Schur complement.
-// One Schur-complement solve of  Ktilde [d; dnu] = [rin; rnu - Aeq dz]  with Ktilde = [[H + dp I, Aeq'], [Aeq, -dd]],
-// added to (or installed in) dz / dnu.  On entry c.t1 holds  Phi rin (+ dz when accumulating)  -- written by assemble()
-// for the first solve of a direction and by the previous call for a refinement solve -- so the Schur right-hand side
-// is simply  Aeq t1 - rnu.  When `more` refinement follows, the same per-knot pass that recovers d also leaves the
-// next residual  res = rin - Aeq' dnu - H d  (unregularised H, i.e. the exact KKT matrix) in c.res and its Phi-image
-// plus the updated dz in c.t1: a refinement step costs two passes and two chains, nothing else.
-template <int M> GDEV_NOINLINE void kkt_solve(const IpmCtx<M>& c, const double* rin, bool accumulate, bool more) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NV = L::NV;
-  const int N = c.N;
-  G_PAR_FOR(j, N + 1) {
-    double v[NX];
-    aeq_row<M>(c, c.t1, j, v);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) sh_sy<M>(c)[j * NX + i] = v[i] - c.rnu[j * NX + i];
-  }
-  G_SYNC();
-  schur_solve<M>(c);
-  G_PAR_FOR(k, N) {
-    double t[NV], d[NV];
-    aeqT_knot<M>(c, sh_sy<M>(c), k, t);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) t[i] = rin[k * NV + i] - t[i];
-    apply_phi<M>(c, k, t, d);
-    double dzn[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { dzn[i] = accumulate ? sh_dz<M>(c)[k * NV + i] + d[i] : d[i]; sh_dz<M>(c)[k * NV + i] = dzn[i]; }
-    if (more) {
-      double hd[NV], pr[NV];
-      apply_H<M>(c, k, d, hd);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { t[i] -= hd[i]; c.res[k * NV + i] = t[i]; }
-      apply_phi<M>(c, k, t, pr);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) c.t1[k * NV + i] = pr[i] + dzn[i];
-    }
-  }
-  {
-    double* __restrict__ dnu = c.dnu;
-    const double* sy = sh_sy<M>(c);
-    const int ne = (N + 1) * NX;
-    if (accumulate) {
-#pragma unroll 4
-      for (int it = G_TID; it < ne; it += G_NTHR) dnu[it] += sy[it];
-    } else {
-#pragma unroll 4
-      for (int it = G_TID; it < ne; it += G_NTHR) dnu[it] = sy[it];
-    }
-  }
-  G_SYNC();
-}
-
-// Solve, then `nref` refinement steps against the exact KKT matrix [[H, Aeq'], [Aeq, 0]].
-template <int M> GDEV_NOINLINE void kkt_solve_refined(const IpmCtx<M>& c, int nref) {
-  kkt_solve<M>(c, c.r, false, nref > 0);
-  for (int it_ref = 1; it_ref <= nref; ++it_ref) kkt_solve<M>(c, c.res, true, it_ref < nref);
-#if defined(GUSTO_HOSTSIM) && defined(GUSTO_DEBUG_KKT)
-  {   // true residuals of the direction against the exact KKT matrix
-    using L = IpmLayout<M>;
-    constexpr int NX = L::NX, NV = L::NV;
-    double rp = 0, rd = 0, np_ = 0, nd = 0;
-    for (int k = 0; k < c.N; ++k) {
-      double at[NV], hd[NV], dk[NV];
-      aeqT_knot<M>(c, c.dnu, k, at);
-      for (int i = 0; i < NV; ++i) dk[i] = c.dz[k * NV + i];
-      apply_H<M>(c, k, dk, hd);
-      for (int i = 0; i < NV; ++i) { rp = fmax(rp, fabs(c.r[k * NV + i] - hd[i] - at[i])); np_ = fmax(np_, fabs(c.r[k * NV + i])); }
-    }
-    for (int j = 0; j <= c.N; ++j) {
-      double v[NX];
-      aeq_row<M>(c, c.dz, j, v);
-      for (int i = 0; i < NX; ++i) { rd = fmax(rd, fabs(c.rnu[j * NX + i] - v[i])); nd = fmax(nd, fabs(c.rnu[j * NX + i])); }
-    }
-    printf("    kkt(nref=%d): |r - H dz - A'dnu| = %.2e (|r| %.2e)   |rnu - A dz| = %.2e (|rnu| %.2e)\n", nref, rp, np_, rd, nd);
-  }
+// ------------------------------------------------------------------------------------------------ chains
+// One n_x x n_x mat-vec per knot with the closed-loop tiles Acl_k, on warp 0: lane i owns row (forward) / column (backward) i
+// and prefetches its slice of the tiles PF knots ahead straight into registers -- no staging ring, no barrier objects; the
+// only per-step synchronisation is one __syncwarp that publishes the new vector in shared memory.  (Round 1 streamed its
+// factor tiles through a TMA ring; an mbarrier try_wait alone costs ~90 cycles per step and the step is ~150 cycles of work.)
+#ifndef GUSTO_CHAIN_PF
+#define GUSTO_CHAIN_PF 3
 #endif
+// forward:  s_{k+1} = Acl_k s_k + d_k   (s_k in the x-slots of dz; slot k+1 holds d_k on entry, slot 0 holds s_0)
+template <int M> GDEV_NOINLINE void chain_forward(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NV = L::NV, LDT = L::LDT, HP = (NX + 1) / 2, PF = NX <= 12 ? GUSTO_CHAIN_PF : 2;
+  const int nt = c.N - 1;
+  double* const y = c.dz;
+  G_ASSUME_SHARED(y);
+  const long long tc0 = g_clock();
+  if (G_TID < G_WARP) {
+#ifdef GUSTO_HOSTSIM
+    for (int k = 0; k < nt; ++k)
+      for (int i = 0; i < NX; ++i) {
+        double a = y[(k + 1) * NV + i];
+        for (int m = 0; m < NX; ++m) a += c.acl[(size_t)k * L::GT + i * LDT + m] * y[k * NV + m];
+        y[(k + 1) * NV + i] = a;
+      }
+#else
+    // every load is unconditional (tile index clamped, idle lanes read row 0): the buffers stay in registers
+    const int i = G_LANE;
+    const bool act = i < NX;
+    const double* src = c.acl + (act ? i : 0) * LDT;
+    g_d2 buf[PF][HP];
+#pragma unroll
+    for (int s2 = 0; s2 < PF; ++s2) {
+      const int ks = s2 < nt ? s2 : nt - 1;
+#pragma unroll
+      for (int m = 0; m < HP; ++m) buf[s2][m] = g_ld2(src + (size_t)ks * L::GT + 2 * m);
+    }
+    // The running vector never makes a shared-memory round trip: lane i keeps s_k[i] in a register and every lane collects
+    // the whole vector with warp shuffles (no __syncwarp on the dependent path); the stores to dz are off that path.
+    double sv = y[act ? i : 0];
+    for (int k0 = 0; k0 < nt; k0 += PF) {
+#pragma unroll
+      for (int s2 = 0; s2 < PF; ++s2) {
+        const int k = k0 + s2 < nt ? k0 + s2 : nt - 1;
+        const bool live = act && (k0 + s2 < nt);
+        double a0 = y[(k + 1) * NV + (act ? i : 0)], a1 = 0.0;       // d_k[i]: independent of the chain
+#pragma unroll
+        for (int m = 0; m < HP; ++m) {
+          a0 = fma(buf[s2][m].x, __shfl_sync(0xffffffffu, sv, 2 * m), a0);
+          if (2 * m + 1 < NX) a1 = fma(buf[s2][m].y, __shfl_sync(0xffffffffu, sv, 2 * m + 1), a1);
+        }
+        const int kn = k + PF < nt ? k + PF : nt - 1;
+#ifndef GUSTO_CHAIN_NOLOAD
+#pragma unroll
+        for (int m = 0; m < HP; ++m) buf[s2][m] = g_ld2(src + (size_t)kn * L::GT + 2 * m);
+#endif
+        if (k0 + s2 < nt) sv = a0 + a1;
+        if (live) y[(k + 1) * NV + i] = sv;
+      }
+    }
+    G_SYNCWARP();
+#endif
+  }
+  G_SYNC();
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[1] += g_clock() - tc0;
+}
+// backward:  vp[k] += Acl_k' vp[k+1]  for k = N-2 .. 0
+template <int M> GDEV_NOINLINE void chain_backward(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, LDT = L::LDT, PF = NX <= 12 ? GUSTO_CHAIN_PF : 2;
+  const int nt = c.N - 1;
+  double* const y = c.vp;
+  G_ASSUME_SHARED(y);
+  const long long tc0 = g_clock();
+  if (G_TID < G_WARP) {
+#ifdef GUSTO_HOSTSIM
+    for (int k = nt - 1; k >= 0; --k)
+      for (int i = 0; i < NX; ++i) {
+        double a = y[k * NX + i];
+        for (int m = 0; m < NX; ++m) a += c.acl[(size_t)k * L::GT + m * LDT + i] * y[(k + 1) * NX + m];
+        y[k * NX + i] = a;
+      }
+#else
+    const int i = G_LANE;
+    const bool act = i < NX;
+    const double* src = c.acl + (act ? i : 0);
+    double buf[PF][NX];
+#pragma unroll
+    for (int s2 = 0; s2 < PF; ++s2) {
+      const int ks = nt - 1 - s2 >= 0 ? nt - 1 - s2 : 0;
+#pragma unroll
+      for (int m = 0; m < NX; ++m) buf[s2][m] = src[(size_t)ks * L::GT + m * LDT];
+    }
+    double sv = y[nt * NX + (act ? i : 0)];
+    for (int k0 = nt - 1; k0 >= 0; k0 -= PF) {
+#pragma unroll
+      for (int s2 = 0; s2 < PF; ++s2) {
+        const int k = k0 - s2 >= 0 ? k0 - s2 : 0;
+        const bool live = act && (k0 - s2 >= 0);
+        double a0 = y[k * NX + (act ? i : 0)], a1 = 0.0;
+#pragma unroll
+        for (int m = 0; m + 1 < NX; m += 2) {
+          a0 = fma(buf[s2][m], __shfl_sync(0xffffffffu, sv, m), a0);
+          a1 = fma(buf[s2][m + 1], __shfl_sync(0xffffffffu, sv, m + 1), a1);
+        }
+        if (NX & 1) a0 = fma(buf[s2][NX - 1], __shfl_sync(0xffffffffu, sv, NX - 1), a0);
+        const int kn = k - PF >= 0 ? k - PF : 0;
+#ifndef GUSTO_CHAIN_NOLOAD
+#pragma unroll
+        for (int m = 0; m < NX; ++m) buf[s2][m] = src[(size_t)kn * L::GT + m * LDT];
+#endif
+        if (k0 - s2 >= 0) sv = a0 + a1;
+        if (live) y[k * NX + i] = sv;
+      }
+    }
+    G_SYNCWARP();
+#endif
+  }
+  G_SYNC();
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[1] += g_clock() - tc0;
+}
+
+// ----------------------------------------------------------------------------------------- per-knot passes
+// The s-form control gradient  rs = ru + Gam' rx  of knot k for the right-hand side in c.r / c.rnu.
+template <int M> GDEV void ric_rhs_knot(const IpmCtx<M>& c, int k, double* rx, double* rs) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, LDT = L::LDT;
+  const double* cr = c.cr + (size_t)k * L::CRW;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) rx[i] = c.r[k * NV + i];
+  if (k == c.N - 1) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) if ((c.pmask >> i) & 1) rx[i] += c.wN * c.rnu[c.N * NX + i];
+  }
+#pragma unroll
+  for (int a = 0; a < NU; ++a) {
+    double v = c.r[k * NV + NX + a];
+    const double* gt = cr + (L::CR_GT + a) * LDT;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += gt[i] * rx[i];
+    rs[a] = v;
+  }
+}
+// Costates for a new right-hand side (the corrector's): bb_k = rx - K'rs - psi_{k-1}, the backward chain, then
+// kap_k = Lam_k^-1 (rs + Bh_k' pit_k).
+template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NU = L::NU, LDT = L::LDT, LDU = L::LDU, NTU = L::NTU;
+  const int N = c.N;
+  double* const vp = sh_vp<M>(c);
+  long long tc0 = g_clock();
+  G_PAR_FOR(k, N) {
+    double rx[NX], rs[NU];
+    ric_rhs_knot<M>(c, k, rx, rs);
+    const double* kt = c.kt + (size_t)k * L::KTW;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = rx[i] - (k >= 1 ? c.psi[(size_t)(k - 1) * NX + i] : 0.0);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v -= kt[i * LDU + a] * rs[a];
+      vp[k * NX + i] = v;
+    }
+  }
+  G_SYNC();
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
+  chain_backward<M>(c);
+  tc0 = g_clock();
+  G_PAR_FOR(k, N) {
+    double rx[NX], rs[NU], Lc[NTU], x[NU];
+    ric_rhs_knot<M>(c, k, rx, rs);
+    if (k < N - 1) {
+      const double* cr = c.cr + (size_t)k * L::CRW;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const double* bt = cr + (L::CR_BT + a) * LDT;
+        double v = rs[a];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += bt[i] * vp[(k + 1) * NX + i];
+        rs[a] = v;
+      }
+    }
+    const double* lp = c.lp + (size_t)k * L::LPW;          // packed lower L^-1:  kap = L^-T (L^-1 rs)
+#pragma unroll
+    for (int t = 0; t < NTU; ++t) Lc[t] = lp[t];
+    tri_lower_mv<NU>(Lc, rs, x);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) rs[a] = x[a];
+    tri_lower_tmv<NU>(Lc, rs, x);
+#pragma unroll
+    for (int a = 0; a < NU; ++a) c.kap[(size_t)k * LDU + a] = x[a];
+  }
+  G_SYNC();
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
+}
+// d_k = Bh_k kap_k + ch_k into the x-slot k+1 of dz, s_0 = rho_0 into slot 0, kap_k into the u-slot k; forward chain; then
+// per knot  u = kap - K s,  x = s + Gam u  and (want_nu) the equality multipliers  dnu_j = F_j^-T (P_j (s_j - ch_{j-1}) - pit_{j-1}).
+template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, NN = L::NN, LDT = L::LDT, LDU = L::LDU;
+  const int N = c.N;
+  double* const dz = sh_dz<M>(c);
+  const double* const vp = sh_vp<M>(c);
+  long long tc0 = g_clock();
+  G_PAR_FOR(k, N) {
+    double kap[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) { kap[a] = c.kap[(size_t)k * LDU + a]; dz[k * NV + NX + a] = kap[a]; }
+    if (k < N - 1) {
+      const double* cr = c.cr + (size_t)k * L::CRW;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = c.ch[(size_t)k * NX + i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += cr[(L::CR_BT + a) * LDT + i] * kap[a];
+        dz[(k + 1) * NV + i] = v;
+      }
+    }
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dz[i] = c.rnu[i];
+    }
+  }
+  G_SYNC();
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
+  chain_forward<M>(c);
+  tc0 = g_clock();
+  G_PAR_FOR(k, N) {
+    double s[NX], u[NU], x[NX];
+    const double* kt = c.kt + (size_t)k * L::KTW;
+    const double* cr = c.cr + (size_t)k * L::CRW;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s[i] = dz[k * NV + i];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = dz[k * NV + NX + a];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v -= kt[i * LDU + a] * s[i];
+      u[a] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = s[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += cr[(L::CR_GT + a) * LDT + i] * u[a];
+      x[i] = v;
+    }
+    if (want_nu && k >= 1) {
+      const double* pk = c.pk + (size_t)k * L::PKW;
+      const double* fi = c.fi + (size_t)k * NN;
+      double w[NX], lam[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) w[i] = s[i] - c.ch[(size_t)(k - 1) * NX + i];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = -vp[k * NX + i];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v += pk[tri(i, j)] * w[j];
+        lam[i] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) if (L::dsame(i, j)) v += fi[i * NX + j] * lam[i];
+        c.dnu[k * NX + j] = v;
+      }
+    }
+    if (want_nu && k == N - 1) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) c.dnu[N * NX + i] = ((c.pmask >> i) & 1) ? c.wN * (x[i] - c.rnu[N * NX + i]) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dz[k * NV + i] = x[i];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) dz[k * NV + NX + a] = u[a];
+  }
+  G_SYNC();
+  if (want_nu) {
+    // row 0 (x_0 = x_init): stationarity in x_0,  dnu_0 = rx_0 - Hx_0 dx_0 - E_1' dnu_1,  E_1 = I + h/2 A_0
+    if (G_TID == 0) {
+      double dx0[NX], hx[NX], e1[NX];
+      for (int i = 0; i < NX; ++i) { dx0[i] = dz[i]; e1[i] = c.dnu[NX + i]; }
+      apply_Hx<M>(c, 0, dx0, hx);
+      for (int e = 0; e < L::ANZ; ++e) e1[T::a_col(e)] += c.hh * c.Ac[e] * c.dnu[NX + T::a_row(e)];
+      for (int i = 0; i < NX; ++i) c.dnu[i] = c.r[i] - hx[i] - e1[i];
+    }
+    G_SYNC();
+  }
+  if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
+}
+// ch_k = -F_{k+1}^-1 rho_{k+1}  (k = 0 .. N-2) for the equality residual in c.rnu
+template <int M> GDEV_NOINLINE void ric_dyn_residual(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NN = L::NN;
+  const int N = c.N;
+  G_PAR_FOR(it, (N - 1) * NX) {
+    const int k = it / NX, i = it - k * NX;
+    const double* fi = c.fi + (size_t)(k + 1) * NN + i * NX;
+    const double* rho = c.rnu + (size_t)(k + 1) * NX;
+    double v = 0.0;
+#pragma unroll
+    for (int j = L::dlo(i); j < L::dhi(i); ++j) v -= fi[j] * rho[j];
+    c.ch[it] = v;
+  }
+  G_SYNC();
 }
 
 // --------------------------------------------------------------------------------------------- slot passes
@@ -1453,7 +1570,8 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
 }
 
 // ------------------------------------------------------------------------------------------------ driver
-// scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance (16-byte aligned).
+// scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance (16-byte aligned, zero-filled
+//          once at allocation: the padding columns of the tile records are never written).
 // smem:    IpmLayout<M>::smem_doubles() doubles of shared memory.
 // On exit Xn/Un of the instance hold the solution and info[IPM_NINFO] = {status, iters, res, mu, obj,...}.
 template <int M>
@@ -1461,7 +1579,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
                              double* smem, double* info) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, NN = L::NN;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const int N = d.N;
   // The context is ONE struct per instance in shared memory (filled by thread 0): phase functions read it with
   // shared loads instead of per-thread local-memory copies.
@@ -1471,7 +1589,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   if (G_TID == 0) {
     c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
     c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
-    c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS]; c.dp = prm.delta_p; c.dd = prm.delta_d;
+    c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];
+    c.wN = prm.wn_base + prm.wn_omega * c.omega;
     c.dow = c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
     for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
@@ -1485,69 +1604,54 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
       dyn_B<M>(d.rp, Bm);
       for (int a = 0; a < NU; ++a) c.bv[a] = Bm[T::b_row(a) * NU + a];
     }
-    const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs;
+    const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs, nn = (size_t)N;
     double* q = scratch;
-    c.r = q; q += nz; c.t1 = q; q += nz; c.res = q; q += nz;
-    c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne; c.resnu = q; q += ne;
-    c.Ac = q; q += L::rnd((size_t)N * L::ANZ);
-    c.sslot = q; q += L::rnd((size_t)N * L::SP * SLOT_W);
+    c.r = q; q += nz;
+    c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne;
+    c.Ac = q; q += L::rnd(nn * L::ANZ);
+    c.sslot = q; q += L::rnd(nn * L::SP * SLOT_W);
     c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
-    c.ost = q; q += L::rnd((size_t)N * no * SLOT_W);
-    c.orow = q; q += L::rnd((size_t)N * no * OROW_W);
-    c.kd = q; q += L::rnd((size_t)N * L::KDW);
-    c.fac = q; q += (size_t)(N + 1) * 2 * L::GT;
-    c.z = smem; c.dz = c.z + L::rnd((size_t)N * NV); c.sy = c.dz + L::rnd((size_t)N * NV); c.ring = c.sy + L::rnd((size_t)(N + 1) * NX);
-    c.red = c.dz + L::work_doubles(N);
+    c.ost = q; q += L::rnd(nn * no * SLOT_W);
+    c.orow = q; q += L::rnd(nn * no * OROW_W);
+    c.kd = q; q += nn * L::KDW;
+    c.cr = q; q += nn * L::CRW;
+    c.acl = q; q += nn * L::GT;
+    c.kt = q; q += nn * L::KTW;
+    c.lp = q; q += nn * L::LPW;
+    c.pk = q; q += nn * L::PKW;
+    c.psi = q; q += L::rnd(nn * NX);
+    c.ch = q; q += L::rnd(nn * NX);
+    c.kap = q; q += nn * L::LDU;
+    c.fi = q; q += nn * L::NN;                                   // last: N * NX * NX may be odd
+    c.z = smem; c.dz = c.z + L::rnd((size_t)N * NV);
+    c.vp = c.dz + L::work_doubles(N);
+    c.red = c.vp + L::rnd((size_t)(N + 1) * NX);
     c.seg = reinterpret_cast<int*>(c.red + G_NTHR + 16);
     c.tab = reinterpret_cast<unsigned char*>(c.red + G_NTHR + 16 + L::seg_doubles(N));
-    for (int i = 0; i < 5; ++i) c.prof[i] = 0;
-    for (int i = 0; i < RING_STAGES; ++i) g_mbar_init(&c.ring_bar[i], 1);
-    c.ring_o = 0;
+    for (int i = 0; i < 4; ++i) c.prof[i] = 0;
     c.floor_ = 0.0;
-    unsigned char* t2 = c.tab + NX * (NX + 1);
-    int n = 0;
-    for (int i = 0; i < NX; ++i) for (int g = 0; g < L::NG; ++g) if (g * L::CG <= i) { t2[n] = (unsigned char)i; t2[L::NLT + n] = (unsigned char)g; ++n; }
-    unsigned char* mt = c.tab + L::TAB_MODEL;                 // a_row | a_col | blk_of | ctrl_of (0xff: no control drives the row)
+    unsigned char* mt = c.tab;                                   // a_row | a_col | blk_of
     for (int e = 0; e < L::ANZ; ++e) { mt[e] = (unsigned char)T::a_row(e); mt[L::ANZ + e] = (unsigned char)T::a_col(e); }
-    for (int i = 0; i < NX; ++i) { mt[2 * L::ANZ + i] = (unsigned char)T::XB_of(i); mt[2 * L::ANZ + NX + i] = (unsigned char)ctrl_of_row<M>(i); }
+    for (int i = 0; i < NX; ++i) mt[2 * L::ANZ + i] = (unsigned char)T::XB_of(i);
   }
   G_SYNC();
-  G_PAR_FOR(t, NX * (NX + 1) / 2) {
-    int i = 0;
-    while ((i + 1) * (i + 2) / 2 <= t) ++i;
-    c.tab[t] = (unsigned char)i; c.tab[NX * (NX + 1) / 2 + t] = (unsigned char)(t - i * (i + 1) / 2);
-  }
 
-  // The solve is attempted with the configured primal regularisation; an attempt that breaks down (non-positive
-  // pivot, NaN) or stalls (no progress of the residual for 12 Newton iterations) is restarted from the same start
-  // point with delta_p x10, at most twice.  The oracle factorises the full KKT matrix (LU) and only regularises on a
-  // failed factorisation (ipm.py); the Schur-complement form used here needs (H + delta_p I)^-1, and on problems
-  // whose H is singular in many directions (no trust region: astrobeeSE3manifold) the right delta_p is
-  // instance-dependent.
   int status = IPM_ITERATION_LIMIT, it_done = 0;
   long long cyc_asm = 0, cyc_fac = 0, cyc_sol = 0, cyc_slot = 0, tc0;
   double res = 1e300, mu = 0;
   const double scd = 1.0 + c.omega;
-  for (int attempt = 0; attempt < 3; ++attempt) {
-  if (attempt > 0) {
-    G_SYNC();
-    if (G_TID == 0) { c.dp *= 10.0; c.floor_ = 0.0; }
-    G_SYNC();
-#ifdef GUSTO_HOSTSIM
-    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  restart with delta_p = %.1e\n", c.dp);
-#endif
-  }
   setup<M>(c);
-  status = IPM_ITERATION_LIMIT;
+  tc0 = g_clock();
+  setup_dynamics<M>(c);
+  const long long cyc_setup = g_clock() - tc0;
   double best = 1e300;
-  int best_it = 0;
+  int stall = 0;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
     G_CTA_RESYNC();
     ++it_done;
     Resid R;
-    bool blocks_ok = true;
     tc0 = g_clock();
-    assemble<M>(c, 0, 0.0, &R, &blocks_ok);
+    assemble<M>(c, 0, 0.0, &R);
     cyc_asm += g_clock() - tc0;
     mu = R.mu;
     res = R.rz / scd;
@@ -1557,15 +1661,23 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
 #endif
     if (res <= prm.tol) { status = IPM_OPTIMAL; break; }
     if (!(res == res) || res > 1e200) { status = IPM_NUMERICAL; break; }
-    if (res < 0.5 * best) { best = res; best_it = iter; }
-    else if (iter - best_it >= 12) break;                       // stalled
+    // The best iterate is kept in Xn / Un (as the oracle keeps it, ipm.py): a solve whose dual residual wanders once the
+    // complementarity sits at its floor is stopped after 8 iterations without improvement and answers with that iterate.
+    if (res < best) {
+      best = res; stall = 0;
+      G_PAR_FOR(k, N) {
+        for (int i = 0; i < NX; ++i) p.Xn[((size_t)b * N + k) * NX + i] = sh_z<M>(c)[k * NV + i];
+        for (int i = 0; i < NU; ++i) p.Un[((size_t)b * N + k) * NU + i] = sh_z<M>(c)[k * NV + NX + i];
+      }
+    } else if (++stall >= 8 && best <= 1e3 * prm.tol) break;
+    // predictor: factorisation sweep with the backward vector pass fused, then the forward pass
     tc0 = g_clock();
-    const bool fac_ok = factorize<M>(c);
+    ric_dyn_residual<M>(c);
+    const bool fac_ok = riccati_factor<M>(c);
     cyc_fac += g_clock() - tc0;
-    if (!(fac_ok && blocks_ok)) { status = IPM_NUMERICAL; break; }   // non-positive pivot
-    // predictor
+    if (!fac_ok) { status = IPM_NUMERICAL; break; }             // non-positive pivot of a Lam_k
     tc0 = g_clock();
-    kkt_solve_refined<M>(c, 0);
+    ric_forward<M>(c, false);
     cyc_sol += g_clock() - tc0;
     double am[5];
     tc0 = g_clock();
@@ -1581,12 +1693,11 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     smu = smu > 0.1 * prm.tol ? smu : 0.1 * prm.tol;
     // corrector
     tc0 = g_clock();
-    assemble<M>(c, 1, smu, &R, &blocks_ok);
+    assemble<M>(c, 1, smu, &R);
     cyc_asm += g_clock() - tc0;
     tc0 = g_clock();
-    // far from the solution the unrefined direction is accurate enough (its KKT residual is ~1e-7 of the rhs): refine
-    // only once the complementarity gap is small
-    kkt_solve_refined<M>(c, (T::HAS_TR && mu > 1e-5) ? 0 : prm.nref);
+    ric_backward<M>(c);
+    ric_forward<M>(c, true);
     cyc_sol += g_clock() - tc0;
     tc0 = g_clock();
     slot_steps<M>(c, 1, smu, 0, 0, 0, am);
@@ -1606,15 +1717,26 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     G_SYNC();
     cyc_slot += g_clock() - tc0;
   }
-  if (status == IPM_ITERATION_LIMIT && res <= 1e3 * prm.tol) status = IPM_OPTIMAL;
+  // A stalled solve is accepted only when its best residual is both within 1e3*tol and far below the SCP's own soft-row
+  // threshold eps (GuSTO's accept test compares raw row values with eps, scp_gusto.jl:318-327), and is labelled as such.
+  const bool use_best = status == IPM_ITERATION_LIMIT && best <= 1e3 * prm.tol && best <= 0.1 * c.eps;
+  if (use_best) {
+    status = IPM_ALMOST_OPTIMAL;
+    res = best;
+    G_SYNC();
+    G_PAR_FOR(k, N) {
+      for (int i = 0; i < NX; ++i) sh_z<M>(c)[k * NV + i] = p.Xn[((size_t)b * N + k) * NX + i];
+      for (int i = 0; i < NU; ++i) sh_z<M>(c)[k * NV + NX + i] = p.Un[((size_t)b * N + k) * NU + i];
+    }
+    G_SYNC();
+  }
   {   // a NaN/Inf anywhere in the iterate is a numerical failure, never an answer
     double badz = 0.0;
     G_PAR_FOR(it, N * NV) { const double v = sh_z<M>(c)[it]; if (!(v == v) || fabs(v) > 1e100) badz = 1.0; }
     if (block_max(badz, c.red) > 0.0) status = IPM_NUMERICAL;
   }
-  if (status == IPM_OPTIMAL) break;
-  }
-  // ---- write the candidate trajectory and the objective (cost + omega * sum t)
+  // ---- write the candidate trajectory and the objective (cost + omega * sum t; for a kept best iterate the slacks are
+  //      taken at their optimal values t = max(c0, 0))
   double obj = 0;
   G_PAR_FOR(k, N) {
     const double wk = (k == 0 || k == N - 1) ? 0.5 * c.h : c.h;
@@ -1623,7 +1745,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   }
   {
     const double omega = c.omega;
-    for_each_row<M>(c, false, [&](double* st, bool has_t, double, double) { if (has_t) obj += omega * st[2]; });
+    for_each_row<M>(c, false, [&](double* st, bool has_t, double c0, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2]); });
   }
   // SCPS.dual (scp_gusto.jl:116, get_dual_jump): row 0 of Aeq is  x_0 = x_init  and the Lagrangian is f + nu'(Aeq z - b)
   if (p.dual) G_PAR_FOR(i, NX) p.dual[(size_t)b * NX + i] = c.nu[i];
@@ -1632,13 +1754,14 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     info[0] = (double)status; info[1] = (double)it_done; info[2] = res; info[3] = mu; info[4] = obj;
 #if !defined(GUSTO_PROF_MODE) || GUSTO_PROF_MODE == 0
     info[5] = (double)(cyc_asm + cyc_slot); info[6] = (double)cyc_fac; info[7] = (double)cyc_sol;   // SM cycles per phase
-#elif GUSTO_PROF_MODE == 1      // developer builds: finer split of the factorisation
-    info[5] = (double)c.prof[0]; info[6] = (double)c.prof[1]; info[7] = (double)cyc_asm;
-#elif GUSTO_PROF_MODE == 2      // ... and of the solves
-    info[5] = (double)c.prof[2]; info[6] = (double)c.prof[3]; info[7] = (double)c.prof[4];
-#else                           // ... and of one sweep step: elimination | wait for the stager + C1 | C2 (packed: X + loop barrier in info[3])
-    info[5] = (double)c.prof[0]; info[6] = (double)(c.prof[1] + c.prof[2]); info[7] = (double)c.prof[3]; info[3] = (double)c.prof[4];
+#elif GUSTO_PROF_MODE == 1      // developer builds: sweep | chains | per-knot passes
+    info[5] = (double)c.prof[0]; info[6] = (double)c.prof[1]; info[7] = (double)c.prof[2];
+#elif GUSTO_PROF_MODE == 2      // ... setup of the dynamics records | assembly | row passes
+    info[5] = (double)cyc_setup; info[6] = (double)cyc_asm; info[7] = (double)cyc_slot;
+#else                           // ... phases of the sweep: A | B | C (info[3] = D)
+    info[5] = (double)c.prof[0]; info[6] = (double)c.prof[1]; info[7] = (double)c.prof[2]; info[3] = (double)c.prof[3];
 #endif
+    (void)cyc_setup;
   }
 }
 

@@ -36,34 +36,14 @@ class GustoConfig(ctypes.Structure):
                 ("ipm_tol", ctypes.c_double), ("ipm_delta_p", ctypes.c_double), ("ipm_delta_d", ctypes.c_double)]
 
 
-NARROW_BOX_TOL = 1e-3
-
-
-def presolve_goals(goal_type, goal_lo, goal_hi, tol=NARROW_BOX_TOL):
-    """Host-side presolve: a BoxGoal coordinate whose width is below `tol` on every instance is handed to the solver as
-    a PointGoal at the box centre (|change| <= tol/2; the astrobeeSE3manifold notebook's BoxGoal(q +- 1e-4) moves by
-    <= 1e-4 and the subproblem objective by < 1e-9).  An interior-point method cannot centre a pair of inequalities
-    2e-4 apart while the other rows are O(1); with the pair as an equality the solves take the oracle's iteration
-    counts.  tol = 0 disables it.  Returns new (goal_type, goal_lo, goal_hi) arrays."""
-    goal_type = np.array(goal_type, copy=True); goal_lo = np.array(goal_lo, dtype=np.float64, copy=True)
-    goal_hi = np.array(goal_hi, dtype=np.float64, copy=True)
-    if tol > 0:
-        narrow = (goal_type == M.GOAL_BOX) & np.all(goal_hi - goal_lo < tol, axis=0)
-        mid = 0.5 * (goal_lo + goal_hi)
-        goal_type[narrow] = M.GOAL_POINT
-        goal_lo[:, narrow] = mid[:, narrow]; goal_hi[:, narrow] = mid[:, narrow]
-    return goal_type, goal_lo, goal_hi
-
-
-def make_config(bp: BatchProblem, device=0, ipm_max_iter=0, ipm_nref=0, ipm_tol=0.0, ipm_delta_p=0.0, ipm_delta_d=0.0,
-                narrow_box_tol=NARROW_BOX_TOL):
+def make_config(bp: BatchProblem, device=0, ipm_max_iter=0, ipm_nref=0, ipm_tol=0.0, ipm_delta_p=0.0, ipm_delta_d=0.0):
     kind, a, b = bp.obstacle_table()
     cfg = GustoConfig()
     cfg.model_id, cfg.N, cfg.B, cfg.n_obs = bp.model.model_id, bp.N, bp.B, int(kind.shape[0])
     cfg.robot_params[:] = list(bp.robot_params())
     cfg.scp_params[:] = list(bp.model.scp_params)
     gt = np.zeros(16, dtype=np.int32)
-    gt[:bp.model.x_dim] = presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi, narrow_box_tol)[0]
+    gt[:bp.model.x_dim] = bp.goal_type          # BoxGoal rows go to the solver as they are (no presolve since round 2)
     cfg.goal_type[:] = list(gt)
     cfg.device = device
     cfg.ipm_max_iter, cfg.ipm_nref = ipm_max_iter, ipm_nref
@@ -152,9 +132,8 @@ class Engine:
         rc = self.lib.gusto_create(ctypes.byref(cfg), kind.ctypes.data_as(_IP), _dp(a), _dp(b), ctypes.byref(self._ctx))
         if rc != 0:
             raise GustoError(f"gusto_create failed ({rc}): {self.lib.gusto_last_error(None).decode()}")
-        _, glo, ghi = presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi, ipm_opts.get("narrow_box_tol", NARROW_BOX_TOL))
         self._chk(self.lib.gusto_set_problems(self._ctx, _dp(np.ascontiguousarray(bp.x_init)),
-                                              _dp(np.ascontiguousarray(glo)), _dp(np.ascontiguousarray(ghi)),
+                                              _dp(np.ascontiguousarray(bp.goal_lo)), _dp(np.ascontiguousarray(bp.goal_hi)),
                                               _dp(np.ascontiguousarray(bp.tf))))
 
     def _chk(self, rc):
@@ -318,6 +297,14 @@ class BatchSCPSolution:
     batch_iterations: int = 0
 
 
+IPM_OPTIMAL, IPM_ITERATION_LIMIT, IPM_NUMERICAL, IPM_ALMOST_OPTIMAL = range(4)
+
+
+def solver_status_ok(status):
+    """scp_gusto.jl:107: OPTIMAL / LOCALLY_SOLVED / ALMOST_LOCALLY_SOLVED continue, anything else returns."""
+    return (status == IPM_OPTIMAL) | (status == IPM_ALMOST_OPTIMAL)
+
+
 def gusto_update(ev, solver_ok, active, Delta, omega, iterations, conv_prev, sp, force=False):
     """Vectorised accept/reject + Delta/omega schedule + convergence test of scp_gusto.jl:119-174 for one outer
     iteration.  All arguments are [B] arrays; returns the new state.  Pure host logic (also used by the gloo tests)."""
@@ -381,7 +368,7 @@ def solve_gusto_batch(engine: Engine, X0=None, U0=None, max_iter=30, force=False
         ti = time.perf_counter()
         engine.set_active(active)
         engine.iterate(out, info)
-        solver_ok = info[:, 0] == 0
+        solver_ok = solver_status_ok(info[:, 0])
         st = gusto_update(out, solver_ok, active, Delta, omega, S.iterations, S.convergence_measure[-1], sp, force)
         engine.accept(st["accept"], st["omega"], st["Delta"])
         J_prev = S.J_true[-1]
@@ -498,7 +485,7 @@ class _ScpStepper:
         e, S = self.engine, self.S
         e.set_active(active)
         out, info = e.iterate()
-        st = gusto_update(out, info[:, 0] == 0, active, self.Delta, self.omega, S.iterations, S.convergence_measure[-1], self.sp)
+        st = gusto_update(out, solver_status_ok(info[:, 0]), active, self.Delta, self.omega, S.iterations, S.convergence_measure[-1], self.sp)
         e.accept(st["accept"], st["omega"], st["Delta"])
         S.J_true.append(np.where(st["accept"], out[:, EV_JTRUE], S.J_true[-1]))
         S.convergence_measure.append(np.where(st["run"], out[:, EV_CONV], S.convergence_measure[-1]))

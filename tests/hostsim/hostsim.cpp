@@ -67,11 +67,8 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
   p.Xp = Xp; p.Up = Up; p.Xn = Xn; p.Un = Un; p.omega = omega; p.delta = delta; p.f = f; p.A = A; p.g = g; p.rows = rows;
   IpmParams prm;
   prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
-  prm.nref = cfg->ipm_nref > 0 ? cfg->ipm_nref : ((cfg->model_id == ASTROBEE_SE3 || cfg->model_id == FREEFLYER_SE2) ? 1 : 2);   // no trust region => H is only regularised by delta_p on free directions: refine twice
-  // astrobeeSE3manifold: no trust region (H singular in many directions) -> larger primal regularisation
   prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
-  prm.delta_p = cfg->ipm_delta_p > 0 ? cfg->ipm_delta_p : (cfg->model_id == ASTROBEE_SE3_MANIFOLD ? 1e-5 : 1e-6);
-  prm.delta_d = cfg->ipm_delta_d > 0 ? cfg->ipm_delta_d : 1e-10;
+  prm.wn_base = 1e8; prm.wn_omega = 1e4;
   switch (cfg->model_id) {
     case DUBINS: run<DUBINS>(d, p, prm, stages, info, eval); break;
     case FREEFLYER_SE2: run<FREEFLYER_SE2>(d, p, prm, stages, info, eval); break;

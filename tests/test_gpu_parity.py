@@ -72,8 +72,8 @@ def test_subproblem_and_evaluation_match_oracle(engines, name, omega):
         Xs, Us, obj, st, lin, rows, _ = solve_subproblem(p, X0[b], U0[b], omega, sp[0], toggle, sp[3])
         assert st == "OPTIMAL"
         assert abs(info[b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
-        # manifold: attitude weakly determined by the cost; BoxGoal(q +- 1e-4) presolved to a PointGoal (host.presolve_goals)
-        xtol, utol = (1e-3, 3e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
+        # manifold: the attitude is only weakly determined by the cost (free inside the quaternion dead-band)
+        xtol, utol = (1e-3, 1e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
         assert np.max(np.abs(Xn[b] - Xs)) < xtol and np.max(np.abs(Un[b] - Us)) < utol
         # evaluation scalars on the GPU's own candidate
         ev = evaluate(p, Xn[b], Un[b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
@@ -88,17 +88,63 @@ def test_subproblem_and_evaluation_match_oracle(engines, name, omega):
         assert np.max(np.abs(Xn[b, -1][sel] - bp.goal_lo[b][sel])) < 1e-7
 
 
-@pytest.mark.parametrize("name", ["dubins", "freeflyerSE2", "astrobeeSE3"])
-def test_full_scp_matches_oracle(engines, host, name):
-    bp, eng = engines[name]
+L3_CASES = [("dubins", dict(B=16, N=30)), ("freeflyerSE2", dict(B=16, N=40)), ("astrobeeSE3", dict(B=16, N=50)),
+            ("astrobeeSE3manifold", dict(B=16, N=60))]
+
+
+@pytest.mark.parametrize("name,kw", L3_CASES)
+def test_full_scp_matches_oracle(host, name, kw):
+    """L3 on 16 instances per model (astrobeeSE3manifold with its notebook goal set, BoxGoal q +- 1e-4, no presolve):
+    identical (converged, successful, iterations) and accept histories, final J_true within 1e-3 relative.  An instance
+    that NEITHER side solves successfully (the reference's own SE3 notebook run ends in "omega_max exceeded") only has to
+    agree on that outcome: its path goes through omega up to 1e10, where no two solvers stop at the same iteration."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    eng = host.Engine(bp, device=0)
     S = host.solve_gusto_batch(eng, max_iter=30)
-    for b in range(min(bp.B, 2)):
+    eng.close()
+    identical = 0
+    for b in range(bp.B):
         R = solve_gusto(to_oracle(bp, b), max_iter=30)
-        assert bool(S.converged[b]) == R.converged and bool(S.successful[b]) == R.successful
-        assert int(S.iterations[b]) == R.iterations
-        assert abs(S.J_true[-1][b] - R.J_true[-1]) <= 1e-3 * max(1e-6, abs(R.J_true[-1]))
+        assert bool(S.successful[b]) == R.successful and bool(S.converged[b]) == R.converged, (name, b)
+        if not R.successful and not R.converged:
+            continue                                   # neither side solves it: only the outcome is compared
+        assert int(S.iterations[b]) == R.iterations, (name, b, int(S.iterations[b]), R.iterations)
+        assert abs(S.J_true[-1][b] - R.J_true[-1]) <= 1e-3 * max(1e-6, abs(R.J_true[-1])), (name, b)
         acc = [bool(a[b]) for a in S.accept_solution[:R.iterations + 1]]
-        assert acc == R.accept_solution
+        assert acc == R.accept_solution, (name, b)
+        identical += 1
+    print(f"[L3] {name}: {identical}/{bp.B} instances with identical decisions, {bp.B - identical} unsolved on both sides")
+    assert identical >= 1
+
+
+@pytest.mark.parametrize("name,kw,width", [("astrobeeSE3manifold", dict(B=3, N=60), 0.1), ("astrobeeSE3", dict(B=3, N=40), 0.05),
+                                           ("freeflyerSE2", dict(B=3, N=30), 0.2)])
+def test_genuine_box_goal_rows_match_oracle(host, name, kw, width):
+    """csbci_goal_constraints (dynamics.jl:37-42, scp_gusto.jl:237-245): hard rows lb <= X[i,N] <= ub at the last knot, on a
+    box wide enough (>= 0.05) that the optimum leaves its centre."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    sel = slice(6, 10) if name == "astrobeeSE3manifold" else slice(0, 2)
+    mid = 0.5 * (bp.goal_lo[:, sel] + bp.goal_hi[:, sel])
+    bp.goal_type = bp.goal_type.copy(); bp.goal_type[sel] = gb.models.GOAL_BOX
+    bp.goal_lo[:, sel] = mid - 0.5 * width; bp.goal_hi[:, sel] = mid + 0.5 * width
+    sp = bp.model.scp_params
+    X0, U0 = bp.init_traj_straightline()
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0)
+    out, info = e.iterate()
+    Xn, Un = e.get_candidate()
+    e.close()
+    toggle = sp[0] / 8 + bp.model.clearance
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[b], U0[b], sp[1], sp[0], toggle, sp[3])
+        assert st == "OPTIMAL" and info[b, 0] == 0
+        assert abs(info[b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
+        assert np.max(np.abs(Un[b] - Us)) < 1e-5
+        xN = Xn[b, -1, sel]
+        assert np.all(xN >= bp.goal_lo[b, sel] - 1e-9) and np.all(xN <= bp.goal_hi[b, sel] + 1e-9)
+        # (the quaternion is only weakly determined by the cost: same 1e-3 as the other attitude comparisons)
+        assert np.max(np.abs(xN - mid[b])) > 1e-3 and np.max(np.abs(xN - Xs[-1, sel])) < (1e-3 if name == "astrobeeSE3manifold" else 1e-4)
 
 
 def test_shard_equivalence_and_ragged_batch(host):
@@ -221,15 +267,11 @@ def test_full_size_batch_properties(host):
     e.close()
 
 
-def test_solver_restarts_instead_of_failing(host):
-    """astrobeeSE3manifold past the first SCP iteration: the default primal regularisation breaks down on some
-    instances (H is singular without a trust region); the kernel restarts with a larger one instead of returning
-    ITERATION_LIMIT / NUMERICAL.  KNOWN GAP: on these later iterations the attitude is only
-    determined inside the quaternion dead-band and the regularised Schur solver may stop at the "almost solved"
-    threshold (1e3 * tol), so the objective is only required to agree with the oracle to 2e-3 relative here (1e-6 on
-    the first iteration, test_subproblem_and_evaluation_match_oracle)."""
+def test_later_scp_iterations_of_the_quaternion_model_match_oracle(host):
+    """astrobeeSE3manifold past the first SCP iteration (Hx singular: no state trust region, the quaternion free inside its
+    dead-band): round 1's regularised Schur solve needed restarts here and agreed with the oracle only to 2e-3; the Riccati
+    solve reproduces the oracle's objective to 1e-6 on every subproblem of the oracle's own SCP path."""
     bp = gb.problems.CONFIGS["astrobeeSE3manifold"](B=2, N=60)
-    sp = bp.model.scp_params
     p = to_oracle(bp, 0)
     trace = []
 
@@ -238,14 +280,14 @@ def test_solver_restarts_instead_of_failing(host):
         trace.append((X.copy(), U.copy(), omega, Delta, res[2]))
         return res
 
-    solve_gusto(p, max_iter=4, subproblem=sub)
+    solve_gusto(p, max_iter=6, subproblem=sub)
     e = host.Engine(bp, device=0)
     for X, U, omega, Delta, obj in trace:
         e.set_trajectory(np.stack([X, X]), np.stack([U, U]))
         e.set_penalties(np.full(2, omega), np.full(2, Delta))
         out, info = e.iterate()
         assert info[0, 0] == 0
-        assert abs(info[0, 4] - obj) <= 2e-3 * abs(obj)
+        assert abs(info[0, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
     e.close()
 
 

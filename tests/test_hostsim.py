@@ -49,9 +49,8 @@ def test_solve_and_evaluate_bodies_match_oracle(name, kw, omega):
         assert st == "OPTIMAL" and hs["info"][b, 0] == 0
         assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
         assert abs(hs["info"][b, 1] - r.iters) <= 3          # same algorithm: Newton iteration counts agree
-        # manifold: the attitude is weakly determined by the cost, and the host presolve hands the BoxGoal(q +- 1e-4) to
-        # the solver as a PointGoal at its centre (host.presolve_goals) while the oracle keeps the box: |dU| <= 3e-5
-        xtol, utol = (1e-3, 3e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
+        # manifold: the attitude is only weakly determined by the cost (free inside the quaternion dead-band)
+        xtol, utol = (1e-3, 1e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
         assert err(hs["Xn"][b], Xs) < xtol and err(hs["Un"][b], Us) < utol
         ev = evaluate(p, hs["Xn"][b], hs["Un"][b], X0[b], U0[b], omega, sp[0], toggle, sp[3], lin, rows)
         o = hs["eval"][b]
@@ -101,3 +100,44 @@ def test_postprocessing_bodies_match_oracle(name, kw):
         assert abs(chk[b, 6] - pp.min_distance(p, X[b])) < 1e-12
         Xo, Uo = pp.interpolate_traj(p, X[b], U[b], nstep)
         assert err(Xf[b], Xo) < 1e-12 and err(Uf[b], Uo) == 0.0
+
+
+@pytest.mark.parametrize("name,kw,width", [("astrobeeSE3manifold", dict(B=2, N=60), 0.1), ("astrobeeSE3manifold", dict(B=1, N=60), 2e-4),
+                                           ("astrobeeSE3", dict(B=2, N=40), 0.05), ("freeflyerSE2", dict(B=2, N=30), 0.2)])
+def test_genuine_box_goal_rows_match_oracle(name, kw, width):
+    """csbci_goal_constraints (dynamics.jl:37-42, scp_gusto.jl:237-245): hard rows lb <= X[i,N] <= ub at the last knot.  The
+    attitude (resp. the whole position) goal becomes a BoxGoal of the given width; 2e-4 is the astrobeeSE3manifold notebook's."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    sel = slice(6, 10) if name == "astrobeeSE3manifold" else slice(0, 2)
+    mid = 0.5 * (bp.goal_lo[:, sel] + bp.goal_hi[:, sel])
+    bp.goal_type = bp.goal_type.copy(); bp.goal_type[sel] = gb.models.GOAL_BOX
+    bp.goal_lo[:, sel] = mid - 0.5 * width; bp.goal_hi[:, sel] = mid + 0.5 * width
+    sp = bp.model.scp_params
+    X0, U0 = bp.init_traj_straightline()
+    hs = hostsim_iterate(bp, X0, U0, 1.0, sp[0])
+    toggle = sp[0] / 8 + bp.model.clearance
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[b], U0[b], 1.0, sp[0], toggle, sp[3])
+        assert st == "OPTIMAL" and hs["info"][b, 0] == 0
+        assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
+        assert abs(hs["info"][b, 1] - r.iters) <= 3
+        assert err(hs["Un"][b], Us) < 1e-5
+        xN = hs["Xn"][b, -1, sel]
+        assert np.all(xN >= bp.goal_lo[b, sel] - 1e-9) and np.all(xN <= bp.goal_hi[b, sel] + 1e-9)
+        if width >= 0.05:       # a box this wide is not an equality in disguise: the optimum leaves its centre
+            assert np.max(np.abs(xN - mid[b])) > 1e-3 and err(hs["Xn"][b, -1, sel], Xs[-1, sel]) < 1e-4
+
+
+def test_full_scp_on_the_quaternion_model_matches_oracle():
+    """L3 on astrobeeSE3manifold (BASELINE configs[4]) with its notebook goal set (PointGoal r, v, w; BoxGoal q +- 1e-4):
+    identical accept / convergence decisions and iteration counts, final true cost within 1e-3 relative."""
+    from util import hostsim_solve_gusto
+    bp = gb.problems.CONFIGS["astrobeeSE3manifold"](B=2, N=60)
+    S = hostsim_solve_gusto(bp, max_iter=30)
+    for b in range(bp.B):
+        R = solve_gusto(to_oracle(bp, b), max_iter=30)
+        assert bool(S["converged"][b]) == R.converged and bool(S["successful"][b]) == R.successful
+        assert int(S["iterations"][b]) == R.iterations
+        assert abs(S["J_true"][b] - R.J_true[-1]) <= 1e-3 * max(1e-6, abs(R.J_true[-1]))
+        assert [bool(a[b]) for a in S["accept"][:R.iterations + 1]] == R.accept_solution

@@ -69,8 +69,7 @@ def hostsim_iterate(bp, Xp, Up, omega, delta, stages=7, Xn=None, Un=None, **ipm_
     delta = np.ascontiguousarray(np.broadcast_to(delta, (B,)), dtype=np.float64).copy()
     f = np.zeros((B, N, nx)); A = np.zeros((B, N, nx, nx)); g = np.zeros((B, N, nx)); rows = np.zeros((B, N, max(no, 1), 5))
     info = np.zeros((B, 8)); ev = np.zeros((B, 8))
-    _, glo, ghi = host.presolve_goals(bp.goal_type, bp.goal_lo, bp.goal_hi)     # what Engine hands to the solver
-    x_init = np.ascontiguousarray(bp.x_init); glo = np.ascontiguousarray(glo); ghi = np.ascontiguousarray(ghi)
+    x_init = np.ascontiguousarray(bp.x_init); glo = np.ascontiguousarray(bp.goal_lo); ghi = np.ascontiguousarray(bp.goal_hi)
     tf = np.ascontiguousarray(bp.tf)
     rc = hostsim_lib().hostsim_iterate(ctypes.byref(cfg), kind.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), dp(a), dp(b),
                                        dp(x_init), dp(glo), dp(ghi), dp(tf), dp(Xp), dp(Up), dp(Xn), dp(Un), dp(omega),
@@ -122,3 +121,32 @@ def hostsim_shoot(bp, p0, x_goal, Xs_prev, nsub=4, max_iter=100, ftol=1e-3):
                                      ctypes.c_double(ftol), dp(Xs), dp(Us), dp(Ps), dp(out))
     assert rc == 0
     return out, Xs, Us, Ps
+
+
+def hostsim_solve_gusto(bp, max_iter=30):
+    """solve_gusto_batch (host.py) with every kernel replaced by its host-simulated body: the L3 check of the kernel
+    arithmetic in the GPU-less container.  Returns dict(converged, successful, iterations, J_true, accept[list], X, U)."""
+    host = gb.engine()
+    M = gb.models
+    B, sp = bp.B, bp.model.scp_params
+    X, U = bp.init_traj_straightline()
+    Delta = np.full(B, sp[M.SP_DELTA0]); omega = np.full(B, sp[M.SP_OMEGA0])
+    ev0 = hostsim_iterate(bp, X, U, omega, Delta, stages=5, Xn=X, Un=U)["eval"]
+    J = ev0[:, 4].copy()
+    iterations = np.zeros(B, np.int64); converged = np.zeros(B, bool); successful = np.zeros(B, bool)
+    active = np.ones(B, bool); conv_prev = np.zeros(B); accept_hist = [np.ones(B, bool)]; newton = []
+    for _ in range(max_iter):
+        hs = hostsim_iterate(bp, X, U, omega, Delta)
+        st = host.gusto_update(hs["eval"], host.solver_status_ok(hs["info"][:, 0]), active, Delta, omega, iterations, conv_prev, sp)
+        acc = st["accept"]
+        X = np.where(acc[:, None, None], hs["Xn"], X); U = np.where(acc[:, None, None], hs["Un"], U)
+        J = np.where(acc, hs["eval"][:, 4], J)
+        conv_prev = np.where(st["run"], hs["eval"][:, 0], conv_prev)
+        accept_hist.append(acc.copy()); newton.append(np.where(active, hs["info"][:, 1], 0))
+        Delta, omega, iterations = st["Delta"], st["omega"], st["iterations"]
+        converged |= st["converged_now"]; successful |= st["successful_now"]
+        active = active & ~st["done"]
+        if not active.any():
+            break
+    return dict(converged=converged, successful=successful, iterations=iterations, J_true=J, accept=accept_hist, X=X, U=U,
+                newton=newton)
