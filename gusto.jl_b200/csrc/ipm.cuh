@@ -138,6 +138,11 @@ constexpr int SLOT_W = 6;     // s, lam, t, lamb, pa (ds*dlam of the predictor),
 constexpr int OROW_W = 5;     // compacted obstacle row: nhat[3], off, knot
 constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cycles: assemble+slots, factorize, kkt solves
 
+#ifndef GUSTO_CHAIN_D
+#define GUSTO_CHAIN_D 4
+#endif
+constexpr int CHAIN_STAGES = GUSTO_CHAIN_D;
+
 GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
 template <int M> struct IpmLayout {
@@ -202,8 +207,8 @@ template <int M> struct IpmLayout {
   static constexpr int GJ_ROWS = (64 / NX) * NX;            // setup_dynamics: (knot, row) pairs of one Gauss-Jordan batch
   static constexpr int GJ_DOUBLES = GJ_ROWS * 2 * NX;
   static_assert(NXP * LDU <= RXS * LDT && GJ_DOUBLES <= FAC_DOUBLES, "aliased tiles do not fit");
-  GHD static int work_doubles(int N) {      // dz, also the tiles of the sweep
-    const int w = (int)rnd((size_t)N * NV);
+  GHD static int work_doubles(int N) {      // dz + the chain ring, also the tiles of the sweep
+    const int w = (int)rnd((size_t)N * NV) + CHAIN_STAGES * GT;
     return (w > FAC_DOUBLES ? w : FAC_DOUBLES) + 2;
   }
   // byte tables with run-time indices: a_row[ANZ], a_col[ANZ], blk_of[NX]
@@ -1119,17 +1124,25 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
 }
 
 // ------------------------------------------------------------------------------------------------ chains
-// One n_x x n_x mat-vec per knot with the closed-loop tiles Acl_k, on warp 0: lane i owns row (forward) / column (backward) i
-// and prefetches its slice of the tiles PF knots ahead straight into registers -- no staging ring, no barrier objects; the
-// only per-step synchronisation is one __syncwarp that publishes the new vector in shared memory.  (Round 1 streamed its
-// factor tiles through a TMA ring; an mbarrier try_wait alone costs ~90 cycles per step and the step is ~150 cycles of work.)
-#ifndef GUSTO_CHAIN_PF
-#define GUSTO_CHAIN_PF 3
+// One n_x x n_x mat-vec per knot with the closed-loop tiles Acl_k, on warp 0.  The tiles stream from global memory (L2 / HBM:
+// with ~220 KB of the SM's shared memory in use L1 is almost gone) into a ring of CHAIN_D stages in the idle part of the work
+// region with 16-byte asynchronous copies (LDGSTS, commit groups): plain loads prefetched into registers were measured to
+// stall on the scoreboard (~1100 cycles per step, ncu long-scoreboard on the first multiply-add), a TMA ring pays ~90 cycles of
+// mbarrier try_wait per step.  The running vector never makes a shared-memory round trip: lane i keeps its entry in a register
+// and every lane collects the vector with warp shuffles; the result stores are off the dependent path.
+#ifndef GUSTO_CHAIN_D
+#define GUSTO_CHAIN_D 4
 #endif
+template <int M> GDEV void chain_fetch(const IpmCtx<M>& c, double* ring, int slot, int k) {
+  using L = IpmLayout<M>;
+  const double* src = c.acl + (size_t)k * L::GT;
+  double* dst = ring + slot * L::GT;
+  G_LANE_FOR(t, L::GT / 2) g_cp_async16(dst + 2 * t, src + 2 * t);
+}
 // forward:  s_{k+1} = Acl_k s_k + d_k   (s_k in the x-slots of dz; slot k+1 holds d_k on entry, slot 0 holds s_0)
 template <int M> GDEV_NOINLINE void chain_forward(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NV = L::NV, LDT = L::LDT, HP = (NX + 1) / 2, PF = NX <= 12 ? GUSTO_CHAIN_PF : 2;
+  constexpr int NX = L::NX, NV = L::NV, LDT = L::LDT, HP = (NX + 1) / 2, D = GUSTO_CHAIN_D;
   const int nt = c.N - 1;
   double* const y = c.dz;
   G_ASSUME_SHARED(y);
@@ -1143,40 +1156,33 @@ template <int M> GDEV_NOINLINE void chain_forward(const IpmCtx<M>& c) {
         y[(k + 1) * NV + i] = a;
       }
 #else
-    // every load is unconditional (tile index clamped, idle lanes read row 0): the buffers stay in registers
+    double* const ring = y + L::rnd((size_t)c.N * NV);          // idle part of the work region
     const int i = G_LANE;
     const bool act = i < NX;
-    const double* src = c.acl + (act ? i : 0) * LDT;
-    g_d2 buf[PF][HP];
+    const int ir = act ? i : 0;
 #pragma unroll
-    for (int s2 = 0; s2 < PF; ++s2) {
-      const int ks = s2 < nt ? s2 : nt - 1;
-#pragma unroll
-      for (int m = 0; m < HP; ++m) buf[s2][m] = g_ld2(src + (size_t)ks * L::GT + 2 * m);
-    }
-    // The running vector never makes a shared-memory round trip: lane i keeps s_k[i] in a register and every lane collects
-    // the whole vector with warp shuffles (no __syncwarp on the dependent path); the stores to dz are off that path.
-    double sv = y[act ? i : 0];
-    for (int k0 = 0; k0 < nt; k0 += PF) {
-#pragma unroll
-      for (int s2 = 0; s2 < PF; ++s2) {
-        const int k = k0 + s2 < nt ? k0 + s2 : nt - 1;
-        const bool live = act && (k0 + s2 < nt);
-        double a0 = y[(k + 1) * NV + (act ? i : 0)], a1 = 0.0;       // d_k[i]: independent of the chain
-#pragma unroll
-        for (int m = 0; m < HP; ++m) {
-          a0 = fma(buf[s2][m].x, __shfl_sync(0xffffffffu, sv, 2 * m), a0);
-          if (2 * m + 1 < NX) a1 = fma(buf[s2][m].y, __shfl_sync(0xffffffffu, sv, 2 * m + 1), a1);
-        }
-        const int kn = k + PF < nt ? k + PF : nt - 1;
-#ifndef GUSTO_CHAIN_NOLOAD
-#pragma unroll
-        for (int m = 0; m < HP; ++m) buf[s2][m] = g_ld2(src + (size_t)kn * L::GT + 2 * m);
+    for (int s2 = 0; s2 < D - 1; ++s2) { if (s2 < nt) chain_fetch<M>(c, ring, s2, s2); g_cp_async_commit(); }
+    double sv = y[ir];
+#ifdef GUSTO_CHAIN_SKIP
+    if (false)
 #endif
-        if (k0 + s2 < nt) sv = a0 + a1;
-        if (live) y[(k + 1) * NV + i] = sv;
+    for (int k = 0; k < nt; ++k) {
+      g_cp_async_wait_group<D - 2>();                            // tile k has landed (this lane's part of it)
+      G_SYNCWARP();                                              // ... all lanes' parts; everyone is done with tile k - 1
+      if (k + D - 1 < nt) chain_fetch<M>(c, ring, (k + D - 1) % D, k + D - 1);
+      g_cp_async_commit();
+      const double* R = ring + (k % D) * L::GT + ir * LDT;
+      double a0 = y[(k + 1) * NV + ir], a1 = 0.0;                // d_k[i]: independent of the chain
+#pragma unroll
+      for (int m = 0; m < HP; ++m) {
+        const g_d2 rv = g_ld2(R + 2 * m);
+        a0 = fma(rv.x, __shfl_sync(0xffffffffu, sv, 2 * m), a0);
+        if (2 * m + 1 < NX) a1 = fma(rv.y, __shfl_sync(0xffffffffu, sv, 2 * m + 1), a1);
       }
+      sv = a0 + a1;
+      if (act) y[(k + 1) * NV + i] = sv;
     }
+    g_cp_async_wait();
     G_SYNCWARP();
 #endif
   }
@@ -1186,7 +1192,7 @@ template <int M> GDEV_NOINLINE void chain_forward(const IpmCtx<M>& c) {
 // backward:  vp[k] += Acl_k' vp[k+1]  for k = N-2 .. 0
 template <int M> GDEV_NOINLINE void chain_backward(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, LDT = L::LDT, PF = NX <= 12 ? GUSTO_CHAIN_PF : 2;
+  constexpr int NX = L::NX, NV = L::NV, LDT = L::LDT, D = GUSTO_CHAIN_D;
   const int nt = c.N - 1;
   double* const y = c.vp;
   G_ASSUME_SHARED(y);
@@ -1200,38 +1206,34 @@ template <int M> GDEV_NOINLINE void chain_backward(const IpmCtx<M>& c) {
         y[k * NX + i] = a;
       }
 #else
+    double* const ring = c.dz + L::rnd((size_t)c.N * NV);
+    G_ASSUME_SHARED(ring);
     const int i = G_LANE;
     const bool act = i < NX;
-    const double* src = c.acl + (act ? i : 0);
-    double buf[PF][NX];
+    const int ir = act ? i : 0;
 #pragma unroll
-    for (int s2 = 0; s2 < PF; ++s2) {
-      const int ks = nt - 1 - s2 >= 0 ? nt - 1 - s2 : 0;
-#pragma unroll
-      for (int m = 0; m < NX; ++m) buf[s2][m] = src[(size_t)ks * L::GT + m * LDT];
-    }
-    double sv = y[nt * NX + (act ? i : 0)];
-    for (int k0 = nt - 1; k0 >= 0; k0 -= PF) {
-#pragma unroll
-      for (int s2 = 0; s2 < PF; ++s2) {
-        const int k = k0 - s2 >= 0 ? k0 - s2 : 0;
-        const bool live = act && (k0 - s2 >= 0);
-        double a0 = y[k * NX + (act ? i : 0)], a1 = 0.0;
-#pragma unroll
-        for (int m = 0; m + 1 < NX; m += 2) {
-          a0 = fma(buf[s2][m], __shfl_sync(0xffffffffu, sv, m), a0);
-          a1 = fma(buf[s2][m + 1], __shfl_sync(0xffffffffu, sv, m + 1), a1);
-        }
-        if (NX & 1) a0 = fma(buf[s2][NX - 1], __shfl_sync(0xffffffffu, sv, NX - 1), a0);
-        const int kn = k - PF >= 0 ? k - PF : 0;
-#ifndef GUSTO_CHAIN_NOLOAD
-#pragma unroll
-        for (int m = 0; m < NX; ++m) buf[s2][m] = src[(size_t)kn * L::GT + m * LDT];
+    for (int s2 = 0; s2 < D - 1; ++s2) { if (nt - 1 - s2 >= 0) chain_fetch<M>(c, ring, s2, nt - 1 - s2); g_cp_async_commit(); }
+    double sv = y[nt * NX + ir];
+#ifdef GUSTO_CHAIN_SKIP
+    if (false)
 #endif
-        if (k0 - s2 >= 0) sv = a0 + a1;
-        if (live) y[k * NX + i] = sv;
+    for (int k = nt - 1, st = 0; k >= 0; --k, ++st) {
+      g_cp_async_wait_group<D - 2>();
+      G_SYNCWARP();
+      if (k - (D - 1) >= 0) chain_fetch<M>(c, ring, (st + D - 1) % D, k - (D - 1));
+      g_cp_async_commit();
+      const double* R = ring + (st % D) * L::GT + ir;
+      double a0 = y[k * NX + ir], a1 = 0.0;
+#pragma unroll
+      for (int m = 0; m + 1 < NX; m += 2) {
+        a0 = fma(R[m * LDT], __shfl_sync(0xffffffffu, sv, m), a0);
+        a1 = fma(R[(m + 1) * LDT], __shfl_sync(0xffffffffu, sv, m + 1), a1);
       }
+      if (NX & 1) a0 = fma(R[(NX - 1) * LDT], __shfl_sync(0xffffffffu, sv, NX - 1), a0);
+      sv = a0 + a1;
+      if (act) y[k * NX + i] = sv;
     }
+    g_cp_async_wait();
     G_SYNCWARP();
 #endif
   }
