@@ -2,6 +2,7 @@
 // Product path only: there is no CPU fallback; every entry point fails with GUSTO_E_NODEVICE / GUSTO_E_CUDA when
 // no B200 is usable.
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,8 @@
 #include "evaluate.cuh"
 #include "postprocess.cuh"
 #include "shooting.cuh"
+#include "scp.cuh"
+#include <dlfcn.h>
 
 using namespace gusto;
 
@@ -101,6 +104,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   const int warp = threadIdx.x >> 5;
   if (warp < nk) {
     const int gk = k0 + warp;
+    if (p.active && !p.active[gk / d.N]) return;          // frozen instance (converged / failed): its blocks are never read again
     linearize_knot<M>(d, p, gk / d.N, gk % d.N, sx + warp * NX, su + warp * NU, ws[warp], sbv);
   }
 }
@@ -206,6 +210,20 @@ struct gusto_ctx {
   bool timed[4] = {false, false, false, false};
   int64_t launches = 0;
   std::string err;
+  // ---- device-resident outer loop (gusto_scp_*) and the status all-gather
+  ScpState scp = {};
+  bool scp_ready = false, scp_begun = false, capturing = false;
+  double *d_X0 = nullptr, *d_U0 = nullptr;       // initial trajectory of the last gusto_scp_begin (restart without H2D)
+  uint8_t* d_done_all = nullptr;                 // [nranks][B] gathered status bytes
+  int* d_nunf = nullptr;                         // [SCP_RING] unfinished instances over all ranks after an iteration
+  int* h_nunf = nullptr;                         // pinned mirror
+  cudaStream_t cstream = nullptr;                // collective + counter read-back, beside the next iteration's kernels
+  cudaEvent_t sev[4] = {}, fev[4] = {};          // iteration finished on the main stream / its counter is on the host
+  cudaGraphExec_t step_graph = nullptr;
+  int scp_iter = 0;                              // outer iterations enqueued since gusto_scp_begin (incl. a speculative one)
+  int scp_real = 0;                              // ... that ran with at least one live instance anywhere
+  void* comm = nullptr;                          // ncclComm_t
+  int rank = 0, nranks = 1;
 };
 
 static std::string g_err;
@@ -248,9 +266,11 @@ static int ipm_smem_doubles_raw(int model, int N) {
 // 16-byte alignment LDS.128 and the TMA ring need
 static int ipm_smem_doubles_of(int model, int N) { return (ipm_smem_doubles_raw(model, N) + 15) & ~15; }
 
+static void scp_release(gusto_ctx* ctx);
+
 extern "C" {
 
-int32_t gusto_version(void) { return 100; }
+int32_t gusto_version(void) { return 200; }
 
 const char* gusto_last_error(const gusto_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
@@ -361,6 +381,7 @@ int32_t gusto_destroy(gusto_ctx* ctx) {
                   ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active,
                   ctx->d_dual, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_p0, ctx->d_xgoal, ctx->d_shoot};
   for (void* q : ptrs) if (q) cudaFree(q);
+  scp_release(ctx);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; ++i) if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -406,7 +427,7 @@ int32_t gusto_set_penalties(gusto_ctx* ctx, const double* omega, const double* d
 static int32_t launch_linearize(gusto_ctx* ctx) {
   const int total = ctx->cfg.B * ctx->cfg.N;
   const int grid = (total + LIN_KNOTS_PER_CTA - 1) / LIN_KNOTS_PER_CTA;
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   switch (ctx->cfg.model_id) {
     case DUBINS: linearize_kernel<DUBINS><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
     case FREEFLYER_SE2: linearize_kernel<FREEFLYER_SE2><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
@@ -414,8 +435,9 @@ static int32_t launch_linearize(gusto_ctx* ctx) {
     default: linearize_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, LIN_KNOTS_PER_CTA * 32, 0, ctx->stream>>>(ctx->ddesc, ctx->p); break;
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  ctx->timed[0] = true; ctx->launches++;
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (!ctx->capturing) ctx->timed[0] = true;
+  ctx->launches++;
   return GUSTO_OK;
 }
 static int32_t launch_solve(gusto_ctx* ctx) {
@@ -425,7 +447,7 @@ static int32_t launch_solve(gusto_ctx* ctx) {
   pack = pack < 1 ? 1 : (pack > ctx->ipm_pack_max ? ctx->ipm_pack_max : pack);
   if (ctx->ipm_pack_force > 0) pack = ctx->ipm_pack_force;
   const int grid = (ctx->cfg.B + pack - 1) / pack, block = IPM_THREADS * pack, smem = ctx->ipm_smem * pack, sd = ctx->ipm_smem / (int)sizeof(double);
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   switch (ctx->cfg.model_id) {
     case DUBINS: ipm_kernel<DUBINS><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
     case FREEFLYER_SE2: ipm_kernel<FREEFLYER_SE2><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
@@ -433,13 +455,14 @@ static int32_t launch_solve(gusto_ctx* ctx) {
     default: ipm_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_scratch, ctx->scratch_stride, ctx->d_info, sd); break;
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  ctx->timed[1] = true; ctx->launches++;
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  if (!ctx->capturing) ctx->timed[1] = true;
+  ctx->launches++;
   return GUSTO_OK;
 }
 static int32_t launch_evaluate(gusto_ctx* ctx) {
   const int grid = ctx->cfg.B;
-  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   switch (ctx->cfg.model_id) {
     case DUBINS: evaluate_kernel<DUBINS><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
     case FREEFLYER_SE2: evaluate_kernel<FREEFLYER_SE2><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
@@ -447,8 +470,9 @@ static int32_t launch_evaluate(gusto_ctx* ctx) {
     default: evaluate_kernel<ASTROBEE_SE3_MANIFOLD><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_eval); break;
   }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-  ctx->timed[2] = true; ctx->launches++;
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  if (!ctx->capturing) ctx->timed[2] = true;
+  ctx->launches++;
   return GUSTO_OK;
 }
 
@@ -494,11 +518,12 @@ int32_t gusto_evaluate(gusto_ctx* ctx, double* out) {
 }
 
 static int32_t launch_accept(gusto_ctx* ctx, const uint8_t* acc_dev, const double* om_dev, const double* de_dev) {
-  CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   accept_kernel<<<ctx->cfg.B, 128, 0, ctx->stream>>>(ctx->p, ctx->cfg.N, ctx->nx, ctx->nu, acc_dev, om_dev, de_dev);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
-  ctx->timed[3] = true; ctx->launches++;
+  if (!ctx->capturing) CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+  if (!ctx->capturing) ctx->timed[3] = true;
+  ctx->launches++;
   return GUSTO_OK;
 }
 
@@ -693,6 +718,267 @@ int32_t gusto_get_shooting_trajectory(gusto_ctx* ctx, double* X, double* U, doub
   if (X) D2H(X, ctx->d_Xs, B * N * ctx->nx);
   if (U) D2H(U, ctx->d_Us, B * N * ctx->nu);
   if (P) D2H(P, ctx->d_Ps, B * N * ctx->nx);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+
+}  // extern "C" (reopened below)
+
+// ------------------------------------------------------------------ device-resident outer loop + status all-gather
+// NCCL is bound at run time (dlopen) so that a single-GPU host needs no NCCL at all; the few entry points used are declared
+// here with their nccl.h signatures (NCCL 2.x ABI: ncclUniqueId is 128 bytes passed by value, ncclUint8 = 1).
+namespace {
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load(std::string& err) {
+  if (g_nccl.h) return true;
+  const char* names[] = {getenv("GUSTO_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) { err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return false; }
+  NcclApi a;
+  a.h = h;
+  a.GetUniqueId = (int (*)(NcclUid*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather) { err = "NCCL library lacks the expected symbols"; return false; }
+  g_nccl = a;
+  return true;
+}
+constexpr int NCCL_UINT8 = 1;
+constexpr int SCP_RING = 4;
+}  // namespace
+
+static const double* dev_sp(const gusto_ctx* ctx) { return reinterpret_cast<const double*>(reinterpret_cast<const char*>(ctx->ddesc) + offsetof(BatchDesc, sp)); }
+
+static void scp_release(gusto_ctx* ctx) {
+  if (ctx->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
+  ScpState& s = ctx->scp;
+  void* ptrs[] = {s.slot, s.iterations, s.conv_prev, s.j_true, s.j_full, s.converged, s.successful, s.done, s.cnt, s.hist,
+                  ctx->d_X0, ctx->d_U0, ctx->d_done_all, ctx->d_nunf};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  if (ctx->h_nunf) cudaFreeHost(ctx->h_nunf);
+  for (int i = 0; i < 4; ++i) { if (ctx->sev[i]) cudaEventDestroy(ctx->sev[i]); if (ctx->fev[i]) cudaEventDestroy(ctx->fev[i]); }
+  if (ctx->cstream) cudaStreamDestroy(ctx->cstream);
+  s = ScpState{};
+  ctx->d_X0 = ctx->d_U0 = nullptr; ctx->d_done_all = nullptr; ctx->d_nunf = nullptr; ctx->h_nunf = nullptr; ctx->cstream = nullptr;
+  ctx->scp_ready = false;
+}
+
+// buffers of the device-resident loop, allocated on first use (or re-allocated when the communicator changes the gather size)
+static int32_t scp_prepare(gusto_ctx* ctx) {
+  if (ctx->scp_ready) return GUSTO_OK;
+  const size_t B = ctx->cfg.B, N = ctx->cfg.N;
+  ScpState& s = ctx->scp;
+  s.max_hist = GUSTO_SCP_MAX_HIST;
+  bool ok = true;
+  auto al = [&](void** q, size_t bytes) { ok = ok && cudaMalloc(q, bytes) == cudaSuccess && cudaMemset(*q, 0, bytes) == cudaSuccess; };
+  al((void**)&s.slot, sizeof(int)); al((void**)&s.iterations, B * sizeof(int));
+  al((void**)&s.conv_prev, B * sizeof(double)); al((void**)&s.j_true, B * sizeof(double)); al((void**)&s.j_full, B * sizeof(double));
+  al((void**)&s.converged, B); al((void**)&s.successful, B); al((void**)&s.done, 2 * B);
+  al((void**)&s.cnt, (size_t)s.max_hist * CNT_W * sizeof(int));
+  al((void**)&s.hist, (size_t)(s.max_hist + 1) * B * HIST_W * sizeof(double));
+  al((void**)&ctx->d_X0, B * N * ctx->nx * sizeof(double)); al((void**)&ctx->d_U0, B * N * ctx->nu * sizeof(double));
+  al((void**)&ctx->d_done_all, (size_t)ctx->nranks * B);
+  al((void**)&ctx->d_nunf, SCP_RING * sizeof(int));
+  ok = ok && cudaMallocHost((void**)&ctx->h_nunf, SCP_RING * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < SCP_RING && ok; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->sev[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->fev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { ctx->err = std::string("gusto_scp: allocation failed: ") + cudaGetErrorString(cudaGetLastError()); scp_release(ctx); return GUSTO_E_ALLOC; }
+  s.active = ctx->d_active;
+  ctx->scp_ready = true;
+  return GUSTO_OK;
+}
+
+static int32_t launch_scp_update(gusto_ctx* ctx) {
+  const int B = ctx->cfg.B;
+  scp_update_kernel<<<B, 128, 0, ctx->stream>>>(ctx->p, ctx->scp, ctx->d_eval, ctx->d_info, B, ctx->cfg.N, ctx->nx, ctx->nu, EVAL_NOUT, IPM_NINFO,
+                                                dev_sp(ctx));
+  CK(cudaGetLastError());
+  scp_advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->scp);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  return GUSTO_OK;
+}
+
+// one outer iteration on the main stream: K1 -> K3 -> K4 -> update (+ accept) -> advance; a CUDA graph after the first call
+static int32_t enqueue_scp_step(gusto_ctx* ctx) {
+  static const bool no_graph = getenv("GUSTO_NO_GRAPH") != nullptr;
+  int32_t rc = GUSTO_OK;
+  if (no_graph) {
+    if ((rc = launch_linearize(ctx)) || (rc = launch_solve(ctx)) || (rc = launch_evaluate(ctx)) || (rc = launch_scp_update(ctx))) return rc;
+    return GUSTO_OK;
+  }
+  if (!ctx->step_graph) {
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = ctx->launches;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    if (!(rc = launch_linearize(ctx)) && !(rc = launch_solve(ctx)) && !(rc = launch_evaluate(ctx))) rc = launch_scp_update(ctx);
+    ctx->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    ctx->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
+    e = cudaGraphInstantiate(&ctx->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { ctx->step_graph = nullptr; ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
+  }
+  CK(cudaGraphLaunch(ctx->step_graph, ctx->stream));
+  ctx->launches += 5;
+  return GUSTO_OK;
+}
+
+// after iteration `it` (its status bytes sit in half it & 1 of scp.done): gather over the ranks, count the unfinished ones,
+// bring the count to the host -- all on the side stream, beside the next iteration's kernels
+static int32_t enqueue_status(gusto_ctx* ctx, int it) {
+  const int r = it % SCP_RING, B = ctx->cfg.B;
+  CK(cudaEventRecord(ctx->sev[r], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->cstream, ctx->sev[r], 0));
+  const uint8_t* send = ctx->scp.done + (size_t)(it & 1) * B;
+  const uint8_t* all = send;
+  if (ctx->comm) {
+    const int e = g_nccl.AllGather(send, ctx->d_done_all, (size_t)B, NCCL_UINT8, ctx->comm, ctx->cstream);
+    if (e != 0) { ctx->err = std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"); return GUSTO_E_CUDA; }
+    all = ctx->d_done_all;
+  }
+  scp_count_kernel<<<1, 256, 0, ctx->cstream>>>(all, B * ctx->nranks, ctx->d_nunf + r);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(ctx->h_nunf + r, ctx->d_nunf + r, sizeof(int), cudaMemcpyDeviceToHost, ctx->cstream));
+  CK(cudaEventRecord(ctx->fev[r], ctx->cstream));
+  return GUSTO_OK;
+}
+
+extern "C" {
+
+int32_t gusto_comm_unique_id(uint8_t* id) {
+  if (!id) { g_err = "gusto_comm_unique_id: null argument"; return GUSTO_E_ARG; }
+  if (!nccl_load(g_err)) return GUSTO_E_STATE;
+  NcclUid u;
+  const int e = g_nccl.GetUniqueId(&u);
+  if (e != 0) { g_err = "ncclGetUniqueId failed"; return GUSTO_E_CUDA; }
+  memcpy(id, u.internal, 128);
+  return GUSTO_OK;
+}
+
+int32_t gusto_comm_init(gusto_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id) {
+  NEED(id);
+  if (nranks < 1 || rank < 0 || rank >= nranks) { ctx->err = "gusto_comm_init: bad rank / nranks"; return GUSTO_E_ARG; }
+  if (!nccl_load(ctx->err)) return GUSTO_E_STATE;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  scp_release(ctx);                                   // the gather buffer depends on nranks
+  NcclUid u;
+  memcpy(u.internal, id, 128);
+  void* comm = nullptr;
+  const int e = g_nccl.CommInitRank(&comm, nranks, u, rank);
+  if (e != 0) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"); return GUSTO_E_CUDA; }
+  ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+  return scp_prepare(ctx);
+}
+
+int32_t gusto_allgather_status(gusto_ctx* ctx, const uint8_t* done_local, uint8_t* done_all, int32_t* n_unfinished) {
+  NEED(done_local);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = scp_prepare(ctx);
+  if (rc) return rc;
+  const size_t B = ctx->cfg.B;
+  CK(cudaMemcpyAsync(ctx->scp.done, done_local, B, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = enqueue_status(ctx, 0))) return rc;
+  if (done_all) {
+    const uint8_t* src = ctx->comm ? ctx->d_done_all : ctx->scp.done;
+    CK(cudaMemcpyAsync(done_all, src, B * ctx->nranks, cudaMemcpyDeviceToHost, ctx->cstream));
+  }
+  CK(cudaStreamSynchronize(ctx->cstream));
+  if (n_unfinished) *n_unfinished = ctx->h_nunf[0];
+  return GUSTO_OK;
+}
+
+int32_t gusto_scp_begin(gusto_ctx* ctx, const double* X0, const double* U0, int32_t force) {
+  NEED(true);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = scp_prepare(ctx);
+  if (rc) return rc;
+  const size_t B = ctx->cfg.B, nX = B * ctx->cfg.N * ctx->nx, nU = B * ctx->cfg.N * ctx->nu;
+  if ((X0 == nullptr) != (U0 == nullptr)) { ctx->err = "gusto_scp_begin: X0 and U0 must both be given or both be NULL"; return GUSTO_E_ARG; }
+  if (X0) { H2D(ctx->d_X0, X0, nX); H2D(ctx->d_U0, U0, nU); }
+  else if (!ctx->scp_begun) { ctx->err = "gusto_scp_begin: no stored initial trajectory (first call needs X0, U0)"; return GUSTO_E_STATE; }
+  // traj = candidate = traj_init; every instance live; J_true[1], rho_vec[2] from K4 on (traj, traj)  (scp_gusto.jl:60-75)
+  CK(cudaMemcpyAsync(ctx->p.Xp, ctx->d_X0, nX * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->p.Up, ctx->d_U0, nU * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->p.Xn, ctx->d_X0, nX * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->p.Un, ctx->d_U0, nU * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_active, 1, B, ctx->stream));
+  ctx->scp.force = force ? 1 : 0;
+  {
+    const int n = (int)B > ctx->scp.max_hist * CNT_W ? (int)B : ctx->scp.max_hist * CNT_W;
+    // omega0 / Delta0 first: K4 reads them
+    scp_begin_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->p, ctx->scp, ctx->d_eval, (int)B, EVAL_NOUT, dev_sp(ctx), 0);
+    CK(cudaGetLastError());
+    if ((rc = launch_linearize(ctx)) || (rc = launch_evaluate(ctx))) return rc;
+    scp_begin_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->p, ctx->scp, ctx->d_eval, (int)B, EVAL_NOUT, dev_sp(ctx), 1);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  ctx->scp_begun = true; ctx->scp_iter = 0; ctx->scp_real = 0;
+  return GUSTO_OK;
+}
+
+int32_t gusto_scp_run(gusto_ctx* ctx, int32_t max_iter, int32_t* batch_iterations, int32_t* n_unfinished) {
+  NEED(true);
+  if (!ctx->scp_begun) { ctx->err = "gusto_scp_run: call gusto_scp_begin first"; return GUSTO_E_STATE; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc;
+  int ran = 0, last = -1;
+  for (int i = 0; i < max_iter; ++i) {
+    const int it = ctx->scp_iter;
+    if ((rc = enqueue_scp_step(ctx)) || (rc = enqueue_status(ctx, it))) return rc;
+    ctx->scp_iter++;
+    ran++;
+    if (i >= 1) {        // the count of the previous iteration, read while this one runs: 0 => this one was a no-op
+      CK(cudaEventSynchronize(ctx->fev[(it - 1) % SCP_RING]));
+      last = ctx->h_nunf[(it - 1) % SCP_RING];
+      if (last == 0) { ran--; break; }
+    }
+  }
+  if (last != 0 && ran > 0) {
+    const int it = ctx->scp_iter - 1;
+    CK(cudaEventSynchronize(ctx->fev[it % SCP_RING]));
+    last = ctx->h_nunf[it % SCP_RING];
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->scp_real += ran;
+  if (batch_iterations) *batch_iterations = ran;
+  if (n_unfinished) *n_unfinished = last < 0 ? 0 : last;
+  return GUSTO_OK;
+}
+
+int32_t gusto_scp_get(gusto_ctx* ctx, int32_t* iterations, uint8_t* converged, uint8_t* successful, double* hist, int32_t n_hist,
+                      int32_t* counters) {
+  NEED(true);
+  if (!ctx->scp_begun) { ctx->err = "gusto_scp_get: call gusto_scp_begin first"; return GUSTO_E_STATE; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B;
+  if (n_hist < 0 || n_hist > ctx->scp.max_hist + 1) { ctx->err = "gusto_scp_get: n_hist out of range"; return GUSTO_E_ARG; }
+  if (iterations) CK(cudaMemcpyAsync(iterations, ctx->scp.iterations, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (converged) CK(cudaMemcpyAsync(converged, ctx->scp.converged, B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (successful) CK(cudaMemcpyAsync(successful, ctx->scp.successful, B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hist && n_hist > 0) D2H(hist, ctx->scp.hist, (size_t)n_hist * B * HIST_W);
+  if (counters && n_hist > 1) CK(cudaMemcpyAsync(counters, ctx->scp.cnt, (size_t)(n_hist - 1) * CNT_W * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return GUSTO_OK;
 }

@@ -24,6 +24,9 @@ SHOOT_NOUT = 8
 SH_STATUS, SH_ITERS, SH_FNORM, SH_JTRUE, SH_CONV, SH_LAMBDA = range(6)
 SOLVE_NINFO = 8
 EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)
+HIST_W = 12
+H_JTRUE, H_JFULL, H_SCP_STATUS, H_SOLVER_STATUS, H_ACCEPT, H_CONV, H_DELTA, H_OMEGA, H_RHO, H_TR_OK, H_INEQ_OK, H_NEWTON = range(12)
+SCP_MAX_HIST = 64
 SCP_STATUS = ("NA", "OK", "InaccurateModel", "ViolatesConstraints", "TrustRegionViolated", "SolverFailed", "Inactive")
 ST_NA, ST_OK, ST_INACCURATE, ST_VIOLATES, ST_TRVIOLATED, ST_SOLVERFAIL, ST_INACTIVE = range(7)
 
@@ -104,12 +107,20 @@ def load_library(path=LIB_PATH):
     lib.gusto_accept_device.argtypes = [vp, vp, vp, vp]
     lib.gusto_stream_handle.argtypes = [vp]
     lib.gusto_stream_handle.restype = i64
+    lib.gusto_scp_begin.argtypes = [vp, _DP, _DP, i32]
+    lib.gusto_scp_run.argtypes = [vp, i32, _IP, _IP]
+    lib.gusto_scp_get.argtypes = [vp, _IP, _BP, _BP, _DP, i32, _IP]
+    lib.gusto_comm_unique_id.argtypes = [_BP]
+    lib.gusto_comm_init.argtypes = [vp, i32, i32, _BP]
+    lib.gusto_allgather_status.argtypes = [vp, _BP, _BP, _IP]
     for name in ("gusto_create", "gusto_destroy", "gusto_set_problems", "gusto_set_trajectory", "gusto_get_trajectory",
                  "gusto_get_candidate", "gusto_set_candidate", "gusto_set_penalties", "gusto_linearize",
                  "gusto_get_blocks", "gusto_solve_subproblem", "gusto_evaluate", "gusto_accept", "gusto_set_active",
                  "gusto_iterate", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
                  "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop", "gusto_check_trajectory",
-                 "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory"):
+                 "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory",
+                 "gusto_scp_begin", "gusto_scp_run", "gusto_scp_get", "gusto_comm_unique_id", "gusto_comm_init",
+                 "gusto_allgather_status"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -270,6 +281,41 @@ class Engine:
     def launch_count(self):
         return int(self.lib.gusto_launch_count(self._ctx))
 
+    # -- device-resident outer loop and the status all-gather (include/gusto_b200.h, "Device-resident outer loop")
+    def scp_begin(self, X0=None, U0=None, force=False):
+        X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64)
+        U0 = None if U0 is None else np.ascontiguousarray(U0, dtype=np.float64)
+        self._chk(self.lib.gusto_scp_begin(self._ctx, _dp(X0), _dp(U0), int(bool(force))))
+
+    def scp_run(self, max_iter):
+        """Up to max_iter outer iterations on the device; returns (iterations that ran, unfinished instances over all ranks)."""
+        n, u = ctypes.c_int32(), ctypes.c_int32()
+        self._chk(self.lib.gusto_scp_run(self._ctx, int(max_iter), ctypes.byref(n), ctypes.byref(u)))
+        return int(n.value), int(u.value)
+
+    def scp_get(self, n_hist, want_hist=True):
+        """(iterations[B], converged[B], successful[B], hist[n_hist, B, HIST_W] or None, counters[n_hist - 1, 4])."""
+        it = np.empty(self.B, np.int32); cv = np.empty(self.B, np.uint8); su = np.empty(self.B, np.uint8)
+        hist = np.empty((n_hist, self.B, HIST_W)) if want_hist else None
+        cnt = np.zeros((max(n_hist - 1, 0), 4), np.int32)
+        self._chk(self.lib.gusto_scp_get(self._ctx, it.ctypes.data_as(_IP), cv.ctypes.data_as(_BP), su.ctypes.data_as(_BP), _dp(hist),
+                                         int(n_hist), cnt.ctypes.data_as(_IP) if n_hist > 1 else None))
+        return it.astype(np.int64), cv.astype(bool), su.astype(bool), hist, cnt
+
+    def comm_init(self, rank, nranks, uid):
+        u = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert u.size == 128
+        self._chk(self.lib.gusto_comm_init(self._ctx, int(rank), int(nranks), u.ctypes.data_as(_BP)))
+        self.nranks = int(nranks)
+
+    def allgather_status(self, done_local):
+        """One all-gather of this rank's B status bytes; returns (done_all[nranks * B], unfinished instances over all ranks)."""
+        d = np.ascontiguousarray(done_local, dtype=np.uint8)
+        out = np.empty(self.B * getattr(self, "nranks", 1), np.uint8)
+        n = ctypes.c_int32()
+        self._chk(self.lib.gusto_allgather_status(self._ctx, d.ctypes.data_as(_BP), out.ctypes.data_as(_BP), ctypes.byref(n)))
+        return out, int(n.value)
+
 
 # ------------------------------------------------------------------------------------------- outer loop
 @dataclass
@@ -295,6 +341,7 @@ class BatchSCPSolution:
     iter_elapsed_times: list = field(default_factory=list)
     total_time: float = 0.0
     batch_iterations: int = 0
+    counters: np.ndarray = None                           # device loop only: per iteration [ran, solved, accepted, still live]
 
 
 IPM_OPTIMAL, IPM_ITERATION_LIMIT, IPM_NUMERICAL, IPM_ALMOST_OPTIMAL = range(4)
@@ -396,6 +443,46 @@ def solve_gusto_batch(engine: Engine, X0=None, U0=None, max_iter=30, force=False
             break
     S.X, S.U = engine.get_trajectory()
     S.total_time = time.perf_counter() - t0
+    return S
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it; the host broadcasts the 128 bytes to the other ranks)."""
+    uid = np.zeros(128, np.uint8)
+    rc = load_library().gusto_comm_unique_id(uid.ctypes.data_as(_BP))
+    if rc != 0:
+        raise GustoError(f"gusto_comm_unique_id failed ({rc}): {load_library().gusto_last_error(None).decode()}")
+    return uid
+
+
+def solve_gusto_batch_device(engine: Engine, X0=None, U0=None, max_iter=30, force=False):
+    """solve_gusto_batch with the outer loop resident on the device (gusto_scp_begin / gusto_scp_run): same decisions, same
+    histories, no host round trip per iteration; with a communicator (Engine.comm_init) every rank stops together."""
+    bp = engine.bp
+    B = bp.B
+    if max_iter > SCP_MAX_HIST:
+        raise ValueError(f"max_iter <= {SCP_MAX_HIST}")
+    if X0 is None:
+        X0, U0 = bp.init_traj_straightline()
+    t0 = time.perf_counter()
+    engine.scp_begin(X0, U0, force)
+    n_it, _ = engine.scp_run(max_iter)
+    it, cv, su, hist, cnt = engine.scp_get(n_it + 1)
+    X, U = engine.get_trajectory()
+    S = BatchSCPSolution(X, U, cv, su, it)
+    S.total_time = time.perf_counter() - t0
+    S.batch_iterations = n_it
+    S.counters = cnt
+    S.rho_vec.append(np.zeros(B))
+    for h in range(n_it + 1):
+        r = hist[h]
+        S.J_true.append(r[:, H_JTRUE].copy()); S.J_full.append(r[:, H_JFULL].copy())
+        S.scp_status.append(r[:, H_SCP_STATUS].astype(np.int32)); S.solver_status.append(r[:, H_SOLVER_STATUS].astype(np.int32))
+        S.accept_solution.append(r[:, H_ACCEPT] > 0.5); S.convergence_measure.append(r[:, H_CONV].copy())
+        S.Delta_vec.append(r[:, H_DELTA].copy()); S.omega_vec.append(r[:, H_OMEGA].copy()); S.rho_vec.append(r[:, H_RHO].copy())
+        S.tr_ok_vec.append(r[:, H_TR_OK] > 0.5); S.ineq_ok_vec.append(r[:, H_INEQ_OK] > 0.5)
+        if h:
+            S.newton_iters.append(r[:, H_NEWTON].copy())
     return S
 
 

@@ -163,6 +163,46 @@ int32_t gusto_accept_device(gusto_ctx* ctx, const uint8_t* accept_dev, const dou
 /* Handle of the context's CUDA stream (cudaStream_t as integer) so that a torch stream can wait on it. */
 int64_t gusto_stream_handle(gusto_ctx* ctx);
 
+/* ---- Device-resident outer loop: a whole solve_gusto_jump! (scp_gusto.jl:49-176) without a host round trip per iteration.
+ * The accept/reject test, the Delta/omega schedule and the convergence test (:119-174) run in one small kernel per iteration
+ * (the same decision table as julia/GuSTOB200.jl and host.py::gusto_update, which stay available for a host that wants the
+ * loop in its own language); one iteration = K1 -> K3 -> K4 -> update(+copy!(SCPS.traj, new_traj), :147), replayed as a CUDA
+ * graph.  The host only reads one counter per iteration (unfinished instances over all ranks), and it reads it while the NEXT
+ * iteration already runs -- when the counter is 0 that extra iteration found every instance frozen and did nothing.
+ *
+ * gusto_scp_begin   traj <- X0,U0 (NULL,NULL: the X0,U0 of the previous begin, kept on the device), Delta0/omega0, every
+ *                   instance live, J_true[1] = cost_true(traj) (:60-75).  force != 0: the reference's force flag (:55,173).
+ * gusto_scp_run     up to max_iter more outer iterations; stops as soon as every instance of every rank is finished
+ *                   (converged, omega > omega_max, or solver failure :107-111).  batch_iterations: iterations that ran with
+ *                   live instances; n_unfinished: instances (all ranks) still live afterwards.
+ * gusto_scp_get     iterations[B], converged[B], successful[B] (SCPS.iterations/converged/successful), and the histories:
+ *                   hist[n_hist][B][GUSTO_HIST_W], slot 0 = initial entry, slot i = after outer iteration i, each record
+ *                   { J_true, J_full, scp_status, solver_status, accept, convergence_measure, Delta, omega, rho, tr_ok, ineq_ok,
+ *                   newton iterations } (types.jl:150-173, scp_gusto.jl:15-19); counters[(n_hist-1)][4] = per iteration
+ *                   { instances that ran, usable solves, accepted, still live afterwards } of THIS rank.  Any pointer may be
+ *                   NULL.  n_hist <= GUSTO_SCP_MAX_HIST + 1.  The trajectory itself: gusto_get_trajectory. */
+#define GUSTO_HIST_W 12
+#define GUSTO_SCP_MAX_HIST 64
+/* scp_status codes of the history records (SCPS.scp_status, scp_gusto.jl:125-145) */
+enum { GUSTO_SCP_NA = 0, GUSTO_SCP_OK, GUSTO_SCP_INACCURATE_MODEL, GUSTO_SCP_VIOLATES_CONSTRAINTS, GUSTO_SCP_TR_VIOLATED,
+       GUSTO_SCP_SOLVER_FAILED, GUSTO_SCP_INACTIVE };
+int32_t gusto_scp_begin(gusto_ctx* ctx, const double* X0, const double* U0, int32_t force);
+int32_t gusto_scp_run(gusto_ctx* ctx, int32_t max_iter, int32_t* batch_iterations, int32_t* n_unfinished);
+int32_t gusto_scp_get(gusto_ctx* ctx, int32_t* iterations, uint8_t* converged, uint8_t* successful, double* hist, int32_t n_hist,
+                      int32_t* counters);
+
+/* ---- Multi-GPU: one context per GPU / process, each owning a contiguous shard of the batch; the path's only exchange is one
+ * all-gather of B status bytes per outer iteration so that every rank stops together.  NCCL is
+ * loaded at run time (dlopen libnccl.so.2; GUSTO_NCCL_LIB overrides) -- a single-GPU host needs none.
+ * gusto_comm_unique_id  rank 0 creates the 128-byte ncclUniqueId; the host language broadcasts it (MPI / a file / torch).
+ * gusto_comm_init       collective: every rank calls it with the same id.  From then on gusto_scp_run gathers the status bytes
+ *                       the update kernel wrote (straight from that buffer, on a side stream, overlapping the next K1).
+ * gusto_allgather_status  the same collective for a host-language loop: done_local[B] (host) -> done_all[nranks*B] (host,
+ *                       may be NULL), n_unfinished = number of zeros over all ranks.  Works without a communicator (1 rank). */
+int32_t gusto_comm_unique_id(uint8_t* id128);
+int32_t gusto_comm_init(gusto_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
+int32_t gusto_allgather_status(gusto_ctx* ctx, const uint8_t* done_local, uint8_t* done_all, int32_t* n_unfinished);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 #include "../../gusto.jl_b200/csrc/evaluate.cuh"
 #include "../../gusto.jl_b200/csrc/postprocess.cuh"
 #include "../../gusto.jl_b200/csrc/shooting.cuh"
+#include "../../gusto.jl_b200/csrc/scp.cuh"
 
 using namespace gusto;
 
@@ -145,5 +146,15 @@ extern "C" int hostsim_shoot(const gusto_config* cfg, const double* x_init, cons
     case ASTROBEE_SE3_MANIFOLD: run_shoot<ASTROBEE_SE3_MANIFOLD>(d, p, p0, x_goal, nsub, max_iter, ftol, Xs, Us, Ps, out); break;
     default: return -1;
   }
+  return 0;
+}
+
+// device-resident outer step (scp.cuh::scp_update_instance), one call per instance: the kernel's decision table on the host
+extern "C" int hostsim_scp_update(int B, const double* ev, const double* info, const double* sp, int force, const uint8_t* active,
+                                  double* delta, double* omega, int* iterations, double* conv_prev, double* j_true, double* j_full,
+                                  uint8_t* converged, uint8_t* successful, double* rec, int* flags) {
+  for (int b = 0; b < B; ++b)
+    flags[b] = scp_update_instance(ev + (size_t)b * EVAL_NOUT, info + (size_t)b * IPM_NINFO, sp, force != 0, active[b] != 0, delta + b, omega + b,
+                                   iterations + b, conv_prev + b, j_true + b, j_full + b, converged + b, successful + b, rec + (size_t)b * HIST_W);
   return 0;
 }

@@ -147,6 +147,42 @@ def test_genuine_box_goal_rows_match_oracle(host, name, kw, width):
         assert np.max(np.abs(xN - mid[b])) > 1e-3 and np.max(np.abs(xN - Xs[-1, sel])) < (1e-3 if name == "astrobeeSE3manifold" else 1e-4)
 
 
+@pytest.mark.parametrize("name,kw", [("dubins", dict(B=12, N=30)), ("freeflyerSE2", dict(B=24, N=40)), ("astrobeeSE3", dict(B=12, N=50)),
+                                     ("astrobeeSE3manifold", dict(B=6, N=60))])
+def test_device_resident_loop_equals_host_loop(host, name, kw):
+    """gusto_scp_begin / gusto_scp_run (accept / reject, Delta / omega schedule, convergence test in scp_update_kernel, one CUDA graph
+    per outer iteration, counter read one iteration late) against the host-language loop over the same kernels: identical
+    histories and bit-identical final trajectories."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    e1 = host.Engine(bp, device=0)
+    S1 = host.solve_gusto_batch(e1, max_iter=30)
+    e1.close()
+    e2 = host.Engine(bp, device=0)
+    S2 = host.solve_gusto_batch_device(e2, max_iter=30)
+    S3 = host.solve_gusto_batch_device(e2, max_iter=30)          # restart on the same context
+    e2.close()
+    for S in (S2, S3):
+        assert S.batch_iterations == S1.batch_iterations
+        assert np.array_equal(S.iterations, S1.iterations) and np.array_equal(S.converged, S1.converged) and np.array_equal(S.successful, S1.successful)
+        assert np.array_equal(S.X, S1.X) and np.array_equal(S.U, S1.U)
+        for h in range(S1.batch_iterations + 1):
+            assert np.array_equal(S.accept_solution[h], S1.accept_solution[h]) and np.array_equal(S.scp_status[h], S1.scp_status[h])
+            assert np.array_equal(S.J_true[h], S1.J_true[h]) and np.array_equal(S.Delta_vec[h], S1.Delta_vec[h]) and np.array_equal(S.omega_vec[h], S1.omega_vec[h])
+            assert np.array_equal(S.convergence_measure[h], S1.convergence_measure[h])
+        ran = S.counters[:, 0]
+        assert ran[0] == bp.B and int(ran.sum()) >= int(S1.iterations.sum())
+
+
+def test_status_allgather_single_rank(host):
+    """gusto_allgather_status without a communicator: the gathered bytes are the local ones, the count is the number of zeros."""
+    bp = gb.problems.config_dubins(B=9, N=30)
+    e = host.Engine(bp, device=0)
+    done = np.array([1, 0, 0, 1, 1, 0, 1, 1, 1], np.uint8)
+    out, n = e.allgather_status(done)
+    assert np.array_equal(out, done) and n == 3
+    e.close()
+
+
 def test_shard_equivalence_and_ragged_batch(host):
     """B*N not a multiple of the 8 knots a linearize CTA stages; shards of a batch give bit-identical results."""
     bp = gb.problems.config_astrobee_se3(B=5, N=21, seed=3)

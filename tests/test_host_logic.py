@@ -56,6 +56,40 @@ def test_vectorised_update_equals_scalar_reference_logic(host):
         assert bool(st["converged_now"][b]) == r["converged"] and bool(st["successful_now"][b]) == r["successful"]
 
 
+@pytest.mark.parametrize("force", [False, True])
+def test_device_update_kernel_logic_equals_host_update(host, force):
+    """scp.cuh::scp_update_instance (the decision table of the device-resident loop, compiled for the host) against
+    host.gusto_update on random evaluation records: accept, Delta, omega, iterations, done, converged, successful, statuses."""
+    import ctypes
+    from util import hostsim_lib
+    rng = np.random.default_rng(3)
+    sp = np.ascontiguousarray(gb.models.AstrobeeSE3().scp_params, dtype=np.float64)
+    B = 5000
+    ev = np.zeros((B, 8)); info = np.zeros((B, 8))
+    ev[:, 0] = rng.choice([1e-4, 4e-3, 0.02, 0.3], B); ev[:, 1] = rng.integers(0, 2, B); ev[:, 2] = rng.integers(0, 2, B)
+    ev[:, 3] = rng.choice([1e-3, 0.02, 0.2], B); ev[:, 4] = rng.random(B)
+    info[:, 0] = rng.choice([0, 0, 0, 0, 1, 2, 3], B); info[:, 1] = rng.integers(5, 20, B); info[:, 4] = rng.random(B)
+    active = rng.random(B) > 0.1
+    Delta = rng.choice([10.0, 5.0, 0.3], B); omega = rng.choice([1.0, 625.0, 5e9, 1e10], B)
+    its = rng.integers(0, 6, B).astype(np.int64); cprev = rng.choice([1e-4, 4e-3, 0.02], B)
+    st = host.gusto_update(ev, host.solver_status_ok(info[:, 0]), active, Delta, omega, its, cprev, sp, force)
+    d2, w2, it2, c2 = Delta.copy(), omega.copy(), its.astype(np.int32), cprev.copy()
+    jt = rng.random(B); jf = rng.random(B); jt0 = jt.copy()
+    cv = np.zeros(B, np.uint8); su = np.zeros(B, np.uint8); rec = np.zeros((B, host.HIST_W)); fl = np.zeros(B, np.int32)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    bp_ = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    act8 = active.astype(np.uint8)
+    assert hostsim_lib().hostsim_scp_update(B, dp(ev), dp(info), dp(sp), int(force), bp_(act8), dp(d2), dp(w2), ip(it2), dp(c2), dp(jt), dp(jf),
+                                            bp_(cv), bp_(su), dp(rec), ip(fl)) == 0
+    assert np.array_equal((fl & 1) > 0, st["accept"]) and np.array_equal(d2, st["Delta"]) and np.array_equal(w2, st["omega"])
+    assert np.array_equal(it2, st["iterations"]) and np.array_equal(cv > 0, st["converged_now"]) and np.array_equal(su > 0, st["successful_now"])
+    assert np.array_equal(((fl & 2) > 0)[active], st["done"][active]) and np.all((fl & 2)[~active] > 0)
+    assert np.array_equal(rec[:, host.H_SCP_STATUS].astype(np.int32), st["status"])
+    assert np.array_equal(jt, np.where(st["accept"], ev[:, 4], jt0))
+    assert np.array_equal(c2, np.where(st["run"], ev[:, 0], cprev))
+
+
 def test_shard_is_a_contiguous_partition(pkg):
     bp = pkg.problems.config_astrobee_se3(B=37, N=10, seed=2)
     parts = [bp.shard(r, 4) for r in range(4)]
