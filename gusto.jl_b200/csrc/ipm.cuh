@@ -181,12 +181,23 @@ template <int M> struct IpmLayout {
   // per-knot Riccati factor of one Newton iteration: K' [NX][LDU], packed P
   static constexpr int KTW = NX * LDU, LPW = (NTU + 1) & ~1, PKW = (NTX + 1) & ~1;   // lp: packed lower L^-1 of Lam = L L'
   GHD static size_t rnd(size_t v) { return (v + 1) & ~(size_t)1; }   // keep every array 16-byte aligned
+  // Global scratch is knot-minor ("field-major"): element e of knot k of a per-knot record lives at  e * NP + k  (NP = N rounded up
+  // to 4, so every field row starts on a 32-byte sector), and likewise  e * NE + j  for the N + 1 equality rows and  f * PP + p  for
+  // the compacted obstacle rows.  The per-knot passes run one THREAD per knot: with this layout a warp's load of one field is 32
+  // consecutive doubles (8 sectors) instead of 32 separate sectors -- those passes were bound by L1 wavefronts / exposed global
+  // latency (ncu round 2: ric_forward 11 % of the kernel's warp time on 2 % of its instructions).  The knot-serial sweep gathers
+  // its inputs with 8-byte asynchronous copies one knot ahead and scatters its factor records with plain stores; only the
+  // closed-loop tiles Acl_k (whole-tile copies of the chains) and the dynamics records of the sweep stay knot-major.
+  GHD static int np_of(int N) { return (N + 3) & ~3; }
+  GHD static int ne_of(int N) { return (N + 1 + 3) & ~3; }
+  GHD static int pp_of(int N, int n_obs) { const int v = N * (T::WS > 0 ? n_obs : 0); return v > 0 ? ((v + 3) & ~3) : 4; }
+  static constexpr int GSW = NU * NX;                       // Gam' / Bh' entries per knot in the field-major copies
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
-    const size_t nz = rnd((size_t)N * NV), ne = rnd((size_t)(N + 1) * NX), no = T::WS > 0 ? n_obs : 0, nn = (size_t)N;
-    return nz /* r */ + 3 * ne /* nu dnu rnu */ + rnd(nn * ANZ) + rnd(nn * SP * SLOT_W) + (size_t)NBOX * SLOT_W +
-           rnd(nn * no * SLOT_W) + rnd(nn * no * OROW_W) + nn * KDW +
-           rnd(nn * NN) /* Fi */ + nn * CRW + nn * GT /* Acl */ + nn * KTW + nn * LPW + nn * PKW + 2 * rnd(nn * NX) /* psi ch */ + nn * LDU /* kap */;
+    const size_t np = np_of(N), ne = ne_of(N), pp = pp_of(N, n_obs), nn = (size_t)N;
+    return np * NV /* r */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * ANZ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
+           pp * SLOT_W + pp * OROW_W + np * KDW + np * NN /* Fi */ + nn * CRW + 2 * np * GSW /* gs bs */ + nn * GT /* Acl */ + np * NX * NU /* K */ +
+           np * NTU /* lp */ + np * NTX /* P */ + 2 * np * NX /* psi ch */ + np * NU /* kap */;
   }
   // shared-memory tiles of the Riccati sweep (doubles); they alias the direction dz
   static constexpr int XSR = RXS + NUP;                     // staged dynamics record: Ah' | Bh' | ch | 0.. | Gam' (row RXS) | 0..
@@ -226,6 +237,7 @@ template <int M> struct IpmCtx {
   const BatchDesc* d;
   const double* rp;
   int N, n_obs, b, nact, pmask, bmask;
+  int NP, NE, PP;         // field strides of the knot-minor scratch arrays (IpmLayout::np_of / ne_of / pp_of)
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
@@ -234,6 +246,7 @@ template <int M> struct IpmCtx {
   // global scratch
   double *nu, *dnu, *r, *rnu, *Ac, *sslot, *bslot, *ost, *orow, *kd;
   double *fi, *cr, *acl, *kt, *lp, *pk, *psi, *ch, *kap;
+  double *xps, *gsum, *gs, *bs;   // Xp field-major | h/2 (g_{j-1} + g_j) per equality row | Gam', Bh' field-major
   // shared
   double *z, *dz, *vp, *red;
   int* seg;
@@ -252,24 +265,27 @@ template <int M> GDEV int* sh_seg(const IpmCtx<M>& c) { return c.seg; }   // (an
 // After eliminating (s, lam [, t, lamb]) the row contributes  kap * gv gv' + lam * hess  to H and  -gv * bt  to the rhs.
 struct Pair { double rc, rt, wa, wb, ba, bb, iw, kap, bt, la; };
 
-GDEV void pair_eval(const double* st, bool has_t, double c0, double omega, double smu, int phase, Pair& q) {
-  const double sa = st[0], la = st[1];
+// A slot record is addressed as st[f * ss], f = 0 .. SLOT_W-1: the records of the special rows and of the compacted obstacle
+// rows are stored field-major ([field][knot] / [field][row]) so that a pass with one thread per knot / per row reads and writes
+// them coalesced; the goal-box records (a handful) are contiguous (ss = 1).
+GDEV void pair_eval(const double* st, size_t ss, bool has_t, double c0, double omega, double smu, int phase, Pair& q) {
+  const double sa = st[0], la = st[ss];
   const double isa = g_rcp(sa);
   q.la = la;
   q.wa = la * isa;
   if (has_t) {
-    const double t = st[2], lb = st[3];
+    const double t = st[2 * ss], lb = st[3 * ss];
     const double it = g_rcp(t);
     q.rc = c0 - t + sa; q.rt = omega - la - lb;
     q.wb = lb * it;
-    const double rsa = sa * la - smu + (phase ? st[4] : 0.0), rsb = t * lb - smu + (phase ? st[5] : 0.0);
+    const double rsa = sa * la - smu + (phase ? st[4 * ss] : 0.0), rsb = t * lb - smu + (phase ? st[5 * ss] : 0.0);
     q.ba = (la * q.rc - rsa) * isa; q.bb = -rsb * it;
     q.iw = g_rcp(q.wa + q.wb);
     q.kap = q.wa * q.wb * q.iw;
     q.bt = q.ba - q.wa * (q.ba + q.bb - q.rt) * q.iw;
   } else {
     q.rc = c0 + sa; q.rt = 0.0; q.wb = 0.0; q.bb = 0.0; q.iw = 0.0;
-    const double rs = sa * la - smu + (phase ? st[4] : 0.0);
+    const double rs = sa * la - smu + (phase ? st[4 * ss] : 0.0);
     q.ba = (la * q.rc - rs) * isa;
     q.kap = q.wa;
     q.bt = q.ba;
@@ -277,11 +293,11 @@ GDEV void pair_eval(const double* st, bool has_t, double c0, double omega, doubl
 }
 
 struct Stat { double rz, rc, mus, np; };   // running max |dual residual|, max |row residual|, sum s*lam, #pairs
-GDEV void pair_stat(const double* st, bool has_t, const Pair& q, Stat& S) {
+GDEV void pair_stat(const double* st, size_t ss, bool has_t, const Pair& q, Stat& S) {
   S.rc = fabs(q.rc) > S.rc ? fabs(q.rc) : S.rc;
   if (!(q.rc == q.rc)) S.rc = 1e300;
-  S.mus += st[0] * st[1]; S.np += 1.0;
-  if (has_t) { S.rz = fabs(q.rt) > S.rz ? fabs(q.rt) : S.rz; S.mus += st[2] * st[3]; S.np += 1.0; }
+  S.mus += st[0] * st[ss]; S.np += 1.0;
+  if (has_t) { S.rz = fabs(q.rt) > S.rz ? fabs(q.rt) : S.rz; S.mus += st[2 * ss] * st[3 * ss]; S.np += 1.0; }
 }
 
 // Step of one row given gdz = gv . dz.
@@ -290,15 +306,15 @@ GDEV void pair_stat(const double* st, bool has_t, const Pair& q, Stat& S) {
 //           (Mehrotra's mu_aff for any step a, so the predictor needs ONE pass over the rows);
 //   mode 2: apply (ap, ad) and accumulate the new complementarity sum / pair count (for the central-path floor).
 struct StepAcc { double amp, amd, c0, c1, c2, np; };
-GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a) {
-  const double sa = st[0], la = st[1];
+GDEV void pair_step(double* st, size_t ss, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a) {
+  const double sa = st[0], la = st[ss];
   if (has_t) {
-    const double t = st[2], lb = st[3];
+    const double t = st[2 * ss], lb = st[3 * ss];
     const double dt = (q.wa * gdz + q.ba + q.bb - q.rt) * q.iw;
     const double dla = q.wa * (gdz - dt) + q.ba, dlb = -q.wb * dt + q.bb, ds = -q.rc - (gdz - dt);
     if (mode == 2) {
       const double s1 = sa + ap * ds, t1 = t + ap * dt, l1 = la + ad * dla, b1 = lb + ad * dlb;
-      st[0] = s1; st[2] = t1; st[1] = l1; st[3] = b1;
+      st[0] = s1; st[2 * ss] = t1; st[ss] = l1; st[3 * ss] = b1;
       a.c0 += s1 * l1 + t1 * b1; a.np += 2.0;
     } else {
       if (ds < 0) { const double v = -sa * g_rcp(ds); a.amp = v < a.amp ? v : a.amp; }
@@ -306,7 +322,7 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
       if (dla < 0) { const double v = -la * g_rcp(dla); a.amd = v < a.amd ? v : a.amd; }
       if (dlb < 0) { const double v = -lb * g_rcp(dlb); a.amd = v < a.amd ? v : a.amd; }
       if (mode == 1) {
-        st[4] = ds * dla; st[5] = dt * dlb;
+        st[4 * ss] = ds * dla; st[5 * ss] = dt * dlb;
         a.c0 += sa * la + t * lb; a.c1 += sa * dla + la * ds + t * dlb + lb * dt; a.c2 += ds * dla + dt * dlb;
       }
     }
@@ -314,24 +330,24 @@ GDEV void pair_step(double* st, bool has_t, const Pair& q, double gdz, int mode,
     const double dla = q.wa * gdz + q.ba, ds = -q.rc - gdz;
     if (mode == 2) {
       const double s1 = sa + ap * ds, l1 = la + ad * dla;
-      st[0] = s1; st[1] = l1;
+      st[0] = s1; st[ss] = l1;
       a.c0 += s1 * l1; a.np += 1.0;
     } else {
       if (ds < 0) { const double v = -sa * g_rcp(ds); a.amp = v < a.amp ? v : a.amp; }
       if (dla < 0) { const double v = -la * g_rcp(dla); a.amd = v < a.amd ? v : a.amd; }
-      if (mode == 1) { st[4] = ds * dla; st[5] = 0.0; a.c0 += sa * la; a.c1 += sa * dla + la * ds; a.c2 += ds * dla; }
+      if (mode == 1) { st[4 * ss] = ds * dla; st[5 * ss] = 0.0; a.c0 += sa * la; a.c1 += sa * dla + la * ds; a.c2 += ds * dla; }
     }
   }
 }
 // Keep a complementarity pair above floor = 1e-4 * mu (wide neighbourhood of the central path, as the oracle does).
 // Applied lazily by the first reader of the row in the next Newton iteration (assemble, phase 0).
-GDEV void pair_floor(double* st, bool has_t, double floor_) {
-  if (st[0] * st[1] < floor_) st[1] = floor_ * g_rcp(st[0]);
-  if (has_t && st[2] * st[3] < floor_) st[3] = floor_ * g_rcp(st[2]);
+GDEV void pair_floor(double* st, size_t ss, bool has_t, double floor_) {
+  if (st[0] * st[ss] < floor_) st[ss] = floor_ * g_rcp(st[0]);
+  if (has_t && st[2 * ss] * st[3 * ss] < floor_) st[3 * ss] = floor_ * g_rcp(st[2 * ss]);
 }
 
-GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega, double t_in = 1.0, double lam_split = 0.5) {
-  for (int i = 0; i < SLOT_W; ++i) st[i] = 0.0;
+GDEV void slot_init(double* st, size_t ss, bool valid, bool has_t, double c0, double omega, double t_in = 1.0, double lam_split = 0.5) {
+  for (int i = 0; i < SLOT_W; ++i) st[i * ss] = 0.0;
   if (!valid) return;
   if (has_t) {
     // interior start of the penalty slack: t_in inside (the oracle uses one unit).  0.25 saves 0.85 Newton iterations of 8.85 on
@@ -339,11 +355,11 @@ GDEV void slot_init(double* st, bool valid, bool has_t, double c0, double omega,
     // (slack_start<M>()), like the refinement count; the optimum reached is the same to the solver tolerance.
     const double t = (c0 > 0 ? c0 : 0.0) + t_in;
     const double sa = t - c0;
-    st[0] = sa > 1e-2 ? sa : 1e-2; st[1] = lam_split * omega; st[2] = t; st[3] = omega - st[1];
+    st[0] = sa > 1e-2 ? sa : 1e-2; st[ss] = lam_split * omega; st[2 * ss] = t; st[3 * ss] = omega - lam_split * omega;
   } else {
     // hard rows: the oracle's s = max(-c, 1e-2), except that a strictly feasible row keeps its exact slack -- a BoxGoal of
     // width 2e-4 (astrobeeSE3manifold notebook) would otherwise start 100x outside its own width on both sides
-    st[0] = -c0 > 1e-2 ? -c0 : (-c0 > 1e-6 ? -c0 : 1e-2); st[1] = 1e-2;
+    st[0] = -c0 > 1e-2 ? -c0 : (-c0 > 1e-6 ? -c0 : 1e-2); st[ss] = 1e-2;
   }
 }
 
@@ -388,7 +404,8 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
   } else if (s < L::S_BALL) {
     // cse_quaternion_norm (astrobee_se3_manifold.jl:308-313): e = a.q - 1, a = qp/|qp|.
     //   hinge  e - eps/omega - t <= 0 (t >= 0)       and the hard row  -e - eps/omega <= 0   
-    const double* qp = c.Xp + k * L::NX + 6;
+    double qp[4];
+    for (int i = 0; i < 4; ++i) qp[i] = c.xps[(size_t)(6 + i) * c.NP + k];
     const double nq = sqrt(qp[0] * qp[0] + qp[1] * qp[1] + qp[2] * qp[2] + qp[3] * qp[3]);
     double ev = -1.0;
     for (int i = 0; i < 4; ++i) ev += qp[i] / nq * x[6 + i];
@@ -416,7 +433,7 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
 template <int M> GDEV double tr_c0(const IpmCtx<M>& c, int k, const double* x) {
   constexpr int NX = IpmCtx<M>::NX;
   double v = -c.dow;
-  for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; }
+  for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[(size_t)i * c.NP + k]; v += dxi * dxi; }
   return v;
 }
 // csbci_goal_constraints (dynamics.jl:37-42): X[i,N] - ub <= 0 (j even), lb - X[i,N] <= 0 (j odd); hard
@@ -496,13 +513,13 @@ template <int M> GDEV void aeq_row(const IpmCtx<M>& c, const double* v, int j, d
   } else {
     const double* vp = v + (j - 1) * NV;
     const double* vc = v + j * NV;
-    const double* Ap = c.Ac + (size_t)(j - 1) * ANZ;
-    const double* Ak = c.Ac + (size_t)j * ANZ;
+    const double* Ak = c.Ac + j;                 // A_j on its pattern, field-major; A_{j-1} one to the left
+    const size_t np = c.NP;
     double acc[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) acc[i] = 0.0;
 #pragma unroll
-    for (int e = 0; e < ANZ; ++e) acc[T::a_row(e)] += Ap[e] * vp[T::a_col(e)] + Ak[e] * vc[T::a_col(e)];
+    for (int e = 0; e < ANZ; ++e) acc[T::a_row(e)] += Ak[e * np - 1] * vp[T::a_col(e)] + Ak[e * np] * vc[T::a_col(e)];
 #pragma unroll
     for (int a = 0; a < NU; ++a) acc[T::b_row(a)] += c.bv[a] * (vp[NX + a] + vc[NX + a]);
 #pragma unroll
@@ -514,19 +531,19 @@ template <int M> GDEV void aeqT_knot(const IpmCtx<M>& c, const double* nu, int k
   using T = Traits<M>;
   constexpr int NX = T::NX, NU = T::NU, ANZ = T::ANZ;
   const int N = c.N;
-  const double* nk = nu + k * NX;          // row k       (knot k as "current")
-  const double* nn = nu + (k + 1) * NX;    // row k + 1   (knot k as "previous")
-  const double* Ak = c.Ac + (size_t)k * ANZ;
+  const double* nk = nu + k;               // row k (knot k as "current"), row k + 1 (knot k as "previous"): field-major [NX][NE]
+  const double* Ak = c.Ac + k;
+  const size_t np = c.NP, ne = c.NE;
   double wv[NX], acc[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
-    const double a = nk[i], b2 = nn[i];
+    const double a = nk[i * ne], b2 = nk[i * ne + 1];
     wv[i] = (k > 0 ? a : 0.0) + (k < N - 1 ? b2 : 0.0);
     out[i] = (k == 0 ? a : -a) + (k == N - 1 ? (((c.pmask >> i) & 1) ? b2 : 0.0) : b2);
     acc[i] = 0.0;
   }
 #pragma unroll
-  for (int e = 0; e < ANZ; ++e) acc[T::a_col(e)] += Ak[e] * wv[T::a_row(e)];
+  for (int e = 0; e < ANZ; ++e) acc[T::a_col(e)] += Ak[e * np] * wv[T::a_row(e)];
 #pragma unroll
   for (int i = 0; i < NX; ++i) out[i] += c.hh * acc[i];
 #pragma unroll
@@ -553,7 +570,8 @@ template <int M> GDEV void apply_Hx(const IpmCtx<M>& c, int k, const double* in,
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX;
-  const double* kd = c.kd + (size_t)k * L::KDW;
+  double kd[L::KDW];
+  for (int i = 0; i < L::KDW; ++i) kd[i] = c.kd[(size_t)i * c.NP + k];
   xblocks_mv<M>(kd + L::KD_HB, in, out);
   if (T::HAS_TR) {
     double s = 0.0;
@@ -602,7 +620,7 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
     if (T::HAS_TR) {
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        gtr[i] = 2.0 * (x[off + i] - c.Xp[k * NX + off + i]);
+        gtr[i] = 2.0 * (x[off + i] - c.xps[(size_t)(off + i) * c.NP + k]);
         gz[off + i] += ka.la_tr * gtr[i];
         rr[i] -= gtr[i] * ka.bt_tr;
         Hb[tri(i, i)] = 2.0 * ka.la_tr;
@@ -614,11 +632,12 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       if (spec_block<M>(s) != B0) continue;
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
-      double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      const size_t ss = c.NP;
+      double* st = c.sslot + (size_t)s * SLOT_W * ss + k;
       Pair q;
-      if (phase == 0) pair_floor(st, o.has_t, c.floor_);
-      pair_eval(st, o.has_t, o.c0, c.omega, smu, phase, q);
-      if (phase == 0) pair_stat(st, o.has_t, q, ka.st);
+      if (phase == 0) pair_floor(st, ss, o.has_t, c.floor_);
+      pair_eval(st, ss, o.has_t, o.c0, c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, ss, o.has_t, q, ka.st);
       block_add<n>(Hb, gz + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
     }
     // convexified obstacle rows (compacted): off - nhat.r - t <= 0
@@ -627,18 +646,18 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       const int s0 = sh_seg<M>(c)[k], s1 = sh_seg<M>(c)[k + 1];
       const double* __restrict__ orow = c.orow;
       double* __restrict__ ost = c.ost;
+      const size_t pp = c.PP;
       for (int p = s0; p < s1; ++p) {
-        if (p + 2 < s1) { g_prefetch_l1(orow + (size_t)(p + 2) * OROW_W); g_prefetch_l1(ost + (size_t)(p + 2) * SLOT_W); }
-        const double* row = orow + (size_t)p * OROW_W;
-        double* st = ost + (size_t)p * SLOT_W;
+        const double* row = orow + p;
+        double* st = ost + p;
         double gv[4] = {0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
-        double v = row[3];
+        double v = row[3 * pp];
 #pragma unroll
-        for (int a = 0; a < WS; ++a) { gv[a] = -row[a]; v -= row[a] * x[a]; }
+        for (int a = 0; a < WS; ++a) { const double ra = row[a * pp]; gv[a] = -ra; v -= ra * x[a]; }
         Pair q;
-        if (phase == 0) pair_floor(st, true, c.floor_);
-        pair_eval(st, true, v, c.omega, smu, phase, q);
-        if (phase == 0) pair_stat(st, true, q, ka.st);
+        if (phase == 0) pair_floor(st, pp, true, c.floor_);
+        pair_eval(st, pp, true, v, c.omega, smu, phase, q);
+        if (phase == 0) pair_stat(st, pp, true, q, ka.st);
         block_add<n>(Hb, gz + off, rr, 0, WS, gv, hq, q, phase);
       }
     }
@@ -653,22 +672,22 @@ GDEV void assemble_xblock(const IpmCtx<M>& c, int k, int phase, double smu, cons
           double* st = c.bslot + (size_t)j * SLOT_W;
           double gv[4] = {side == 0 ? 1.0 : -1.0, 0, 0, 0}, hq[4] = {0, 0, 0, 0};
           Pair q;
-          if (phase == 0) pair_floor(st, false, c.floor_);
-          pair_eval(st, false, box_c0<M>(c, j, x), c.omega, smu, phase, q);
-          if (phase == 0) pair_stat(st, false, q, ka.st);
+          if (phase == 0) pair_floor(st, 1, false, c.floor_);
+          pair_eval(st, 1, false, box_c0<M>(c, j, x), c.omega, smu, phase, q);
+          if (phase == 0) pair_stat(st, 1, false, q, ka.st);
           block_add<n>(Hb, gz + off, rr, i, 1, gv, hq, q, phase);
         }
       }
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
-      c.r[k * NV + off + i] = rr[i] - gz[off + i];
+      c.r[(size_t)(off + i) * c.NP + k] = rr[i] - gz[off + i];
       if (phase == 0) { const double a = fabs(gz[off + i]); ka.st.rz = a > ka.st.rz ? a : ka.st.rz; if (!(a == a)) ka.st.rz = 1e300; }
     }
     if (phase == 0) {
-      double* kd = c.kd + (size_t)k * L::KDW;
+      double* kd = c.kd + k;
 #pragma unroll
-      for (int i = 0; i < npk; ++i) kd[L::KD_HB + T::XB_pk(B0) + i] = Hb[i];
+      for (int i = 0; i < npk; ++i) kd[(size_t)(L::KD_HB + T::XB_pk(B0) + i) * c.NP] = Hb[i];
     }
     assemble_xblock<M, B0 + 1>(c, k, phase, smu, x, gz, ka);
   }
@@ -692,22 +711,23 @@ GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
       if (!o.valid) continue;
-      double* st = c.sslot + ((size_t)k * L::SP + s) * SLOT_W;
+      const size_t ss = c.NP;
+      double* st = c.sslot + (size_t)s * SLOT_W * ss + k;
       Pair q;
-      if (phase == 0) pair_floor(st, false, c.floor_);
-      pair_eval(st, false, o.c0, c.omega, smu, phase, q);
-      if (phase == 0) pair_stat(st, false, q, ka.st);
+      if (phase == 0) pair_floor(st, ss, false, c.floor_);
+      pair_eval(st, ss, false, o.c0, c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, ss, false, q, ka.st);
       block_add<n>(Hb, gz + NX + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) {
-      c.r[k * NV + NX + off + i] = rr[i] - gz[NX + off + i];
+      c.r[(size_t)(NX + off + i) * c.NP + k] = rr[i] - gz[NX + off + i];
       if (phase == 0) { const double a = fabs(gz[NX + off + i]); ka.st.rz = a > ka.st.rz ? a : ka.st.rz; if (!(a == a)) ka.st.rz = 1e300; }
     }
     if (phase == 0) {
-      double* kd = c.kd + (size_t)k * L::KDW;
+      double* kd = c.kd + k;
 #pragma unroll
-      for (int i = 0; i < npk; ++i) kd[L::KD_HU + T::UB_pk(B0) + i] = Hb[i];
+      for (int i = 0; i < npk; ++i) kd[(size_t)(L::KD_HU + T::UB_pk(B0) + i) * c.NP] = Hb[i];
     }
     assemble_ublock<M, B0 + 1>(c, k, phase, smu, x, wk, gz, ka);
   }
@@ -733,21 +753,22 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
     KnotAcc<M> ka;
     ka.la_tr = 0; ka.bt_tr = 0; ka.kap_tr = 0; ka.st = S;
     if (T::HAS_TR) {
-      double* st = c.sslot + ((size_t)k * L::SP + L::S_TR) * SLOT_W;
+      const size_t ss = c.NP;
+      double* st = c.sslot + (size_t)L::S_TR * SLOT_W * ss + k;
       Pair q;
-      if (phase == 0) pair_floor(st, true, c.floor_);
-      pair_eval(st, true, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
-      if (phase == 0) pair_stat(st, true, q, ka.st);
+      if (phase == 0) pair_floor(st, ss, true, c.floor_);
+      pair_eval(st, ss, true, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, ss, true, q, ka.st);
       ka.la_tr = q.la; ka.bt_tr = q.bt; ka.kap_tr = q.kap;
     }
     assemble_xblock<M, 0>(c, k, phase, smu, x, gz, ka);
     assemble_ublock<M, 0>(c, k, phase, smu, x, wk, gz, ka);
     S = ka.st;
     if (phase == 0 && T::HAS_TR) {
-      double* kd = c.kd + (size_t)k * L::KDW;
+      double* kd = c.kd + k;
       const double sk = sqrt(ka.kap_tr);
 #pragma unroll
-      for (int i = 0; i < NX; ++i) kd[L::KD_W + i] = sk * (2.0 * (x[i] - c.Xp[k * NX + i]));
+      for (int i = 0; i < NX; ++i) kd[(size_t)(L::KD_W + i) * c.NP] = sk * (2.0 * (x[i] - c.xps[(size_t)i * c.NP + k]));
     }
   }
   if (phase == 0) {
@@ -758,11 +779,8 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       aeq_row<M>(c, sh_z<M>(c), j, v);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double t = v[i];
-        if (j == 0) t -= c.x_init[i];
-        else if (j == N) t -= ((c.pmask >> i) & 1) ? c.goal_lo[i] : 0.0;
-        else t += c.hh * (c.g[(j - 1) * NX + i] + c.g[j * NX + i]);
-        c.rnu[j * NX + i] = -t;
+        const double t = v[i] + c.gsum[(size_t)i * c.NE + j];     // gsum: -x_init | h/2 (g_{j-1} + g_j) | -goal (setup)
+        c.rnu[(size_t)i * c.NE + j] = -t;
         const double a = fabs(t);
         rpmax = a > rpmax ? a : rpmax;
         if (!(a == a)) rpmax = 1e300;
@@ -800,7 +818,7 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
       double* row = rows + t * W2;
       for (int j = 0; j < W2; ++j) row[j] = 0.0;
       row[i] = 1.0; row[NX + i] = 1.0;
-      if (k < N) for (int e = 0; e < ANZ; ++e) if (T::a_row(e) == i) row[T::a_col(e)] -= hh * c.Ac[(size_t)k * ANZ + e];
+      if (k < N) for (int e = 0; e < ANZ; ++e) if (T::a_row(e) == i) row[T::a_col(e)] -= hh * c.Ac[(size_t)e * c.NP + k];
     }
     G_SYNC();
     // the decoupled blocks are eliminated side by side: step t uses pivot dlo + t of every block
@@ -830,14 +848,18 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
       const int kb = t / NX, i = t - kb * NX, k = k0 + kb;
       if (k >= N) continue;
       const double* w = rows + t * W2 + NX;
-      double* fo = c.fi + (size_t)k * NN + i * NX;
-      for (int j = 0; j < NX; ++j) fo[j] = w[j];
+      double* fo = c.fi + (size_t)(i * NX) * c.NP + k;
+      for (int j = 0; j < NX; ++j) fo[(size_t)j * c.NP] = w[j];
       double* cr = c.cr + (size_t)k * L::CRW;
-      for (int a = 0; a < NU; ++a) cr[(L::CR_GT + a) * LDT + i] = k == 0 ? 0.0 : hh * c.bv[a] * w[T::b_row(a)];
+      for (int a = 0; a < NU; ++a) {
+        const double gv = k == 0 ? 0.0 : hh * c.bv[a] * w[T::b_row(a)];
+        cr[(L::CR_GT + a) * LDT + i] = gv;
+        c.gs[(size_t)(a * NX + i) * c.NP + k] = gv;
+      }
       if (k >= 1) {
         double ah[NX];
         for (int j = 0; j < NX; ++j) ah[j] = w[j];
-        for (int e = 0; e < ANZ; ++e) ah[T::a_col(e)] += hh * c.Ac[(size_t)(k - 1) * ANZ + e] * w[T::a_row(e)];
+        for (int e = 0; e < ANZ; ++e) ah[T::a_col(e)] += hh * c.Ac[(size_t)e * c.NP + k - 1] * w[T::a_row(e)];
         double* crp = c.cr + (size_t)(k - 1) * L::CRW;
         for (int j = 0; j < NX; ++j) crp[(L::CR_AT + j) * LDT + i] = ah[j];
       }
@@ -853,7 +875,9 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
     double v = c.cr[(size_t)(k + 1) * L::CRW + (L::CR_GT + a) * LDT + i];
     for (int m = L::dlo(i); m < L::dhi(i); ++m) v += cr[(L::CR_AT + m) * LDT + i] * gk[m];
     c.cr[(size_t)k * L::CRW + (L::CR_BT + a) * LDT + i] = v;
+    c.bs[(size_t)(a * NX + i) * c.NP + k] = v;
   }
+  G_PAR_FOR(r, NU * NX) c.bs[(size_t)r * c.NP + N - 1] = 0.0;      // no dynamics after the last knot
   G_SYNC();
 }
 
@@ -868,10 +892,10 @@ template <int M> GDEV void ric_stage_async(const IpmCtx<M>& c, int k, double* ti
   G_PAR_FOR(t, (NX + NU) * LDT / 2) g_cp_async16(XS + 2 * t, cr + 2 * t);
   G_PAR_FOR(t, NU * LDT / 2) g_cp_async16(XS + L::RXS * LDT + 2 * t, cr + L::CR_GT * LDT + 2 * t);
   double* SB = tile + L::F_SB + buf * L::SBW;
-  const double* kd = c.kd + (size_t)k * L::KDW;
-  G_PAR_FOR(t, L::KDW) g_cp_async8(SB + t, kd + t);
-  G_PAR_FOR(t, NV) g_cp_async8(SB + L::KDW + t, c.r + (size_t)k * NV + t);
-  if (k < c.N - 1) G_PAR_FOR(t, NX) g_cp_async8(SB + L::KDW + NV + t, c.ch + (size_t)k * NX + t);
+  const size_t np = c.NP;
+  G_PAR_FOR(t, L::KDW) g_cp_async8(SB + t, c.kd + t * np + k);
+  G_PAR_FOR(t, NV) g_cp_async8(SB + L::KDW + t, c.r + t * np + k);
+  if (k < c.N - 1) G_PAR_FOR(t, NX) g_cp_async8(SB + L::KDW + NV + t, c.ch + t * np + k);
 }
 // Dense stage inputs of knot k from its staging buffer, by the lanes of ONE warp (no barrier): lane i builds row i of Hx_k
 // (+ w_N on the PointGoal coordinates of the last knot) and of Hu_k, q = rx (+ w_N rho_N), ru, and ch_k into its row of the
@@ -924,7 +948,7 @@ template <int M> GDEV void ric_stage_build(const IpmCtx<M>& c, int k, double* ti
       Qd[i * LDT + q] = v;
     }
     double qv = SB[L::KDW + i];
-    if (pin) qv += c.wN * c.rnu[N * NX + i];
+    if (pin) qv += c.wN * c.rnu[(size_t)i * c.NE + N];
     vec[L::V_Q + buf * L::KP + i] = qv;
     XS[(NX + NU) * LDT + i] = last ? 0.0 : SB[L::KDW + NV + i];
   }
@@ -1015,7 +1039,7 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
         if (i < NX) {
           const double ps = Z1[(NX + NU) * LDT + i];             // psi_k = P_{k+1} ch_k  (Z1 is recycled after phase C)
           pit[i] = pn[i] - ps;
-          c.psi[(size_t)k * NX + i] = ps;
+          c.psi[(size_t)i * c.NP + k] = ps;
         } else {
           const int a = i - NX;
           double v = ruv[a];
@@ -1061,9 +1085,9 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
         }
       }
       if (G_LANE == 0) {
-        double* lp = c.lp + (size_t)k * L::LPW;
+        double* lp = c.lp + k;
 #pragma unroll
-        for (int t = 0; t < NTU; ++t) lp[t] = Lv[t];
+        for (int t = 0; t < NTU; ++t) lp[(size_t)t * c.NP] = Lv[t];
       }
     }
     if (w1) {
@@ -1090,13 +1114,13 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
         if (r < NX && q < NX) {
           const double pv = Wn[r * LDT + q] - v;
           Wn[r * LDT + q] = pv;
-          if (q <= r) c.pk[(size_t)k * L::PKW + tri(r, q)] = pv;
+          if (q <= r) c.pk[(size_t)tri(r, q) * c.NP + k] = pv;
         }
       });
       g_tile_grid<KSU, MT_X, 1, false, true>(Yt, LDU, 0, Li, LDU, 0, [&](int r, int a, double v) {
         if (a < NU) {
-          if (r < NX) c.kt[(size_t)k * L::KTW + r * LDU + a] = v;
-          else if (r == NX) c.kap[(size_t)k * LDU + a] = v;
+          if (r < NX) c.kt[(size_t)(r * NU + a) * c.NP + k] = v;
+          else if (r == NX) c.kap[(size_t)a * c.NP + k] = v;
         }
       });
     }
@@ -1245,20 +1269,21 @@ template <int M> GDEV_NOINLINE void chain_backward(const IpmCtx<M>& c) {
 // The s-form control gradient  rs = ru + Gam' rx  of knot k for the right-hand side in c.r / c.rnu.
 template <int M> GDEV void ric_rhs_knot(const IpmCtx<M>& c, int k, double* rx, double* rs) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, LDT = L::LDT;
-  const double* cr = c.cr + (size_t)k * L::CRW;
+  constexpr int NX = L::NX, NU = L::NU;
+  const size_t np = c.NP;
+  const double* r = c.r + k;
 #pragma unroll
-  for (int i = 0; i < NX; ++i) rx[i] = c.r[k * NV + i];
+  for (int i = 0; i < NX; ++i) rx[i] = r[i * np];
   if (k == c.N - 1) {
 #pragma unroll
-    for (int i = 0; i < NX; ++i) if ((c.pmask >> i) & 1) rx[i] += c.wN * c.rnu[c.N * NX + i];
+    for (int i = 0; i < NX; ++i) if ((c.pmask >> i) & 1) rx[i] += c.wN * c.rnu[(size_t)i * c.NE + c.N];
   }
+  const double* gs = c.gs + k;
 #pragma unroll
   for (int a = 0; a < NU; ++a) {
-    double v = c.r[k * NV + NX + a];
-    const double* gt = cr + (L::CR_GT + a) * LDT;
+    double v = r[(NX + a) * np];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += gt[i] * rx[i];
+    for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += gs[(a * NX + i) * np] * rx[i];
     rs[a] = v;
   }
 }
@@ -1266,19 +1291,20 @@ template <int M> GDEV void ric_rhs_knot(const IpmCtx<M>& c, int k, double* rx, d
 // kap_k = Lam_k^-1 (rs + Bh_k' pit_k).
 template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NU = L::NU, LDT = L::LDT, LDU = L::LDU, NTU = L::NTU;
+  constexpr int NX = L::NX, NU = L::NU, NTU = L::NTU;
   const int N = c.N;
+  const size_t np = c.NP;
   double* const vp = sh_vp<M>(c);
   long long tc0 = g_clock();
   G_PAR_FOR(k, N) {
     double rx[NX], rs[NU];
     ric_rhs_knot<M>(c, k, rx, rs);
-    const double* kt = c.kt + (size_t)k * L::KTW;
+    const double* kt = c.kt + k;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double v = rx[i] - (k >= 1 ? c.psi[(size_t)(k - 1) * NX + i] : 0.0);
+      double v = rx[i] - (k >= 1 ? c.psi[i * np + k - 1] : 0.0);
 #pragma unroll
-      for (int a = 0; a < NU; ++a) v -= kt[i * LDU + a] * rs[a];
+      for (int a = 0; a < NU; ++a) v -= kt[(i * NU + a) * np] * rs[a];
       vp[k * NX + i] = v;
     }
   }
@@ -1290,25 +1316,24 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
     double rx[NX], rs[NU], Lc[NTU], x[NU];
     ric_rhs_knot<M>(c, k, rx, rs);
     if (k < N - 1) {
-      const double* cr = c.cr + (size_t)k * L::CRW;
+      const double* bs = c.bs + k;
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
-        const double* bt = cr + (L::CR_BT + a) * LDT;
         double v = rs[a];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += bt[i] * vp[(k + 1) * NX + i];
+        for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += bs[(a * NX + i) * np] * vp[(k + 1) * NX + i];
         rs[a] = v;
       }
     }
-    const double* lp = c.lp + (size_t)k * L::LPW;          // packed lower L^-1:  kap = L^-T (L^-1 rs)
+    const double* lp = c.lp + k;                           // packed lower L^-1:  kap = L^-T (L^-1 rs)
 #pragma unroll
-    for (int t = 0; t < NTU; ++t) Lc[t] = lp[t];
+    for (int t = 0; t < NTU; ++t) Lc[t] = lp[t * np];
     tri_lower_mv<NU>(Lc, rs, x);
 #pragma unroll
     for (int a = 0; a < NU; ++a) rs[a] = x[a];
     tri_lower_tmv<NU>(Lc, rs, x);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) c.kap[(size_t)k * LDU + a] = x[a];
+    for (int a = 0; a < NU; ++a) c.kap[a * np + k] = x[a];
   }
   G_SYNC();
   if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
@@ -1318,28 +1343,29 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
 template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
-  constexpr int NX = L::NX, NU = L::NU, NV = L::NV, NN = L::NN, LDT = L::LDT, LDU = L::LDU;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const int N = c.N;
+  const size_t np = c.NP, ne = c.NE;
   double* const dz = sh_dz<M>(c);
   const double* const vp = sh_vp<M>(c);
   long long tc0 = g_clock();
   G_PAR_FOR(k, N) {
     double kap[NU];
 #pragma unroll
-    for (int a = 0; a < NU; ++a) { kap[a] = c.kap[(size_t)k * LDU + a]; dz[k * NV + NX + a] = kap[a]; }
+    for (int a = 0; a < NU; ++a) { kap[a] = c.kap[a * np + k]; dz[k * NV + NX + a] = kap[a]; }
     if (k < N - 1) {
-      const double* cr = c.cr + (size_t)k * L::CRW;
+      const double* bs = c.bs + k;
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = c.ch[(size_t)k * NX + i];
+        double v = c.ch[i * np + k];
 #pragma unroll
-        for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += cr[(L::CR_BT + a) * LDT + i] * kap[a];
+        for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += bs[(a * NX + i) * np] * kap[a];
         dz[(k + 1) * NV + i] = v;
       }
     }
     if (k == 0) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) dz[i] = c.rnu[i];
+      for (int i = 0; i < NX; ++i) dz[i] = c.rnu[i * ne];
     }
   }
   G_SYNC();
@@ -1348,48 +1374,48 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
   tc0 = g_clock();
   G_PAR_FOR(k, N) {
     double s[NX], u[NU], x[NX];
-    const double* kt = c.kt + (size_t)k * L::KTW;
-    const double* cr = c.cr + (size_t)k * L::CRW;
+    const double* kt = c.kt + k;
+    const double* gs = c.gs + k;
 #pragma unroll
     for (int i = 0; i < NX; ++i) s[i] = dz[k * NV + i];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
       double v = dz[k * NV + NX + a];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v -= kt[i * LDU + a] * s[i];
+      for (int i = 0; i < NX; ++i) v -= kt[(i * NU + a) * np] * s[i];
       u[a] = v;
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       double v = s[i];
 #pragma unroll
-      for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += cr[(L::CR_GT + a) * LDT + i] * u[a];
+      for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += gs[(a * NX + i) * np] * u[a];
       x[i] = v;
     }
     if (want_nu && k >= 1) {
-      const double* pk = c.pk + (size_t)k * L::PKW;
-      const double* fi = c.fi + (size_t)k * NN;
+      const double* pk = c.pk + k;
+      const double* fi = c.fi + k;
       double w[NX], lam[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) w[i] = s[i] - c.ch[(size_t)(k - 1) * NX + i];
+      for (int i = 0; i < NX; ++i) w[i] = s[i] - c.ch[i * np + k - 1];
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         double v = -vp[k * NX + i];
 #pragma unroll
-        for (int j = 0; j < NX; ++j) v += pk[tri(i, j)] * w[j];
+        for (int j = 0; j < NX; ++j) v += pk[tri(i, j) * np] * w[j];
         lam[i] = v;
       }
 #pragma unroll
       for (int j = 0; j < NX; ++j) {
         double v = 0.0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) if (L::dsame(i, j)) v += fi[i * NX + j] * lam[i];
-        c.dnu[k * NX + j] = v;
+        for (int i = 0; i < NX; ++i) if (L::dsame(i, j)) v += fi[(i * NX + j) * np] * lam[i];
+        c.dnu[j * ne + k] = v;
       }
     }
     if (want_nu && k == N - 1) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) c.dnu[N * NX + i] = ((c.pmask >> i) & 1) ? c.wN * (x[i] - c.rnu[N * NX + i]) : 0.0;
+      for (int i = 0; i < NX; ++i) c.dnu[i * ne + N] = ((c.pmask >> i) & 1) ? c.wN * (x[i] - c.rnu[i * ne + N]) : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) dz[k * NV + i] = x[i];
@@ -1401,10 +1427,10 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
     // row 0 (x_0 = x_init): stationarity in x_0,  dnu_0 = rx_0 - Hx_0 dx_0 - E_1' dnu_1,  E_1 = I + h/2 A_0
     if (G_TID == 0) {
       double dx0[NX], hx[NX], e1[NX];
-      for (int i = 0; i < NX; ++i) { dx0[i] = dz[i]; e1[i] = c.dnu[NX + i]; }
+      for (int i = 0; i < NX; ++i) { dx0[i] = dz[i]; e1[i] = c.dnu[i * ne + 1]; }
       apply_Hx<M>(c, 0, dx0, hx);
-      for (int e = 0; e < L::ANZ; ++e) e1[T::a_col(e)] += c.hh * c.Ac[e] * c.dnu[NX + T::a_row(e)];
-      for (int i = 0; i < NX; ++i) c.dnu[i] = c.r[i] - hx[i] - e1[i];
+      for (int e = 0; e < L::ANZ; ++e) e1[T::a_col(e)] += c.hh * c.Ac[e * np] * c.dnu[T::a_row(e) * ne + 1];
+      for (int i = 0; i < NX; ++i) c.dnu[i * ne] = c.r[i * np] - hx[i] - e1[i];
     }
     G_SYNC();
   }
@@ -1413,16 +1439,17 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
 // ch_k = -F_{k+1}^-1 rho_{k+1}  (k = 0 .. N-2) for the equality residual in c.rnu
 template <int M> GDEV_NOINLINE void ric_dyn_residual(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
-  constexpr int NX = L::NX, NN = L::NN;
+  constexpr int NX = L::NX;
   const int N = c.N;
+  const size_t np = c.NP, ne = c.NE;
   G_PAR_FOR(it, (N - 1) * NX) {
-    const int k = it / NX, i = it - k * NX;
-    const double* fi = c.fi + (size_t)(k + 1) * NN + i * NX;
-    const double* rho = c.rnu + (size_t)(k + 1) * NX;
+    const int i = it / (N - 1), k = it - i * (N - 1);          // knot fastest: coalesced
+    const double* fi = c.fi + (size_t)(i * NX) * np + k + 1;
+    const double* rho = c.rnu + k + 1;
     double v = 0.0;
 #pragma unroll
-    for (int j = L::dlo(i); j < L::dhi(i); ++j) v -= fi[j] * rho[j];
-    c.ch[it] = v;
+    for (int j = L::dlo(i); j < L::dhi(i); ++j) v -= fi[j * np] * rho[j * ne];
+    c.ch[i * np + k] = v;
   }
   G_SYNC();
 }
@@ -1435,22 +1462,22 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
   using T = Traits<M>;
   constexpr int NX = L::NX, NV = L::NV;
   const int N = c.N;
+  const size_t np = c.NP;
   G_PAR_FOR(it, N * L::SP) {
-    if (it + G_NTHR < N * L::SP) g_prefetch_l1(c.sslot + (size_t)(it + G_NTHR) * SLOT_W);
-    const int k = it / L::SP, s = it - k * L::SP;
+    const int s = it / N, k = it - s * N;                    // knot fastest: the field rows of a slot are read coalesced
     const double* x = sh_z<M>(c) + k * NV;
-    double* st = c.sslot + (size_t)it * SLOT_W;
+    double* st = c.sslot + (size_t)s * SLOT_W * np + k;
     if (T::HAS_TR && s == L::S_TR) {
       double v = -c.dow, gdz = 0.0;
-      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.Xp[k * NX + i]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
-      fn(st, true, v, gdz);
+      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[i * np + k]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
+      fn(st, np, true, v, gdz);
     } else {
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
       if (!o.valid) continue;
       double gdz = 0.0;
       if (want_gdz) { const double* dv = sh_dz<M>(c) + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[a]; }
-      fn(st, o.has_t, o.c0, gdz);
+      fn(st, np, o.has_t, o.c0, gdz);
     }
   }
   if (c.bmask != 0) {
@@ -1458,7 +1485,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
       if (!((c.bmask >> (j >> 1)) & 1)) continue;
       const double* x = sh_z<M>(c) + (N - 1) * NV;
       const double gdz = ((j & 1) == 0 ? 1.0 : -1.0) * sh_dz<M>(c)[(N - 1) * NV + (j >> 1)];
-      fn(c.bslot + (size_t)j * SLOT_W, false, box_c0<M>(c, j, x), gdz);
+      fn(c.bslot + (size_t)j * SLOT_W, (size_t)1, false, box_c0<M>(c, j, x), gdz);
     }
   }
   if (T::WS > 0) {
@@ -1468,16 +1495,16 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     const double* zs = sh_z<M>(c);
     const double* dzs = sh_dz<M>(c);
     const int nact = c.nact;
+    const size_t pp = c.PP;
     for (int p = G_TID; p < nact; p += G_NTHR) {
-      if (p + G_NTHR < nact) { g_prefetch_l1(orow + (size_t)(p + G_NTHR) * OROW_W); g_prefetch_l1(ost + (size_t)(p + G_NTHR) * SLOT_W); }
-      const double* row = orow + (size_t)p * OROW_W;
-      const int k = (int)row[4];
+      const double* row = orow + p;
+      const int k = (int)row[4 * pp];
       const double* x = zs + k * NV;
       const double* dv = dzs + k * NV;
-      double v = row[3], gdz = 0.0;
+      double v = row[3 * pp], gdz = 0.0;
 #pragma unroll
-      for (int a = 0; a < WS; ++a) { v -= row[a] * x[a]; gdz -= row[a] * dv[a]; }
-      fn(ost + (size_t)p * SLOT_W, true, v, gdz);
+      for (int a = 0; a < WS; ++a) { const double ra = row[a * pp]; v -= ra * x[a]; gdz -= ra * dv[a]; }
+      fn(ost + p, pp, true, v, gdz);
     }
   }
 }
@@ -1487,10 +1514,10 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
 template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* out) {
   StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.c0 = 0.0; acc.c1 = 0.0; acc.c2 = 0.0; acc.np = 0.0;
   const double omega = c.omega;
-  for_each_row<M>(c, true, [&](double* st, bool has_t, double c0, double gdz) {
+  for_each_row<M>(c, true, [&](double* st, size_t ss, bool has_t, double c0, double gdz) {
     Pair q;
-    pair_eval(st, has_t, c0, omega, smu, phase, q);
-    pair_step(st, has_t, q, gdz, mode, ap, ad, acc);
+    pair_eval(st, ss, has_t, c0, omega, smu, phase, q);
+    pair_step(st, ss, has_t, q, gdz, mode, ap, ad, acc);
   });
   if (mode != 2) {
     out[0] = -block_max(-acc.amp, c.red);
@@ -1521,10 +1548,21 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
   const int N = c.N;
   // start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); multipliers 0
+  const size_t np = c.NP, ne = c.NE, pp = c.PP;
   G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; sh_z<M>(c)[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
-  G_PAR_FOR(it, (N + 1) * NX) c.nu[it] = 0.0;
-  // A_k on its sparsity pattern
-  G_PAR_FOR(it, N * ANZ) { const int k = it / ANZ, e = it - k * ANZ; c.Ac[it] = c.A[(size_t)k * NX * NX + T::a_row(e) * NX + T::a_col(e)]; }
+  G_PAR_FOR(it, NX * (int)ne) c.nu[it] = 0.0;
+  // field-major copies of the inputs the per-knot passes read every Newton iteration: Xp, A_k on its sparsity pattern, and the
+  // constant part of the equality residual  -x_init | h/2 (g_{j-1} + g_j) | -goal
+  G_PAR_FOR(it, N * NX) { const int i = it / N, k = it - i * N; c.xps[i * np + k] = c.Xp[k * NX + i]; }
+  G_PAR_FOR(it, N * ANZ) { const int e = it / N, k = it - e * N; c.Ac[e * np + k] = c.A[(size_t)k * NX * NX + T::a_row(e) * NX + T::a_col(e)]; }
+  G_PAR_FOR(it, (N + 1) * NX) {
+    const int i = it / (N + 1), j = it - i * (N + 1);
+    double v;
+    if (j == 0) v = -c.x_init[i];
+    else if (j == N) v = ((c.pmask >> i) & 1) ? -c.goal_lo[i] : 0.0;
+    else v = c.hh * (c.g[(j - 1) * NX + i] + c.g[j * NX + i]);
+    c.gsum[i * ne + j] = v;
+  }
   // obstacle rows inside the toggle distance, compacted knot by knot (astrobee_se3.jl:293)
   if (T::WS > 0) {
     G_PAR_FOR(k, N) {
@@ -1547,26 +1585,26 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
       for (int i = 0; i < c.n_obs; ++i) {
         const double* row = c.rows + ((size_t)k * c.n_obs + i) * 5;
         if (!(row[4] < c.toggle)) continue;
-        double* o = c.orow + (size_t)p * OROW_W;
+        double* o = c.orow + p;
         double v = row[3];
-        for (int a = 0; a < 3; ++a) { o[a] = row[a]; if (a < T::WS) v -= row[a] * x[a]; }
-        o[3] = row[3]; o[4] = (double)k;
-        slot_init(c.ost + (size_t)p * SLOT_W, true, true, v, c.omega, slack_start<M>(), slack_lam_split<M>());
+        for (int a = 0; a < 3; ++a) { o[a * pp] = row[a]; if (a < T::WS) v -= row[a] * x[a]; }
+        o[3 * pp] = row[3]; o[4 * pp] = (double)k;
+        slot_init(c.ost + p, pp, true, true, v, c.omega, slack_start<M>(), slack_lam_split<M>());
         ++p;
       }
     }
   }
   // special rows: slacks one unit inside
   G_PAR_FOR(it, N * L::SP) {
-    const int k = it / L::SP, s = it - k * L::SP;
+    const int s = it / N, k = it - s * N;
     const double* x = sh_z<M>(c) + k * NV;
-    double* st = c.sslot + (size_t)it * SLOT_W;
-    if (T::HAS_TR && s == L::S_TR) slot_init(st, true, true, tr_c0<M>(c, k, x), c.omega, slack_start<M>(), slack_lam_split<M>());
-    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, o.valid, o.has_t, o.c0, c.omega, slack_start<M>(), slack_lam_split<M>()); }
+    double* st = c.sslot + (size_t)s * SLOT_W * np + k;
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, true, -c.dow, c.omega, slack_start<M>(), slack_lam_split<M>());   // x = xp at the start
+    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega, slack_start<M>(), slack_lam_split<M>()); }
   }
   G_PAR_FOR(j, L::NBOX) {
     const bool valid = (c.bmask >> (j >> 1)) & 1;
-    slot_init(c.bslot + (size_t)j * SLOT_W, valid, false, valid ? box_c0<M>(c, j, sh_z<M>(c) + (N - 1) * NV) : 0.0, c.omega);
+    slot_init(c.bslot + (size_t)j * SLOT_W, 1, valid, false, valid ? box_c0<M>(c, j, sh_z<M>(c) + (N - 1) * NV) : 0.0, c.omega);
   }
   G_SYNC();
 }
@@ -1606,25 +1644,29 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
       dyn_B<M>(d.rp, Bm);
       for (int a = 0; a < NU; ++a) c.bv[a] = Bm[T::b_row(a) * NU + a];
     }
-    const size_t nz = L::rnd((size_t)N * NV), ne = L::rnd((size_t)(N + 1) * NX), no = c.n_obs, nn = (size_t)N;
-    double* q = scratch;
-    c.r = q; q += nz;
-    c.nu = q; q += ne; c.dnu = q; q += ne; c.rnu = q; q += ne;
-    c.Ac = q; q += L::rnd(nn * L::ANZ);
-    c.sslot = q; q += L::rnd(nn * L::SP * SLOT_W);
+    c.NP = L::np_of(N); c.NE = L::ne_of(N); c.PP = L::pp_of(N, c.n_obs);
+    const size_t np = c.NP, ne = c.NE, pp = c.PP, nn = (size_t)N;
+    double* q = scratch;                                         // same order and sizes as IpmLayout::scratch_doubles
+    c.r = q; q += np * NV;
+    c.nu = q; q += ne * NX; c.dnu = q; q += ne * NX; c.rnu = q; q += ne * NX;
+    c.gsum = q; q += ne * NX;
+    c.xps = q; q += np * NX;
+    c.Ac = q; q += np * L::ANZ;
+    c.sslot = q; q += np * L::SP * SLOT_W;
     c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
-    c.ost = q; q += L::rnd(nn * no * SLOT_W);
-    c.orow = q; q += L::rnd(nn * no * OROW_W);
-    c.kd = q; q += nn * L::KDW;
+    c.ost = q; q += pp * SLOT_W;
+    c.orow = q; q += pp * OROW_W;
+    c.kd = q; q += np * L::KDW;
+    c.fi = q; q += np * L::NN;
     c.cr = q; q += nn * L::CRW;
+    c.gs = q; q += np * L::GSW; c.bs = q; q += np * L::GSW;
     c.acl = q; q += nn * L::GT;
-    c.kt = q; q += nn * L::KTW;
-    c.lp = q; q += nn * L::LPW;
-    c.pk = q; q += nn * L::PKW;
-    c.psi = q; q += L::rnd(nn * NX);
-    c.ch = q; q += L::rnd(nn * NX);
-    c.kap = q; q += nn * L::LDU;
-    c.fi = q; q += nn * L::NN;                                   // last: N * NX * NX may be odd
+    c.kt = q; q += np * NX * NU;
+    c.lp = q; q += np * L::NTU;
+    c.pk = q; q += np * L::NTX;
+    c.psi = q; q += np * NX;
+    c.ch = q; q += np * NX;
+    c.kap = q; q += np * NU;
     c.z = smem; c.dz = c.z + L::rnd((size_t)N * NV);
     c.vp = c.dz + L::work_doubles(N);
     c.red = c.vp + L::rnd((size_t)(N + 1) * NX);
@@ -1712,7 +1754,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     {
       double* __restrict__ nu = c.nu;
       const double* __restrict__ dnu = c.dnu;
-      const int ne = (N + 1) * NX;
+      const int ne = c.NE * NX;                                  // (padding entries are zero and stay zero)
 #pragma unroll 4
       for (int it = G_TID; it < ne; it += G_NTHR) nu[it] += ad * dnu[it];
     }
@@ -1747,10 +1789,10 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   }
   {
     const double omega = c.omega;
-    for_each_row<M>(c, false, [&](double* st, bool has_t, double c0, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2]); });
+    for_each_row<M>(c, false, [&](double* st, size_t ss, bool has_t, double c0, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2 * ss]); });
   }
   // SCPS.dual (scp_gusto.jl:116, get_dual_jump): row 0 of Aeq is  x_0 = x_init  and the Lagrangian is f + nu'(Aeq z - b)
-  if (p.dual) G_PAR_FOR(i, NX) p.dual[(size_t)b * NX + i] = c.nu[i];
+  if (p.dual) G_PAR_FOR(i, NX) p.dual[(size_t)b * NX + i] = c.nu[(size_t)i * c.NE];
   obj = block_sum(obj, c.red);
   if (G_TID == 0) {
     info[0] = (double)status; info[1] = (double)it_done; info[2] = res; info[3] = mu; info[4] = obj;
