@@ -103,7 +103,9 @@ inline void g_mbar_wait(unsigned long long*, unsigned) {}
 inline void g_fence_proxy_async() {}
 inline void g_fence_proxy_async_global() {}
 inline void g_prefetch_l1(const void*) {}
+inline void g_prefetch_l2(const void*) {}
 #else
+__device__ __forceinline__ void g_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void g_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void g_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // generic-proxy GLOBAL writes that a later cp.async.bulk (async proxy) reads back need the unqualified cross-proxy fence

@@ -780,10 +780,23 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         const double t = v[i] + c.gsum[(size_t)i * c.NE + j];     // gsum: -x_init | h/2 (g_{j-1} + g_j) | -goal (setup)
+        v[i] = t;
         c.rnu[(size_t)i * c.NE + j] = -t;
         const double a = fabs(t);
         rpmax = a > rpmax ? a : rpmax;
         if (!(a == a)) rpmax = 1e300;
+      }
+      // ch_{j-1} = -F_j^-1 rho_j  (rho_j = rnu_j = -t): the affine term of the shifted-state recursion, by the thread that holds rho_j
+      if (j >= 1 && j < N) {
+        const double* fi = c.fi + j;
+        const size_t np = c.NP;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double s2 = 0.0;
+#pragma unroll
+          for (int m = 0; m < NX; ++m) if (L::dsame(i, m)) s2 += fi[(size_t)(i * NX + m) * np] * v[m];
+          c.ch[(size_t)i * np + j - 1] = s2;
+        }
       }
     }
     out->rz = block_max(S.rz, c.red);
@@ -1436,24 +1449,6 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
   }
   if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
 }
-// ch_k = -F_{k+1}^-1 rho_{k+1}  (k = 0 .. N-2) for the equality residual in c.rnu
-template <int M> GDEV_NOINLINE void ric_dyn_residual(const IpmCtx<M>& c) {
-  using L = IpmLayout<M>;
-  constexpr int NX = L::NX;
-  const int N = c.N;
-  const size_t np = c.NP, ne = c.NE;
-  G_PAR_FOR(it, (N - 1) * NX) {
-    const int i = it / (N - 1), k = it - i * (N - 1);          // knot fastest: coalesced
-    const double* fi = c.fi + (size_t)(i * NX) * np + k + 1;
-    const double* rho = c.rnu + k + 1;
-    double v = 0.0;
-#pragma unroll
-    for (int j = L::dlo(i); j < L::dhi(i); ++j) v -= fi[j * np] * rho[j * ne];
-    c.ch[i * np + k] = v;
-  }
-  G_SYNC();
-}
-
 // --------------------------------------------------------------------------------------------- slot passes
 // Flat pass over every live row.  FN(st, has_t, c0, gdz) is called once per row; `want_gdz` says whether the
 // directional derivative gv.dz is needed.
@@ -1690,6 +1685,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   const long long cyc_setup = g_clock() - tc0;
   double best = 1e300;
   int stall = 0;
+  bool broke = false;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
     G_CTA_RESYNC();
     ++it_done;
@@ -1716,10 +1712,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     } else if (++stall >= 8 && best <= 1e3 * prm.tol) break;
     // predictor: factorisation sweep with the backward vector pass fused, then the forward pass
     tc0 = g_clock();
-    ric_dyn_residual<M>(c);
     const bool fac_ok = riccati_factor<M>(c);
     cyc_fac += g_clock() - tc0;
-    if (!fac_ok) { status = IPM_NUMERICAL; break; }             // non-positive pivot of a Lam_k
+    if (!fac_ok) { broke = true; break; }                       // non-positive pivot of a Lam_k: see below
     tc0 = g_clock();
     ric_forward<M>(c, false);
     cyc_sol += g_clock() - tc0;
@@ -1749,7 +1744,16 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     if (mu < 1.0) { tau = 1.0 - mu; tau = tau > 0.995 ? tau : 0.995; tau = tau < 0.999999 ? tau : 0.999999; }
     double ap = tau * am[0], ad = tau * am[1];
     ap = ap < 1.0 ? ap : 1.0; ad = ad < 1.0 ? ad : 1.0;
+#ifdef GUSTO_HOSTSIM
+    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("        a_aff=%.3g sigma=%.3g smu=%.3g ap=%.3g ad=%.3g\n", a_aff, sigma, smu, ap, ad);
+#endif
     slot_steps<M>(c, 1, smu, 2, ap, ad, am);
+    // Safeguard against cycling: plain Mehrotra steps can jam when a few complementarity pairs sit far below the central path
+    // (astrobeeSE3manifold instance 347 of the B = 1024 batch: BoxGoal rows 2e-4 apart, steps alternate between a blocked
+    // dual and a blocked primal step, the residual wanders at 2e-3 for 50 iterations).  After two iterations without
+    // improvement and a short step, the pairs are pulled back to 1e-2 mu instead of 1e-4 mu for the next iteration; solves
+    // that improve every iteration never get here.
+    if (stall >= 2 && (ap < ad ? ap : ad) < 0.5) { if (G_TID == 0) c.floor_ *= 100.0; G_SYNC(); }
     G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
     {
       double* __restrict__ nu = c.nu;
@@ -1763,7 +1767,12 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   }
   // A stalled solve is accepted only when its best residual is both within 1e3*tol and far below the SCP's own soft-row
   // threshold eps (GuSTO's accept test compares raw row values with eps, scp_gusto.jl:318-327), and is labelled as such.
+  // The same holds for a factorisation that breaks down (a Lam_k loses positive definiteness in floating point) once the iterate
+  // is that close: at omega = 1e6 and mu = 1e-9 the active soft rows put lam / s ~ 1e15 into Hx, and P_k = W - Y'Y cancels to
+  // O(1) errors (freeflyerSE2 instance 10 of the L3 batch, Newton iteration 19, residual 1.6e-7) -- the attainable precision is
+  // reached.  A breakdown anywhere else is a NUMERICAL failure (info[3] = -1 tells it apart from a NaN).
   const bool use_best = status == IPM_ITERATION_LIMIT && best <= 1e3 * prm.tol && best <= 0.1 * c.eps;
+  if (broke && !use_best) { status = IPM_NUMERICAL; mu = -1.0; }
   if (use_best) {
     status = IPM_ALMOST_OPTIMAL;
     res = best;
