@@ -3,7 +3,7 @@
 The directory name (`gusto.jl_b200`) is not a valid Python identifier; load it with
 `__graft_entry__.load_package()` which registers it as the module `gusto_b200`.
 """
-from . import models, problems  # noqa: F401
+from . import models, problems, trajio  # noqa: F401
 
 
 def engine():

@@ -198,6 +198,8 @@ struct gusto_ctx {
   double *d_dual = nullptr, *d_Xs = nullptr, *d_Us = nullptr, *d_Ps = nullptr, *d_p0 = nullptr, *d_xgoal = nullptr, *d_shoot = nullptr;
   uint8_t* d_accept = nullptr;
   uint8_t* d_active = nullptr;
+  double *d_check = nullptr, *d_interp = nullptr;     // outputs of gusto_check_trajectory / gusto_interpolate_trajectory
+  size_t interp_cap = 0;                              // doubles allocated behind d_interp
   size_t scratch_stride = 0;
   int ipm_smem = 0;          // dynamic shared memory of ONE instance group (bytes)
   int ipm_pack_max = 1;      // groups per CTA allowed by shared memory / registers
@@ -342,9 +344,10 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   {
     double* tmp = new double[2 * B];
     for (size_t i = 0; i < B; ++i) { tmp[i] = cfg->scp_params[SP_OMEGA0]; tmp[B + i] = cfg->scp_params[SP_DELTA0]; }
-    cudaMemcpy(p.omega, tmp, B * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(p.delta, tmp + B, B * sizeof(double), cudaMemcpyHostToDevice);
+    const bool copied = cudaMemcpy(p.omega, tmp, B * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+                        cudaMemcpy(p.delta, tmp + B, B * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     delete[] tmp;
+    if (!copied) { ctx->err = std::string("gusto_create: initial penalties: ") + cudaGetErrorString(cudaGetLastError()); return fail(GUSTO_E_CUDA); }
   }
   ctx->ipm_smem = ipm_smem_doubles_of(cfg->model_id, (int)N) * (int)sizeof(double);
   cudaError_t e = cudaSuccess;
@@ -379,7 +382,7 @@ int32_t gusto_destroy(gusto_ctx* ctx) {
   BatchPtrs& p = ctx->p;
   void* ptrs[] = {ctx->ddesc, ctx->d_tf, ctx->d_xinit, ctx->d_glo, ctx->d_ghi, p.Xp, p.Up, p.Xn, p.Un, p.omega, p.delta,
                   ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active,
-                  ctx->d_dual, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_p0, ctx->d_xgoal, ctx->d_shoot};
+                  ctx->d_dual, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_p0, ctx->d_xgoal, ctx->d_shoot, ctx->d_check, ctx->d_interp};
   for (void* q : ptrs) if (q) cudaFree(q);
   scp_release(ctx);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -612,8 +615,8 @@ int32_t gusto_check_trajectory(gusto_ctx* ctx, double* out) {
   NEED(out);
   CK(cudaSetDevice(ctx->cfg.device));
   const int grid = ctx->cfg.B;
-  double* d_out = nullptr;
-  CK(cudaMalloc((void**)&d_out, (size_t)grid * CHECK_NOUT * sizeof(double)));
+  if (!ctx->d_check) CK(cudaMalloc((void**)&ctx->d_check, (size_t)grid * CHECK_NOUT * sizeof(double)));
+  double* d_out = ctx->d_check;
   switch (ctx->cfg.model_id) {
     case DUBINS: check_kernel<DUBINS><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
     case FREEFLYER_SE2: check_kernel<FREEFLYER_SE2><<<grid, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, d_out); break;
@@ -623,7 +626,6 @@ int32_t gusto_check_trajectory(gusto_ctx* ctx, double* out) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)grid * CHECK_NOUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
   if (e != cudaSuccess) { ctx->err = std::string("gusto_check_trajectory: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
   ctx->launches++;
   return GUSTO_OK;
@@ -635,11 +637,14 @@ int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xful
   CK(cudaSetDevice(ctx->cfg.device));
   const size_t B = ctx->cfg.B, nseg = ctx->cfg.N - 1, nf = (size_t)nstep * nseg;
   const size_t nX = B * (nf + 1) * ctx->nx, nU = B * nf * ctx->nu;
-  double *dX = nullptr, *dU = nullptr;
-  if (cudaMalloc((void**)&dX, nX * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&dU, nU * sizeof(double)) != cudaSuccess) {
-    if (dX) cudaFree(dX);
-    ctx->err = "gusto_interpolate_trajectory: cudaMalloc failed"; return GUSTO_E_ALLOC;
+  if (ctx->interp_cap < nX + nU) {                     // grown on demand, kept for the next call
+    if (ctx->d_interp) { cudaFree(ctx->d_interp); ctx->d_interp = nullptr; ctx->interp_cap = 0; }
+    if (cudaMalloc((void**)&ctx->d_interp, (nX + nU) * sizeof(double)) != cudaSuccess) {
+      ctx->d_interp = nullptr; ctx->err = "gusto_interpolate_trajectory: cudaMalloc failed"; return GUSTO_E_ALLOC;
+    }
+    ctx->interp_cap = nX + nU;
   }
+  double *dX = ctx->d_interp, *dU = ctx->d_interp + nX;
   const int total = (int)(B * nseg), grid = (total + 127) / 128;
   switch (ctx->cfg.model_id) {
     case DUBINS: interp_kernel<DUBINS><<<grid, 128, 0, ctx->stream>>>(ctx->ddesc, ctx->p, nstep, dX, dU); break;
@@ -651,7 +656,6 @@ int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xful
   if (e == cudaSuccess) e = cudaMemcpyAsync(Xfull, dX, nX * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(Ufull, dU, nU * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(dX); cudaFree(dU);
   if (e != cudaSuccess) { ctx->err = std::string("gusto_interpolate_trajectory: ") + cudaGetErrorString(e); return GUSTO_E_CUDA; }
   ctx->launches++;
   return GUSTO_OK;
@@ -665,6 +669,37 @@ int32_t gusto_get_duals(gusto_ctx* ctx, double* dual) {
   return GUSTO_OK;
 }
 
+// buffers of the shooting refinement, all or nothing: a later call must never find d_Xs set and the others missing
+static int32_t shoot_alloc(gusto_ctx* ctx) {
+  if (ctx->d_Xs) return GUSTO_OK;
+  const size_t B = ctx->cfg.B, N = ctx->cfg.N, nx = ctx->nx, nu = ctx->nu;
+  const bool ok = cudaMalloc((void**)&ctx->d_Xs, B * N * nx * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->d_Us, B * N * nu * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->d_Ps, B * N * nx * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->d_p0, B * nx * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->d_xgoal, B * nx * sizeof(double)) == cudaSuccess &&
+                  cudaMalloc((void**)&ctx->d_shoot, B * SHOOT_NOUT * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    double** bufs[] = {&ctx->d_Xs, &ctx->d_Us, &ctx->d_Ps, &ctx->d_p0, &ctx->d_xgoal, &ctx->d_shoot};
+    for (double** q : bufs) { if (*q) cudaFree(*q); *q = nullptr; }
+    ctx->err = "gusto_shoot: cudaMalloc failed";
+    return GUSTO_E_ALLOC;
+  }
+  return GUSTO_OK;
+}
+
+int32_t gusto_set_shooting_trajectory(gusto_ctx* ctx, const double* X, const double* U) {
+  NEED(X && U);
+  CK(cudaSetDevice(ctx->cfg.device));
+  int32_t rc = shoot_alloc(ctx);
+  if (rc) return rc;
+  const size_t B = ctx->cfg.B, N = ctx->cfg.N;
+  H2D(ctx->d_Xs, X, B * N * ctx->nx); H2D(ctx->d_Us, U, B * N * ctx->nu);
+  CK(cudaMemsetAsync(ctx->d_Ps, 0, B * N * ctx->nx * sizeof(double), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
 int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int32_t nsub, int32_t max_iter, double ftol, double* out) {
   NEED(out);
   const int model = ctx->cfg.model_id;
@@ -674,14 +709,9 @@ int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int3
   if (nsub < 1 || max_iter < 0 || !(ftol > 0.0)) { ctx->err = "gusto_shoot: need nsub >= 1, max_iter >= 0, ftol > 0"; return GUSTO_E_ARG; }
   CK(cudaSetDevice(ctx->cfg.device));
   const size_t B = ctx->cfg.B, N = ctx->cfg.N, nx = ctx->nx, nu = ctx->nu;
-  if (!ctx->d_Xs) {    // SS.traj starts as the trajectory held by the context at the first attempt (traj_opt.jl:18)
-    bool ok = cudaMalloc((void**)&ctx->d_Xs, B * N * nx * sizeof(double)) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_Us, B * N * nu * sizeof(double)) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_Ps, B * N * nx * sizeof(double)) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_p0, B * nx * sizeof(double)) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_xgoal, B * nx * sizeof(double)) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_shoot, B * SHOOT_NOUT * sizeof(double)) == cudaSuccess;
-    if (!ok) { ctx->err = "gusto_shoot: cudaMalloc failed"; return GUSTO_E_ALLOC; }
+  if (!ctx->d_Xs) {    // SS.traj not seeded by gusto_set_shooting_trajectory: it starts as the trajectory held by the context
+    int32_t rc = shoot_alloc(ctx);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_Xs, ctx->p.Xp, B * N * nx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_Us, ctx->p.Up, B * N * nu * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_Ps, 0, B * N * nx * sizeof(double), ctx->stream));

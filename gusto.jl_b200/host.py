@@ -97,6 +97,7 @@ def load_library(path=LIB_PATH):
     lib.gusto_get_duals.argtypes = [vp, _DP]
     lib.gusto_shoot.argtypes = [vp, _DP, _DP, i32, i32, ctypes.c_double, _DP]
     lib.gusto_get_shooting_trajectory.argtypes = [vp, _DP, _DP, _DP]
+    lib.gusto_set_shooting_trajectory.argtypes = [vp, _DP, _DP]
     lib.gusto_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.gusto_timer_start.argtypes = [vp]
     lib.gusto_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
@@ -119,7 +120,7 @@ def load_library(path=LIB_PATH):
                  "gusto_iterate", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
                  "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop", "gusto_check_trajectory",
                  "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory",
-                 "gusto_scp_begin", "gusto_scp_run", "gusto_scp_get", "gusto_comm_unique_id", "gusto_comm_init",
+                 "gusto_set_shooting_trajectory", "gusto_scp_begin", "gusto_scp_run", "gusto_scp_get", "gusto_comm_unique_id", "gusto_comm_init",
                  "gusto_allgather_status"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -259,6 +260,11 @@ class Engine:
         x_goal = None if x_goal is None else np.ascontiguousarray(x_goal, dtype=np.float64)
         self._chk(self.lib.gusto_shoot(self._ctx, _dp(p0), _dp(x_goal), int(nsub), int(max_iter), float(ftol), _dp(out)))
         return out
+
+    def set_shooting_trajectory(self, X, U):
+        """Seed SS.traj (the reference starts it as deepcopy(traj_init), traj_opt.jl:16)."""
+        self._chk(self.lib.gusto_set_shooting_trajectory(self._ctx, _dp(np.ascontiguousarray(X, dtype=np.float64)),
+                                                         _dp(np.ascontiguousarray(U, dtype=np.float64))))
 
     def get_shooting_trajectory(self):
         X = np.empty((self.B, self.N, self.nx)); U = np.empty((self.B, self.N, self.nu)); P = np.empty((self.B, self.N, self.nx))
@@ -510,6 +516,9 @@ def solve_scp_shooting_batch(engine: Engine, X0=None, U0=None, max_iter=30, nsub
     B = bp.B
     thr = bp.model.scp_params[M.SP_CONVTHR]
     # solve_method!(SCPS, SCPP, solver, 1): the batched loop below is solve_gusto_batch unrolled one iteration at a time
+    if X0 is None:
+        X0, U0 = bp.init_traj_straightline()
+    engine.set_shooting_trajectory(X0, U0)                               # TOS.SS = ShootingSolution(SP, deepcopy(traj_init))
     st = _ScpStepper(engine, X0, U0)
     st.step(np.ones(B, bool))
     S = st.S

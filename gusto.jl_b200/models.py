@@ -144,11 +144,17 @@ def _f32(v):
     return np.asarray(v, dtype=np.float32).astype(np.float64)
 
 
-def ISSCorner(add_obstacles=False):
-    """environment/iss_corner.jl:11-39 (+ add_obstacles! :52-63).  Geometry comes from data/iss_corner.json,
-    extracted from the reference's iss_corner.mat by tools/extract_iss_corner.py (float32-rounded, quirk q7)."""
-    with open(os.path.join(_DATA, "iss_corner.json")) as f:
-        d = json.load(f)
+def ISSCorner(add_obstacles=False, mat_path=None):
+    """environment/iss_corner.jl:11-39 (+ add_obstacles! :52-63).  With `mat_path` (or $GUSTO_ISS_CORNER_MAT) the geometry is read
+    at run time from the reference's own src/environment/iss_corner.mat, as ISSCorner{T}() does with matread; otherwise from the
+    packaged data/iss_corner.json, the same numbers extracted once by tools/extract_iss_corner.py (float32-rounded, quirk q7)."""
+    mat_path = mat_path or os.environ.get("GUSTO_ISS_CORNER_MAT")
+    if mat_path:
+        from .trajio import load_iss_corner_mat
+        d = load_iss_corner_mat(mat_path)
+    else:
+        with open(os.path.join(_DATA, "iss_corner.json")) as f:
+            d = json.load(f)
     env = Environment("ISSCorner",
                       keepin_zones=[(np.array(z["lo"]), np.array(z["hi"])) for z in d["keepin_zones"]],
                       keepout_zones=[(np.array(z["lo"]), np.array(z["hi"])) for z in d["keepout_zones"]])

@@ -14,7 +14,8 @@
  *                                 convex_ineq_satisfied_gusto_jump (:121), trust_region_ratio_gusto (:124),
  *                                 cost_true (:146), JuMP.objective_value (:116)
  *     gusto_accept             <- copy!(SCPS.traj, new_traj) (:147) and the Delta/omega pushes (:125-145,156)
- * The trust-region update and convergence test themselves (:119-174) stay in the host language.
+ * The trust-region update and convergence test themselves (:119-174) stay in the host language -- or, for a caller that wants a
+ * whole solve without a host round trip per iteration, run in the library's own update kernel (gusto_scp_run below; same table).
  *
  * Conventions
  *   - every function returns 0 on success, <0 on error (GUSTO_E_*); it never throws.  gusto_last_error() returns a
@@ -41,8 +42,11 @@ enum { GUSTO_DUBINS = 0, GUSTO_FREEFLYER_SE2 = 1, GUSTO_ASTROBEE_SE3 = 2, GUSTO_
 enum { GUSTO_OBS_BOX = 0, GUSTO_OBS_SPHERE = 1 };
 /* goal_type per state coordinate: none / PointGoal (equality) / BoxGoal (inequality)  (src/goals.jl) */
 enum { GUSTO_GOAL_FREE = 0, GUSTO_GOAL_POINT = 1, GUSTO_GOAL_BOX = 2 };
-/* per-instance convex-solver status (MOI-like): OPTIMAL / ITERATION_LIMIT / NUMERICAL_ERROR */
-enum { GUSTO_SOLVER_OPTIMAL = 0, GUSTO_SOLVER_ITERATION_LIMIT = 1, GUSTO_SOLVER_NUMERICAL = 2 };
+/* per-instance convex-solver status (MOI-like): OPTIMAL / ITERATION_LIMIT / NUMERICAL_ERROR / ALMOST_OPTIMAL (the solve
+ * stalled or broke down within 1e3 * tol of the tolerance and below 0.1 * eps of the SCP's own soft-row threshold and answers
+ * with its best iterate: the MOI.ALMOST_LOCALLY_SOLVED the reference accepts next to OPTIMAL, scp_gusto.jl:107).  For a
+ * NUMERICAL status info[3] = -1 marks a factorisation breakdown (otherwise a NaN / Inf appeared). */
+enum { GUSTO_SOLVER_OPTIMAL = 0, GUSTO_SOLVER_ITERATION_LIMIT = 1, GUSTO_SOLVER_NUMERICAL = 2, GUSTO_SOLVER_ALMOST_OPTIMAL = 3 };
 enum {
   GUSTO_OK = 0, GUSTO_E_ARG = -1, GUSTO_E_CUDA = -2, GUSTO_E_ALLOC = -3, GUSTO_E_STATE = -4, GUSTO_E_NODEVICE = -5
 };
@@ -65,11 +69,10 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal                                                                */
   /* convex-solver controls (0 selects the default) */
   int32_t ipm_max_iter;    /* default 60   */
-  int32_t ipm_nref;        /* refinement steps of the corrector solve; default 1 (as the oracle) for the models with a
-                              state trust region, 2 for dubins / astrobeeSE3manifold */
+  int32_t ipm_nref;        /* accepted and ignored since round 2 (the Riccati solve needs no iterative refinement) */
   double ipm_tol;          /* default 1e-8 */
-  double ipm_delta_p;      /* default 1e-6 */
-  double ipm_delta_d;      /* default 1e-10 */
+  double ipm_delta_p;      /* accepted and ignored since round 2 (no primal regularisation) */
+  double ipm_delta_d;      /* accepted and ignored since round 2 (PointGoal rows: penalty 1e8 + 1e4 omega, csrc/ipm.cuh) */
 } gusto_config;
 
 /* Create a context for a batch of B instances sharing robot / model / environment.
@@ -138,12 +141,14 @@ int32_t gusto_interpolate_trajectory(gusto_ctx* ctx, int32_t nstep, double* Xful
  * out[B*GUSTO_SHOOT_NOUT] = { status (0 :Optimal, 1 :Diverged), LM iterations, |x_goal - x(tf)|_inf, J_true (cost_true of the
  * new trajectory), convergence_metric(new, SS.traj) (traj_opt.jl:74-85), final damping, 0, 0 }; J_true and the metric are NaN
  * for a diverged attempt (shooting.jl:16-22,41-47).  A converged attempt replaces the shooting trajectory SS.traj kept on
- * the device (initially the context's trajectory at the first call); gusto_get_shooting_trajectory downloads it
- * (X[B*N*n_x], U[B*N*n_u] = get_control, costates P[B*N*n_x]; any pointer may be NULL). */
+ * the device; gusto_get_shooting_trajectory downloads it (X[B*N*n_x], U[B*N*n_u] = get_control, costates P[B*N*n_x]; any
+ * pointer may be NULL).  gusto_set_shooting_trajectory seeds SS.traj (the reference: ShootingSolution(SP, deepcopy(traj_init)),
+ * traj_opt.jl:16); without it the first gusto_shoot seeds SS.traj with the context's accepted trajectory at that moment. */
 #define GUSTO_SHOOT_NOUT 8
 int32_t gusto_get_duals(gusto_ctx* ctx, double* dual);
 int32_t gusto_shoot(gusto_ctx* ctx, const double* p0, const double* x_goal, int32_t nsub, int32_t max_iter, double ftol, double* out);
 int32_t gusto_get_shooting_trajectory(gusto_ctx* ctx, double* X, double* U, double* P);
+int32_t gusto_set_shooting_trajectory(gusto_ctx* ctx, const double* X, const double* U);
 
 /* Timing of the last call of each kernel on this context, in milliseconds (CUDA events on the context's stream):
  * ms[0] linearize, ms[1] solve, ms[2] evaluate, ms[3] accept. */
