@@ -10,13 +10,14 @@
 # SCPSolution / SCPParam_GuSTO histories (types.jl:150-173, scp_gusto.jl:4-24).  The outer trust-region update and
 # convergence test (scp_gusto.jl:119-174) run here in Julia; linearization, the convex subproblem and the evaluation
 # scalars run in libgusto_b200.so through `ccall` (include/gusto_b200.h).  `solve_SCP_batch!` drives B independent
-# problems that share robot / model / environment through one context.
+# problems that share robot / model / environment through one context with the same Julia loop; `solve_SCP_batch_device!`
+# hands the whole outer loop to the library (gusto_scp_run) and is the multi-GPU entry point (one process per GPU).
 #
 # NOTE: Julia is not installed in the build or GPU containers of this project, so this file has been reviewed against
 # include/gusto_b200.h and gusto.jl_b200/host.py (which implements the identical loop and IS tested) but never executed.
 module GuSTOB200
 
-export solve_gusto_b200!, solve_SCP_batch!, GustoContext
+export solve_gusto_b200!, solve_SCP_batch!, solve_SCP_batch_device!, solve_shooting_b200!, comm_unique_id, GustoContext
 
 const LIB = get(ENV, "GUSTO_B200_LIB", joinpath(@__DIR__, "..", "libgusto_b200.so"))
 
@@ -107,8 +108,6 @@ function obstacle_table(env, model)
   return kinds, a, b
 end
 
-const NARROW_BOX_TOL = 1e-3
-
 # Final-time goals -> per-coordinate (type, lo, hi)   (goals.jl; registries e.g. astrobee_se3.jl:339-345)
 function flatten_goals(goal_set, x_dim, tf_guess)
   gtype = zeros(Int32, 16); lo = zeros(x_dim); hi = zeros(x_dim)
@@ -121,15 +120,11 @@ function flatten_goals(goal_set, x_dim, tf_guess)
       gtype[ind] .= GOAL_BOX; lo[ind] = goal.params.lower_bound; hi[ind] = goal.params.upper_bound
     end
   end
-  # presolve (host.py::presolve_goals): a BoxGoal coordinate narrower than NARROW_BOX_TOL is handed to the solver as a
-  # PointGoal at its centre (the astrobeeSE3manifold notebook's BoxGoal(q +- 1e-4) moves by <= 1e-4)
-  for i in 1:x_dim
-    if gtype[i] == GOAL_BOX && hi[i] - lo[i] < NARROW_BOX_TOL
-      gtype[i] = GOAL_POINT; lo[i] = hi[i] = 0.5 * (lo[i] + hi[i])
-    end
-  end
+  # BoxGoal rows go to the solver as they are (csbci_goal_constraints, dynamics.jl:37-42): no presolve since round 2
   return gtype, lo, hi
 end
+
+solver_status_symbol(s) = s == 0 ? :OPTIMAL : s == 1 ? :ITERATION_LIMIT : s == 3 ? :ALMOST_OPTIMAL : :NUMERICAL_ERROR
 
 scp_params(alg, param) = Float64[alg.Δ0, alg.ω0, alg.ω_max, alg.ε, alg.ρ0, alg.ρ1, alg.β_succ, alg.β_fail, alg.γ_fail,
                                  param.convergence_threshold]
@@ -180,6 +175,33 @@ function shoot!(ctx, p0, x_goal, out; nsub::Integer=4, max_iter::Integer=100, ft
 end
 get_shooting_trajectory!(ctx, X, U, P) = GC.@preserve X U P check(ctx, ccall((:gusto_get_shooting_trajectory, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, X, U, P))
+# device-resident outer loop and the status all-gather (include/gusto_b200.h)
+const HIST_W = 12
+scp_begin!(ctx, X, U, force::Bool) = GC.@preserve X U check(ctx, ccall((:gusto_scp_begin, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), ctx.ptr, X, U, Int32(force)))
+function scp_run!(ctx, max_iter::Integer)
+  n = Ref{Int32}(0); u = Ref{Int32}(0)
+  check(ctx, ccall((:gusto_scp_run, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}), ctx.ptr, Int32(max_iter), n, u))
+  return Int(n[]), Int(u[])
+end
+scp_get!(ctx, iterations::Vector{Int32}, converged::Vector{UInt8}, successful::Vector{UInt8}, hist::Array{Float64,3}) =
+  GC.@preserve iterations converged successful hist check(ctx, ccall((:gusto_scp_get, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Int32}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Float64}, Int32, Ptr{Int32}), ctx.ptr, iterations, converged, successful, hist,
+    Int32(size(hist, 3)), Ptr{Int32}(C_NULL)))
+function comm_unique_id()
+  id = zeros(UInt8, 128)
+  rc = ccall((:gusto_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id)
+  rc == 0 || error("gusto_comm_unique_id failed ($rc): " * unsafe_string(ccall((:gusto_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+  return id
+end
+comm_init!(ctx, rank::Integer, nranks::Integer, id::Vector{UInt8}) = GC.@preserve id check(ctx, ccall((:gusto_comm_init, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx.ptr, Int32(rank), Int32(nranks), id))
+function allgather_status!(ctx, done::Vector{UInt8})
+  n = Ref{Int32}(0)
+  GC.@preserve done check(ctx, ccall((:gusto_allgather_status, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}, Ref{Int32}),
+    ctx.ptr, done, Ptr{UInt8}(C_NULL), n))
+  return Int(n[])
+end
 accept!(ctx, acc::Vector{UInt8}, ω, Δ) = GC.@preserve acc ω Δ check(ctx, ccall((:gusto_accept, LIB), Int32,
     (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, acc, ω, Δ))
 
@@ -195,7 +217,7 @@ success, replaces `SS.traj`.  DubinsCar and AstrobeeSE3Manifold only (the models
 function solve_shooting_b200!(SS, SP; device::Int=0, nsub::Int=4)
   model, robot, env = SP.PD.model, SP.PD.robot, SP.PD.env
   x_dim, u_dim, N = model.x_dim, model.u_dim, SP.N
-  gtype = fill(GOAL_POINT, x_dim)
+  gtype = zeros(Int32, 16); gtype[1:x_dim] .= GOAL_POINT             # goal_type::NTuple{16,Int32}: padded like flatten_goals
   ctx = GustoContext(robot, model, env, N, 1, gtype, Main.SCPParam_GuSTO(model), (convergence_threshold = 0.0,); device=device)   # SCP parameters unused by K7
   xg = Float64.(SP.x_goal)
   set_problems!(ctx, Float64.(SP.PD.x_init), xg, xg, Float64[SP.tf])
@@ -209,7 +231,7 @@ function solve_shooting_b200!(SS, SP; device::Int=0, nsub::Int=4)
     get_shooting_trajectory!(ctx, X, U, P)
     push!(SS.prob_status, :Optimal); push!(SS.J_true, out[4]); push!(SS.convergence_measure, out[5])
     push!(SS.iter_elapsed_times, iter_elapsed_time)
-    SS.traj.X = X; SS.traj.U = U; SS.traj.Tf = SP.tf; SS.traj.dt = SP.tf/(N-1)
+    SS.traj.X = X; SS.traj.U = U; SS.traj.Tf = SP.tf; SS.traj.dt = SP.tf/(N-1)   # fresh arrays: what copy!(::Trajectory, ::Trajectory) does (types.jl:247-252)
   else
     push!(SS.prob_status, :Diverged); push!(SS.J_true, NaN); push!(SS.convergence_measure, NaN)
     push!(SS.iter_elapsed_times, iter_elapsed_time)
@@ -251,10 +273,10 @@ function solve_gusto_b200!(SCPS, SCPP, solver="B200", max_iter=30, force=false; 
   while SCPS.iterations < iter_cap
     time_start = time_ns()
     iterate!(ctx, out, info)                                               # K1+K2, K3, K4
-    push!(SCPS.solver_status, info[1] == 0 ? :OPTIMAL : (info[1] == 1 ? :ITERATION_LIMIT : :NUMERICAL_ERROR))
-    if info[1] != 0
+    push!(SCPS.solver_status, solver_status_symbol(info[1]))
+    if !(info[1] == 0 || info[1] == 3)                                     # :107-111 (OPTIMAL / ALMOST_OPTIMAL continue)
       push!(SCPS.iter_elapsed_times, (time_ns() - time_start)/10^9)
-      return
+      break                                                                # SCPS.traj = last accepted iterate, copied below
     end
     conv, tr_ok, ineq_ok, ρ, J_new, J_full = out[1], out[2] > 0.5, out[3] > 0.5, out[4], out[5], info[5]
     push!(SCPS.convergence_measure, conv); push!(SCPS.J_full, J_full)
@@ -299,6 +321,9 @@ function solve_gusto_b200!(SCPS, SCPP, solver="B200", max_iter=30, force=false; 
       force ? continue : break
     end
   end
+  # every exit path (converged, iteration cap, omega_max, solver failure) leaves the last ACCEPTED iterate in SCPS.traj, as the
+  # reference does by copying on every accepted iteration (:147); X, U are fresh arrays, which is what copy!(::Trajectory,
+  # ::Trajectory) assigns (types.jl:247-252: a.X = deepcopy(b.X))
   get_trajectory!(ctx, X, U)
   SCPS.traj.X = X; SCPS.traj.U = U
   SCPS.dual = zeros(x_dim); get_duals!(ctx, SCPS.dual)     # -JuMP.dual of the init constraints (:116, get_dual_jump): p0 of the shooting refinement
@@ -338,7 +363,7 @@ function solve_SCP_batch!(TOPs::Vector, init_method; max_iter::Int=30, force::Bo
     acc = zeros(UInt8, B)
     for b in 1:B
       active[b] || continue
-      if info[1, b] != 0; active[b] = false; continue; end            # :107-111
+      if !(info[1, b] == 0 || info[1, b] == 3); active[b] = false; continue; end            # :107-111
       conv, tr_ok, ineq_ok, ρ = out[1, b], out[2, b] > 0.5, out[3, b] > 0.5, out[4, b]
       accepted = false
       if tr_ok
@@ -362,10 +387,48 @@ function solve_SCP_batch!(TOPs::Vector, init_method; max_iter::Int=30, force::Bo
       conv_prev[b] = conv
     end
     accept!(ctx, acc, ω, Δ)
-    any(active) || break
+    # one status all-gather per outer iteration (in-library NCCL when a communicator was set up with comm_init!; the local
+    # count otherwise): every rank leaves the loop in the same iteration
+    allgather_status!(ctx, UInt8.(.!active)) == 0 && break
   end
   get_trajectory!(ctx, X, U)
   return X, U, converged, successful, iterations
+end
+
+"""
+    solve_SCP_batch_device!(TOPs, init_method; max_iter=30, force=false, device=0, rank=0, nranks=1, comm_id=nothing)
+
+The same batched solve with the outer loop resident on the device (`gusto_scp_begin` / `gusto_scp_run`, include/gusto_b200.h):
+accept / reject, the Δ / ω schedule and the convergence test of scp_gusto.jl:119-174 run in the library's update kernel, one
+CUDA graph per outer iteration, and the host reads one counter per iteration.  Multi-GPU: one Julia process per GPU, each with
+its shard of `TOPs`; rank 0 calls `comm_unique_id()` and ships the 128 bytes to the others (MPI.Bcast!, a file, ...), every rank
+passes them as `comm_id` together with `rank` / `nranks`; the library then all-gathers the status bytes over NCCL once per
+iteration and all ranks stop together.  Returns (X, U, converged, successful, iterations, hist) with
+hist (12, B, batch_iterations + 1): the per-iteration records described at `gusto_scp_get`.
+"""
+function solve_SCP_batch_device!(TOPs::Vector, init_method; max_iter::Int=30, force::Bool=false, device::Int=0,
+                                 rank::Int=0, nranks::Int=1, comm_id=nothing)
+  B = length(TOPs); T1 = TOPs[1]
+  model, robot, env, N = T1.PD.model, T1.PD.robot, T1.PD.env, T1.N
+  x_dim, u_dim = model.x_dim, model.u_dim
+  alg = Main.SCPParam_GuSTO(model); param = Main.SCPParam(model, T1.fixed_final_time)
+  gtype, _, _ = flatten_goals(T1.PD.goal_set, x_dim, T1.tf_guess)
+  x_init = zeros(x_dim, B); glo = zeros(x_dim, B); ghi = zeros(x_dim, B); tf = zeros(B)
+  X = zeros(x_dim, N, B); U = zeros(u_dim, N, B)
+  for (b, TOP) in enumerate(TOPs)
+    _, lo, hi = flatten_goals(TOP.PD.goal_set, x_dim, TOP.tf_guess)
+    x_init[:, b] = TOP.PD.x_init; glo[:, b] = lo; ghi[:, b] = hi; tf[b] = TOP.tf_guess
+    traj = init_method(TOP); X[:, :, b] = traj.X; U[:, :, b] = traj.U
+  end
+  ctx = GustoContext(robot, model, env, N, B, gtype, alg, param; device=device)
+  set_problems!(ctx, x_init, glo, ghi, tf)
+  nranks > 1 && comm_init!(ctx, rank, nranks, comm_id)
+  scp_begin!(ctx, X, U, force)
+  n_it, _ = scp_run!(ctx, max_iter)
+  iterations = zeros(Int32, B); converged = zeros(UInt8, B); successful = zeros(UInt8, B); hist = zeros(HIST_W, B, n_it + 1)
+  scp_get!(ctx, iterations, converged, successful, hist)
+  get_trajectory!(ctx, X, U)
+  return X, U, converged .!= 0, successful .!= 0, Int.(iterations), hist
 end
 
 # ------------------------------------------------------------------------------------- BulletCollision stand-in
