@@ -57,16 +57,21 @@ def make_problem(pkg, name, B, N, seed, **extra):
     return fn(**kw)
 
 
+A_NNZ = {"dubins": 2, "freeflyerSE2": 3, "astrobeeSE3": 27, "astrobeeSE3manifold": 33}    # Traits<M>::ANZ (csrc/common.cuh)
+
+
 def algorithmic_bytes(bp):
-    """Bytes one (instance, SCP iteration) must move at minimum, per kernel."""
+    """Bytes one (instance, SCP iteration) must move at minimum, per kernel: the trajectory, the
+    linearization blocks (A on its sparsity pattern, f, g) and the obstacle rows, each touched once per kernel."""
     nx, nu, N = bp.model.x_dim, bp.model.u_dim, bp.N
     no = int(bp.obstacle_table()[0].shape[0])
     traj = N * (nx + nu)
-    blocks = N * (nx * nx + 2 * nx)          # A, f, g
+    anz = A_NNZ[bp.model.name]
+    blocks = N * (anz + 2 * nx)              # A (pattern), f, g
     rows = N * no * 5
     k12 = traj + blocks + rows               # read traj, write blocks + rows
-    k3 = traj + N * (nx * nx + nx) + rows + traj   # read Xp/Up, A, g, rows; write candidate
-    k4 = 2 * traj + N * (nx * nx + nx) + rows      # read both trajectories, A, f, rows
+    k3 = traj + N * (anz + nx) + rows + traj   # read Xp/Up, A, g, rows; write candidate
+    k4 = 2 * traj + N * (anz + nx) + rows      # read both trajectories, A, f, rows
     return dict(linearize=8 * k12, solve=8 * k3, evaluate=8 * k4)
 
 

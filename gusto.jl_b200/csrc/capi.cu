@@ -18,6 +18,7 @@
 #include "postprocess.cuh"
 #include "shooting.cuh"
 #include "scp.cuh"
+#include "blocks.cuh"
 #include <dlfcn.h>
 
 using namespace gusto;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   __shared__ alignas(16) double sx[KPC * NX];
   __shared__ alignas(16) double su[KPC * NU];
   __shared__ double ws[KPC][NX * NX + NX];
+  __shared__ double outs[(T::ANZ + 2 * NX + 5 * (T::WS > 0 ? MAX_OBS : 0)) * KPC];     // the CTA's blocks, [field][knot of the CTA]
   __shared__ alignas(8) unsigned long long mbar;
   __shared__ double sbv[NU > 0 ? NU : 1];
   const BatchDesc& d = *dp;
@@ -102,10 +104,23 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
     __syncthreads();
   }
   const int warp = threadIdx.x >> 5;
-  if (warp < nk) {
-    const int gk = k0 + warp;
-    if (p.active && !p.active[gk / d.N]) return;          // frozen instance (converged / failed): its blocks are never read again
-    linearize_knot<M>(d, p, gk / d.N, gk % d.N, sx + warp * NX, su + warp * NU, ws[warp], sbv);
+  const int n_obs = T::WS > 0 ? d.n_obs : 0, nfield = T::ANZ + 2 * NX + 5 * n_obs;
+  if (warp < nk && !(p.active && !p.active[(k0 + warp) / d.N]))     // (frozen instance: its blocks are never read again)
+    linearize_knot<M>(d, sx + warp * NX, su + warp * NU, ws[warp], sbv, outs + warp, outs + T::ANZ * KPC + warp,
+                      outs + (T::ANZ + NX) * KPC + warp, outs + (T::ANZ + 2 * NX) * KPC + warp, KPC);
+  __syncthreads();
+  // write-out: every field row of the knot-minor layout receives the CTA's 8 consecutive knots as 64 contiguous bytes
+  const size_t np = g_np(d.N);
+  for (int idx = threadIdx.x; idx < nfield * KPC; idx += blockDim.x) {
+    const int fld = idx / KPC, kk = idx - fld * KPC;
+    if (kk >= nk) continue;
+    const int gk = k0 + kk, b = gk / d.N, k = gk - b * d.N;
+    if (p.active && !p.active[b]) continue;
+    const double v = outs[idx];
+    if (fld < T::ANZ) p.A[((size_t)b * T::ANZ + fld) * np + k] = v;
+    else if (fld < T::ANZ + NX) p.f[((size_t)b * NX + fld - T::ANZ) * np + k] = v;
+    else if (fld < T::ANZ + 2 * NX) p.g[((size_t)b * NX + fld - T::ANZ - NX) * np + k] = v;
+    else p.rows[((size_t)b * 5 * n_obs + fld - T::ANZ - 2 * NX) * np + k] = v;
   }
 }
 
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(IPM_THREADS * IPM_MAX_PACK, 1) ipm_kernel(cons
 
 // K4.  Grid: B CTAs.
 template <int M>
-__global__ void __launch_bounds__(EVAL_THREADS) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
+__global__ void __launch_bounds__(EVAL_THREADS, 4) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
   using T = Traits<M>;
   __shared__ double red[EVAL_THREADS];
   const int b = blockIdx.x;
@@ -248,6 +263,14 @@ static void dims_of(int model, int* nx, int* nu) {
     default: *nx = 0; *nu = 0;
   }
 }
+static int anz_of(int model) {
+  switch (model) {
+    case DUBINS: return blocks_anz<DUBINS>();
+    case FREEFLYER_SE2: return blocks_anz<FREEFLYER_SE2>();
+    case ASTROBEE_SE3: return blocks_anz<ASTROBEE_SE3>();
+    default: return blocks_anz<ASTROBEE_SE3_MANIFOLD>();
+  }
+}
 static size_t scratch_doubles_of(int model, int N, int n_obs) {
   switch (model) {
     case DUBINS: return IpmLayout<DUBINS>::scratch_doubles(N, 0);
@@ -330,7 +353,8 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   ok = ok && alloc(&ctx->d_tf, B) && alloc(&ctx->d_xinit, B * nx) && alloc(&ctx->d_glo, B * nx) && alloc(&ctx->d_ghi, B * nx);
   ok = ok && alloc(&p.Xp, B * N * nx) && alloc(&p.Up, B * N * nu) && alloc(&p.Xn, B * N * nx) && alloc(&p.Un, B * N * nu);
   ok = ok && alloc(&p.omega, B) && alloc(&p.delta, B) && alloc(&ctx->d_omega_in, B) && alloc(&ctx->d_delta_in, B);
-  ok = ok && alloc(&p.f, B * N * nx) && alloc(&p.A, B * N * nx * nx) && alloc(&p.g, B * N * nx) && alloc(&p.rows, B * N * no * 5);
+  const size_t NPk = g_np((int)N);                                      // knot-minor block layout (BatchPtrs, common.cuh)
+  ok = ok && alloc(&p.f, B * nx * NPk) && alloc(&p.A, B * anz_of(cfg->model_id) * NPk) && alloc(&p.g, B * nx * NPk) && alloc(&p.rows, B * 5 * no * NPk);
   ctx->scratch_stride = scratch_doubles_of(cfg->model_id, (int)N, h.n_obs);
   ok = ok && alloc(&ctx->d_scratch, B * ctx->scratch_stride);
   ok = ok && alloc(&ctx->d_info, B * IPM_NINFO) && alloc(&ctx->d_eval, B * EVAL_NOUT) && alloc(&ctx->d_dual, B * nx);
@@ -491,12 +515,20 @@ int32_t gusto_linearize(gusto_ctx* ctx) {
 int32_t gusto_get_blocks(gusto_ctx* ctx, double* f, double* A, double* g, double* rows) {
   NEED(true);
   CK(cudaSetDevice(ctx->cfg.device));
-  const size_t BN = (size_t)ctx->cfg.B * ctx->cfg.N;
-  if (f) D2H(f, ctx->p.f, BN * ctx->nx);
-  if (A) D2H(A, ctx->p.A, BN * ctx->nx * ctx->nx);
-  if (g) D2H(g, ctx->p.g, BN * ctx->nx);
-  if (rows && ctx->hdesc.n_obs > 0) D2H(rows, ctx->p.rows, BN * ctx->hdesc.n_obs * 5);
+  // test hook: the kernels keep the blocks knot-minor with A on its sparsity pattern; the caller gets the dense knot-major arrays
+  const int B = ctx->cfg.B, N = ctx->cfg.N, no = ctx->hdesc.n_obs, anz = anz_of(ctx->cfg.model_id);
+  const size_t np = g_np(N);
+  std::vector<double> fc((size_t)B * ctx->nx * np), gc(fc.size()), Ac((size_t)B * anz * np), rc((size_t)B * 5 * (no > 0 ? no : 1) * np);
+  D2H(fc.data(), ctx->p.f, fc.size()); D2H(gc.data(), ctx->p.g, gc.size()); D2H(Ac.data(), ctx->p.A, Ac.size());
+  if (no > 0) D2H(rc.data(), ctx->p.rows, (size_t)B * 5 * no * np);
   CK(cudaStreamSynchronize(ctx->stream));
+  const double* rcp = (rows && no > 0) ? rc.data() : nullptr;
+  switch (ctx->cfg.model_id) {
+    case DUBINS: blocks_unpack<DUBINS>(B, N, no, fc.data(), Ac.data(), gc.data(), rcp, f, A, g, rows); break;
+    case FREEFLYER_SE2: blocks_unpack<FREEFLYER_SE2>(B, N, no, fc.data(), Ac.data(), gc.data(), rcp, f, A, g, rows); break;
+    case ASTROBEE_SE3: blocks_unpack<ASTROBEE_SE3>(B, N, no, fc.data(), Ac.data(), gc.data(), rcp, f, A, g, rows); break;
+    default: blocks_unpack<ASTROBEE_SE3_MANIFOLD>(B, N, no, fc.data(), Ac.data(), gc.data(), rcp, f, A, g, rows); break;
+  }
   return GUSTO_OK;
 }
 

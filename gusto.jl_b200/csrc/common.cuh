@@ -372,15 +372,18 @@ struct BatchPtrs {
   double* Xp;  double* Up;     // accepted (previous) trajectory   [B][N][NX], [B][N][NU]
   double* Xn;  double* Un;     // candidate trajectory from the convex solve
   double* omega; double* delta;  // [B] current penalty weight / trust-region size
-  // linearization blocks written by linearize_kernel and consumed in place by the solve / evaluate kernels
-  double* f;       // [B][N][NX]
-  double* A;       // [B][N][NX][NX] row-major: A[i][j] = d f_i / d x_j
-  double* g;       // [B][N][NX]      f - A Xp - B Up  (affine part of the trapezoid row, halves summed by the consumer)
+  // linearization blocks written by linearize_kernel and consumed in place by the solve / evaluate kernels, knot-minor per
+  // instance (NP = g_np(N) doubles per field row; the consumers run one thread per knot and read every field coalesced):
+  double* f;       // [B][NX][NP]
+  double* A;       // [B][ANZ][NP]    A = d f / d x on its static sparsity pattern (Traits<M>::a_row / a_col), e.g. 27 of 144 entries
+  double* g;       // [B][NX][NP]     f - A Xp - B Up  (affine part of the trapezoid row, halves summed by the consumer)
   const uint8_t* active;  // [B] instances still iterating (solve/evaluate skip the others); may be null
-  double* rows;    // [B][N][n_obs][5] (nhat_x, nhat_y, nhat_z, off, dist0): row value = off - nhat.r, active iff dist0 < toggle
+  double* rows;    // [B][5][n_obs][NP] (nhat_x, nhat_y, nhat_z, off, dist0): row value = off - nhat.r, active iff dist0 < toggle
   double* dual;    // [B][NX] multiplier of the init rows X[:,1] = x_init of the last solve (= -JuMP.dual, get_dual_jump); may be null
 };
 
 GHD double sq(double a) { return a * a; }
+// knots per field row of the knot-minor block / scratch layouts: N rounded up to 4 (every row starts on a 32-byte sector)
+GHD constexpr int g_np(int N) { return (N + 3) & ~3; }
 
 }  // namespace gusto

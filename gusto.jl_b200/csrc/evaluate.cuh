@@ -60,9 +60,10 @@ GDEV void evaluate_instance(const BatchDesc& d, const BatchPtrs& p, int b, const
   const double eps = d.sp[SP_EPS], cl = d.rp[RP_CLEAR], R = d.rp[RP_RADIUS];
   const double toggle = Delta / 8.0 + cl;                       // scp_gusto.jl:76,156
   const double* Xp = p.Xp + (size_t)b * N * NX;
-  const double* F = p.f + (size_t)b * N * NX;
-  const double* A = p.A + (size_t)b * N * NX * NX;
-  const double* rows = p.rows + (size_t)b * N * d.n_obs * 5;
+  const size_t np = g_np(N), fs = (size_t)d.n_obs * np;
+  const double* F = p.f + (size_t)b * NX * np;
+  const double* A = p.A + (size_t)b * T::ANZ * np;                 // sparsity pattern of A, knot-minor
+  const double* rows = p.rows + (size_t)b * 5 * fs;
 
   double num = 0, den = 0, Jt = 0, Jpen = 0, mdx2 = 0, mnx2 = 0, msoft = -1e300, meq = 0;
   G_PAR_FOR(k, N) {
@@ -79,12 +80,11 @@ GDEV void evaluate_instance(const BatchDesc& d, const BatchPtrs& p, int b, const
     if (k < N - 1) {
       double fn[NX], e2 = 0, l2 = 0;
       dyn_f<M>(x, u, d.rp, fn);
-      for (int i = 0; i < NX; ++i) {
-        double lin = F[k * NX + i];
-        for (int j = 0; j < NX; ++j) lin += A[(k * NX + i) * NX + j] * dx[j];
-        e2 += sq(fn[i] - lin);
-        l2 += lin * lin;
-      }
+      double lin[NX];
+      for (int i = 0; i < NX; ++i) lin[i] = F[i * np + k];
+#pragma unroll
+      for (int e = 0; e < T::ANZ; ++e) lin[T::a_row(e)] += A[e * np + k] * dx[T::a_col(e)];
+      for (int i = 0; i < NX; ++i) { e2 += sq(fn[i] - lin[i]); l2 += lin[i] * lin[i]; }
       num += sqrt(e2);
       den += sqrt(l2);
     }
@@ -117,12 +117,12 @@ GDEV void evaluate_instance(const BatchDesc& d, const BatchPtrs& p, int b, const
   if (T::WS > 0) {
     constexpr int WS = T::WS > 0 ? T::WS : 1;
     G_PAR_FOR(it, N * d.n_obs) {
-      const int k = it / d.n_obs, i = it - k * d.n_obs;
+      const int i = it / N, k = it - i * N;                         // knot fastest: coalesced row reads
       double r[3], r0[3];
-      workspace_location<WS>(X + k * NX, r);
+      workspace_location<WS>(X + k * NX, r);                        // (the instance's trajectories are L1-resident by now)
       workspace_location<WS>(Xp + k * NX, r0);
-      const double* row = rows + (size_t)it * 5;
-      const double linr = row[3] - (row[0] * r[0] + row[1] * r[1] + row[2] * r[2]);
+      const double* row = rows + (size_t)i * np + k;
+      const double linr = row[3 * fs] - (row[0] * r[0] + row[fs] * r[1] + row[2 * fs] * r[2]);
       double d1, n1[3];
       signed_distance<WS>(r, d.obs_kind[i], d.obs_a[i], d.obs_b[i], R, &d1, n1);
       num += fabs((cl - d1) - linr);
@@ -135,7 +135,7 @@ GDEV void evaluate_instance(const BatchDesc& d, const BatchPtrs& p, int b, const
         num += fabs((cl - d1) - lina);
         den += fabs(lina);
       }
-      if (row[4] < toggle) {           // convexified row is live (astrobee_se3.jl:293)
+      if (row[4 * fs] < toggle) {      // convexified row is live (astrobee_se3.jl:293)
         msoft = linr > msoft ? linr : msoft;
         Jpen += omega * linr > 0 ? omega * linr : 0;
       }

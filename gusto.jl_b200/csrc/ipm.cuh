@@ -195,7 +195,7 @@ template <int M> struct IpmLayout {
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
     const size_t np = np_of(N), ne = ne_of(N), pp = pp_of(N, n_obs), nn = (size_t)N;
-    return np * NV /* r */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * ANZ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
+    return np * NV /* r */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
            pp * SLOT_W + pp * OROW_W + np * KDW + np * NN /* Fi */ + nn * CRW + 2 * np * GSW /* gs bs */ + nn * GT /* Acl */ + np * NX * NU /* K */ +
            np * NTU /* lp */ + np * NTX /* P */ + 2 * np * NX /* psi ch */ + np * NU /* kap */;
   }
@@ -241,10 +241,10 @@ template <int M> struct IpmCtx {
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
-  const double *Xp, *Up, *A, *g, *rows, *x_init, *goal_lo, *goal_hi;
+  const double *Xp, *Up, *Ac, *g, *rows, *x_init, *goal_lo, *goal_hi;   // Ac, g, rows: the linearize kernel's blocks, knot-minor, read in place
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
   // global scratch
-  double *nu, *dnu, *r, *rnu, *Ac, *sslot, *bslot, *ost, *orow, *kd;
+  double *nu, *dnu, *r, *rnu, *sslot, *bslot, *ost, *orow, *kd;
   double *fi, *cr, *acl, *kt, *lp, *pk, *psi, *ch, *kap;
   double *xps, *gsum, *gs, *bs;   // Xp field-major | h/2 (g_{j-1} + g_j) per equality row | Gam', Bh' field-major
   // shared
@@ -1546,23 +1546,23 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   const size_t np = c.NP, ne = c.NE, pp = c.PP;
   G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; sh_z<M>(c)[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
   G_PAR_FOR(it, NX * (int)ne) c.nu[it] = 0.0;
-  // field-major copies of the inputs the per-knot passes read every Newton iteration: Xp, A_k on its sparsity pattern, and the
-  // constant part of the equality residual  -x_init | h/2 (g_{j-1} + g_j) | -goal
+  // field-major copies of what the per-knot passes read every Newton iteration besides the linearize kernel's blocks (A_k on its
+  // sparsity pattern is read in place): Xp, and the constant part of the equality residual  -x_init | h/2 (g_{j-1} + g_j) | -goal
   G_PAR_FOR(it, N * NX) { const int i = it / N, k = it - i * N; c.xps[i * np + k] = c.Xp[k * NX + i]; }
-  G_PAR_FOR(it, N * ANZ) { const int e = it / N, k = it - e * N; c.Ac[e * np + k] = c.A[(size_t)k * NX * NX + T::a_row(e) * NX + T::a_col(e)]; }
   G_PAR_FOR(it, (N + 1) * NX) {
     const int i = it / (N + 1), j = it - i * (N + 1);
     double v;
     if (j == 0) v = -c.x_init[i];
     else if (j == N) v = ((c.pmask >> i) & 1) ? -c.goal_lo[i] : 0.0;
-    else v = c.hh * (c.g[(j - 1) * NX + i] + c.g[j * NX + i]);
+    else v = c.hh * (c.g[i * np + j - 1] + c.g[i * np + j]);
     c.gsum[i * ne + j] = v;
   }
   // obstacle rows inside the toggle distance, compacted knot by knot (astrobee_se3.jl:293)
   if (T::WS > 0) {
     G_PAR_FOR(k, N) {
       int cnt = 0;
-      for (int i = 0; i < c.n_obs; ++i) cnt += (c.rows[((size_t)k * c.n_obs + i) * 5 + 4] < c.toggle) ? 1 : 0;
+      const double* dist = c.rows + 4 * (size_t)c.n_obs * np + k;                    // field 4 (dist0) of [5][n_obs][NP]
+      for (int i = 0; i < c.n_obs; ++i) cnt += (dist[i * np] < c.toggle) ? 1 : 0;
       sh_seg<M>(c)[k + 1] = cnt;
     }
     G_SYNC();
@@ -1578,12 +1578,14 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
       int p = sh_seg<M>(c)[k];
       const double* x = sh_z<M>(c) + k * NV;
       for (int i = 0; i < c.n_obs; ++i) {
-        const double* row = c.rows + ((size_t)k * c.n_obs + i) * 5;
-        if (!(row[4] < c.toggle)) continue;
+        const size_t fs = (size_t)c.n_obs * np;
+        const double* row = c.rows + (size_t)i * np + k;
+        if (!(row[4 * fs] < c.toggle)) continue;
         double* o = c.orow + p;
-        double v = row[3];
-        for (int a = 0; a < 3; ++a) { o[a * pp] = row[a]; if (a < T::WS) v -= row[a] * x[a]; }
-        o[3 * pp] = row[3]; o[4 * pp] = (double)k;
+        const double off = row[3 * fs];
+        double v = off;
+        for (int a = 0; a < 3; ++a) { const double ra = row[a * fs]; o[a * pp] = ra; if (a < T::WS) v -= ra * x[a]; }
+        o[3 * pp] = off; o[4 * pp] = (double)k;
         slot_init(c.ost + p, pp, true, true, v, c.omega, slack_start<M>(), slack_lam_split<M>());
         ++p;
       }
@@ -1630,8 +1632,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.pmask = 0; c.bmask = 0;
     for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
     c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
-    c.A = p.A + (size_t)b * N * NX * NX; c.g = p.g + (size_t)b * N * NX;
-    c.rows = p.rows + (size_t)b * N * d.n_obs * 5;
+    c.Ac = p.A + (size_t)b * L::ANZ * g_np(N); c.g = p.g + (size_t)b * NX * g_np(N);
+    c.rows = p.rows + (size_t)b * 5 * d.n_obs * g_np(N);
     c.x_init = p.x_init + (size_t)b * NX; c.goal_lo = p.goal_lo + (size_t)b * NX; c.goal_hi = p.goal_hi + (size_t)b * NX;
     {
       double Bm[NX * NU];
@@ -1646,7 +1648,6 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.nu = q; q += ne * NX; c.dnu = q; q += ne * NX; c.rnu = q; q += ne * NX;
     c.gsum = q; q += ne * NX;
     c.xps = q; q += np * NX;
-    c.Ac = q; q += np * L::ANZ;
     c.sslot = q; q += np * L::SP * SLOT_W;
     c.bslot = q; q += (size_t)L::NBOX * SLOT_W;
     c.ost = q; q += pp * SLOT_W;

@@ -4,8 +4,10 @@
 // affine part of dynamics_constraints (:151-165) and ncsi_obstacle_avoidance_constraints_convexified
 // (:282-305, one BulletCollision.distance query per (knot, obstacle)).  Emits, per knot, the blocks the convex
 // solve and the evaluation kernel consume in place:
-//   f[NX], A[NX][NX], g[NX] = f - A x - B u            (trapezoid row k: h/2 (g_{k-1} + g_k) is its constant)
-//   rows[n_obs][5] = (nhat, off = clearance - dist0 + nhat.r0, dist0)
+//   f[NX], A on its sparsity pattern [ANZ], g[NX] = f - A x - B u   (trapezoid row k: h/2 (g_{k-1} + g_k) is its constant)
+//   rows[5][n_obs] = (nhat, off = clearance - dist0 + nhat.r0, dist0)
+// all knot-minor per instance (BatchPtrs, common.cuh): the 8 warps of a CTA hold 8 consecutive knots, so every field row
+// receives 64 contiguous bytes per CTA.
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
@@ -21,15 +23,17 @@ template <int M> GDEV void dyn_B_columns(const double* rp, double* bv) {
   dyn_B<M>(rp, Bm);
   for (int a = 0; a < T::NU; ++a) bv[a] = Bm[T::b_row(a) * T::NU + a];
 }
+// Output of one knot: field e of A at oA[e * es], of f / g at of[i * es] / og[i * es], field q of obstacle row i at
+// orows[(q * n_obs + i) * es].  The kernel stages the 8 knots of a CTA in shared memory (es = 8) and writes every field row of the
+// knot-minor global layout as 64 contiguous bytes; the host simulation writes the global layout directly (es = NP).
 template <int M>
-GDEV void linearize_knot(const BatchDesc& d, const BatchPtrs& p, int b, int k, const double* x, const double* u,
-                         double* ws, const double* bv) {
+GDEV void linearize_knot(const BatchDesc& d, const double* x, const double* u, double* ws, const double* bv,
+                         double* oA, double* of, double* og, double* orows, size_t es) {
   using T = Traits<M>;
   constexpr int NX = T::NX, NU = T::NU;
   double* sA = ws;             // [NX*NX]
   double* sf = ws + NX * NX;   // [NX]
   const int lane = G_LANE;
-  const size_t gk = (size_t)b * d.N + k;
 
   for (int i = lane; i < NX * NX; i += G_NLANE) sA[i] = 0.0;
   G_SYNCWARP();
@@ -38,36 +42,43 @@ GDEV void linearize_knot(const BatchDesc& d, const BatchPtrs& p, int b, int k, c
     dyn_A<M>(x, d.rp, sA);
   }
   G_SYNCWARP();
-  // coalesced stores of A and f
-  double* gA = p.A + gk * (NX * NX);
-  for (int i = lane; i < NX * NX; i += G_NLANE) gA[i] = sA[i];
-  double* gf = p.f + gk * NX;
-  double* gg = p.g + gk * NX;
+  // A on its sparsity pattern, f and g: one field row each
+  for (int e = lane; e < T::ANZ; e += G_NLANE) oA[e * es] = sA[T::a_row(e) * NX + T::a_col(e)];
   for (int i = lane; i < NX; i += G_NLANE) {
     double acc = sf[i];
     for (int j = 0; j < NX; ++j) acc -= sA[i * NX + j] * x[j];
     // B is constant with one entry per column (B[b_row(a)][a] = bv[a], Traits<M>::b_row): no matrix is rebuilt
 #pragma unroll
     for (int a = 0; a < NU; ++a) if (T::b_row(a) == i) acc -= bv[a] * u[a];
-    gf[i] = sf[i];
-    gg[i] = acc;
+    of[i * es] = sf[i];
+    og[i * es] = acc;
   }
   // obstacle rows: one lane per collision component
   if (T::WS > 0) {
     double r0[3];
     workspace_location<T::WS>(x, r0);
-    double* grow = p.rows + gk * (size_t)d.n_obs * 5;
+    const size_t fs = (size_t)d.n_obs * es;                                  // field stride
     for (int i = lane; i < d.n_obs; i += G_NLANE) {
       double dist, nh[3];
       signed_distance<(T::WS > 0 ? T::WS : 1)>(r0, d.obs_kind[i], d.obs_a[i], d.obs_b[i], d.rp[RP_RADIUS], &dist, nh);
-      grow[i * 5 + 0] = nh[0];
-      grow[i * 5 + 1] = nh[1];
-      grow[i * 5 + 2] = nh[2];
-      grow[i * 5 + 3] = d.rp[RP_CLEAR] - dist + nh[0] * r0[0] + nh[1] * r0[1] + nh[2] * r0[2];
-      grow[i * 5 + 4] = dist;
+      double* o = orows + i * es;
+      o[0] = nh[0];
+      o[fs] = nh[1];
+      o[2 * fs] = nh[2];
+      o[3 * fs] = d.rp[RP_CLEAR] - dist + nh[0] * r0[0] + nh[1] * r0[1] + nh[2] * r0[2];
+      o[4 * fs] = dist;
     }
   }
   G_SYNCWARP();
+}
+
+// the knot-minor global layout written directly (host simulation; BatchPtrs, common.cuh)
+template <int M>
+GDEV void linearize_knot_global(const BatchDesc& d, const BatchPtrs& p, int b, int k, const double* x, const double* u, double* ws, const double* bv) {
+  using T = Traits<M>;
+  const size_t np = g_np(d.N);
+  linearize_knot<M>(d, x, u, ws, bv, p.A + (size_t)b * T::ANZ * np + k, p.f + (size_t)b * T::NX * np + k, p.g + (size_t)b * T::NX * np + k,
+                    p.rows + (size_t)b * 5 * d.n_obs * np + k, np);
 }
 
 }  // namespace gusto

@@ -16,6 +16,7 @@
 #include "../../gusto.jl_b200/csrc/postprocess.cuh"
 #include "../../gusto.jl_b200/csrc/shooting.cuh"
 #include "../../gusto.jl_b200/csrc/scp.cuh"
+#include "../../gusto.jl_b200/csrc/blocks.cuh"
 
 using namespace gusto;
 
@@ -34,7 +35,7 @@ static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stag
     dyn_B_columns<M>(d.rp, bv);
     for (int b = 0; b < B; ++b)
       for (int k = 0; k < N; ++k)
-        linearize_knot<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data(), bv);
+        linearize_knot_global<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data(), bv);
   }
   if (stages & 2) {
     std::vector<double> scratch(L::scratch_doubles(N, d.n_obs)), smem(L::smem_doubles(N, 1));
@@ -65,18 +66,37 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
   p.active = nullptr;
   p.dual = g_dual;
   p.tf = tf; p.x_init = x_init; p.goal_lo = goal_lo; p.goal_hi = goal_hi;
-  p.Xp = Xp; p.Up = Up; p.Xn = Xn; p.Un = Un; p.omega = omega; p.delta = delta; p.f = f; p.A = A; p.g = g; p.rows = rows;
+  p.Xp = Xp; p.Up = Up; p.Xn = Xn; p.Un = Un; p.omega = omega; p.delta = delta;
+  // the kernels keep the blocks knot-minor (A on its sparsity pattern); callers of this harness pass / receive the dense arrays
+  const size_t np = g_np(d.N), no1 = d.n_obs > 0 ? d.n_obs : 1;
+  int nx = 0, anz = 0;
+  switch (cfg->model_id) {
+    case DUBINS: nx = Traits<DUBINS>::NX; anz = Traits<DUBINS>::ANZ; break;
+    case FREEFLYER_SE2: nx = Traits<FREEFLYER_SE2>::NX; anz = Traits<FREEFLYER_SE2>::ANZ; break;
+    case ASTROBEE_SE3: nx = Traits<ASTROBEE_SE3>::NX; anz = Traits<ASTROBEE_SE3>::ANZ; break;
+    case ASTROBEE_SE3_MANIFOLD: nx = Traits<ASTROBEE_SE3_MANIFOLD>::NX; anz = Traits<ASTROBEE_SE3_MANIFOLD>::ANZ; break;
+    default: return -1;
+  }
+  std::vector<double> fc((size_t)d.B * nx * np), gc(fc.size()), Ac((size_t)d.B * anz * np), rc((size_t)d.B * 5 * no1 * np);
+  p.f = fc.data(); p.A = Ac.data(); p.g = gc.data(); p.rows = rc.data();
   IpmParams prm;
   prm.max_iter = cfg->ipm_max_iter > 0 ? cfg->ipm_max_iter : 60;
   prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
   prm.wn_base = 1e8; prm.wn_omega = 1e4;
+#define HS_CASE(MM)                                                                                                         \
+  case MM:                                                                                                                  \
+    if (!(stages & 1)) blocks_pack<MM>(d.B, d.N, d.n_obs, f, A, g, rows, fc.data(), Ac.data(), gc.data(), rc.data());          \
+    run<MM>(d, p, prm, stages, info, eval);                                                                                 \
+    blocks_unpack<MM>(d.B, d.N, d.n_obs, fc.data(), Ac.data(), gc.data(), d.n_obs > 0 ? rc.data() : nullptr, f, A, g, rows); \
+    break;
   switch (cfg->model_id) {
-    case DUBINS: run<DUBINS>(d, p, prm, stages, info, eval); break;
-    case FREEFLYER_SE2: run<FREEFLYER_SE2>(d, p, prm, stages, info, eval); break;
-    case ASTROBEE_SE3: run<ASTROBEE_SE3>(d, p, prm, stages, info, eval); break;
-    case ASTROBEE_SE3_MANIFOLD: run<ASTROBEE_SE3_MANIFOLD>(d, p, prm, stages, info, eval); break;
+    HS_CASE(DUBINS)
+    HS_CASE(FREEFLYER_SE2)
+    HS_CASE(ASTROBEE_SE3)
+    HS_CASE(ASTROBEE_SE3_MANIFOLD)
     default: return -1;
   }
+#undef HS_CASE
   return 0;
 }
 

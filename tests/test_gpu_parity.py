@@ -173,6 +173,23 @@ def test_device_resident_loop_equals_host_loop(host, name, kw):
         assert ran[0] == bp.B and int(ran.sum()) >= int(S1.iterations.sum())
 
 
+def test_freeflyer_notebook_first_iterations_match_the_recorded_run_on_the_gpu(host):
+    """The CUDA path against the reference's own recorded JuMP + Gurobi run (examples/freeflyerSE2.ipynb cell 3, N = 200): the
+    first six iterations are accepted at omega = 1, Delta = 3 with J_true and convergence_measure within a few percent of the
+    recorded values (see the same test on the oracle in test_oracle.py for what limits the agreement)."""
+    from test_oracle import NOTEBOOK_J_TRUE, NOTEBOOK_CONV
+    bp = gb.problems.config_freeflyer_notebook(N=200)
+    e = host.Engine(bp, device=0)
+    S = host.solve_gusto_batch_device(e, max_iter=40)
+    e.close()
+    assert all(bool(S.accept_solution[i][0]) for i in range(7)) and all(int(S.scp_status[i][0]) == host.ST_OK for i in range(1, 7))
+    assert all(S.omega_vec[i][0] == 1.0 and S.Delta_vec[i][0] == 3.0 for i in range(7))
+    for i in range(6):
+        assert abs(S.J_true[i + 1][0] - NOTEBOOK_J_TRUE[i]) <= 0.05 * NOTEBOOK_J_TRUE[i]
+        assert abs(S.convergence_measure[i + 1][0] - NOTEBOOK_CONV[i]) <= 0.15 * NOTEBOOK_CONV[i]
+    assert bool(S.converged[0]) and bool(S.successful[0])
+
+
 def test_status_allgather_single_rank(host):
     """gusto_allgather_status without a communicator: the gathered bytes are the local ones, the count is the number of zeros."""
     bp = gb.problems.config_dubins(B=9, N=30)

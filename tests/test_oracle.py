@@ -121,17 +121,27 @@ def test_scp_converges_on_every_model(name, kw):
     assert S.Delta_vec[0] == bp.model.scp_params[0] and S.omega_vec[0] == 1.0
 
 
-@pytest.mark.slow
-def test_freeflyer_notebook_run_is_inside_the_recorded_band():
-    """examples/freeflyerSE2.ipynb cell 3 (Gurobi + Bullet, N=200): converged, 28 iterations, first accepted
-    J_true = 0.152419, final J_true = 0.111656, omega escalates 1 -> 10 -> 100.  Bullet's cylinder hull and Gurobi's
-    tolerances are not reproducible here, so this is a loose band (N=100 to keep the CPU suite short)."""
-    bp = gb.problems.config_freeflyer_notebook(N=100)
+# examples/freeflyerSE2.ipynb cell 3: the one trace of the reference's own JuMP + Gurobi run that the repository holds
+NOTEBOOK_J_TRUE = [0.152419, 0.0865004, 0.0744733, 0.0664654, 0.0638019, 0.0619878]
+NOTEBOOK_CONV = [0.140958, 0.0771133, 0.0749378, 0.0593635, 0.0354587, 0.0181484]
+
+
+def test_freeflyer_notebook_first_iterations_match_the_recorded_run():
+    """Pinned against the reference itself: examples/freeflyerSE2.ipynb cell 3 records the JuMP + Gurobi + Bullet run at N = 200
+    (28 iterations).  Its first six iterations are all accepted with status OK at omega = 1, Delta = 3; the oracle reproduces
+    those decisions and the recorded J_true / convergence_measure of every one of them to a few percent (the residual is the
+    collision geometry: Bullet's tessellated cylinder hull and margin against the closed-form signed distance).
+    From iteration 7 on the recorded run rejects steps (InaccurateModel, a Bullet-specific ratio) and its path is not
+    reproducible; the oracle converges in 17 accepted iterations with J_true inside the recorded range."""
+    bp = gb.problems.config_freeflyer_notebook(N=200)
     S = solve_gusto(to_oracle(bp, 0), max_iter=40)
-    assert S.converged
-    assert 0.05 < S.J_true[1] < 0.5          # recorded 0.1524 at N=200
-    assert 0.03 < S.J_true[-1] < 0.3         # recorded 0.1117
-    assert 5 <= S.iterations <= 40
+    assert S.accept_solution[:7] == [True] * 7 and S.scp_status[1:7] == ["OK"] * 6
+    assert all(w == 1.0 for w in S.omega_vec[:7]) and all(d == 3.0 for d in S.Delta_vec[:7])
+    for i in range(6):
+        assert abs(S.J_true[i + 1] - NOTEBOOK_J_TRUE[i]) <= 0.05 * NOTEBOOK_J_TRUE[i], (i, S.J_true[i + 1])
+        assert abs(S.convergence_measure[i + 1] - NOTEBOOK_CONV[i]) <= 0.15 * NOTEBOOK_CONV[i], (i, S.convergence_measure[i + 1])
+    assert S.converged and S.successful and 10 <= S.iterations <= 28
+    assert 0.0496451 * 0.9 <= S.J_true[-1] <= 0.111656 * 1.1      # recorded: minimum over the run .. final value
 
 
 def test_golden_vectors():
