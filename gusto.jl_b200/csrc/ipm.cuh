@@ -1527,14 +1527,17 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
 
 // --------------------------------------------------------------------------------------------------- setup
 #ifndef GUSTO_SLACK_START_SE3
-#define GUSTO_SLACK_START_SE3 0.25
+#define GUSTO_SLACK_START_SE3 0.02
 #endif
 template <int M> GHD constexpr double slack_start() { return M == ASTROBEE_SE3 ? GUSTO_SLACK_START_SE3 : 1.0; }
 // ... and how the penalty weight omega = lam + lam_t (dual feasibility of t) is split at the start: most soft rows end
 // inactive (lam -> 0, lam_t -> omega), so starting lam at 0.1 omega instead of 0.5 omega saves another 0.8 Newton
-// iterations on astrobeeSE3 (8.01 -> 7.23, solve 5.87 -> 5.34 ms; 0.02 would give 6.86 but starts badly centred)
+// iterations on astrobeeSE3 (8.01 -> 7.23, solve 5.87 -> 5.34 ms in round 1).  Round 2 (with the centrality safeguard in the
+// driver): scanned on the CPU build of this source over real SCP solves (tools/newton_probe.py, 40 instances each of the easy and
+// the hard tier; same optimum, same SCP decisions everywhere) -- (t_in, split) = (0.25, 0.1): 6.80 / 8.60 Newton iterations per
+// solve (easy / hard), (0.1, 0.03): 6.23 / 8.18, (0.03, 0.05): 5.89 / 7.98, (0.02, 0.02): 5.65 / 8.16, (0.01, 0.01): 5.35 / 8.38.
 #ifndef GUSTO_LAM_SPLIT_SE3
-#define GUSTO_LAM_SPLIT_SE3 0.1
+#define GUSTO_LAM_SPLIT_SE3 0.02
 #endif
 template <int M> GHD constexpr double slack_lam_split() { return M == ASTROBEE_SE3 ? GUSTO_LAM_SPLIT_SE3 : 0.5; }
 template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
