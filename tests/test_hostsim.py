@@ -48,7 +48,7 @@ def test_solve_and_evaluate_bodies_match_oracle(name, kw, omega):
         Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[b], U0[b], omega, sp[0], toggle, sp[3])
         assert st == "OPTIMAL" and hs["info"][b, 0] == 0
         assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
-        assert abs(hs["info"][b, 1] - r.iters) <= 3          # same algorithm: Newton iteration counts agree
+        assert hs["info"][b, 1] <= r.iters + 3               # same algorithm; the kernel's start point (slack_start / slack_lam_split) saves iterations
         # manifold: the attitude is only weakly determined by the cost (free inside the quaternion dead-band)
         xtol, utol = (1e-3, 1e-5) if name == "astrobeeSE3manifold" else (1e-4, 1e-5)
         assert err(hs["Xn"][b], Xs) < xtol and err(hs["Un"][b], Us) < utol
@@ -121,7 +121,7 @@ def test_genuine_box_goal_rows_match_oracle(name, kw, width):
         Xs, Us, obj, st, lin, rows, r = solve_subproblem(p, X0[b], U0[b], 1.0, sp[0], toggle, sp[3])
         assert st == "OPTIMAL" and hs["info"][b, 0] == 0
         assert abs(hs["info"][b, 4] - obj) <= 1e-6 * max(1.0, abs(obj))
-        assert abs(hs["info"][b, 1] - r.iters) <= 3
+        assert hs["info"][b, 1] <= r.iters + 3
         assert err(hs["Un"][b], Us) < 1e-5
         xN = hs["Xn"][b, -1, sel]
         assert np.all(xN >= bp.goal_lo[b, sel] - 1e-9) and np.all(xN <= bp.goal_hi[b, sel] + 1e-9)
