@@ -131,17 +131,27 @@ def config_astrobee_se3(B=1024, N=50, seed=None, hard=False, tf=70.0):
                         name=f"astrobeeSE3{'-hard' if hard else ''} B={B} N={N}")
 
 
-def config_astrobee_se3_manifold(B=1024, N=60, seed=None, hard=False, tf=70.0, eps_q=1e-4):
+def config_astrobee_se3_manifold(B=1024, N=60, seed=None, hard=False, tf=70.0, eps_q=1e-4, tier="notebook"):
     """C5: quaternion state [r v qw qx qy qz w]; goals as examples/astrobeeSE3manifold.ipynb cell 1
-    (PointGoal r, v, w; BoxGoal q +- 1e-4); add_obstacles! => 26 + 4 boxes + 2 spheres."""
+    (PointGoal r, v, w; BoxGoal q +- 1e-4); add_obstacles! => 26 + 4 boxes + 2 spheres.
+    tier "notebook" (default): endpoints around the notebook's own [11.2,-0.8,5.6] -> [10.9,3.0,5.0];
+    tier "zones": SURVEY C5 read literally, "as C3": start anywhere in keep-in zone 8, goal anywhere in zone 5, both inside the
+    hatch cross-section (line of sight), at least 0.1 m from every one of the 32 collision components."""
     rng = np.random.default_rng(B + 5 if seed is None else seed)
     robot, model, env = M.Astrobee3D(), M.AstrobeeSE3Manifold(), M.ISSCorner(add_obstacles=True)
-    # Notebook-like difficulty (examples/astrobeeSE3manifold.ipynb: [11.2,-0.8,5.6] -> [10.9,3.0,5.0]): start above
-    # the first obstacle box in module 8, goal just past the hatch and before the box that blocks module 5;
-    # both endpoints at least 0.1 m (signed distance) from every collision component.
     table = env.obstacle_table()
-    r0 = _sample_box(rng, B, [10.70, -0.90, 5.30], [11.25, 0.90, 5.70], table, robot.r, 0.1)
-    r1 = _sample_box(rng, B, [10.64, 2.90, 4.48], [11.25, 3.20, 5.15], table, robot.r, 0.1)
+    if tier == "zones":
+        margin = robot.r + model.clearance + 0.05
+        z8, z5 = env.keepin_zones[7], env.keepin_zones[4]
+        sect_lo, sect_hi = np.array([10.64, -np.inf, 4.48]), np.array([11.25, np.inf, 5.15])
+        r0 = _sample_box(rng, B, np.maximum(z8[0] + margin, sect_lo), np.minimum(z8[1] - margin, sect_hi), table, robot.r, 0.1)
+        r1 = _sample_box(rng, B, np.maximum(z5[0] + margin, sect_lo), np.minimum(z5[1] - margin, sect_hi), table, robot.r, 0.1)
+    else:
+        # Notebook-like difficulty (examples/astrobeeSE3manifold.ipynb: [11.2,-0.8,5.6] -> [10.9,3.0,5.0]): start above
+        # the first obstacle box in module 8, goal just past the hatch and before the box that blocks module 5;
+        # both endpoints at least 0.1 m (signed distance) from every collision component.
+        r0 = _sample_box(rng, B, [10.70, -0.90, 5.30], [11.25, 0.90, 5.70], table, robot.r, 0.1)
+        r1 = _sample_box(rng, B, [10.64, 2.90, 4.48], [11.25, 3.20, 5.15], table, robot.r, 0.1)
     x_init = np.zeros((B, 13)); lo = np.zeros((B, 13)); hi = np.zeros((B, 13))
     x_init[:, 0:3] = r0
     x_init[:, 6] = 1.0
@@ -152,7 +162,7 @@ def config_astrobee_se3_manifold(B=1024, N=60, seed=None, hard=False, tf=70.0, e
     gtype = np.full(13, M.GOAL_POINT, dtype=np.int32)
     gtype[6:10] = M.GOAL_BOX
     return BatchProblem(robot, model, env, N, np.full(B, tf), x_init, gtype, lo, hi,
-                        name=f"astrobeeSE3manifold B={B} N={N}")
+                        name=f"astrobeeSE3manifold{'-zones' if tier == 'zones' else ''} B={B} N={N}")
 
 
 def config_freeflyer_se2(B=256, N=40, seed=None):

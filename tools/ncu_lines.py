@@ -8,7 +8,7 @@ with
 of the SAME build of the library, by instruction offset inside the kernel's section, and aggregates by function (line ranges of
 gusto.jl_b200/csrc/ipm.cuh found by a small parser) and by line.
 
-  python tools/ncu_lines.py <report.ncu-rep> <libgusto_b200.so> <kernel mangled-name substring> [--top N] [--md out.md]
+  python tools/ncu_lines.py <report.ncu-rep> <libgusto_b200.so> <kernel mangled-name substring> [--kernel <regex for a multi-kernel report>] [--top N] [--md out.md]
 """
 import collections
 import csv
@@ -50,12 +50,21 @@ def disasm(lib, kernel_sub):
     return out
 
 
-def ncu_rows(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+def ncu_rows(rep, kfilter=None):
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"]
+    if kfilter:
+        cmd += ["-k", "regex:" + kfilter, "-c", "1"]
+    raw = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
-    return hdr, [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    out = []
+    for r in rows[hi + 1:]:
+        if r and r[0] in ("Kernel Name", "Address"):      # the next launch of a multi-launch report
+            break
+        if len(r) == len(hdr):
+            out.append(r)
+    return hdr, out
 
 
 def function_ranges(path):
@@ -77,7 +86,8 @@ def main():
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
     md = sys.argv[sys.argv.index("--md") + 1] if "--md" in sys.argv else None
     dis = disasm(lib, ksub)
-    hdr, rows = ncu_rows(rep)
+    kf = sys.argv[sys.argv.index("--kernel") + 1] if "--kernel" in sys.argv else None
+    hdr, rows = ncu_rows(rep, kf)
     ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     base = int(rows[0][ia], 16)
