@@ -15,7 +15,7 @@ if mode == "gpu":
     pkg = entry.build(); host = pkg.engine()
     bp = pkg.problems.CONFIGS[name](B=B)
     eng = host.Engine(bp)
-    S = host.solve_gusto_batch(eng, max_iter=30)
+    S = host.solve_gusto_batch_device(eng, max_iter=30)          # the device-resident loop (same decisions as the host loop: GPU test)
     np.savez(sys.argv[4], converged=S.converged, successful=S.successful, iterations=S.iterations,
              J_true=np.array(S.J_true)[-1], omega=np.array(S.omega_vec)[-1])
     print(name, "B", B, "converged", int(S.converged.sum()), "successful", int(S.successful.sum()))
