@@ -195,7 +195,7 @@ template <int M> struct IpmLayout {
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
     const size_t np = np_of(N), ne = ne_of(N), pp = pp_of(N, n_obs), nn = (size_t)N;
-    return np * NV /* r */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
+    return 3 * np * NV /* r ra rb */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
            pp * SLOT_W + pp * OROW_W + np * KDW + np * NN /* Fi */ + nn * CRW + 2 * np * GSW /* gs bs */ + nn * GT /* Acl */ + np * NX * NU /* K */ +
            np * NTU /* lp */ + np * NTX /* P */ + 2 * np * NX /* psi ch */ + np * NU /* kap */;
   }
@@ -247,6 +247,7 @@ template <int M> struct IpmCtx {
   double *nu, *dnu, *r, *rnu, *sslot, *bslot, *ost, *orow, *kd;
   double *fi, *cr, *acl, *kt, *lp, *pk, *psi, *ch, *kap;
   double *xps, *gsum, *gs, *bs;   // Xp field-major | h/2 (g_{j-1} + g_j) per equality row | Gam', Bh' field-major
+  double *ra, *rb;                // corrector right-hand side  r_corr = r + smu ra + rb  (predictor_pass)
   // shared
   double *z, *dz, *vp, *red;
   int* seg;
@@ -263,7 +264,7 @@ template <int M> GDEV int* sh_seg(const IpmCtx<M>& c) { return c.seg; }   // (an
 // ------------------------------------------------------------------------------------------- slot algebra
 // One inequality  c0(z) [- t] + s = 0, s >= 0 (multiplier lam) [, t >= 0 (multiplier lamb), cost omega*t].
 // After eliminating (s, lam [, t, lamb]) the row contributes  kap * gv gv' + lam * hess  to H and  -gv * bt  to the rhs.
-struct Pair { double rc, rt, wa, wb, ba, bb, iw, kap, bt, la; };
+struct Pair { double rc, rt, wa, wb, ba, bb, iw, kap, bt, la, isa, itv; };
 
 // A slot record is addressed as st[f * ss], f = 0 .. SLOT_W-1: the records of the special rows and of the compacted obstacle
 // rows are stored field-major ([field][knot] / [field][row]) so that a pass with one thread per knot / per row reads and writes
@@ -273,9 +274,11 @@ GDEV void pair_eval(const double* st, size_t ss, bool has_t, double c0, double o
   const double isa = g_rcp(sa);
   q.la = la;
   q.wa = la * isa;
+  q.isa = isa; q.itv = 0.0;
   if (has_t) {
     const double t = st[2 * ss], lb = st[3 * ss];
     const double it = g_rcp(t);
+    q.itv = it;
     q.rc = c0 - t + sa; q.rt = omega - la - lb;
     q.wb = lb * it;
     const double rsa = sa * la - smu + (phase ? st[4 * ss] : 0.0), rsb = t * lb - smu + (phase ? st[5 * ss] : 0.0);
@@ -1525,6 +1528,108 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
   }
 }
 
+// Predictor pass (round 2): one pass over the rows, ONE THREAD PER KNOT, that does what the flat affine-step pass and the second
+// assembly pass did together.  For every row of its knot the thread evaluates the affine step (step limits, the products
+// ds dlam / dt dlamb kept in the slot record, the coefficients of Mehrotra's mu_aff) and accumulates how the row's right-hand
+// side term  -gv bt  changes from the predictor to the corrector: bt is affine in the centering target and in the two products,
+//   dbt = smu X + Y,   X = isa (1 - wa iw) - wa iw it,   Y = -pa isa (1 - wa iw) + pb wa iw it      (hard row: X = isa, Y = -pa isa)
+// so  r_corr = r_aff + smu ra + rb  with  ra = -sum gv X,  rb = -sum gv Y  per knot -- known before sigma is.  After the group
+// reductions every thread forms sigma and the centering target and the right-hand side is updated in place.  Returns smu.
+template <int M> GDEV void pred_row(double* st, size_t ss, bool has_t, double c0, double gdz, double omega, StepAcc& acc, double& X, double& Y) {
+  Pair q;
+  pair_eval(st, ss, has_t, c0, omega, 0.0, 0, q);
+  pair_step(st, ss, has_t, q, gdz, 1, 0.0, 0.0, acc);
+  const double pa = st[4 * ss];
+  if (has_t) {
+    const double pb = st[5 * ss], wi = q.wa * q.iw, om = 1.0 - wi;
+    X = q.isa * om - wi * q.itv;
+    Y = -pa * q.isa * om + pb * wi * q.itv;
+  } else {
+    X = q.isa;
+    Y = -pa * q.isa;
+  }
+}
+template <int M> GDEV_NOINLINE double predictor_pass(const IpmCtx<M>& c, double npair, double mu, double tol, double* a_aff_out) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  const int N = c.N;
+  const size_t np = c.NP, pp = c.PP;
+  const double omega = c.omega;
+  StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.c0 = 0.0; acc.c1 = 0.0; acc.c2 = 0.0; acc.np = 0.0;
+  G_PAR_FOR(k, N) {
+    const double* x = sh_z<M>(c) + k * NV;
+    const double* dv = sh_dz<M>(c) + k * NV;
+    double ra[NV], rb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { ra[i] = 0.0; rb[i] = 0.0; }
+    double X, Y;
+    if (T::HAS_TR) {
+      double gv[NX], v = -c.dow, gdz = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[i * np + k]; gv[i] = 2.0 * dxi; v += dxi * dxi; gdz += gv[i] * dv[i]; }
+      pred_row<M>(c.sslot + (size_t)L::S_TR * SLOT_W * np + k, np, true, v, gdz, omega, acc, X, Y);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { ra[i] -= gv[i] * X; rb[i] -= gv[i] * Y; }
+    }
+#pragma unroll
+    for (int s = L::S_NORM; s < L::SP; ++s) {
+      SpecEval o;
+      spec_eval<M>(c, k, s, x, x + NX, o);
+      if (!o.valid) continue;
+      const int base = (spec_is_u<M>(s) ? NX : 0) + spec_i0<M>(s);
+      double gdz = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[base + a];
+      pred_row<M>(c.sslot + (size_t)s * SLOT_W * np + k, np, o.has_t, o.c0, gdz, omega, acc, X, Y);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (a < o.n) { ra[base + a] -= o.gv[a] * X; rb[base + a] -= o.gv[a] * Y; }
+    }
+    if (T::WS > 0) {
+      constexpr int WS = T::WS > 0 ? T::WS : 1;
+      const int s0 = sh_seg<M>(c)[k], s1 = sh_seg<M>(c)[k + 1];
+      for (int p = s0; p < s1; ++p) {
+        const double* row = c.orow + p;
+        double g3[WS], v = row[3 * pp], gdz = 0.0;
+#pragma unroll
+        for (int a = 0; a < WS; ++a) { g3[a] = -row[a * pp]; v += g3[a] * x[a]; gdz += g3[a] * dv[a]; }
+        pred_row<M>(c.ost + p, pp, true, v, gdz, omega, acc, X, Y);
+#pragma unroll
+        for (int a = 0; a < WS; ++a) { ra[a] -= g3[a] * X; rb[a] -= g3[a] * Y; }
+      }
+    }
+    if (k == N - 1 && c.bmask != 0) {
+      for (int j = 0; j < L::NBOX; ++j) {
+        const int i = j >> 1;
+        if (!((c.bmask >> i) & 1)) continue;
+        const double sg = (j & 1) == 0 ? 1.0 : -1.0;
+        pred_row<M>(c.bslot + (size_t)j * SLOT_W, 1, false, box_c0<M>(c, j, x), sg * dv[i], omega, acc, X, Y);
+        for (int q2 = 0; q2 < NX; ++q2) if (q2 == i) { ra[q2] -= sg * X; rb[q2] -= sg * Y; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { c.ra[i * np + k] = ra[i]; c.rb[i * np + k] = rb[i]; }
+  }
+  const double amp = -block_max(-acc.amp, c.red), amd = -block_max(-acc.amd, c.red);
+  const double s0 = block_sum(acc.c0, c.red), s1 = block_sum(acc.c1, c.red), s2 = block_sum(acc.c2, c.red);
+  double a_aff = amp < amd ? amp : amd;
+  a_aff = a_aff < 1.0 ? a_aff : 1.0;
+  double mu_aff = s0 + a_aff * (s1 + a_aff * s2);
+  mu_aff = npair > 0 ? mu_aff / npair : 0.0;
+  double sigma = mu > 0 ? (mu_aff / mu) : 0.0;
+  sigma = sigma * sigma * sigma;
+  double smu = sigma * mu;
+  smu = smu > 0.1 * tol ? smu : 0.1 * tol;
+  G_PAR_FOR(it, N * NV) {
+    const int i = it / N, k = it - i * N;
+    const size_t o = i * np + k;
+    c.r[o] += smu * c.ra[o] + c.rb[o];
+  }
+  G_SYNC();
+  *a_aff_out = a_aff;
+  return smu;
+}
+
 // --------------------------------------------------------------------------------------------------- setup
 #ifndef GUSTO_SLACK_START_SE3
 #define GUSTO_SLACK_START_SE3 0.0005
@@ -1637,6 +1742,41 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   G_SYNC();
 }
 
+// Restart of a solve that cycles: keep the primal iterate z and the equality multipliers, put every slack / multiplier pair back
+// to the well-centred cold start of the oracle (slacks one unit inside, penalty weight split evenly) evaluated AT z, and drop the
+// pending centrality floor.  The obstacle-row compaction (a function of Xp only) is unchanged.
+template <int M> GDEV_NOINLINE void restart_slots(IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NV = L::NV;
+  const int N = c.N;
+  const size_t np = c.NP, pp = c.PP;
+  G_PAR_FOR(it, N * L::SP) {
+    const int s = it / N, k = it - s * N;
+    const double* x = sh_z<M>(c) + k * NV;
+    double* st = c.sslot + (size_t)s * SLOT_W * np + k;
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, true, tr_c0<M>(c, k, x), c.omega);
+    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega); }
+  }
+  G_PAR_FOR(j, L::NBOX) {
+    const bool valid = (c.bmask >> (j >> 1)) & 1;
+    slot_init(c.bslot + (size_t)j * SLOT_W, 1, valid, false, valid ? box_c0<M>(c, j, sh_z<M>(c) + (N - 1) * NV) : 0.0, c.omega);
+  }
+  if (T::WS > 0) {
+    constexpr int WS = T::WS > 0 ? T::WS : 1;
+    for (int p = G_TID; p < c.nact; p += G_NTHR) {
+      const double* row = c.orow + p;
+      const double* x = sh_z<M>(c) + (int)row[4 * pp] * NV;
+      double v = row[3 * pp];
+#pragma unroll
+      for (int a = 0; a < WS; ++a) v -= row[a * pp] * x[a];
+      slot_init(c.ost + p, pp, true, true, v, c.omega);
+    }
+  }
+  if (G_TID == 0) c.floor_ = 0.0;
+  G_SYNC();
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 // scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance (16-byte aligned, zero-filled
 //          once at allocation: the padding columns of the tile records are never written).
@@ -1675,7 +1815,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.NP = L::np_of(N); c.NE = L::ne_of(N); c.PP = L::pp_of(N, c.n_obs);
     const size_t np = c.NP, ne = c.NE, pp = c.PP, nn = (size_t)N;
     double* q = scratch;                                         // same order and sizes as IpmLayout::scratch_doubles
-    c.r = q; q += np * NV;
+    c.r = q; q += np * NV; c.ra = q; q += np * NV; c.rb = q; q += np * NV;
     c.nu = q; q += ne * NX; c.dnu = q; q += ne * NX; c.rnu = q; q += ne * NX;
     c.gsum = q; q += ne * NX;
     c.xps = q; q += np * NX;
@@ -1718,6 +1858,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   double best = 1e300;
   int stall = 0;
   bool broke = false;
+  int restarts = 0;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
     G_CTA_RESYNC();
     ++it_done;
@@ -1752,20 +1893,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     cyc_sol += g_clock() - tc0;
     double am[5];
     tc0 = g_clock();
-    slot_steps<M>(c, 0, 0.0, 1, 0, 0, am);
-    double a_aff = am[0] < am[1] ? am[0] : am[1];
-    a_aff = a_aff < 1.0 ? a_aff : 1.0;
+    double a_aff = 1.0;
+    const double smu = predictor_pass<M>(c, R.npair, mu, prm.tol, &a_aff);     // affine step, sigma, corrector right-hand side
     cyc_slot += g_clock() - tc0;
-    double mu_aff = am[2] + a_aff * (am[3] + a_aff * am[4]);
-    mu_aff = R.npair > 0 ? mu_aff / R.npair : 0.0;
-    double sigma = mu > 0 ? (mu_aff / mu) : 0.0;
-    sigma = sigma * sigma * sigma;
-    double smu = sigma * mu;
-    smu = smu > 0.1 * prm.tol ? smu : 0.1 * prm.tol;
-    // corrector
-    tc0 = g_clock();
-    assemble<M>(c, 1, smu, &R);
-    cyc_asm += g_clock() - tc0;
     tc0 = g_clock();
     ric_backward<M>(c);
     ric_forward<M>(c, true);
@@ -1777,7 +1907,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     double ap = tau * am[0], ad = tau * am[1];
     ap = ap < 1.0 ? ap : 1.0; ad = ad < 1.0 ? ad : 1.0;
 #ifdef GUSTO_HOSTSIM
-    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("        a_aff=%.3g sigma=%.3g smu=%.3g ap=%.3g ad=%.3g\n", a_aff, sigma, smu, ap, ad);
+    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("        a_aff=%.3g smu=%.3g ap=%.3g ad=%.3g\n", a_aff, smu, ap, ad);
 #endif
     slot_steps<M>(c, 1, smu, 2, ap, ad, am);
     // Safeguard against cycling: plain Mehrotra steps can jam when a few complementarity pairs sit far below the central path
@@ -1786,6 +1916,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     // improvement and a short step, the pairs are pulled back to 1e-2 mu instead of 1e-4 mu for the next iteration; solves
     // that improve every iteration never get here.
     if (stall >= 2 && (ap < ad ? ap : ad) < 0.5) { if (G_TID == 0) c.floor_ *= 100.0; G_SYNC(); }
+    // ... and when that does not help either (astrobeeSE3manifold instance 151, fifth SCP iteration: a 4-cycle at mu = 5e-9 with the
+    // dual residual at 1e-2), the pairs are re-centred from scratch around the current primal iterate, at most twice per solve.
+    if (stall >= 6 && restarts < 2) { ++restarts; stall = 0; restart_slots<M>(c); }
     G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
     {
       double* __restrict__ nu = c.nu;
