@@ -325,11 +325,9 @@ def main():
 
         def e2e_step(record):
             om.numpy()[...] = st8["omega"]; de.numpy()[...] = st8["Delta"]; act8.numpy()[...] = st8["active"]
-            eng.set_trajectory(hb["Xh"].numpy(), hb["Uh"].numpy())     # H2D: this step's accepted trajectory
-            eng.set_penalties(om.numpy(), de.numpy())                   # H2D
-            eng.set_active(act8.numpy())                                # H2D
-            eng.iterate(oute.numpy(), infoe.numpy())                    # kernels + D2H of the scalars
-            eng.get_candidate(hb["Xc"].numpy(), hb["Uc"].numpy())       # D2H: the step's result
+            # H2D: this step's accepted trajectory, penalties, active flags; kernels; D2H: scalars + the step's result (candidate)
+            eng.iterate_host(hb["Xh"].numpy(), hb["Uh"].numpy(), om.numpy(), de.numpy(), act8.numpy(), oute.numpy(), infoe.numpy(),
+                             hb["Xc"].numpy(), hb["Uc"].numpy())
             o = oute.numpy()
             s = host.gusto_update(o, host.solver_status_ok(infoe.numpy()[:, 0]), st8["active"], st8["Delta"], st8["omega"], st8["iters"],
                                   st8["conv"], sp, False)
@@ -369,8 +367,8 @@ def main():
         d2h = 8 * (B * N * (nx + nu) + B * (host.EVAL_NOUT + host.SOLVE_NINFO))
         e2e = {"value": ec[0] / (te_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": te_ms / args.steps, "steps": args.steps,
-               "note": "host-language outer loop over the C ABI (gusto_set_trajectory / gusto_iterate / gusto_get_candidate / "
-                       "gusto_allgather_status), pinned host buffers, same real-solve iterations as `value`"}
+               "note": "host-language outer loop over the C ABI (gusto_iterate_host: upload trajectory + penalties, three kernels, download "
+                       "scalars + candidate; then gusto_allgather_status), pinned host buffers, same real-solve iterations as `value`"}
 
     # ---------------- hard tier of the same workload (reported separately with its convergence rate)
     if not args.no_extras and args.config == "astrobeeSE3" and world == 1:

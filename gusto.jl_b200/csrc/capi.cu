@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   __shared__ double outs[(T::ANZ + 2 * NX + 5 * (T::WS > 0 ? MAX_OBS : 0)) * KPC];     // the CTA's blocks, [field][knot of the CTA]
   __shared__ alignas(8) unsigned long long mbar;
   __shared__ double sbv[NU > 0 ? NU : 1];
+  __shared__ unsigned char pat[T::ANZ];                    // a_row(e) * NX + a_col(e)
   const BatchDesc& d = *dp;
   if (threadIdx.x == 0) dyn_B_columns<M>(d.rp, sbv);     // visible after the barrier / mbarrier wait below
   const int total = d.B * d.N;
@@ -103,11 +104,21 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
     for (int i = threadIdx.x; i < nk * NU; i += blockDim.x) su[i] = gu[i];
     __syncthreads();
   }
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_obs = T::WS > 0 ? d.n_obs : 0, nfield = T::ANZ + 2 * NX + 5 * n_obs;
-  if (warp < nk && !(p.active && !p.active[(k0 + warp) / d.N]))     // (frozen instance: its blocks are never read again)
-    linearize_knot<M>(d, sx + warp * NX, su + warp * NU, ws[warp], sbv, outs + warp, outs + T::ANZ * KPC + warp,
-                      outs + (T::ANZ + NX) * KPC + warp, outs + (T::ANZ + 2 * NX) * KPC + warp, KPC);
+  if (threadIdx.x < T::ANZ) pat[threadIdx.x] = (unsigned char)(T::a_row(threadIdx.x) * NX + T::a_col(threadIdx.x));
+  for (int i = threadIdx.x; i < KPC * (NX * NX + NX); i += blockDim.x) (&ws[0][0])[i] = 0.0;
+  __syncthreads();
+  const bool live = warp < nk && !(p.active && !p.active[(k0 + warp) / d.N]);     // (frozen instance: its blocks are never read again)
+  // phase 1: the serial part (f and the 24 closed-form entries of A) of ALL the CTA's knots on the lanes of warp 0 -- one
+  // instruction stream for 8 knots instead of 8 streams with one active lane each; meanwhile every warp does the obstacle rows
+  // of its own knot, which need the state only
+  if (warp == 0 && lane < nk && !(p.active && !p.active[(k0 + lane) / d.N])) linearize_fA<M>(d, sx + lane * NX, su + lane * NU, ws[lane]);
+  if (live) linearize_rows<M>(d, sx + warp * NX, outs + (T::ANZ + 2 * NX) * KPC + warp, KPC);
+  __syncthreads();
+  // phase 2: A on its pattern, f and g of the warp's knot
+  if (live) linearize_emit<M>(sx + warp * NX, su + warp * NU, ws[warp], sbv, pat, outs + warp, outs + T::ANZ * KPC + warp,
+                              outs + (T::ANZ + NX) * KPC + warp, KPC);
   __syncthreads();
   // write-out: every field row of the knot-minor layout receives the CTA's 8 consecutive knots as 64 contiguous bytes
   const size_t np = g_np(d.N);
@@ -592,6 +603,27 @@ int32_t gusto_iterate(gusto_ctx* ctx, double* out, double* info) {
   if ((rc = launch_evaluate(ctx))) return rc;
   D2H(out, ctx->d_eval, (size_t)ctx->cfg.B * EVAL_NOUT);
   if (info) D2H(info, ctx->d_info, (size_t)ctx->cfg.B * IPM_NINFO);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+// One outer iteration for a host-language loop that keeps the trajectories on the HOST: every copy is enqueued on the context
+// stream around the three kernels and there is ONE synchronisation at the end (the separate calls synchronise six times).
+int32_t gusto_iterate_host(gusto_ctx* ctx, const double* X, const double* U, const double* omega, const double* delta, const uint8_t* active,
+                           double* out, double* info, double* Xn, double* Un) {
+  NEED(out);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B, nX = B * ctx->cfg.N * ctx->nx, nU = B * ctx->cfg.N * ctx->nu;
+  if ((X == nullptr) != (U == nullptr) || (Xn == nullptr) != (Un == nullptr)) { ctx->err = "gusto_iterate_host: X/U and Xn/Un come in pairs"; return GUSTO_E_ARG; }
+  if (X) { H2D(ctx->p.Xp, X, nX); H2D(ctx->p.Up, U, nU); }
+  if (omega) H2D(ctx->p.omega, omega, B);
+  if (delta) H2D(ctx->p.delta, delta, B);
+  if (active) CK(cudaMemcpyAsync(ctx->d_active, active, B, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc;
+  if ((rc = launch_linearize(ctx)) || (rc = launch_solve(ctx)) || (rc = launch_evaluate(ctx))) return rc;
+  D2H(out, ctx->d_eval, B * EVAL_NOUT);
+  if (info) D2H(info, ctx->d_info, B * IPM_NINFO);
+  if (Xn) { D2H(Xn, ctx->p.Xn, nX); D2H(Un, ctx->p.Un, nU); }
   CK(cudaStreamSynchronize(ctx->stream));
   return GUSTO_OK;
 }

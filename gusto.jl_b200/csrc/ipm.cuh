@@ -1918,7 +1918,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     if (stall >= 2 && (ap < ad ? ap : ad) < 0.5) { if (G_TID == 0) c.floor_ *= 100.0; G_SYNC(); }
     // ... and when that does not help either (astrobeeSE3manifold instance 151, fifth SCP iteration: a 4-cycle at mu = 5e-9 with the
     // dual residual at 1e-2), the pairs are re-centred from scratch around the current primal iterate, at most twice per solve.
-    if (stall >= 6 && restarts < 2) { ++restarts; stall = 0; restart_slots<M>(c); }
+    if (stall >= 12 && restarts < 2) { ++restarts; stall = 0; restart_slots<M>(c); }
     G_PAR_FOR(it, N * NV) sh_z<M>(c)[it] += ap * sh_dz<M>(c)[it];
     {
       double* __restrict__ nu = c.nu;

@@ -23,27 +23,29 @@ template <int M> GDEV void dyn_B_columns(const double* rp, double* bv) {
   dyn_B<M>(rp, Bm);
   for (int a = 0; a < T::NU; ++a) bv[a] = Bm[T::b_row(a) * T::NU + a];
 }
-// Output of one knot: field e of A at oA[e * es], of f / g at of[i * es] / og[i * es], field q of obstacle row i at
+// One knot in three parts, so that the kernel can run the serial part of all the knots of a CTA on the lanes of ONE warp:
+//   linearize_fA    (one thread)   f and the dense A into the knot's scratch ws[NX*NX + NX] (zero-filled by the caller)
+//   linearize_emit  (one warp)     A on its sparsity pattern, f, g = f - A x - B u
+//   linearize_rows  (one warp)     obstacle rows, one lane per collision component (needs the state only)
+// Output addressing: field e of A at oA[e * es], of f / g at of[i * es] / og[i * es], field q of obstacle row i at
 // orows[(q * n_obs + i) * es].  The kernel stages the 8 knots of a CTA in shared memory (es = 8) and writes every field row of the
 // knot-minor global layout as 64 contiguous bytes; the host simulation writes the global layout directly (es = NP).
+// pat[ANZ]: a_row(e) * NX + a_col(e) (the kernel keeps it in shared memory; evaluating the pattern functions per entry and knot
+// was 17 % of the kernel's instructions).
+template <int M> GDEV void linearize_fA(const BatchDesc& d, const double* x, const double* u, double* ws) {
+  using T = Traits<M>;
+  dyn_f<M>(x, u, d.rp, ws + T::NX * T::NX);
+  dyn_A<M>(x, d.rp, ws);
+}
 template <int M>
-GDEV void linearize_knot(const BatchDesc& d, const double* x, const double* u, double* ws, const double* bv,
-                         double* oA, double* of, double* og, double* orows, size_t es) {
+GDEV void linearize_emit(const double* x, const double* u, const double* ws, const double* bv, const unsigned char* pat,
+                         double* oA, double* of, double* og, size_t es) {
   using T = Traits<M>;
   constexpr int NX = T::NX, NU = T::NU;
-  double* sA = ws;             // [NX*NX]
-  double* sf = ws + NX * NX;   // [NX]
+  const double* sA = ws;             // [NX*NX]
+  const double* sf = ws + NX * NX;   // [NX]
   const int lane = G_LANE;
-
-  for (int i = lane; i < NX * NX; i += G_NLANE) sA[i] = 0.0;
-  G_SYNCWARP();
-  if (lane == 0) {
-    dyn_f<M>(x, u, d.rp, sf);
-    dyn_A<M>(x, d.rp, sA);
-  }
-  G_SYNCWARP();
-  // A on its sparsity pattern, f and g: one field row each
-  for (int e = lane; e < T::ANZ; e += G_NLANE) oA[e * es] = sA[T::a_row(e) * NX + T::a_col(e)];
+  for (int e = lane; e < T::ANZ; e += G_NLANE) oA[e * es] = sA[pat[e]];
   for (int i = lane; i < NX; i += G_NLANE) {
     double acc = sf[i];
     for (int j = 0; j < NX; ++j) acc -= sA[i * NX + j] * x[j];
@@ -53,8 +55,11 @@ GDEV void linearize_knot(const BatchDesc& d, const double* x, const double* u, d
     of[i * es] = sf[i];
     og[i * es] = acc;
   }
-  // obstacle rows: one lane per collision component
+}
+template <int M> GDEV void linearize_rows(const BatchDesc& d, const double* x, double* orows, size_t es) {
+  using T = Traits<M>;
   if (T::WS > 0) {
+    const int lane = G_LANE;
     double r0[3];
     workspace_location<T::WS>(x, r0);
     const size_t fs = (size_t)d.n_obs * es;                                  // field stride
@@ -69,16 +74,19 @@ GDEV void linearize_knot(const BatchDesc& d, const double* x, const double* u, d
       o[4 * fs] = dist;
     }
   }
-  G_SYNCWARP();
 }
 
-// the knot-minor global layout written directly (host simulation; BatchPtrs, common.cuh)
+// the knot-minor global layout written directly, one knot after the other (host simulation; BatchPtrs, common.cuh)
 template <int M>
 GDEV void linearize_knot_global(const BatchDesc& d, const BatchPtrs& p, int b, int k, const double* x, const double* u, double* ws, const double* bv) {
   using T = Traits<M>;
   const size_t np = g_np(d.N);
-  linearize_knot<M>(d, x, u, ws, bv, p.A + (size_t)b * T::ANZ * np + k, p.f + (size_t)b * T::NX * np + k, p.g + (size_t)b * T::NX * np + k,
-                    p.rows + (size_t)b * 5 * d.n_obs * np + k, np);
+  unsigned char pat[T::ANZ];
+  for (int e = 0; e < T::ANZ; ++e) pat[e] = (unsigned char)(T::a_row(e) * T::NX + T::a_col(e));
+  for (int i = 0; i < T::NX * T::NX + T::NX; ++i) ws[i] = 0.0;
+  linearize_fA<M>(d, x, u, ws);
+  linearize_emit<M>(x, u, ws, bv, pat, p.A + (size_t)b * T::ANZ * np + k, p.f + (size_t)b * T::NX * np + k, p.g + (size_t)b * T::NX * np + k, np);
+  linearize_rows<M>(d, x, p.rows + (size_t)b * 5 * d.n_obs * np + k, np);
 }
 
 }  // namespace gusto

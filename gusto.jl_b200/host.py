@@ -92,6 +92,7 @@ def load_library(path=LIB_PATH):
     lib.gusto_accept.argtypes = [vp, _BP, _DP, _DP]
     lib.gusto_set_active.argtypes = [vp, _BP]
     lib.gusto_iterate.argtypes = [vp, _DP, _DP]
+    lib.gusto_iterate_host.argtypes = [vp, _DP, _DP, _DP, _DP, _BP, _DP, _DP, _DP, _DP]
     lib.gusto_check_trajectory.argtypes = [vp, _DP]
     lib.gusto_interpolate_trajectory.argtypes = [vp, i32, _DP, _DP]
     lib.gusto_get_duals.argtypes = [vp, _DP]
@@ -117,7 +118,7 @@ def load_library(path=LIB_PATH):
     for name in ("gusto_create", "gusto_destroy", "gusto_set_problems", "gusto_set_trajectory", "gusto_get_trajectory",
                  "gusto_get_candidate", "gusto_set_candidate", "gusto_set_penalties", "gusto_linearize",
                  "gusto_get_blocks", "gusto_solve_subproblem", "gusto_evaluate", "gusto_accept", "gusto_set_active",
-                 "gusto_iterate", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
+                 "gusto_iterate", "gusto_iterate_host", "gusto_last_kernel_ms", "gusto_device_ptr", "gusto_iterate_device",
                  "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop", "gusto_check_trajectory",
                  "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory",
                  "gusto_set_shooting_trajectory", "gusto_scp_begin", "gusto_scp_run", "gusto_scp_get", "gusto_comm_unique_id", "gusto_comm_init",
@@ -222,6 +223,12 @@ class Engine:
         info = np.empty((self.B, SOLVE_NINFO)) if info is None else info
         self._chk(self.lib.gusto_iterate(self._ctx, _dp(out), _dp(info)))
         return out, info
+
+    def iterate_host(self, X, U, omega, delta, active, out, info, Xn, Un):
+        """One outer iteration with host-resident trajectories: H2D of (X, U, omega, delta, active), the three kernels, D2H of
+        (out, info, Xn, Un), one synchronisation.  All arrays must be C-contiguous (float64; active uint8); any input may be None."""
+        ab = None if active is None else active.ctypes.data_as(_BP)
+        self._chk(self.lib.gusto_iterate_host(self._ctx, _dp(X), _dp(U), _dp(omega), _dp(delta), ab, _dp(out), _dp(info), _dp(Xn), _dp(Un)))
 
     def iterate_device(self):
         self._chk(self.lib.gusto_iterate_device(self._ctx))

@@ -159,6 +159,10 @@ linearize!(ctx) = check(ctx, ccall((:gusto_linearize, LIB), Int32, (Ptr{Cvoid},)
 evaluate!(ctx, out) = GC.@preserve out check(ctx, ccall((:gusto_evaluate, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.ptr, out))
 iterate!(ctx, out, info) = GC.@preserve out info check(ctx, ccall((:gusto_iterate, LIB), Int32,
     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, out, info))
+# one iteration with host-resident trajectories: uploads (X, U, ω, Δ, active), runs K1 -> K3 -> K4, downloads (out, info, Xn, Un)
+iterate_host!(ctx, X, U, ω, Δ, act::Vector{UInt8}, out, info, Xn, Un) = GC.@preserve X U ω Δ act out info Xn Un check(ctx, ccall((:gusto_iterate_host, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+    ctx.ptr, X, U, ω, Δ, act, out, info, Xn, Un))
 # post-processing of the accepted trajectory (dynamics_constraint_satisfaction, verify_collision_free, interpolate_traj:
 # dynamics/astrobee_se3.jl:495-562).  out is B x 8 (see GUSTO_CHECK_NOUT in the header); Xfull / Ufull are
 # (x_dim, nstep*(N-1)+1, B) and (u_dim, nstep*(N-1), B).

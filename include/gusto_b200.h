@@ -118,6 +118,13 @@ int32_t gusto_set_active(gusto_ctx* ctx, const uint8_t* active);
  * linearize -> solve -> evaluate, a single D2H copy of out[B*GUSTO_EVAL_NOUT] and info[B*GUSTO_SOLVE_NINFO]. */
 int32_t gusto_iterate(gusto_ctx* ctx, double* out, double* info);
 
+/* The same iteration for a host-language loop that keeps the trajectories on the HOST (pinned buffers recommended): uploads
+ * the accepted trajectory X, U (NULL, NULL: keep the device copy), the penalties omega / delta and the active flags (each may be
+ * NULL), runs linearize -> solve -> evaluate, downloads out / info (info may be NULL) and the candidate Xn, Un (NULL, NULL: skip)
+ * -- all enqueued on the context stream with one synchronisation at the end. */
+int32_t gusto_iterate_host(gusto_ctx* ctx, const double* X, const double* U, const double* omega, const double* delta,
+                           const uint8_t* active, double* out, double* info, double* Xn, double* Un);
+
 /* Post-processing of the ACCEPTED trajectory (SCPS.traj), SURVEY.md section 8(f):
  * out[B*GUSTO_CHECK_NOUT] = { dynamics_constraint_satisfaction (dynamics/astrobee_se3.jl:529-540: sum_k |(X_{k+1}-X_k)/dt -
  * f(X_k,U_k)|_1), max |X_{k+1} - X_k - h/2 (f_k + f_{k+1})| (nonlinear trapezoid defect), verify_collision_free (:542-562)

@@ -190,6 +190,26 @@ def test_freeflyer_notebook_first_iterations_match_the_recorded_run_on_the_gpu(h
     assert bool(S.converged[0]) and bool(S.successful[0])
 
 
+def test_fused_host_iteration_equals_the_separate_calls(host):
+    """gusto_iterate_host (uploads, three kernels, downloads, one synchronisation) against set_trajectory + set_penalties +
+    set_active + iterate + get_candidate: bit-identical outputs."""
+    bp = gb.problems.config_astrobee_se3(B=9, N=20, seed=4)
+    X0, U0 = bp.init_traj_straightline()
+    om = np.full(bp.B, 5.0); de = np.full(bp.B, 4.0); act = np.ones(bp.B, np.uint8); act[3] = 0
+    e = host.Engine(bp, device=0)
+    e.set_trajectory(X0, U0); e.set_candidate(X0, U0); e.set_penalties(om, de); e.set_active(act)
+    o1, i1 = e.iterate()
+    X1, U1 = e.get_candidate()
+    e.close()
+    e = host.Engine(bp, device=0)
+    e.set_candidate(X0, U0)
+    o2 = np.empty_like(o1); i2 = np.empty_like(i1); X2 = np.empty_like(X1); U2 = np.empty_like(U1)
+    e.iterate_host(np.ascontiguousarray(X0), np.ascontiguousarray(U0), om, de, act, o2, i2, X2, U2)
+    e.close()
+    live = act > 0
+    assert np.array_equal(X1, X2) and np.array_equal(U1, U2) and np.array_equal(o1[live], o2[live]) and np.array_equal(i1[live, :5], i2[live, :5])
+
+
 def test_status_allgather_single_rank(host):
     """gusto_allgather_status without a communicator: the gathered bytes are the local ones, the count is the number of zeros."""
     bp = gb.problems.config_dubins(B=9, N=30)
