@@ -38,10 +38,32 @@
 // (compacted to the obstacle rows inside the toggle distance), per-knot Hessian blocks, the per-solve dynamics records
 // and the per-iteration Riccati factors (Acl, K, chol(Lam), P) live in a per-instance global scratch.
 // All arithmetic is FP64 (the reference is Float64 throughout).
-#pragma once
+//
+// This header is included once per ALGORITHM (no include guard): GUSTO_IPM_ALG = 0 (default) is the GuSTO subproblem described
+// above and lives in the inline namespace gusto::ipm_gusto; GUSTO_IPM_ALG = 1 is the TrajOpt subproblem of solve_trajopt_jump!
+// (/root/reference/src/scp/scp_trajopt.jl:159-279) in gusto::ipm_trajopt -- same kernel skeleton, compiled
+// separately so that the GuSTO kernel's code does not change by a single instruction.  What differs under TrajOpt:
+//   * the state trust region is a HARD row  |x_k - xp_k|^2 - s <= 0  (:165-173; `delta` carries s, `omega` carries mu);
+//   * the control balls are mu-penalised hinge rows like every other inequality (:222-233); toggle distance = clearance + 1 (:65);
+//   * the dynamics rows are l1-PENALISED (:257-275):  d_j(z) - p_j + n_j = 0,  p, n >= 0,  cost mu 1'(p + n).  Eliminating
+//     (p, n) and their multipliers leaves the Newton system  [[H, Aeq'], [Aeq, -D]]  with a positive diagonal
+//     D_j = p/lam_p + n/lam_n on the dynamics rows: in the shifted-state recursion row j becomes  s_j = Ah s_{j-1} + Bh u_{j-1} +
+//     ch_{j-1} + w_j  with a "process noise" w_j = -F_j^-1 D_j dnu_j of cost  1/2 w' W_j^-1 w,  W_j = F_j^-1 D_j F_j^-T.  Minimising
+//     over w_j first replaces the cost-to-go of knot j by  P~ = P - P V (I + V'P V)^-1 V'P,  p~ = N'p,  N = I - V (I + V'PV)^-1 V'P
+//     (V = F^-1 D^1/2; one n_x x n_x Cholesky per knot: the noise phase of riccati_factor) and the realised state is
+//     s_j = N_j s^_j + W_j p~_j.  The chains run with  G_k = N_{k+1} Acl_k  (forward on the realised states, backward on the
+//     pre-noise costates  w_k = p_k - P_k ch_{k-1}), so chain_forward / chain_backward are shared with GuSTO unchanged.
 #include "common.cuh"
 #include "models.cuh"
 #include "evaluate.cuh"   // block_sum / block_max
+#ifndef GUSTO_IPM_ALG
+#define GUSTO_IPM_ALG 0
+#endif
+#if GUSTO_IPM_ALG == 0
+#define GUSTO_IPM_NS_OPEN inline namespace ipm_gusto {
+#else
+#define GUSTO_IPM_NS_OPEN namespace ipm_trajopt {
+#endif
 #ifdef GUSTO_HOSTSIM
 #include <cstdio>
 #include <cstdlib>
@@ -81,6 +103,8 @@
 
 namespace gusto {
 
+#ifndef GUSTO_IPM_COMMON_DEFINED
+#define GUSTO_IPM_COMMON_DEFINED
 #ifdef GUSTO_HOSTSIM
 GDEV long long g_clock() { return 0; }
 #else
@@ -144,6 +168,10 @@ constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cy
 constexpr int CHAIN_STAGES = GUSTO_CHAIN_D;
 
 GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+#endif   // GUSTO_IPM_COMMON_DEFINED
+
+GUSTO_IPM_NS_OPEN
+constexpr bool kTO = GUSTO_IPM_ALG == 1;     // TrajOpt subproblem (see the file header)
 
 template <int M> struct IpmLayout {
   using T = Traits<M>;
@@ -192,12 +220,16 @@ template <int M> struct IpmLayout {
   GHD static int ne_of(int N) { return (N + 1 + 3) & ~3; }
   GHD static int pp_of(int N, int n_obs) { const int v = N * (T::WS > 0 ? n_obs : 0); return v > 0 ? ((v + 3) & ~3) : 4; }
   static constexpr int GSW = NU * NX;                       // Gam' / Bh' entries per knot in the field-major copies
+  // TrajOpt: record of one l1-penalised dynamics row entry (row j, coordinate i), field-major [field][i][j]:
+  //   p, lam_p, n, lam_n, pa = dp dlam_p, pb = dn dlam_n (predictor products)
+  static constexpr int DSLOT_W = 6;
   // doubles of global scratch per instance
   GHD static size_t scratch_doubles(int N, int n_obs) {
     const size_t np = np_of(N), ne = ne_of(N), pp = pp_of(N, n_obs), nn = (size_t)N;
     return 3 * np * NV /* r ra rb */ + 3 * ne * NX /* nu dnu rnu */ + ne * NX /* gsum */ + np * NX /* xps */ + np * SP * SLOT_W + (size_t)NBOX * SLOT_W +
            pp * SLOT_W + pp * OROW_W + np * KDW + np * NN /* Fi */ + nn * CRW + 2 * np * GSW /* gs bs */ + nn * GT /* Acl */ + np * NX * NU /* K */ +
-           np * NTU /* lp */ + np * NTX /* P */ + 2 * np * NX /* psi ch */ + np * NU /* kap */;
+           np * NTU /* lp */ + np * NTX /* P */ + 2 * np * NX /* psi ch */ + np * NU /* kap */ +
+           (kTO ? ne * NX * (DSLOT_W + 1) /* dslot dd */ + np * NTX /* P~ */ + np * NN /* N */ : 0);
   }
   // shared-memory tiles of the Riccati sweep (doubles); they alias the direction dz
   static constexpr int XSR = RXS + NUP;                     // staged dynamics record: Ah' | Bh' | ch | 0.. | Gam' (row RXS) | 0..
@@ -214,7 +246,13 @@ template <int M> struct IpmLayout {
   static constexpr int F_SB = F_HU + NUP * LDU;             // two of them
   static constexpr int F_VEC = F_SB + 2 * SBW;              // q[2][KP] | ru[2][KU] | pit[KP]
   static constexpr int V_Q = 0, V_RU = 2 * KP, V_PIT = V_RU + 2 * KU, VECW = V_PIT + KP;
-  static constexpr int FAC_DOUBLES = F_VEC + VECW;
+  // TrajOpt noise phase: F_j^-1 | W = F^-1 D F^-T, then P~ | [I + W P | I] (two tiles) | N = (I + W P)^-1 | Acl of the knot |
+  // vectors D_j, p~, w, pivot index
+  static constexpr int LDN = NX | 1;                        // odd row stride: column walks are conflict-free
+  static constexpr int NTILE = NX * LDN;
+  static constexpr int F_NV = F_VEC + VECW, F_NZ = F_NV + NTILE, F_NT = F_NZ + NTILE, F_NY = F_NT + NTILE, F_NN = F_NY + NTILE,
+                       F_NA = F_NN + NTILE, F_NVEC = F_NA + NTILE;
+  static constexpr int FAC_DOUBLES = kTO ? F_NVEC + 3 * KP + 2 : F_VEC + VECW;
   static constexpr int GJ_ROWS = (64 / NX) * NX;            // setup_dynamics: (knot, row) pairs of one Gauss-Jordan batch
   static constexpr int GJ_DOUBLES = GJ_ROWS * 2 * NX;
   static_assert(NXP * LDU <= RXS * LDT && GJ_DOUBLES <= FAC_DOUBLES, "aliased tiles do not fit");
@@ -225,7 +263,7 @@ template <int M> struct IpmLayout {
   // byte tables with run-time indices: a_row[ANZ], a_col[ANZ], blk_of[NX]
   static constexpr int TAB_DOUBLES = (2 * ANZ + NX + 7) / 8;
   GHD static int seg_doubles(int N) { return (N + 4) / 2 + 2; }
-  static constexpr int CTX_DOUBLES = 80;                   // the per-instance context struct (IpmCtx) lives in shared memory too
+  static constexpr int CTX_DOUBLES = kTO ? 88 : 80;                   // the per-instance context struct (IpmCtx) lives in shared memory too
   GHD static int smem_doubles(int N, int nthr) {
     return CTX_DOUBLES + (int)rnd((size_t)N * NV) + work_doubles(N) + (int)rnd((size_t)(N + 1) * NX) + nthr + 16 + seg_doubles(N) + TAB_DOUBLES;
   }
@@ -248,6 +286,7 @@ template <int M> struct IpmCtx {
   double *fi, *cr, *acl, *kt, *lp, *pk, *psi, *ch, *kap;
   double *xps, *gsum, *gs, *bs;   // Xp field-major | h/2 (g_{j-1} + g_j) per equality row | Gam', Bh' field-major
   double *ra, *rb;                // corrector right-hand side  r_corr = r + smu ra + rb  (predictor_pass)
+  double *dslot, *dd, *pkt, *nm;  // TrajOpt: l1 records of the dynamics rows | D_j | P~_k | N_k = (I + W_k P_k)^-1, field-major
   // shared
   double *z, *dz, *vp, *red;
   int* seg;
@@ -366,6 +405,56 @@ GDEV void slot_init(double* st, size_t ss, bool valid, bool has_t, double c0, do
   }
 }
 
+// ------------------------------------------------------------------------- TrajOpt: l1-penalised dynamics rows
+// Entry i of row j:  d(z) - p + n = 0,  p, n >= 0 (multipliers lp, ln),  cost mu (p + n);  nu is the row's multiplier.
+//   stationarity   rp = mu - nu - lp,  rn = mu + nu - ln;      complementarity  p lp = n ln = smu
+//   Newton         dlp = -dnu + rp,  dp = (-(p lp - smu + pa) - p dlp) / lp;   dln = dnu + rn,  dn = (-(n ln - smu + pb) - n dln) / ln
+//   so             dp - dn = D dnu + beta,   D = p/lp + n/ln,   and the row reads   Aeq dz - D dnu = -(d - p + n) + beta.
+// st addresses the record with field stride fs (IpmLayout::DSLOT_W fields).
+struct L1Pair { double p, lp, n, ln, rp, rn, ilp, iln; };
+GDEV void l1_eval(const double* st, size_t fs, double mu, double nu, L1Pair& q) {
+  q.p = st[0]; q.lp = st[fs]; q.n = st[2 * fs]; q.ln = st[3 * fs];
+  q.rp = mu - nu - q.lp; q.rn = mu + nu - q.ln;
+  q.ilp = g_rcp(q.lp); q.iln = g_rcp(q.ln);
+}
+// diff = (d - p + n) + (Aeq dz)_row is what dp - dn must equal for the linearised row to hold.  Of the two slacks, the one with the
+// smaller p / lam ratio is taken from its complementarity equation (exact in dnu); the other follows from the row: along a relaxed
+// defect direction p / lam_p reaches 1e9 and would turn the rounding error of dnu into an O(1e-2) error of dp.
+GDEV void l1_dir(const double* st, size_t fs, const L1Pair& q, double dnu, double diff, double smu, int phase, double& dp, double& dlp, double& dn, double& dln) {
+  dlp = -dnu + q.rp; dln = dnu + q.rn;
+  if (q.p * q.ilp <= q.n * q.iln) {
+    dp = (-(q.p * q.lp - smu + (phase ? st[4 * fs] : 0.0)) - q.p * dlp) * q.ilp;
+    dn = dp - diff;
+  } else {
+    dn = (-(q.n * q.ln - smu + (phase ? st[5 * fs] : 0.0)) - q.n * dln) * q.iln;
+    dp = dn + diff;
+  }
+}
+// modes as pair_step
+GDEV void l1_step(double* st, size_t fs, const L1Pair& q, double dnu, double diff, double smu, int phase, int mode, double ap, double ad, StepAcc& a) {
+  double dp, dlp, dn, dln;
+  l1_dir(st, fs, q, dnu, diff, smu, phase, dp, dlp, dn, dln);
+  if (mode == 2) {
+    const double p1 = q.p + ap * dp, n1 = q.n + ap * dn, lp1 = q.lp + ad * dlp, ln1 = q.ln + ad * dln;
+    st[0] = p1; st[fs] = lp1; st[2 * fs] = n1; st[3 * fs] = ln1;
+    a.c0 += p1 * lp1 + n1 * ln1; a.np += 2.0;
+  } else {
+    if (dp < 0) { const double v = -q.p * g_rcp(dp); a.amp = v < a.amp ? v : a.amp; }
+    if (dn < 0) { const double v = -q.n * g_rcp(dn); a.amp = v < a.amp ? v : a.amp; }
+    if (dlp < 0) { const double v = -q.lp * g_rcp(dlp); a.amd = v < a.amd ? v : a.amd; }
+    if (dln < 0) { const double v = -q.ln * g_rcp(dln); a.amd = v < a.amd ? v : a.amd; }
+    if (mode == 1) {
+      st[4 * fs] = dp * dlp; st[5 * fs] = dn * dln;
+      a.c0 += q.p * q.lp + q.n * q.ln; a.c1 += q.p * dlp + q.lp * dp + q.n * dln + q.ln * dn; a.c2 += dp * dlp + dn * dln;
+    }
+  }
+}
+// start: p - n = d (zero row residual), both t0 inside, multipliers at mu (zero dual residual with nu = 0)
+GDEV void l1_init(double* st, size_t fs, double d, double mu) {
+  const double t0 = 1e-2;
+  st[0] = (d > 0 ? d : 0.0) + t0; st[fs] = mu; st[2 * fs] = (d < 0 ? -d : 0.0) + t0; st[3 * fs] = mu; st[4 * fs] = 0.0; st[5 * fs] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------- special slots
 // The rows of a knot other than trust region / obstacles / goal box: each lives on <= 4 coordinates [i0, i0+n) of x
 // (or u for the control balls), inside one Hessian block.
@@ -418,7 +507,7 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
     o.c0 = (hinge ? ev : -ev) - c.eow;
   } else {
     // control balls cover k = 1..N-1 only (astrobee_se3.jl:370-371, quirk q3)
-    o.is_u = true; o.has_t = false;
+    o.is_u = true; o.has_t = kTO;                              // TrajOpt penalises them with mu (scp_trajopt.jl:222-233)
     int i0, i1; double scale[3], rad;
     ctrl_ball<M>(s - L::S_BALL, rp, &i0, &i1, scale, &rad);
     o.i0 = i0; o.n = i1 - i0;
@@ -433,6 +522,7 @@ GDEV void spec_eval(const IpmCtx<M>& c, int k, int s, const double* x, const dou
 }
 
 // stri_state_trust_region (astrobee_se3.jl:308-311) in slack-scaled form: |x - xp|^2 - Delta/omega - t <= 0
+// (TrajOpt: the hard row |x - xp|^2 - s <= 0, scp_trajopt.jl:165-173; c.dow carries s)
 template <int M> GDEV double tr_c0(const IpmCtx<M>& c, int k, const double* x) {
   constexpr int NX = IpmCtx<M>::NX;
   double v = -c.dow;
@@ -717,9 +807,9 @@ GDEV void assemble_ublock(const IpmCtx<M>& c, int k, int phase, double smu, cons
       const size_t ss = c.NP;
       double* st = c.sslot + (size_t)s * SLOT_W * ss + k;
       Pair q;
-      if (phase == 0) pair_floor(st, ss, false, c.floor_);
-      pair_eval(st, ss, false, o.c0, c.omega, smu, phase, q);
-      if (phase == 0) pair_stat(st, ss, false, q, ka.st);
+      if (phase == 0) pair_floor(st, ss, o.has_t, c.floor_);
+      pair_eval(st, ss, o.has_t, o.c0, c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, ss, o.has_t, q, ka.st);
       block_add<n>(Hb, gz + NX + off, rr, o.i0 - off, o.n, o.gv, o.hq, q, phase);
     }
 #pragma unroll
@@ -759,9 +849,9 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       const size_t ss = c.NP;
       double* st = c.sslot + (size_t)L::S_TR * SLOT_W * ss + k;
       Pair q;
-      if (phase == 0) pair_floor(st, ss, true, c.floor_);
-      pair_eval(st, ss, true, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
-      if (phase == 0) pair_stat(st, ss, true, q, ka.st);
+      if (phase == 0) pair_floor(st, ss, !kTO, c.floor_);
+      pair_eval(st, ss, !kTO, tr_c0<M>(c, k, x), c.omega, smu, phase, q);
+      if (phase == 0) pair_stat(st, ss, !kTO, q, ka.st);
       ka.la_tr = q.la; ka.bt_tr = q.bt; ka.kap_tr = q.kap;
     }
     assemble_xblock<M, 0>(c, k, phase, smu, x, gz, ka);
@@ -782,12 +872,36 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
       aeq_row<M>(c, sh_z<M>(c), j, v);
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        const double t = v[i] + c.gsum[(size_t)i * c.NE + j];     // gsum: -x_init | h/2 (g_{j-1} + g_j) | -goal (setup)
+        double t = v[i] + c.gsum[(size_t)i * c.NE + j];           // gsum: -x_init | h/2 (g_{j-1} + g_j) | -goal (setup)
+        if (kTO && j >= 1 && j < N) {
+          // l1-penalised dynamics row: residual d - p + n, reduced right-hand side rho' = -(d - p + n) + beta (predictor: smu = 0)
+          const size_t fs = (size_t)NX * c.NE;
+          double* st = c.dslot + (size_t)i * c.NE + j;
+          if (st[0] * st[fs] < c.floor_) st[fs] = c.floor_ * g_rcp(st[0]);
+          if (st[2 * fs] * st[3 * fs] < c.floor_) st[3 * fs] = c.floor_ * g_rcp(st[2 * fs]);
+          L1Pair q;
+          l1_eval(st, fs, c.omega, c.nu[(size_t)i * c.NE + j], q);
+          const double re = t - q.p + q.n;
+          const double beta = -q.p - q.p * q.rp * q.ilp + q.n + q.n * q.rn * q.iln;
+          c.dd[(size_t)i * c.NE + j] = q.p * q.ilp + q.n * q.iln;
+#ifdef GUSTO_HOSTSIM
+          if (getenv("GUSTO_DSCALE")) c.dd[(size_t)i * c.NE + j] *= atof(getenv("GUSTO_DSCALE"));
+#endif
+          const double ad = fabs(q.rp) > fabs(q.rn) ? fabs(q.rp) : fabs(q.rn);
+          S.rz = ad > S.rz ? ad : S.rz;
+          if (!(ad == ad)) S.rz = 1e300;
+          S.mus += q.p * q.lp + q.n * q.ln; S.np += 2.0;
+          const double a = fabs(re);
+          rpmax = a > rpmax ? a : rpmax;
+          if (!(a == a)) rpmax = 1e300;
+          t = re - beta;                                          // = -rho'
+        } else {
+          const double a = fabs(t);
+          rpmax = a > rpmax ? a : rpmax;
+          if (!(a == a)) rpmax = 1e300;
+        }
         v[i] = t;
         c.rnu[(size_t)i * c.NE + j] = -t;
-        const double a = fabs(t);
-        rpmax = a > rpmax ? a : rpmax;
-        if (!(a == a)) rpmax = 1e300;
       }
       // ch_{j-1} = -F_j^-1 rho_j  (rho_j = rnu_j = -t): the affine term of the shifted-state recursion, by the thread that holds rho_j
       if (j >= 1 && j < N) {
@@ -1034,6 +1148,101 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
     const double* qv = vec + L::V_Q + cur * L::KP;
     const double* ruv = vec + L::V_RU + cur * L::KU;
     const double* pn = vp + (k + 1) * NX;
+    if (kTO && k < N - 1) {
+      // ---- TrajOpt noise phase (file header): the l1-penalised dynamics row j = k + 1 lets the realised state deviate from the
+      //      prediction at a quadratic price; minimising over that deviation first turns (P_j, p_j) into (P~_j, p~_j).
+      constexpr int LDN = L::LDN;
+      const int j = k + 1;
+      const size_t np = c.NP, ne = c.NE;
+      double* const Vt = tile + L::F_NV;
+      double* const Zt = tile + L::F_NZ;
+      double* const Aug = tile + L::F_NT;                       // [NX][2 NX], spans F_NT and F_NY
+      double* const Nt = tile + L::F_NN;
+      double* const tv = tile + L::F_NVEC;
+      double* const ptil = tv + L::KP;
+      double* const wv = ptil + L::KP;
+      int* const ipiv = reinterpret_cast<int*>(wv + L::KP);
+      // Fi_j and D_j to shared memory, then W = Fi D Fi'
+      G_PAR_FOR(it, NX * NX + NX) {
+        if (it < NX * NX) { const int i = it / NX, m = it - i * NX; Vt[i * LDN + m] = L::dsame(i, m) ? c.fi[(size_t)(i * NX + m) * np + j] : 0.0; }
+        else tv[it - NX * NX] = c.dd[(size_t)(it - NX * NX) * ne + j];
+      }
+      G_SYNC();
+      G_PAR_FOR(it, NX * NX) {
+        const int i = it / NX, m = it - i * NX;
+        double a = 0.0;
+        for (int l = 0; l < NX; ++l) a += Vt[i * LDN + l] * tv[l] * Vt[m * LDN + l];
+        Zt[i * LDN + m] = a;                                    // W
+      }
+      G_SYNC();
+      // [I + W P | I]  and  w_j = p_j - P_j ch_k  (the pre-noise costate the chains carry)
+      constexpr int LD2 = 2 * NX;
+      G_PAR_FOR(it, NX * NX + NX) {
+        if (it < NX * NX) {
+          const int i = it / NX, q = it - i * NX;
+          double a = i == q ? 1.0 : 0.0;
+          for (int m = 0; m < NX; ++m) a += Zt[i * LDN + m] * Pp[m * LDT + q];
+          Aug[i * LD2 + q] = a;
+          Aug[i * LD2 + NX + q] = i == q ? 1.0 : 0.0;
+        } else {
+          const int i = it - NX * NX;
+          double a = pn[i];
+          for (int q = 0; q < NX; ++q) a -= Pp[i * LDT + q] * XS[(NX + NU) * LDT + q];
+          wv[i] = a;
+        }
+      }
+      G_SYNC();
+      // N = (I + W P)^-1 by Gauss-Jordan with row pivoting, one thread per row.  (The textbook forms  N = I - V T^-1 V'P,
+      // P~ = P - P V T^-1 V'P  cancel catastrophically once a defect row is relaxed -- D = p / lam_p ~ 1e6 -- and P~ ~ W^-1 << P.)
+      for (int cc = 0; cc < NX; ++cc) {
+        if (G_TID == 0) {
+          int pr = cc;
+          double best = fabs(Aug[cc * LD2 + cc]);
+          for (int r = cc + 1; r < NX; ++r) { const double v = fabs(Aug[r * LD2 + cc]); if (v > best) { best = v; pr = r; } }
+          if (!(best > 1e-300)) bad = 1.0;
+          ipiv[0] = pr;
+        }
+        G_SYNC();
+        const int pr = ipiv[0];
+        if (pr != cc) G_PAR_FOR(q, LD2) { const double t2 = Aug[cc * LD2 + q]; Aug[cc * LD2 + q] = Aug[pr * LD2 + q]; Aug[pr * LD2 + q] = t2; }
+        G_SYNC();
+        G_PAR_FOR(r, NX) {
+          if (r == cc) continue;
+          const double f = Aug[r * LD2 + cc] * g_rcp(Aug[cc * LD2 + cc]);
+          for (int q = 0; q < LD2; ++q) Aug[r * LD2 + q] -= f * Aug[cc * LD2 + q];
+        }
+        G_SYNC();
+      }
+      G_PAR_FOR(it, NX * NX) {
+        const int i = it / NX, q = it - i * NX;
+        const double a = Aug[i * LD2 + NX + q] * g_rcp(Aug[i * LD2 + i]);
+        Nt[i * LDN + q] = a;
+        c.nm[(size_t)it * np + j] = a;
+      }
+      G_SYNC();
+      G_PAR_FOR(it, NX * NX + NX) {
+        if (it < NX * NX) {                                     // P~ = P N, symmetrised (a product: no cancellation)
+          const int i = it / NX, q = it - i * NX;
+          double a = 0.0;
+          for (int m = 0; m < NX; ++m) a += Pp[i * LDT + m] * Nt[m * LDN + q] + Pp[q * LDT + m] * Nt[m * LDN + i];
+          Zt[i * LDN + q] = 0.5 * a;
+        } else {                                                // p~ = N'p
+          const int i = it - NX * NX;
+          double a = 0.0;
+          for (int m = 0; m < NX; ++m) a += Nt[m * LDN + i] * pn[m];
+          ptil[i] = a;
+        }
+      }
+      G_SYNC();
+      G_PAR_FOR(it, NX * NX) {
+        const int i = it / NX, q = it - i * NX;
+        const double a = Zt[i * LDN + q];
+        Pp[i * LDT + q] = a;
+        if (q <= i) c.pkt[(size_t)tri(i, q) * np + j] = a;
+      }
+      G_SYNC();
+      pn = ptil;
+    }
     // ---- phase A
     if (k >= 1) ric_stage_async<M>(c, k - 1, tile, nxt);
     auto z1_store = [&](int r, int q, double v) { if (r <= NX + NU && q < NX) Z1[r * LDT + q] = v; };
@@ -1142,7 +1351,10 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
     }
     if (w1) {
       g_tile_grid<KSU, MT_X, MT_X, false, false>(BL, LDU, 0, Yt, LDU, 0, [&](int r, int q, double v) {
-        if (r < NX && q < NX) c.acl[(size_t)k * L::GT + r * LDT + q] = XS[q * LDT + r] - v;
+        if (r < NX && q < NX) {
+          if (kTO && k < N - 1) tile[L::F_NA + r * L::LDN + q] = XS[q * LDT + r] - v;      // multiplied by N_{k+1} below
+          else c.acl[(size_t)k * L::GT + r * LDT + q] = XS[q * LDT + r] - v;
+        }
       });
       G_LANE_FOR(i, NX) {
         double v = qv[i];
@@ -1150,10 +1362,22 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
 #pragma unroll
         for (int a = 0; a < NU; ++a) v -= Yt[i * LDU + a] * Yt[NX * LDU + a];
         vp[k * NX + i] = v;
-        if (k < N - 1) vp[(k + 1) * NX + i] = pit[i];
+        if (kTO) { if (k < N - 1) vp[(k + 1) * NX + i] = tile[L::F_NVEC + 2 * L::KP + i]; }
+        else if (k < N - 1) vp[(k + 1) * NX + i] = pit[i];
       }
     }
     G_SYNC();
+    if (kTO && k < N - 1) {                                       // chain tile G_k = N_{k+1} Acl_k
+      const double* Nt = tile + L::F_NN;
+      const double* At = tile + L::F_NA;
+      G_PAR_FOR(it, NX * NX) {
+        const int r = it / NX, q = it - r * NX;
+        double a = 0.0;
+        for (int m = 0; m < NX; ++m) a += Nt[r * L::LDN + m] * At[m * L::LDN + q];
+        c.acl[(size_t)k * L::GT + r * LDT + q] = a;
+      }
+      G_SYNC();
+    }
     GUSTO_PROF_TICK(3);
   }
   bad = block_max(bad, c.red);
@@ -1303,6 +1527,40 @@ template <int M> GDEV void ric_rhs_knot(const IpmCtx<M>& c, int k, double* rx, d
     rs[a] = v;
   }
 }
+// TrajOpt: out = W_j t,  W_j = F_j^-1 D_j F_j^-T  (the "noise covariance" of the l1-penalised dynamics row j)
+template <int M> GDEV void noise_W(const IpmCtx<M>& c, int j, const double* t, double* out) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX;
+  const size_t np = c.NP, ne = c.NE;
+  const double* fi = c.fi + j;
+  double y[NX];
+#pragma unroll
+  for (int m = 0; m < NX; ++m) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) if (L::dsame(i, m)) a += fi[(size_t)(i * NX + m) * np] * t[i];
+    y[m] = a * c.dd[(size_t)m * ne + j];
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int m = 0; m < NX; ++m) if (L::dsame(i, m)) a += fi[(size_t)(i * NX + m) * np] * y[m];
+    out[i] = a;
+  }
+}
+// out = Sym(packed, field-major at knot k) * v
+template <int M> GDEV void packed_mv(const double* pk_k, size_t np, const double* v, double* out) {
+  constexpr int NX = IpmLayout<M>::NX;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < NX; ++q) a += pk_k[(size_t)tri(i, q) * np] * v[q];
+    out[i] = a;
+  }
+}
+
 // Costates for a new right-hand side (the corrector's): bb_k = rx - K'rs - psi_{k-1}, the backward chain, then
 // kap_k = Lam_k^-1 (rs + Bh_k' pit_k).
 template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
@@ -1317,8 +1575,20 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
     ric_rhs_knot<M>(c, k, rx, rs);
     const double* kt = c.kt + k;
 #pragma unroll
+    double psi[NX];
+    if (kTO) {     // the corrector changed ch (predictor_pass): psi_{k-1} = P_k ch_{k-1} with the PRE-noise P_k (chain variable w)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) psi[i] = 0.0;
+      if (k >= 1) {
+        double chv[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) chv[i] = c.ch[i * np + k - 1];
+        packed_mv<M>(c.pk + k, np, chv, psi);
+      }
+    }
+#pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double v = rx[i] - (k >= 1 ? c.psi[i * np + k - 1] : 0.0);
+      double v = rx[i] - (kTO ? psi[i] : (k >= 1 ? c.psi[i * np + k - 1] : 0.0));
 #pragma unroll
       for (int a = 0; a < NU; ++a) v -= kt[(i * NU + a) * np] * rs[a];
       vp[k * NX + i] = v;
@@ -1332,12 +1602,28 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
     double rx[NX], rs[NU], Lc[NTU], x[NU];
     ric_rhs_knot<M>(c, k, rx, rs);
     if (k < N - 1) {
+      double pit[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pit[i] = vp[(k + 1) * NX + i];
+      if (kTO) {   // pit_k = N_{k+1}' w_{k+1}  (a product: N is tiny along a relaxed defect direction)
+        double ww[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) ww[i] = pit[i];
+        const double* nm = c.nm + k + 1;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int m = 0; m < NX; ++m) a += nm[(size_t)(m * NX + i) * np] * ww[m];
+          pit[i] = a;
+        }
+      }
       const double* bs = c.bs + k;
 #pragma unroll
       for (int a = 0; a < NU; ++a) {
         double v = rs[a];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += bs[(a * NX + i) * np] * vp[(k + 1) * NX + i];
+        for (int i = 0; i < NX; ++i) if (L::dsame(i, Traits<M>::b_row(a))) v += bs[(a * NX + i) * np] * pit[i];
         rs[a] = v;
       }
     }
@@ -1372,12 +1658,36 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
     if (k < N - 1) {
       const double* bs = c.bs + k;
 #pragma unroll
+      double dk[NX], bk[NX];
+#pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = c.ch[i * np + k];
+        double v = 0.0;
 #pragma unroll
         for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += bs[(a * NX + i) * np] * kap[a];
-        dz[(k + 1) * NV + i] = v;
+        bk[i] = v;
+        dk[i] = v + c.ch[i * np + k];
       }
+      if (kTO) {   // realised state: s_{k+1} = N_{k+1} (Acl_k s_k + d_k + W_{k+1} p_{k+1}),  p_{k+1} = w_{k+1} + P_{k+1} ch_k  (products only)
+        double pj[NX], wt[NX], chv[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) chv[i] = c.ch[i * np + k];
+        packed_mv<M>(c.pk + k + 1, np, chv, pj);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) pj[i] += vp[(k + 1) * NX + i];
+        noise_W<M>(c, k + 1, pj, wt);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) wt[i] += dk[i];
+        const double* nm = c.nm + k + 1;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double a = 0.0;
+#pragma unroll
+          for (int m = 0; m < NX; ++m) a += nm[(size_t)(i * NX + m) * np] * wt[m];
+          dk[i] = a;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dz[(k + 1) * NV + i] = dk[i];
     }
     if (k == 0) {
 #pragma unroll
@@ -1452,6 +1762,28 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
   }
   if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
 }
+// TrajOpt: step of the l1 records of the dynamics rows, one thread per row j = 1 .. N-1 (modes as pair_step)
+template <int M> GDEV void l1_rows_step(const IpmCtx<M>& c, double smu, int phase, int mode, double ap, double ad, StepAcc& acc) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX;
+  const int N = c.N;
+  const size_t ne = c.NE, fs = (size_t)NX * ne;
+  G_PAR_FOR(j1, N - 1) {
+    const int j = j1 + 1;
+    double v[NX], adz[NX];
+    aeq_row<M>(c, sh_z<M>(c), j, v);
+    aeq_row<M>(c, sh_dz<M>(c), j, adz);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double* st = c.dslot + (size_t)i * ne + j;
+      L1Pair q;
+      l1_eval(st, fs, c.omega, c.nu[(size_t)i * ne + j], q);
+      const double diff = v[i] + c.gsum[(size_t)i * ne + j] - q.p + q.n + adz[i];
+      l1_step(st, fs, q, c.dnu[(size_t)i * ne + j], diff, smu, phase, mode, ap, ad, acc);
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------- slot passes
 // Flat pass over every live row.  FN(st, has_t, c0, gdz) is called once per row; `want_gdz` says whether the
 // directional derivative gv.dz is needed.
@@ -1468,7 +1800,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     if (T::HAS_TR && s == L::S_TR) {
       double v = -c.dow, gdz = 0.0;
       for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[i * np + k]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
-      fn(st, np, true, v, gdz);
+      fn(st, np, !kTO, v, gdz);
     } else {
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
@@ -1517,6 +1849,7 @@ template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, do
     pair_eval(st, ss, has_t, c0, omega, smu, phase, q);
     pair_step(st, ss, has_t, q, gdz, mode, ap, ad, acc);
   });
+  if (kTO) l1_rows_step<M>(c, smu, phase, mode, ap, ad, acc);
   if (mode != 2) {
     out[0] = -block_max(-acc.amp, c.red);
     out[1] = -block_max(-acc.amd, c.red);
@@ -1568,7 +1901,7 @@ template <int M> GDEV_NOINLINE double predictor_pass(const IpmCtx<M>& c, double 
       double gv[NX], v = -c.dow, gdz = 0.0;
 #pragma unroll
       for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[i * np + k]; gv[i] = 2.0 * dxi; v += dxi * dxi; gdz += gv[i] * dv[i]; }
-      pred_row<M>(c.sslot + (size_t)L::S_TR * SLOT_W * np + k, np, true, v, gdz, omega, acc, X, Y);
+      pred_row<M>(c.sslot + (size_t)L::S_TR * SLOT_W * np + k, np, !kTO, v, gdz, omega, acc, X, Y);
 #pragma unroll
       for (int i = 0; i < NX; ++i) { ra[i] -= gv[i] * X; rb[i] -= gv[i] * Y; }
     }
@@ -1610,6 +1943,7 @@ template <int M> GDEV_NOINLINE double predictor_pass(const IpmCtx<M>& c, double 
 #pragma unroll
     for (int i = 0; i < NV; ++i) { c.ra[i * np + k] = ra[i]; c.rb[i * np + k] = rb[i]; }
   }
+  if (kTO) l1_rows_step<M>(c, 0.0, 0, 1, 0.0, 0.0, acc);      // affine step of the l1-penalised dynamics rows (dz, dnu of the predictor solve)
   const double amp = -block_max(-acc.amp, c.red), amd = -block_max(-acc.amd, c.red);
   const double s0 = block_sum(acc.c0, c.red), s1 = block_sum(acc.c1, c.red), s2 = block_sum(acc.c2, c.red);
   double a_aff = amp < amd ? amp : amd;
@@ -1625,9 +1959,46 @@ template <int M> GDEV_NOINLINE double predictor_pass(const IpmCtx<M>& c, double 
     const size_t o = i * np + k;
     c.r[o] += smu * c.ra[o] + c.rb[o];
   }
+  if (kTO) {     // corrector right-hand side of the dynamics rows: beta changes by (smu - pa)/lp - (smu - pb)/ln, and ch with it
+    const size_t ne = c.NE, fs = (size_t)NX * ne;
+    G_PAR_FOR(j1, N - 1) {
+      const int j = j1 + 1;
+      double v[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const double* st = c.dslot + (size_t)i * ne + j;
+        const double rho = c.rnu[(size_t)i * ne + j] + (smu - st[4 * fs]) * g_rcp(st[fs]) - (smu - st[5 * fs]) * g_rcp(st[3 * fs]);
+        c.rnu[(size_t)i * ne + j] = rho;
+        v[i] = -rho;
+      }
+      const double* fi = c.fi + j;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NX; ++m) if (L::dsame(i, m)) s2 += fi[(size_t)(i * NX + m) * np] * v[m];
+        c.ch[(size_t)i * np + j - 1] = s2;
+      }
+    }
+  }
   G_SYNC();
   *a_aff_out = a_aff;
   return smu;
+}
+
+// TrajOpt: (re)start of the l1 records of the dynamics rows at the current primal iterate
+template <int M> GDEV void l1_init_rows(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX;
+  const int N = c.N;
+  const size_t ne = c.NE, fs = (size_t)NX * ne;
+  G_PAR_FOR(j1, N - 1) {
+    const int j = j1 + 1;
+    double v[NX];
+    aeq_row<M>(c, sh_z<M>(c), j, v);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) l1_init(c.dslot + (size_t)i * ne + j, fs, v[i] + c.gsum[(size_t)i * ne + j], c.omega);
+  }
 }
 
 // --------------------------------------------------------------------------------------------------- setup
@@ -1732,7 +2103,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     const int s = it / N, k = it - s * N;
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)s * SLOT_W * np + k;
-    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, true, -c.dow, c.omega, slack_start<M>(), slack_lam_split<M>());   // x = xp at the start
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, !kTO, -c.dow, c.omega, slack_start<M>(), slack_lam_split<M>());   // x = xp at the start
     else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega, slack_start<M>(), slack_lam_split<M>()); }
   }
   G_PAR_FOR(j, L::NBOX) {
@@ -1740,6 +2111,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     slot_init(c.bslot + (size_t)j * SLOT_W, 1, valid, false, valid ? box_c0<M>(c, j, sh_z<M>(c) + (N - 1) * NV) : 0.0, c.omega);
   }
   G_SYNC();
+  if (kTO) { l1_init_rows<M>(c); G_SYNC(); }
 }
 
 // Restart of a solve that cycles: keep the primal iterate z and the equality multipliers, put every slack / multiplier pair back
@@ -1755,7 +2127,7 @@ template <int M> GDEV_NOINLINE void restart_slots(IpmCtx<M>& c) {
     const int s = it / N, k = it - s * N;
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)s * SLOT_W * np + k;
-    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, true, tr_c0<M>(c, k, x), c.omega);
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, !kTO, tr_c0<M>(c, k, x), c.omega);
     else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega); }
   }
   G_PAR_FOR(j, L::NBOX) {
@@ -1773,9 +2145,45 @@ template <int M> GDEV_NOINLINE void restart_slots(IpmCtx<M>& c) {
       slot_init(c.ost + p, pp, true, true, v, c.omega);
     }
   }
+  if (kTO) l1_init_rows<M>(c);
   if (G_TID == 0) c.floor_ = 0.0;
   G_SYNC();
 }
+
+#ifdef GUSTO_HOSTSIM
+// Host-simulation self check (GUSTO_HOSTSIM_CHECK=1): residual of the Newton system the Riccati solve claims to have solved,
+//   H dz + Aeq' dnu = r   and   Aeq dz - D dnu = rnu   (D = 0 outside TrajOpt; the PointGoal rows carry 1/w_N).
+template <int M> inline void kkt_check(const IpmCtx<M>& c, const char* tag) {
+  using L = IpmLayout<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
+  const int N = c.N;
+  const double* dz = c.dz;
+  double e1 = 0, e2 = 0, n1 = 0, n2 = 0;
+  for (int k = 0; k < N; ++k) {
+    double at[NV], hx[NX], hu[NU], kd[L::KDW];
+    aeqT_knot<M>(c, c.dnu, k, at);
+    apply_Hx<M>(c, k, dz + k * NV, hx);
+    for (int i = 0; i < L::KDW; ++i) kd[i] = c.kd[(size_t)i * c.NP + k];
+    ublocks_mv<M>(kd + L::KD_HU, dz + k * NV + NX, hu);
+    for (int i = 0; i < NV; ++i) {
+      const double lhs = (i < NX ? hx[i] : hu[i - NX]) + at[i], rhs = c.r[(size_t)i * c.NP + k];
+      e1 = fmax(e1, fabs(lhs - rhs)); n1 = fmax(n1, fabs(rhs));
+      if (getenv("GUSTO_HOSTSIM_CHECK")[0] == '2' && fabs(lhs - rhs) > 1e-7) printf("      stat k=%d i=%d lhs %.6e rhs %.6e\n", k, i, lhs, rhs);
+    }
+  }
+  for (int j = 0; j < N; ++j) {
+    double v[NX];
+    aeq_row<M>(c, dz, j, v);
+    for (int i = 0; i < NX; ++i) {
+      const double D = (kTO && j >= 1) ? c.dd[(size_t)i * c.NE + j] : 0.0;
+      const double lhs = v[i] - D * c.dnu[(size_t)i * c.NE + j], rhs = c.rnu[(size_t)i * c.NE + j];
+      e2 = fmax(e2, fabs(lhs - rhs)); n2 = fmax(n2, fabs(rhs));
+      if (getenv("GUSTO_HOSTSIM_CHECK")[0] == '2' && fabs(lhs - rhs) > 1e-7) printf("      row j=%d i=%d lhs %.6e rhs %.6e\n", j, i, lhs, rhs);
+    }
+  }
+  printf("    kkt[%s] stationarity %.3e (rhs %.3e)  rows %.3e (rhs %.3e)\n", tag, e1, n1, e2, n2);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ driver
 // scratch: IpmLayout<M>::scratch_doubles() doubles of global memory owned by this instance (16-byte aligned, zero-filled
@@ -1797,9 +2205,11 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   if (G_TID == 0) {
     c.d = &d; c.rp = d.rp; c.N = N; c.n_obs = (T::WS > 0) ? d.n_obs : 0; c.b = b; c.nact = 0;
     c.h = p.tf[b] / (N - 1); c.hh = 0.5 * c.h; c.omega = p.omega[b]; c.Delta = p.delta[b];
-    c.toggle = c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];
-    c.wN = prm.wn_base + prm.wn_omega * c.omega;
-    c.dow = c.Delta / c.omega; c.eow = c.eps / c.omega;
+    c.toggle = kTO ? d.rp[RP_CLEAR] + 1.0 : c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];   // scp_gusto.jl:76 | scp_trajopt.jl:65
+    // TrajOpt: the noise phase forms P~ = P - X'X at the last knot, where P carries w_N: a smaller penalty keeps that difference
+    // accurate (the row error after a step is dnu_N / w_N and vanishes with the step, as a proximal multiplier update does)
+    c.wN = kTO ? 1e-3 * (prm.wn_base + prm.wn_omega * c.omega) : prm.wn_base + prm.wn_omega * c.omega;
+    c.dow = kTO ? c.Delta : c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
     for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
     c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
@@ -1834,6 +2244,10 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.psi = q; q += np * NX;
     c.ch = q; q += np * NX;
     c.kap = q; q += np * NU;
+    if (kTO) {
+      c.dslot = q; q += ne * NX * L::DSLOT_W; c.dd = q; q += ne * NX;
+      c.pkt = q; q += np * L::NTX; c.nm = q; q += np * L::NN;
+    } else { c.dslot = nullptr; c.dd = nullptr; c.pkt = nullptr; c.nm = nullptr; }
     c.z = smem; c.dz = c.z + L::rnd((size_t)N * NV);
     c.vp = c.dz + L::work_doubles(N);
     c.red = c.vp + L::rnd((size_t)(N + 1) * NX);
@@ -1889,8 +2303,11 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     cyc_fac += g_clock() - tc0;
     if (!fac_ok) { broke = true; break; }                       // non-positive pivot of a Lam_k: see below
     tc0 = g_clock();
-    ric_forward<M>(c, false);
+    ric_forward<M>(c, kTO);                                       // TrajOpt: the affine step of the l1 rows needs dnu
     cyc_sol += g_clock() - tc0;
+#ifdef GUSTO_HOSTSIM
+    if (getenv("GUSTO_HOSTSIM_CHECK")) { if (!kTO) ric_forward<M>(c, true); kkt_check<M>(c, "pred"); }
+#endif
     double am[5];
     tc0 = g_clock();
     double a_aff = 1.0;
@@ -1900,6 +2317,9 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     ric_backward<M>(c);
     ric_forward<M>(c, true);
     cyc_sol += g_clock() - tc0;
+#ifdef GUSTO_HOSTSIM
+    if (getenv("GUSTO_HOSTSIM_CHECK")) kkt_check<M>(c, "corr");
+#endif
     tc0 = g_clock();
     slot_steps<M>(c, 1, smu, 0, 0, 0, am);
     double tau = 0.995;
@@ -1964,6 +2384,13 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   {
     const double omega = c.omega;
     for_each_row<M>(c, false, [&](double* st, size_t ss, bool has_t, double c0, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2 * ss]); });
+    if (kTO) {   // + mu |d_j(z)|_1 over the dynamics rows (the l1 slacks at their optimal values)
+      G_PAR_FOR(j1, N - 1) {
+        double v[NX];
+        aeq_row<M>(c, sh_z<M>(c), j1 + 1, v);
+        for (int i = 0; i < NX; ++i) obj += omega * fabs(v[i] + c.gsum[(size_t)i * c.NE + j1 + 1]);
+      }
+    }
   }
   // SCPS.dual (scp_gusto.jl:116, get_dual_jump): row 0 of Aeq is  x_0 = x_init  and the Lagrangian is f + nu'(Aeq z - b)
   if (p.dual) G_PAR_FOR(i, NX) p.dual[(size_t)b * NX + i] = c.nu[(size_t)i * c.NE];
@@ -1983,7 +2410,10 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   }
 }
 
+}  // namespace ipm_gusto / ipm_trajopt
 }  // namespace gusto
+#undef GUSTO_IPM_NS_OPEN
+#undef GUSTO_PROF_TICK
 
 #ifndef GUSTO_HOSTSIM
 #undef block_sum

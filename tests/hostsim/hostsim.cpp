@@ -12,6 +12,9 @@
 #include "../../gusto.jl_b200/csrc/common.cuh"
 #include "../../gusto.jl_b200/csrc/linearize.cuh"
 #include "../../gusto.jl_b200/csrc/ipm.cuh"
+#undef GUSTO_IPM_ALG
+#define GUSTO_IPM_ALG 1                      // second inclusion: the TrajOpt subproblem (namespace gusto::ipm_trajopt)
+#include "../../gusto.jl_b200/csrc/ipm.cuh"
 #include "../../gusto.jl_b200/csrc/evaluate.cuh"
 #include "../../gusto.jl_b200/csrc/postprocess.cuh"
 #include "../../gusto.jl_b200/csrc/shooting.cuh"
@@ -23,6 +26,9 @@ using namespace gusto;
 // optional [B][n_x] buffer that receives SCPS.dual (the init-row multipliers) of the next hostsim_iterate call
 static double* g_dual = nullptr;
 extern "C" void hostsim_set_dual_buffer(double* dual) { g_dual = dual; }
+// 0 = GuSTO subproblem, 1 = TrajOpt subproblem (omega carries mu, delta carries s) for the next hostsim_iterate calls
+static int g_alg = 0;
+extern "C" void hostsim_set_algorithm(int alg) { g_alg = alg; }
 
 template <int M>
 static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stages, double* info, double* eval) {
@@ -37,7 +43,13 @@ static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stag
       for (int k = 0; k < N; ++k)
         linearize_knot_global<M>(d, p, b, k, p.Xp + ((size_t)b * N + k) * T::NX, p.Up + ((size_t)b * N + k) * T::NU, ws.data(), bv);
   }
-  if (stages & 2) {
+  if ((stages & 2) && g_alg == 1) {
+    if constexpr (M == FREEFLYER_SE2 || M == ASTROBEE_SE3) {
+      using LT = ipm_trajopt::IpmLayout<M>;
+      std::vector<double> scratch(LT::scratch_doubles(N, d.n_obs)), smem(LT::smem_doubles(N, 1));
+      for (int b = 0; b < B; ++b) ipm_trajopt::ipm_solve_instance<M>(d, p, prm, b, scratch.data(), smem.data(), info + (size_t)b * IPM_NINFO);
+    }
+  } else if (stages & 2) {
     std::vector<double> scratch(L::scratch_doubles(N, d.n_obs)), smem(L::smem_doubles(N, 1));
     for (int b = 0; b < B; ++b) ipm_solve_instance<M>(d, p, prm, b, scratch.data(), smem.data(), info + (size_t)b * IPM_NINFO);
   }
