@@ -14,7 +14,11 @@
 #include "common.cuh"
 #include "linearize.cuh"
 #include "ipm.cuh"
+#undef GUSTO_IPM_ALG
+#define GUSTO_IPM_ALG 1            // second inclusion: the TrajOpt subproblem, namespace gusto::ipm_trajopt (see ipm.cuh)
+#include "ipm.cuh"
 #include "evaluate.cuh"
+#include "trajopt.cuh"
 #include "postprocess.cuh"
 #include "shooting.cuh"
 #include "scp.cuh"
@@ -148,6 +152,53 @@ __global__ void __launch_bounds__(IPM_THREADS * IPM_MAX_PACK, 1) ipm_kernel(cons
   ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem + (size_t)sub * smem_doubles, info + (size_t)b * IPM_NINFO);
 }
 
+// K3, TrajOpt subproblem (scp_trajopt.jl:159-279): same launch shape, the second compilation of ipm.cuh.
+template <int M>
+__global__ void __launch_bounds__(IPM_THREADS * IPM_MAX_PACK, 1) ipm_trajopt_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, IpmParams prm,
+                                                                  double* scratch, size_t stride, double* info, int smem_doubles) {
+  extern __shared__ __align__(16) double smem[];
+  const int sub = threadIdx.x / IPM_THREADS;
+  const int b = blockIdx.x * (blockDim.x / IPM_THREADS) + sub;
+  if (b >= dp->B) return;
+  if (p.active && !p.active[b]) return;
+  ipm_trajopt::ipm_solve_instance<M>(*dp, p, prm, b, scratch + (size_t)b * stride, smem + (size_t)sub * smem_doubles, info + (size_t)b * IPM_NINFO);
+}
+// TrajOpt evaluation scalars (trajopt.cuh).  Grid: B CTAs.
+template <int M>
+__global__ void __launch_bounds__(EVAL_THREADS) trajopt_evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
+  using T = Traits<M>;
+  __shared__ double red[EVAL_THREADS];
+  const int b = blockIdx.x;
+  if (p.active && !p.active[b]) return;
+  trajopt_evaluate_instance<M>(*dp, p, b, p.Xn + (size_t)b * dp->N * T::NX, p.Un + (size_t)b * dp->N * T::NU, out + (size_t)b * TRAJOPT_NOUT, red);
+}
+// accepted trajectory against a marked reference trajectory: evaluate_ctol numerator / denominator, evaluate_xtol, cost_true of both
+template <int M>
+__global__ void __launch_bounds__(EVAL_THREADS) trajopt_compare_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, const double* Xr, const double* Ur, double* out) {
+  using T = Traits<M>;
+  constexpr int NX = T::NX, NU = T::NU;
+  __shared__ double red[EVAL_THREADS];
+  const int b = blockIdx.x, N = dp->N;
+  const double* X = p.Xp + (size_t)b * N * NX;
+  const double* U = p.Up + (size_t)b * N * NU;
+  const double* Xb = Xr + (size_t)b * N * NX;
+  const double* Ub = Ur + (size_t)b * N * NU;
+  double* o = out + (size_t)b * 5;
+  trajopt_ctol_instance<M>(*dp, p, b, X, U, Xb, Ub, o, red);
+  const double h = p.tf[b] / (N - 1);
+  double mdx2 = 0, mnx2 = 0, J = 0, Jr = 0;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    double dx2 = 0, nx2 = 0, uu = 0, ur = 0;
+    for (int i = 0; i < NX; ++i) { const double dxi = X[k * NX + i] - Xb[k * NX + i]; dx2 += dxi * dxi; nx2 += X[k * NX + i] * X[k * NX + i]; }
+    for (int i = 0; i < NU; ++i) { uu += U[k * NU + i] * U[k * NU + i]; ur += Ub[k * NU + i] * Ub[k * NU + i]; }
+    mdx2 = dx2 > mdx2 ? dx2 : mdx2; mnx2 = nx2 > mnx2 ? nx2 : mnx2;
+    const double wk = (k == 0 || k == N - 1) ? 0.5 * h : h;
+    J += wk * uu; Jr += wk * ur;
+  }
+  mdx2 = block_max(mdx2, red); mnx2 = block_max(mnx2, red); J = block_sum(J, red); Jr = block_sum(Jr, red);
+  if (threadIdx.x == 0) { o[2] = sqrt(mdx2) / sqrt(mnx2); o[3] = J; o[4] = Jr; }
+}
+
 // K4.  Grid: B CTAs.
 template <int M>
 __global__ void __launch_bounds__(EVAL_THREADS, 4) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
@@ -252,6 +303,12 @@ struct gusto_ctx {
   int scp_real = 0;                              // ... that ran with at least one live instance anywhere
   void* comm = nullptr;                          // ncclComm_t
   int rank = 0, nranks = 1;
+  // ---- TrajOpt variant (gusto_trajopt_*): own solver scratch / launch shape, two reference trajectories, evaluation outputs
+  bool to_ready = false;
+  double *d_to_scratch = nullptr, *d_to_eval = nullptr, *d_to_cmp = nullptr;
+  double* d_to_ref[4] = {nullptr, nullptr, nullptr, nullptr};    // X, U of slot 0 (old_penalty_traj) and slot 1 (old_convex_traj)
+  size_t to_stride = 0;
+  int to_smem = 0, to_pack_max = 1;
 };
 
 static std::string g_err;
@@ -419,6 +476,8 @@ int32_t gusto_destroy(gusto_ctx* ctx) {
                   ctx->d_omega_in, ctx->d_delta_in, p.f, p.A, p.g, p.rows, ctx->d_scratch, ctx->d_info, ctx->d_eval, ctx->d_accept, ctx->d_active,
                   ctx->d_dual, ctx->d_Xs, ctx->d_Us, ctx->d_Ps, ctx->d_p0, ctx->d_xgoal, ctx->d_shoot, ctx->d_check, ctx->d_interp};
   for (void* q : ptrs) if (q) cudaFree(q);
+  void* to_ptrs[] = {ctx->d_to_scratch, ctx->d_to_eval, ctx->d_to_cmp, ctx->d_to_ref[0], ctx->d_to_ref[1], ctx->d_to_ref[2], ctx->d_to_ref[3]};
+  for (void* q : to_ptrs) if (q) cudaFree(q);
   scp_release(ctx);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; ++i) if (ctx->tev[i]) cudaEventDestroy(ctx->tev[i]);
@@ -644,6 +703,120 @@ int32_t gusto_accept_device(gusto_ctx* ctx, const uint8_t* accept_dev, const dou
   CK(cudaSetDevice(ctx->cfg.device));
   int32_t rc = launch_accept(ctx, accept_dev, omega_dev, delta_dev);
   if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ TrajOpt variant
+static bool trajopt_model(int model) { return model == FREEFLYER_SE2 || model == ASTROBEE_SE3; }
+
+int32_t gusto_trajopt_enable(gusto_ctx* ctx) {
+  NEED(true);
+  if (ctx->to_ready) return GUSTO_OK;
+  // SCPParam_TrajOpt exists for these models only among the in-scope ones; astrobeeSE3manifold would need its quaternion rows as
+  // hard per-knot equalities (scp_trajopt.jl:199-207), which the Riccati solve does not carry
+  if (!trajopt_model(ctx->cfg.model_id)) { ctx->err = "gusto_trajopt_enable: TrajOpt is built for freeflyerSE2 and astrobeeSE3"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int N = ctx->cfg.N, no = ctx->hdesc.n_obs;
+  const size_t B = ctx->cfg.B, nX = B * N * ctx->nx, nU = B * N * ctx->nu;
+  int sd;
+  if (ctx->cfg.model_id == FREEFLYER_SE2) { ctx->to_stride = ipm_trajopt::IpmLayout<FREEFLYER_SE2>::scratch_doubles(N, no); sd = ipm_trajopt::IpmLayout<FREEFLYER_SE2>::smem_doubles(N, IPM_THREADS); }
+  else { ctx->to_stride = ipm_trajopt::IpmLayout<ASTROBEE_SE3>::scratch_doubles(N, no); sd = ipm_trajopt::IpmLayout<ASTROBEE_SE3>::smem_doubles(N, IPM_THREADS); }
+  ctx->to_smem = ((sd + 15) & ~15) * (int)sizeof(double);
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device);
+  int pm = max_optin / ctx->to_smem;
+  ctx->to_pack_max = pm < 1 ? 1 : (pm > IPM_MAX_PACK ? IPM_MAX_PACK : pm);
+  const int smem_attr = ctx->to_smem * ctx->to_pack_max;
+  if (ctx->cfg.model_id == FREEFLYER_SE2) CK(cudaFuncSetAttribute(ipm_trajopt_kernel<FREEFLYER_SE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  else CK(cudaFuncSetAttribute(ipm_trajopt_kernel<ASTROBEE_SE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_attr));
+  auto alloc = [&](double** ptr, size_t n) {
+    if (cudaMalloc((void**)ptr, n * sizeof(double)) != cudaSuccess) return false;
+    return cudaMemset(*ptr, 0, n * sizeof(double)) == cudaSuccess;
+  };
+  const bool ok = alloc(&ctx->d_to_scratch, B * ctx->to_stride) && alloc(&ctx->d_to_eval, B * TRAJOPT_NOUT) && alloc(&ctx->d_to_cmp, B * 5) &&
+                  alloc(&ctx->d_to_ref[0], nX) && alloc(&ctx->d_to_ref[1], nU) && alloc(&ctx->d_to_ref[2], nX) && alloc(&ctx->d_to_ref[3], nU);
+  if (!ok) {
+    double** all[] = {&ctx->d_to_scratch, &ctx->d_to_eval, &ctx->d_to_cmp, &ctx->d_to_ref[0], &ctx->d_to_ref[1], &ctx->d_to_ref[2], &ctx->d_to_ref[3]};
+    for (double** q : all) { if (*q) cudaFree(*q); *q = nullptr; }
+    ctx->err = "gusto_trajopt_enable: cudaMalloc failed";
+    return GUSTO_E_ALLOC;
+  }
+  ctx->to_ready = true;
+  return GUSTO_OK;
+}
+
+static int32_t launch_trajopt_solve(gusto_ctx* ctx) {
+  int pack = (ctx->cfg.B + ctx->nsm - 1) / ctx->nsm;
+  pack = pack < 1 ? 1 : (pack > ctx->to_pack_max ? ctx->to_pack_max : pack);
+  const int grid = (ctx->cfg.B + pack - 1) / pack, block = IPM_THREADS * pack, smem = ctx->to_smem * pack, sd = ctx->to_smem / (int)sizeof(double);
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (ctx->cfg.model_id == FREEFLYER_SE2) ipm_trajopt_kernel<FREEFLYER_SE2><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_to_scratch, ctx->to_stride, ctx->d_info, sd);
+  else ipm_trajopt_kernel<ASTROBEE_SE3><<<grid, block, smem, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->prm, ctx->d_to_scratch, ctx->to_stride, ctx->d_info, sd);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed[1] = true;
+  ctx->launches++;
+  return GUSTO_OK;
+}
+static int32_t launch_trajopt_evaluate(gusto_ctx* ctx) {
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (ctx->cfg.model_id == FREEFLYER_SE2) trajopt_evaluate_kernel<FREEFLYER_SE2><<<ctx->cfg.B, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_to_eval);
+  else trajopt_evaluate_kernel<ASTROBEE_SE3><<<ctx->cfg.B, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_to_eval);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timed[2] = true;
+  ctx->launches++;
+  return GUSTO_OK;
+}
+
+int32_t gusto_trajopt_iterate(gusto_ctx* ctx, const double* mu, const double* s, const uint8_t* active, double* out, double* info) {
+  NEED(out);
+  if (!ctx->to_ready) { ctx->err = "gusto_trajopt_iterate: call gusto_trajopt_enable first"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B;
+  if (mu) H2D(ctx->p.omega, mu, B);
+  if (s) H2D(ctx->p.delta, s, B);
+  if (active) CK(cudaMemcpyAsync(ctx->d_active, active, B, cudaMemcpyHostToDevice, ctx->stream));
+  int32_t rc;
+  if ((rc = launch_linearize(ctx)) || (rc = launch_trajopt_solve(ctx)) || (rc = launch_trajopt_evaluate(ctx))) return rc;
+  D2H(out, ctx->d_to_eval, B * TRAJOPT_NOUT);
+  if (info) D2H(info, ctx->d_info, B * IPM_NINFO);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_trajopt_mark(gusto_ctx* ctx, int32_t slot, const uint8_t* which) {
+  NEED(true);
+  if (!ctx->to_ready || slot < 0 || slot > 1) { ctx->err = "gusto_trajopt_mark: enable first; slot is 0 or 1"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t B = ctx->cfg.B, sx = (size_t)ctx->cfg.N * ctx->nx, su = (size_t)ctx->cfg.N * ctx->nu;
+  if (!which) {
+    CK(cudaMemcpyAsync(ctx->d_to_ref[2 * slot], ctx->p.Xp, B * sx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_to_ref[2 * slot + 1], ctx->p.Up, B * su * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    for (size_t b = 0; b < B; ++b) {          // runs of flagged instances, one copy per run
+      if (!which[b]) continue;
+      size_t e = b;
+      while (e + 1 < B && which[e + 1]) ++e;
+      CK(cudaMemcpyAsync(ctx->d_to_ref[2 * slot] + b * sx, ctx->p.Xp + b * sx, (e - b + 1) * sx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_to_ref[2 * slot + 1] + b * su, ctx->p.Up + b * su, (e - b + 1) * su * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      b = e;
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return GUSTO_OK;
+}
+
+int32_t gusto_trajopt_compare(gusto_ctx* ctx, int32_t slot, double* out) {
+  NEED(out);
+  if (!ctx->to_ready || slot < 0 || slot > 1) { ctx->err = "gusto_trajopt_compare: enable first; slot is 0 or 1"; return GUSTO_E_ARG; }
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->cfg.model_id == FREEFLYER_SE2) trajopt_compare_kernel<FREEFLYER_SE2><<<ctx->cfg.B, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_to_ref[2 * slot], ctx->d_to_ref[2 * slot + 1], ctx->d_to_cmp);
+  else trajopt_compare_kernel<ASTROBEE_SE3><<<ctx->cfg.B, EVAL_THREADS, 0, ctx->stream>>>(ctx->ddesc, ctx->p, ctx->d_to_ref[2 * slot], ctx->d_to_ref[2 * slot + 1], ctx->d_to_cmp);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  D2H(out, ctx->d_to_cmp, (size_t)ctx->cfg.B * 5);
   CK(cudaStreamSynchronize(ctx->stream));
   return GUSTO_OK;
 }

@@ -1574,7 +1574,6 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
     double rx[NX], rs[NU];
     ric_rhs_knot<M>(c, k, rx, rs);
     const double* kt = c.kt + k;
-#pragma unroll
     double psi[NX];
     if (kTO) {     // the corrector changed ch (predictor_pass): psi_{k-1} = P_k ch_{k-1} with the PRE-noise P_k (chain variable w)
 #pragma unroll
@@ -1657,7 +1656,6 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
     for (int a = 0; a < NU; ++a) { kap[a] = c.kap[a * np + k]; dz[k * NV + NX + a] = kap[a]; }
     if (k < N - 1) {
       const double* bs = c.bs + k;
-#pragma unroll
       double dk[NX], bk[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) {

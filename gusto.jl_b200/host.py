@@ -25,6 +25,8 @@ SH_STATUS, SH_ITERS, SH_FNORM, SH_JTRUE, SH_CONV, SH_LAMBDA = range(6)
 SOLVE_NINFO = 8
 EV_CONV, EV_TR_OK, EV_INEQ_OK, EV_RHO, EV_JTRUE, EV_JFULL, EV_MAXDX2, EV_MAXSOFT = range(8)
 HIST_W = 12
+TRAJOPT_NOUT = 8
+TO_XTOL, TO_RHO, TO_JTRUE, TO_JPREV, TO_MAXDX2, TO_NUM, TO_DEN, TO_DEFECT = range(8)
 H_JTRUE, H_JFULL, H_SCP_STATUS, H_SOLVER_STATUS, H_ACCEPT, H_CONV, H_DELTA, H_OMEGA, H_RHO, H_TR_OK, H_INEQ_OK, H_NEWTON = range(12)
 SCP_MAX_HIST = 64
 SCP_STATUS = ("NA", "OK", "InaccurateModel", "ViolatesConstraints", "TrustRegionViolated", "SolverFailed", "Inactive")
@@ -115,6 +117,10 @@ def load_library(path=LIB_PATH):
     lib.gusto_comm_unique_id.argtypes = [_BP]
     lib.gusto_comm_init.argtypes = [vp, i32, i32, _BP]
     lib.gusto_allgather_status.argtypes = [vp, _BP, _BP, _IP]
+    lib.gusto_trajopt_enable.argtypes = [vp]
+    lib.gusto_trajopt_iterate.argtypes = [vp, _DP, _DP, _BP, _DP, _DP]
+    lib.gusto_trajopt_mark.argtypes = [vp, i32, _BP]
+    lib.gusto_trajopt_compare.argtypes = [vp, i32, _DP]
     for name in ("gusto_create", "gusto_destroy", "gusto_set_problems", "gusto_set_trajectory", "gusto_get_trajectory",
                  "gusto_get_candidate", "gusto_set_candidate", "gusto_set_penalties", "gusto_linearize",
                  "gusto_get_blocks", "gusto_solve_subproblem", "gusto_evaluate", "gusto_accept", "gusto_set_active",
@@ -122,7 +128,7 @@ def load_library(path=LIB_PATH):
                  "gusto_accept_device", "gusto_timer_start", "gusto_timer_stop", "gusto_check_trajectory",
                  "gusto_interpolate_trajectory", "gusto_get_duals", "gusto_shoot", "gusto_get_shooting_trajectory",
                  "gusto_set_shooting_trajectory", "gusto_scp_begin", "gusto_scp_run", "gusto_scp_get", "gusto_comm_unique_id", "gusto_comm_init",
-                 "gusto_allgather_status"):
+                 "gusto_allgather_status", "gusto_trajopt_enable", "gusto_trajopt_iterate", "gusto_trajopt_mark", "gusto_trajopt_compare"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -232,6 +238,28 @@ class Engine:
 
     def iterate_device(self):
         self._chk(self.lib.gusto_iterate_device(self._ctx))
+
+    # ---- TrajOpt variant (solve_trajopt_jump!, scp_trajopt.jl)
+    def trajopt_enable(self):
+        self._chk(self.lib.gusto_trajopt_enable(self._ctx))
+
+    def trajopt_iterate(self, mu, s, active=None, out=None, info=None):
+        """linearize -> TrajOpt subproblem -> evaluation of the candidate: out[B, TRAJOPT_NOUT], info[B, SOLVE_NINFO]."""
+        out = np.empty((self.B, TRAJOPT_NOUT)) if out is None else out
+        info = np.empty((self.B, SOLVE_NINFO)) if info is None else info
+        ab = None if active is None else np.ascontiguousarray(active, dtype=np.uint8).ctypes.data_as(_BP)
+        self._chk(self.lib.gusto_trajopt_iterate(self._ctx, _dp(np.ascontiguousarray(mu, dtype=np.float64)),
+                                                 _dp(np.ascontiguousarray(s, dtype=np.float64)), ab, _dp(out), _dp(info)))
+        return out, info
+
+    def trajopt_mark(self, slot, which=None):
+        wb = None if which is None else np.ascontiguousarray(which, dtype=np.uint8).ctypes.data_as(_BP)
+        self._chk(self.lib.gusto_trajopt_mark(self._ctx, slot, wb))
+
+    def trajopt_compare(self, slot):
+        out = np.empty((self.B, 5))
+        self._chk(self.lib.gusto_trajopt_compare(self._ctx, slot, _dp(out)))
+        return out
 
     def accept_device(self, accept_ptr, omega_ptr, delta_ptr):
         self._chk(self.lib.gusto_accept_device(self._ctx, accept_ptr, omega_ptr, delta_ptr))
@@ -600,3 +628,149 @@ class _ScpStepper:
         S.batch_iterations += 1
         S.X, S.U = e.get_trajectory()
         return st
+
+
+# ------------------------------------------------------------------------------------------------ TrajOpt variant
+@dataclass
+class BatchTrajOptSolution:
+    """Per-instance SCPSolution histories + SCPParam_TrajOpt vectors (scp_trajopt.jl:3-22) of a batched solve_trajopt_jump!."""
+    X: np.ndarray
+    U: np.ndarray
+    converged: np.ndarray
+    iterations: np.ndarray
+    J_true: list = field(default_factory=list)            # per instance: list of floats
+    J_full: list = field(default_factory=list)
+    solver_status: list = field(default_factory=list)
+    convergence_measure: list = field(default_factory=list)
+    rho_vec: list = field(default_factory=list)
+    mu_vec: list = field(default_factory=list)
+    s_vec: list = field(default_factory=list)
+    xtol_vec: list = field(default_factory=list)
+    ftol_vec: list = field(default_factory=list)
+    ctol_vec: list = field(default_factory=list)
+    newton_iters: list = field(default_factory=list)
+    batch_solves: int = 0
+    total_time: float = 0.0
+
+
+def _trajopt_instance(prm, H):
+    """The three nested loops of solve_trajopt_jump! (scp_trajopt.jl:71-155) for ONE instance, as a coroutine: it yields the device
+    work it needs next -- ("mark", slot) = copy!(old_*_traj, SCPS.traj) (:73, :76), ("solve", mu, s) = one convex subproblem with
+    the step installed (:83-133), ("compare", slot) = evaluate_ftol / evaluate_xtol / evaluate_ctol against a marked trajectory
+    (:140-141, :148) -- and is resumed with the result.  The batch driver runs B of them in lockstep, one kernel launch per
+    request kind.  Repairs of the reference routine (it cannot run as written) are listed in oracle/gusto_oracle/trajopt.py and
+    DESIGN.md: real copies for old_penalty_traj / old_convex_traj after the trust loop, xtol_vec[end] in :142."""
+    mu0, s0, c, tp, tm, kfac, ftol, xtol, ctol = prm[:9]
+    max_pen, max_cvx, max_tr = int(prm[9]), int(prm[10]), int(prm[11])
+    H["mu_vec"].append(mu0); H["s_vec"].append(s0)
+    cs = xs = False
+    for _pen in range(max_pen):
+        if cs:
+            break
+        yield ("mark", 0)
+        for _cvx in range(max_cvx):
+            yield ("mark", 1)
+            if cs:
+                break
+            if xs:
+                xs = False
+                break
+            for _tr in range(max_tr):
+                ok, ev, info = yield ("solve", H["mu_vec"][-1], H["s_vec"][-1])
+                H["solver_status"].append(int(info[0])); H["newton_iters"].append(int(info[1]))
+                if not ok:                                            # no iterate to continue from (the reference only warns, :108-111)
+                    return
+                H["xtol_vec"].append(ev[TO_XTOL]); H["convergence_measure"].append(ev[TO_XTOL]); H["J_full"].append(info[4])
+                H["rho_vec"].append(ev[TO_RHO])
+                H["s_vec"].append((tp if ev[TO_RHO] > c else tm) * H["s_vec"][-1])          # :122-126
+                H["J_true"].append(ev[TO_JTRUE]); H["iterations"] += 1
+                if H["s_vec"][-1] < xtol:                             # :134
+                    xs = True
+                    break
+            cmp = yield ("compare", 1)
+            H["ftol_vec"].append(abs(cmp[3] - cmp[4]) / abs(cmp[3])); H["xtol_vec"].append(cmp[2])
+            if H["ftol_vec"][-1] < ftol or H["xtol_vec"][-1] < xtol:  # :142
+                cs = True
+                break
+        cmp = yield ("compare", 0)
+        H["ctol_vec"].append(cmp[0] / cmp[1])
+        if H["ctol_vec"][-1] < ctol:                                  # :148
+            cs = True
+            H["converged"] = True
+            break
+        H["mu_vec"].append(H["mu_vec"][-1] * kfac)                    # :154
+
+
+def solve_trajopt_batch(engine: Engine, X0=None, U0=None, params=None, verbose=False):
+    """Batched solve_trajopt_jump! (scp_trajopt.jl:33-157): the loops above per instance, every subproblem solve / evaluation of
+    the whole batch in one kernel launch."""
+    bp = engine.bp
+    B = bp.B
+    prm = M.TRAJOPT_PARAMS[bp.model.model_id] if params is None else params
+    if X0 is None:
+        X0, U0 = bp.init_traj_straightline()
+    t0 = time.perf_counter()
+    engine.trajopt_enable()
+    engine.set_trajectory(X0, U0)
+    engine.set_candidate(X0, U0)
+    mu = np.full(B, prm[0]); s = np.full(B, prm[1])
+    engine.set_penalties(mu, s)
+    engine.linearize()
+    J0 = engine.evaluate()[:, EV_JTRUE]                               # :64
+    hist = [dict(mu_vec=[], s_vec=[], solver_status=[-1], newton_iters=[], xtol_vec=[0.0], convergence_measure=[0.0], J_full=[], rho_vec=[0.0],
+                 J_true=[float(J0[b])], ftol_vec=[0.0], ctol_vec=[0.0], iterations=0, converged=False) for b in range(B)]
+    gens = [_trajopt_instance(prm, hist[b]) for b in range(B)]
+    req = [None] * B
+    for b in range(B):
+        req[b] = next(gens[b])
+    nsolve = 0
+
+    def advance(b, value):
+        try:
+            req[b] = gens[b].send(value)
+        except StopIteration:
+            req[b] = None
+
+    while any(r is not None for r in req):
+        # bookkeeping requests first, one device call per kind, until every live instance waits for a solve
+        for _ in range(16):
+            pending = [b for b in range(B) if req[b] is not None and req[b][0] != "solve"]
+            if not pending:
+                break
+            for slot in (0, 1):
+                which = np.zeros(B, np.uint8)
+                for b in pending:
+                    if req[b] == ("mark", slot):
+                        which[b] = 1
+                if which.any():
+                    engine.trajopt_mark(slot, which)
+                    for b in np.nonzero(which)[0]:
+                        advance(b, None)
+            for slot in (1, 0):
+                idx = [b for b in range(B) if req[b] == ("compare", slot)]
+                if idx:
+                    cmpv = engine.trajopt_compare(slot)
+                    for b in idx:
+                        advance(b, cmpv[b])
+        live = np.array([r is not None for r in req])
+        if not live.any():
+            break
+        for b in range(B):
+            if live[b]:
+                mu[b], s[b] = req[b][1], req[b][2]
+        ev, info = engine.trajopt_iterate(mu, s, live.astype(np.uint8))
+        ok = solver_status_ok(info[:, 0])
+        engine.accept((live & ok).astype(np.uint8))                   # copy!(SCPS.traj, new_traj), :128
+        nsolve += 1
+        if verbose:
+            print(f"[trajopt] solve {nsolve:2d} live {int(live.sum()):5d} newton {info[live, 1].mean():.1f} mu {mu[live].max():g} s in [{s[live].min():g}, {s[live].max():g}]")
+        for b in range(B):
+            if live[b]:
+                advance(b, (bool(ok[b]), ev[b].copy(), info[b].copy()))
+    X, U = engine.get_trajectory()
+    S = BatchTrajOptSolution(X, U, np.array([h["converged"] for h in hist]), np.array([h["iterations"] for h in hist]))
+    for key in ("J_true", "J_full", "solver_status", "convergence_measure", "rho_vec", "mu_vec", "s_vec", "xtol_vec", "ftol_vec", "ctol_vec", "newton_iters"):
+        setattr(S, key, [h[key] for h in hist])
+    S.batch_solves = nsolve
+    S.total_time = time.perf_counter() - t0
+    return S

@@ -247,3 +247,11 @@ class GoalSet:
             else:
                 gtype[idx], lo[idx], hi[idx] = GOAL_BOX, g.params.lower_bound, g.params.upper_bound
         return gtype, lo, hi
+
+
+# SCPParam_TrajOpt(model): mu0, s0, c, tau_plus, tau_minus, k, ftol, xtol, ctol, max_penalty_iteration, max_convex_iteration,
+# max_trust_iteration (dynamics/astrobee_se3.jl:50-64, freeflyer_se2.jl:49-63)
+TRAJOPT_PARAMS = {
+    ASTROBEE_SE3: np.array([1.0, 10.0, 10.0, 2.0, 0.5, 5.0, 0.01, 0.01, 0.01, 5, 5, 5]),
+    FREEFLYER_SE2: np.array([1.0, 1.0, 10.0, 2.0, 0.5, 5.0, 0.01, 0.1, 0.01, 5, 5, 5]),
+}

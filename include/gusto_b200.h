@@ -215,6 +215,30 @@ int32_t gusto_comm_unique_id(uint8_t* id128);
 int32_t gusto_comm_init(gusto_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
 int32_t gusto_allgather_status(gusto_ctx* ctx, const uint8_t* done_local, uint8_t* done_all, int32_t* n_unfinished);
 
+/* ---- TrajOpt SCP variant: solve_trajopt_jump! (/root/reference/src/scp/scp_trajopt.jl:33-157) behind the
+ * same solve_method! slot.  The convex subproblem (:159-279) is solved on the device by a second compilation of the solve kernel:
+ * HARD state trust region |X_k - Xp_k|^2 <= s (:165-173), hard boundary conditions (:175-195), every other inequality -- the control
+ * balls included -- as a mu-penalised hinge (:222-233), the dynamics rows l1-penalised with weight mu (:257-275; the literal code leaves
+ * one of its two slack vectors unbounded below, the restated form is the file's own equality penalty :236-246), toggle distance
+ * clearance + 1 (:65).  The three nested loops (:71-155) stay in the host language (julia/GuSTOB200.jl solve_trajopt_b200!, Python twin
+ * host.solve_trajopt_batch); they need per iteration:
+ * gusto_trajopt_enable   allocates the variant's solver scratch and reference-trajectory buffers (freeflyerSE2 and astrobeeSE3: the
+ *                        in-scope models with a SCPParam_TrajOpt; GUSTO_E_ARG otherwise).
+ * gusto_trajopt_iterate  mu[B], s[B], active[B] (each may be NULL: keep) -> linearize, solve, evaluate the candidate against the
+ *                        accepted trajectory: out[B*GUSTO_TRAJOPT_NOUT] = { evaluate_xtol (convergence_metric, :281-283),
+ *                        trust_region_ratio_trajopt (astrobee_se3.jl:419-459), cost_true(candidate), cost_true(accepted), max_k |dX_k|^2,
+ *                        ratio numerator, ratio denominator, sum of |linearised dynamics rows| }, info as gusto_solve_subproblem.
+ *                        The step is installed with gusto_accept (the reference accepts every step, :128).
+ * gusto_trajopt_mark     copies the accepted trajectory into reference slot 0 (old_penalty_traj, :73) or 1 (old_convex_traj, :76)
+ *                        for the instances flagged in which[B] (NULL: all).
+ * gusto_trajopt_compare  accepted trajectory against reference slot: out[B*5] = { evaluate_ctol numerator, denominator (:288-312 as
+ *                        restated in oracle/gusto_oracle/trajopt.py), evaluate_xtol, cost_true(accepted), cost_true(reference) }. */
+#define GUSTO_TRAJOPT_NOUT 8
+int32_t gusto_trajopt_enable(gusto_ctx* ctx);
+int32_t gusto_trajopt_iterate(gusto_ctx* ctx, const double* mu, const double* s, const uint8_t* active, double* out, double* info);
+int32_t gusto_trajopt_mark(gusto_ctx* ctx, int32_t slot, const uint8_t* which);
+int32_t gusto_trajopt_compare(gusto_ctx* ctx, int32_t slot, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ from .models import f_dyn, FREEFLYER_SE2, ASTROBEE_SE3
 from .sdf import signed_distance
 from .subproblem import Problem, linearize, obstacle_rows, workspace_location, QCQP, GOAL_POINT, GOAL_BOX
 from .ipm import solve_qcqp
-from .scp import cost_true, convergence_metric
+from .scp import cost_true, convergence_metric, FREEFLYER_ARM_OFFSET
 
 # SCPParam_TrajOpt(model): mu0, s0, c, tau_plus, tau_minus, k, ftol, xtol, ctol, max_penalty, max_convex, max_trust
 TRAJOPT_PARAMS = {
@@ -216,12 +216,31 @@ def trust_region_ratio_trajopt(p: Problem, X, U, Xp, Up, lin):
     if p.n_obs:
         cl, R = m.robot_params[9], m.robot_params[4]
         r0, r = workspace_location(m, Xp), workspace_location(m, X)
-        d0, _ = signed_distance(r0, p.obstacles, R, m.ws_dim)
-        d1, n1 = signed_distance(r, p.obstacles, R, m.ws_dim)
-        hat = cl - (d1 + np.einsum("kij,kj->ki", n1, r - r0))
-        num += float(np.sum((cl - d0) - (cl - d1)))
-        den += float(np.sum((cl - d0) - hat))
+        offsets = [np.zeros(3)] + ([FREEFLYER_ARM_OFFSET] if m.model_id == FREEFLYER_SE2 else [])   # env_.convex_robot_components
+        for off in offsets:
+            d0, _ = signed_distance(r0 + off, p.obstacles, R, m.ws_dim)
+            d1, n1 = signed_distance(r + off, p.obstacles, R, m.ws_dim)
+            hat = cl - (d1 + np.einsum("kij,kj->ki", n1, r - r0))
+            num += float(np.sum((cl - d0) - (cl - d1)))
+            den += float(np.sum((cl - d0) - hat))
     return num / den
+
+
+def penalized_cost_trajopt(p: Problem, X, U, mu, lin, rows):
+    """Objective of the TrajOpt subproblem at (X, U) with every slack at its optimal value (scp_trajopt.jl:213-279)."""
+    m = p.model
+    J = cost_true(p, U)
+    for (idx, lim) in m.soft_norm_rows:
+        J += mu * float(np.sum(np.maximum(np.sum(X[:, idx] ** 2, axis=-1) - lim ** 2, 0.0)))
+    for (i, sign, bound) in m.soft_lin_rows:
+        J += mu * float(np.sum(np.maximum(sign * X[:, i] - bound, 0.0)))
+    if p.n_obs:
+        v = rows["off"] - np.einsum("kij,kj->ki", rows["nhat"], workspace_location(m, X))
+        J += mu * float(np.sum(np.maximum(np.where(rows["active"], v, 0.0), 0.0)))
+    for (idx, scale, rad) in m.ctrl_balls:
+        J += mu * float(np.sum(np.maximum(np.sum((U[:-1][:, idx] * np.asarray(scale)) ** 2, axis=-1) - rad ** 2, 0.0)))
+    J += mu * float(np.sum(np.abs(linearized_defect(p, X, U, lin))))
+    return J
 
 
 def constraint_classes(p: Problem, X, U):

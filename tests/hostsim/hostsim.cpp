@@ -16,6 +16,7 @@
 #define GUSTO_IPM_ALG 1                      // second inclusion: the TrajOpt subproblem (namespace gusto::ipm_trajopt)
 #include "../../gusto.jl_b200/csrc/ipm.cuh"
 #include "../../gusto.jl_b200/csrc/evaluate.cuh"
+#include "../../gusto.jl_b200/csrc/trajopt.cuh"
 #include "../../gusto.jl_b200/csrc/postprocess.cuh"
 #include "../../gusto.jl_b200/csrc/shooting.cuh"
 #include "../../gusto.jl_b200/csrc/scp.cuh"
@@ -55,8 +56,10 @@ static void run(const BatchDesc& d, BatchPtrs& p, const IpmParams& prm, int stag
   }
   if (stages & 4) {
     double red[4];
-    for (int b = 0; b < B; ++b)
-      evaluate_instance<M>(d, p, b, p.Xn + (size_t)b * N * T::NX, p.Un + (size_t)b * N * T::NU, eval + (size_t)b * EVAL_NOUT, red);
+    for (int b = 0; b < B; ++b) {
+      if (g_alg == 1) trajopt_evaluate_instance<M>(d, p, b, p.Xn + (size_t)b * N * T::NX, p.Un + (size_t)b * N * T::NU, eval + (size_t)b * TRAJOPT_NOUT, red);
+      else evaluate_instance<M>(d, p, b, p.Xn + (size_t)b * N * T::NX, p.Un + (size_t)b * N * T::NU, eval + (size_t)b * EVAL_NOUT, red);
+    }
   }
 }
 
@@ -109,6 +112,38 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
     default: return -1;
   }
 #undef HS_CASE
+  return 0;
+}
+
+// TrajOpt: (X, U) against a reference trajectory (trajopt_ctol_instance), out[B][2]
+template <int M>
+static void run_ctol(const BatchDesc& d, BatchPtrs& p, const double* X, const double* U, const double* Xr, const double* Ur, double* out) {
+  using T = Traits<M>;
+  double red[4];
+  const size_t sx = (size_t)d.N * T::NX, su = (size_t)d.N * T::NU;
+  for (int b = 0; b < d.B; ++b) trajopt_ctol_instance<M>(d, p, b, X + b * sx, U + b * su, Xr + b * sx, Ur + b * su, out + (size_t)b * 2, red);
+}
+extern "C" int hostsim_trajopt_ctol(const gusto_config* cfg, const int32_t* obs_kind, const double* obs_a, const double* obs_b,
+                                    const double* goal_lo, const double* goal_hi, const double* tf, const double* X, const double* U,
+                                    const double* Xr, const double* Ur, double* out) {
+  BatchDesc d;
+  memset(&d, 0, sizeof(d));
+  d.model_id = cfg->model_id; d.N = cfg->N; d.B = cfg->B; d.n_obs = cfg->model_id == DUBINS ? 0 : cfg->n_obs;
+  for (int i = 0; i < 16; ++i) d.rp[i] = cfg->robot_params[i];
+  for (int i = 0; i < 10; ++i) d.sp[i] = cfg->scp_params[i];
+  for (int i = 0; i < MAX_NX; ++i) d.goal_type[i] = cfg->goal_type[i];
+  for (int i = 0; i < d.n_obs; ++i) {
+    d.obs_kind[i] = obs_kind[i];
+    for (int a = 0; a < 3; ++a) { d.obs_a[i][a] = obs_a[i * 3 + a]; d.obs_b[i][a] = obs_b[i * 3 + a]; }
+  }
+  BatchPtrs p;
+  memset(&p, 0, sizeof(p));
+  p.tf = tf; p.goal_lo = goal_lo; p.goal_hi = goal_hi;
+  switch (cfg->model_id) {
+    case FREEFLYER_SE2: run_ctol<FREEFLYER_SE2>(d, p, X, U, Xr, Ur, out); break;
+    case ASTROBEE_SE3: run_ctol<ASTROBEE_SE3>(d, p, X, U, Xr, Ur, out); break;
+    default: return -1;
+  }
   return 0;
 }
 

@@ -399,3 +399,92 @@ def test_converged_trajectories_are_dynamically_consistent_and_collision_free(ho
     assert np.all(chk[:, 2] == 1.0) and chk[:, 6].min() >= 0.0
     assert chk[:, 7].max() <= 1.0 + 1e-6
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------- TrajOpt variant
+TRAJOPT_CASES = [("freeflyerSE2", dict(B=6, N=30)), ("astrobeeSE3", dict(B=6, N=30))]
+
+
+@pytest.mark.parametrize("name,kw", TRAJOPT_CASES)
+@pytest.mark.parametrize("tier", [0, 1, 2])
+def test_trajopt_subproblem_matches_oracle(host, name, kw, tier):
+    """The TrajOpt subproblem kernel (second compilation of ipm.cuh: hard trust ball, mu-penalised rows, l1-penalised dynamics)
+    and its evaluation kernel against the oracle restatement of scp_trajopt.jl:159-279, through the C ABI."""
+    from gusto_oracle import trajopt as to
+    from gusto_oracle.scp import cost_true, convergence_metric
+    bp = gb.problems.CONFIGS[name](**kw)
+    prm = to.TRAJOPT_PARAMS[bp.model.model_id]
+    mu, s = [(prm[0], prm[1]), (5.0, 0.25 * prm[1]), (125.0, 0.05)][tier]
+    X0, U0 = bp.init_traj_straightline()
+    eng = host.Engine(bp, device=0)
+    eng.trajopt_enable()
+    eng.set_trajectory(X0, U0)
+    ev, info = eng.trajopt_iterate(np.full(bp.B, mu), np.full(bp.B, s))
+    Xn, Un = eng.get_candidate()
+    eng.close()
+    assert np.all(info[:, 0] == 0), info[:, :3]
+    for b in range(0, bp.B, 2):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, r = to.solve_trajopt_subproblem(p, X0[b], U0[b], mu, s)
+        assert st == "OPTIMAL"
+        if p.model.has_trust_region:
+            assert np.max(np.sum((Xn[b] - X0[b]) ** 2, axis=-1)) <= s + 1e-8
+        Jk = to.penalized_cost_trajopt(p, Xn[b], Un[b], mu, lin, rows)
+        Jo = to.penalized_cost_trajopt(p, Xs, Us, mu, lin, rows)
+        assert abs(Jk - Jo) <= 2e-6 * max(1.0, abs(Jo)), (Jk, Jo)
+        assert abs(info[b, 4] - Jk) <= 1e-6 * max(1.0, abs(Jk))
+        if tier < 2:
+            assert np.max(np.abs(Xn[b] - Xs)) < 1e-4 and np.max(np.abs(Un[b] - Us)) < 1e-5
+        assert abs(ev[b, 0] - convergence_metric(Xn[b], X0[b])) < 1e-12
+        rho = to.trust_region_ratio_trajopt(p, Xn[b], Un[b], X0[b], U0[b], lin)
+        assert abs(ev[b, 1] - rho) <= 1e-9 * max(1.0, abs(rho))
+        assert abs(ev[b, 2] - cost_true(p, Un[b])) < 1e-12
+
+
+@pytest.mark.parametrize("name,kw", TRAJOPT_CASES)
+def test_trajopt_full_solve_matches_oracle(host, name, kw):
+    """L3 for solve_trajopt_jump!: the batched host loop over the CUDA kernels against the oracle's loop, per instance."""
+    from gusto_oracle import trajopt as to
+    bp = gb.problems.CONFIGS[name](**kw)
+    eng = host.Engine(bp, device=0)
+    S = host.solve_trajopt_batch(eng)
+    # reference-trajectory kernel against the oracle's evaluate_ctol on the final trajectories
+    X0, U0 = bp.init_traj_straightline()
+    eng.trajopt_mark(0)
+    cmp_same = eng.trajopt_compare(0)
+    assert np.all(cmp_same[:, 0] == 0.0) and np.all(cmp_same[:, 2] == 0.0)
+    eng.close()
+    for b in range(bp.B):
+        R = to.solve_trajopt(to_oracle(bp, b))
+        assert int(S.iterations[b]) == R.iterations and bool(S.converged[b]) == R.converged
+        assert np.array_equal(np.array(S.s_vec[b]), np.array(R.s_vec)) and np.array_equal(np.array(S.mu_vec[b]), np.array(R.mu_vec))
+        assert abs(S.J_true[b][-1] - R.J_true[-1]) <= 1e-6 * max(1e-6, abs(R.J_true[-1]))
+        assert np.max(np.abs(np.array(S.ctol_vec[b]) - np.array(R.ctol_vec))) < 1e-6
+        assert np.max(np.abs(S.X[b] - R.X)) < 1e-4
+
+
+def test_trajopt_batch_of_256_and_unsupported_models(host):
+    """A packed batch (several instance groups per CTA) solves every instance and reproduces a small batch of the same instances
+    bit for bit; models without a SCPParam_TrajOpt answer with an error code."""
+    bp = gb.problems.CONFIGS["astrobeeSE3"](B=256, N=50, seed=11)
+    X0, U0 = bp.init_traj_straightline()
+    eng = host.Engine(bp, device=0)
+    eng.trajopt_enable()
+    eng.set_trajectory(X0, U0)
+    ev, info = eng.trajopt_iterate(np.full(bp.B, 1.0), np.full(bp.B, 10.0))
+    Xn, Un = eng.get_candidate()
+    eng.close()
+    assert np.all(info[:, 0] == 0) and info[:, 1].max() <= 20
+    sub = bp.shard(0, 32)                                             # the first 8 instances, one group per CTA
+    e2 = host.Engine(sub, device=0)
+    e2.trajopt_enable()
+    e2.set_trajectory(X0[:8], U0[:8])
+    e2.trajopt_iterate(np.full(8, 1.0), np.full(8, 10.0))
+    X8, U8 = e2.get_candidate()
+    e2.close()
+    assert np.array_equal(X8, Xn[:8]) and np.array_equal(U8, Un[:8])
+    bd = gb.problems.CONFIGS["dubins"](B=2, N=30)
+    ed = host.Engine(bd, device=0)
+    with pytest.raises(host.GustoError):
+        ed.trajopt_enable()
+    ed.close()

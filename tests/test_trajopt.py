@@ -1,0 +1,84 @@
+"""TrajOpt SCP variant (solve_trajopt_jump!, /root/reference/src/scp/scp_trajopt.jl): the kernel bodies run through
+the single-thread host simulation against the oracle restatement (oracle/gusto_oracle/trajopt.py), and the host loop
+(host.solve_trajopt_batch) against the oracle's loop.  The reference routine cannot run as written; what was repaired is listed in the
+oracle module.  The -m gpu counterpart lives in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from util import gb, to_oracle, hostsim_trajopt_iterate, hostsim_trajopt_ctol, HostsimTrajOptEngine
+from gusto_oracle import trajopt as to
+from gusto_oracle.scp import cost_true, convergence_metric
+
+CASES = [("freeflyerSE2", dict(B=2, N=30)), ("astrobeeSE3", dict(B=2, N=30))]
+
+
+def err(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+@pytest.mark.parametrize("tier", [0, 1, 2])
+def test_trajopt_subproblem_body_matches_oracle(name, kw, tier):
+    """(mu, s): the model's defaults | a tighter ball at 5 mu | mu = 125 with a trust ball the straight line cannot leave far enough
+    to meet the dynamics -- the l1 rows stay active and the minimiser is not unique in X (only the objective is compared there)."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    prm = to.TRAJOPT_PARAMS[bp.model.model_id]
+    mu, s = [(prm[0], prm[1]), (5.0, 0.25 * prm[1]), (125.0, 0.05)][tier]
+    X0, U0 = bp.init_traj_straightline()
+    hs = hostsim_trajopt_iterate(bp, X0, U0, mu, s)
+    for b in range(bp.B):
+        p = to_oracle(bp, b)
+        Xs, Us, obj, st, lin, rows, r = to.solve_trajopt_subproblem(p, X0[b], U0[b], mu, s)
+        assert st == "OPTIMAL" and hs["info"][b, 0] == 0
+        Xk, Uk = hs["Xn"][b], hs["Un"][b]
+        # feasibility of the hard rows: trust ball, initial state, point goal
+        if p.model.has_trust_region:
+            assert np.max(np.sum((Xk - X0[b]) ** 2, axis=-1)) <= s + 1e-8
+        assert err(Xk[0], bp.x_init[b]) < 1e-8
+        pin = bp.goal_type == gb.models.GOAL_POINT
+        assert err(Xk[-1, pin], bp.goal_lo[b, pin]) < 1e-6
+        # optimality: same objective (both evaluated with the slacks at their optimal values)
+        Jk = to.penalized_cost_trajopt(p, Xk, Uk, mu, lin, rows)
+        Jo = to.penalized_cost_trajopt(p, Xs, Us, mu, lin, rows)
+        assert abs(Jk - Jo) <= 2e-6 * max(1.0, abs(Jo)), (Jk, Jo)
+        assert abs(hs["info"][b, 4] - Jk) <= 1e-6 * max(1.0, abs(Jk))
+        assert hs["info"][b, 1] <= r.iters + 3
+        if tier < 2:
+            assert err(Xk, Xs) < 1e-4 and err(Uk, Us) < 1e-5
+        # evaluation scalars of the candidate
+        o = hs["eval"][b]
+        assert abs(o[0] - convergence_metric(Xk, X0[b])) < 1e-12
+        rho = to.trust_region_ratio_trajopt(p, Xk, Uk, X0[b], U0[b], lin)
+        assert abs(o[1] - rho) <= 1e-9 * max(1.0, abs(rho))
+        assert abs(o[2] - cost_true(p, Uk)) < 1e-12 and abs(o[3] - cost_true(p, U0[b])) < 1e-12
+        assert abs(o[7] - np.sum(np.abs(to.linearized_defect(p, Xk, Uk, lin)))) < 1e-10
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_trajopt_ctol_body_matches_oracle(name, kw):
+    bp = gb.problems.CONFIGS[name](**kw)
+    X0, U0 = bp.init_traj_straightline()
+    rng = np.random.default_rng(5)
+    X = X0 + 0.2 * rng.normal(size=X0.shape); U = U0 + 0.02 * rng.normal(size=U0.shape)
+    Xr = X0 + 0.2 * rng.normal(size=X0.shape); Ur = U0 + 0.02 * rng.normal(size=U0.shape)
+    out = hostsim_trajopt_ctol(bp, X, U, Xr, Ur)
+    for b in range(bp.B):
+        ref = to.evaluate_ctol(to_oracle(bp, b), X[b], U[b], Xr[b], Ur[b])
+        assert abs(out[b, 0] / out[b, 1] - ref) <= 1e-12 * max(1.0, ref)
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_trajopt_full_solve_matches_oracle(name, kw):
+    """L3: host.solve_trajopt_batch over the host-simulated kernels against the oracle's loop -- same number of convex solves, same
+    trust-region / penalty schedules, same stopping decisions, final cost within 1e-6."""
+    bp = gb.problems.CONFIGS[name](**kw)
+    S = gb.engine().solve_trajopt_batch(HostsimTrajOptEngine(bp))
+    for b in range(bp.B):
+        R = to.solve_trajopt(to_oracle(bp, b))
+        assert int(S.iterations[b]) == R.iterations and bool(S.converged[b]) == R.converged
+        assert np.allclose(S.s_vec[b], R.s_vec, rtol=0, atol=0) and np.allclose(S.mu_vec[b], R.mu_vec, rtol=0, atol=0)
+        assert abs(S.J_true[b][-1] - R.J_true[-1]) <= 1e-6 * max(1e-6, abs(R.J_true[-1]))
+        assert err(S.ctol_vec[b], R.ctol_vec) < 1e-6 and err(S.ftol_vec[b], R.ftol_vec) < 1e-6
+        big = np.abs(np.array(R.rho_vec)) > 1e-4
+        assert err(np.array(S.rho_vec[b])[big], np.array(R.rho_vec)[big]) < 1e-5
+        assert all(st == 0 for st in S.solver_status[b][1:])

@@ -150,3 +150,83 @@ def hostsim_solve_gusto(bp, max_iter=30):
             break
     return dict(converged=converged, successful=successful, iterations=iterations, J_true=J, accept=accept_hist, X=X, U=U,
                 newton=newton)
+
+
+# --------------------------------------------------------------------------------- TrajOpt variant on the host simulation
+def hostsim_trajopt_iterate(bp, Xp, Up, mu, s, stages=7):
+    """linearize | TrajOpt subproblem | TrajOpt evaluation kernel bodies on the host (omega carries mu, delta carries s)."""
+    lib = hostsim_lib()
+    lib.hostsim_set_algorithm(1)
+    try:
+        return hostsim_iterate(bp, Xp, Up, mu, s, stages=stages)
+    finally:
+        lib.hostsim_set_algorithm(0)
+
+
+def hostsim_trajopt_ctol(bp, X, U, Xr, Ur):
+    host = gb.engine()
+    cfg, (kind, a, b) = host.make_config(bp, 0)
+    dp = lambda arr: np.ascontiguousarray(arr, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    out = np.zeros((bp.B, 2))
+    keep = [np.ascontiguousarray(v, dtype=np.float64) for v in (bp.goal_lo, bp.goal_hi, bp.tf, X, U, Xr, Ur)]
+    rc = hostsim_lib().hostsim_trajopt_ctol(ctypes.byref(cfg), kind.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), dp(a), dp(b),
+                                            *[v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for v in keep], dp(out))
+    assert rc == 0
+    return out
+
+
+class HostsimTrajOptEngine:
+    """Stands in for host.Engine under host.solve_trajopt_batch with every kernel replaced by its host-simulated body: the L3 check
+    of the TrajOpt kernels' arithmetic and of the host loop in the GPU-less container."""
+
+    def __init__(self, bp):
+        self.bp, self.B = bp, bp.B
+
+    def trajopt_enable(self):
+        self.ref = [None, None]
+
+    def set_trajectory(self, X, U):
+        self.X, self.U = np.array(X, dtype=np.float64), np.array(U, dtype=np.float64)
+
+    def set_candidate(self, X, U):
+        self.Xn, self.Un = np.array(X, dtype=np.float64), np.array(U, dtype=np.float64)
+
+    def set_penalties(self, mu, s):
+        self.mu, self.s = np.array(mu, dtype=np.float64), np.array(s, dtype=np.float64)
+
+    def linearize(self):
+        pass
+
+    def evaluate(self):
+        return hostsim_iterate(self.bp, self.X, self.U, 1.0, 1.0, stages=5, Xn=self.Xn, Un=self.Un)["eval"]
+
+    def trajopt_mark(self, slot, which=None):
+        w = np.ones(self.B, bool) if which is None else np.asarray(which, bool)
+        if self.ref[slot] is None:
+            self.ref[slot] = (self.X.copy(), self.U.copy())
+        self.ref[slot][0][w] = self.X[w]; self.ref[slot][1][w] = self.U[w]
+
+    def trajopt_compare(self, slot):
+        Xr, Ur = self.ref[slot]
+        c = hostsim_trajopt_ctol(self.bp, self.X, self.U, Xr, Ur)
+        out = np.zeros((self.B, 5))
+        out[:, :2] = c
+        h = self.bp.tf / (self.bp.N - 1)
+        for b in range(self.B):
+            out[b, 2] = np.max(np.linalg.norm(self.X[b] - Xr[b], axis=-1)) / np.max(np.linalg.norm(self.X[b], axis=-1))
+            for col, Uv in ((3, self.U[b]), (4, Ur[b])):
+                uu = np.sum(Uv * Uv, axis=-1)
+                out[b, col] = np.sum(0.5 * h[b] * (uu[:-1] + uu[1:]))
+        return out
+
+    def trajopt_iterate(self, mu, s, active=None, out=None, info=None):
+        hs = hostsim_trajopt_iterate(self.bp, self.X, self.U, mu, s)
+        self.Xn, self.Un = hs["Xn"], hs["Un"]
+        return hs["eval"], hs["info"]
+
+    def accept(self, accept, omega=None, delta=None):
+        a = np.asarray(accept, bool)
+        self.X[a] = self.Xn[a]; self.U[a] = self.Un[a]
+
+    def get_trajectory(self):
+        return self.X.copy(), self.U.copy()
