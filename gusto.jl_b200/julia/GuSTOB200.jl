@@ -17,7 +17,7 @@
 # include/gusto_b200.h and gusto.jl_b200/host.py (which implements the identical loop and IS tested) but never executed.
 module GuSTOB200
 
-export solve_gusto_b200!, solve_SCP_batch!, solve_SCP_batch_device!, solve_shooting_b200!, comm_unique_id, GustoContext
+export solve_trajopt_b200!, solve_gusto_b200!, solve_SCP_batch!, solve_SCP_batch_device!, solve_shooting_b200!, comm_unique_id, GustoContext
 
 const LIB = get(ENV, "GUSTO_B200_LIB", joinpath(@__DIR__, "..", "libgusto_b200.so"))
 
@@ -331,6 +331,99 @@ function solve_gusto_b200!(SCPS, SCPP, solver="B200", max_iter=30, force=false; 
   get_trajectory!(ctx, X, U)
   SCPS.traj.X = X; SCPS.traj.U = U
   SCPS.dual = zeros(x_dim); get_duals!(ctx, SCPS.dual)     # -JuMP.dual of the init constraints (:116, get_dual_jump): p0 of the shooting refinement
+  return
+end
+
+# ------------------------------------------------------------------------------------- TrajOpt plug-in (SURVEY 8(f)-1)
+const TRAJOPT_NOUT = 8
+trajopt_enable!(ctx) = check(ctx, ccall((:gusto_trajopt_enable, LIB), Int32, (Ptr{Cvoid},), ctx.ptr))
+trajopt_iterate!(ctx, μ, s, act::Vector{UInt8}, out, info) = GC.@preserve μ s act out info check(ctx, ccall((:gusto_trajopt_iterate, LIB), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}), ctx.ptr, μ, s, act, out, info))
+trajopt_mark!(ctx, slot::Integer) = check(ctx, ccall((:gusto_trajopt_mark, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}), ctx.ptr, Int32(slot), C_NULL))
+trajopt_compare!(ctx, slot::Integer, out) = GC.@preserve out check(ctx, ccall((:gusto_trajopt_compare, LIB), Int32,
+    (Ptr{Cvoid}, Int32, Ptr{Float64}), ctx.ptr, Int32(slot), out))
+
+"""
+    solve_trajopt_b200!(SCPS, SCPP, solver="B200", max_iter=125, force=false; device=0, kwarg...)
+
+Same slot and contract as `solve_trajopt_jump!` (scp_trajopt.jl:33-157): the three nested loops (penalty / convex / trust) stay here,
+every convex subproblem (:159-279) and every evaluation scalar runs on the device.  The reference routine cannot run as written; this
+restates it with the repairs listed in oracle/gusto_oracle/trajopt.py (bounded l1 dynamics penalty, real copies for
+old_penalty_traj / old_convex_traj after the trust loop, `xtol_vec[end]` in :142, evaluate_ctol over the model's constraint classes).
+Un-executed here (no Julia in the build image); gusto.jl_b200/host.py::solve_trajopt_batch is the tested twin.
+"""
+function solve_trajopt_b200!(SCPS, SCPP, solver="B200", max_iter=125, force=false; device::Int=0, kwarg...)
+  N = SCPP.N
+  param, model, robot, env = SCPP.param, SCPP.PD.model, SCPP.PD.robot, SCPP.PD.env
+  param.alg = Main.SCPParam_TrajOpt(model)                                   # :44
+  alg = param.alg
+  x_dim, u_dim = model.x_dim, model.u_dim
+  gtype, glo, ghi = flatten_goals(SCPP.PD.goal_set, x_dim, SCPP.tf_guess)
+  gusto_alg = Main.SCPParam_GuSTO(model)                                     # only fills the configuration slots TrajOpt does not read
+  ctx = GustoContext(robot, model, env, N, 1, gtype, gusto_alg, param; device=device)
+  trajopt_enable!(ctx)
+  set_problems!(ctx, Float64.(SCPP.PD.x_init), glo, ghi, Float64[SCPS.traj.Tf])
+  X = Matrix{Float64}(SCPS.traj.X); U = Matrix{Float64}(SCPS.traj.U)
+  set_trajectory!(ctx, X, U); set_candidate!(ctx, X, U)
+  ev = zeros(EVAL_NOUT); out = zeros(TRAJOPT_NOUT); info = zeros(SOLVE_NINFO); cmp = zeros(5); live = UInt8[1]
+  linearize!(ctx); evaluate!(ctx, ev)
+  push!(SCPS.J_true, ev[5])                                                  # :64
+  param.obstacle_toggle_distance = model.clearance + 1.                      # :65 (the kernel applies the same constant)
+  constraints_satisfied = false; xtol_satisfied = false; failed = false
+  for penalty_iteration in 1:alg.max_penalty_iteration
+    (constraints_satisfied || failed) && break
+    trajopt_mark!(ctx, 0)                                                    # :73
+    for convex_iteration in 1:alg.max_convex_iteration
+      trajopt_mark!(ctx, 1)                                                  # :76
+      (constraints_satisfied || failed) && break
+      if xtol_satisfied
+        xtol_satisfied = false
+        break
+      end
+      for trust_iteration in 1:alg.max_trust_iteration
+        time_start = time_ns()
+        trajopt_iterate!(ctx, Float64[alg.mu_vec[end]], Float64[alg.s_vec[end]], live, out, info)
+        push!(SCPS.solver_status, solver_status_symbol(info[1]))
+        if !(info[1] == 0 || info[1] == 3)                                   # :107-111 warns and goes on; there is no iterate to go on with
+          push!(SCPS.iter_elapsed_times, (time_ns() - time_start)/10^9)
+          failed = true
+          break
+        end
+        push!(alg.xtol_vec, out[1]); push!(SCPS.convergence_measure, out[1]); push!(SCPS.J_full, info[5])
+        push!(alg.ρ_vec, out[2])
+        push!(alg.s_vec, (out[2] > alg.c ? alg.τ_plus : alg.τ_minus)*alg.s_vec[end])      # :122-126
+        accept!(ctx, live, Float64[alg.mu_vec[end]], Float64[alg.s_vec[end]])            # copy!(SCPS.traj, new_traj), :128
+        iter_elapsed_time = (time_ns() - time_start)/10^9
+        push!(SCPS.J_true, out[3]); push!(SCPS.iter_elapsed_times, iter_elapsed_time)
+        SCPS.total_time += iter_elapsed_time
+        SCPS.iterations += 1
+        if alg.s_vec[end] < alg.xtol
+          xtol_satisfied = true
+          break
+        end
+      end
+      failed && break
+      trajopt_compare!(ctx, 1, cmp)                                          # :140-141
+      push!(alg.ftol_vec, abs(cmp[4] - cmp[5])/abs(cmp[4])); push!(alg.xtol_vec, cmp[3])
+      if alg.ftol_vec[end] < alg.ftol || alg.xtol_vec[end] < alg.xtol
+        constraints_satisfied = true
+        break
+      end
+    end
+    failed && break
+    trajopt_compare!(ctx, 0, cmp)                                            # :148
+    push!(alg.ctol_vec, cmp[1]/cmp[2])
+    if alg.ctol_vec[end] < alg.ctol
+      constraints_satisfied = true
+      SCPS.converged = true
+      break
+    else
+      push!(alg.mu_vec, alg.mu_vec[end]*alg.k)
+    end
+  end
+  get_trajectory!(ctx, X, U)
+  SCPS.traj.X = X; SCPS.traj.U = U
+  SCPS.dual = zeros(x_dim); get_duals!(ctx, SCPS.dual)
   return
 end
 

@@ -40,7 +40,8 @@ def test_trajopt_subproblem_body_matches_oracle(name, kw, tier):
         # optimality: same objective (both evaluated with the slacks at their optimal values)
         Jk = to.penalized_cost_trajopt(p, Xk, Uk, mu, lin, rows)
         Jo = to.penalized_cost_trajopt(p, Xs, Us, mu, lin, rows)
-        assert abs(Jk - Jo) <= 2e-6 * max(1.0, abs(Jo)), (Jk, Jo)
+        # never worse than the oracle's optimum; on tier 2 (degenerate l1 rows) the generic oracle IPM stalls ~1e-5 above it
+        assert Jk <= Jo + 2e-6 * max(1.0, abs(Jo)) and Jo - Jk <= (1e-4 if tier == 2 else 2e-6) * max(1.0, abs(Jo)), (Jk, Jo)
         assert abs(hs["info"][b, 4] - Jk) <= 1e-6 * max(1.0, abs(Jk))
         assert hs["info"][b, 1] <= r.iters + 3
         if tier < 2:
