@@ -934,6 +934,102 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 // (knot, row) pair, 64 / NX knots at a time, rows in shared memory (the pivot row is read by the other rows of its knot);
 // F is a small perturbation of the identity (h/2 |A_ii| << 1), so there is no pivoting (a breakdown surfaces as NaN ->
 // IPM_NUMERICAL).
+// (round 2, late) One THREAD per knot: the decoupled blocks of F_k are inverted in registers by an unrolled in-place Gauss-Jordan
+// (no pivoting: F is a small perturbation of the identity), so the whole pass has no barrier -- the cooperative version (one
+// thread per (knot, row), pivot rows through shared memory, 2 barriers per pivot, 64 / NX knots at a time) took 580 k cycles per
+// solve on the headline batch, 6.5 % of the kernel.  -DGUSTO_SETUP_COOP restores it.
+template <int M, int LO, int HI> GDEV void setup_dynamics_block(const IpmCtx<M>& c, int k) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, ANZ = L::ANZ, LDT = L::LDT, n = HI - LO;
+  const int N = c.N;
+  const size_t np = c.NP;
+  const double hh = c.hh;
+  double a[n][n];
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) a[i][j] = i == j ? 1.0 : 0.0;
+#pragma unroll
+  for (int e = 0; e < ANZ; ++e)
+    if (T::a_row(e) >= LO && T::a_row(e) < HI) a[T::a_row(e) - LO][T::a_col(e) - LO] -= hh * c.Ac[(size_t)e * np + k];
+  // in-place Gauss-Jordan inverse
+#pragma unroll
+  for (int p = 0; p < n; ++p) {
+    const double ip = 1.0 / a[p][p];
+    a[p][p] = 1.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) a[p][j] *= ip;
+#pragma unroll
+    for (int r = 0; r < n; ++r) {
+      if (r == p) continue;
+      const double f = a[r][p];
+      a[r][p] = 0.0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) a[r][j] -= f * a[p][j];
+    }
+  }
+  // Fi_k (rows of this block; entries outside the block stay at the zero the scratch was allocated with)
+#pragma unroll
+  for (int i = 0; i < n; ++i)
+#pragma unroll
+    for (int j = 0; j < n; ++j) c.fi[(size_t)((LO + i) * NX + LO + j) * np + k] = a[i][j];
+  // Gam_k' (column b_row(a) of Fi_k scaled; zero outside the block of the driven coordinate, and for k = 0)
+  double* cr = c.cr + (size_t)k * L::CRW;
+#pragma unroll
+  for (int q = 0; q < NU; ++q) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double gv = 0.0;
+      if (T::b_row(q) >= LO && T::b_row(q) < HI && k > 0) gv = hh * c.bv[q] * a[i][T::b_row(q) - LO];
+      cr[(L::CR_GT + q) * LDT + LO + i] = gv;
+      c.gs[(size_t)(q * NX + LO + i) * np + k] = gv;
+    }
+  }
+  // Ah_{k-1}' = (Fi_k E_k)',  E_k = I + h/2 A_{k-1}: column LO + i of every row j of the record of knot k - 1
+  if (k >= 1) {
+    double ah[n][n];
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = 0; j < n; ++j) ah[i][j] = a[i][j];
+#pragma unroll
+    for (int e = 0; e < ANZ; ++e)
+      if (T::a_row(e) >= LO && T::a_row(e) < HI) {
+        const double av = hh * c.Ac[(size_t)e * np + k - 1];
+#pragma unroll
+        for (int i = 0; i < n; ++i) ah[i][T::a_col(e) - LO] += av * a[i][T::a_row(e) - LO];
+      }
+    double* crp = c.cr + (size_t)(k - 1) * L::CRW;
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) crp[(L::CR_AT + j) * LDT + LO + i] = (j >= LO && j < HI) ? ah[i][j - LO] : 0.0;
+  }
+  if (k == N - 1) {      // no dynamics after the last knot
+#pragma unroll
+    for (int j = 0; j < NX + NU; ++j)
+#pragma unroll
+      for (int i = 0; i < n; ++i) cr[j * LDT + LO + i] = 0.0;
+  }
+}
+#ifndef GUSTO_SETUP_COOP
+template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, LDT = L::LDT;
+  static_assert(L::dcheck(), "Traits<M>::DSPLIT does not decouple the pattern of A");
+  const int N = c.N;
+  G_PAR_FOR(k, N) {
+    if constexpr (T::DSPLIT > 0) {
+      setup_dynamics_block<M, 0, T::DSPLIT>(c, k);
+      setup_dynamics_block<M, T::DSPLIT, NX>(c, k);
+    } else {
+      setup_dynamics_block<M, 0, NX>(c, k);
+    }
+  }
+  G_SYNC();
+#else
 template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
@@ -997,6 +1093,7 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
     }
     G_SYNC();
   }
+#endif
   // Bh_k = Ah_k Gam_k + Gam_{k+1}
   G_PAR_FOR(it, (N - 1) * NU * NX) {
     const int k = it / (NU * NX), r = it - k * (NU * NX), a = r / NX, i = r - a * NX;
@@ -1561,9 +1658,60 @@ template <int M> GDEV void packed_mv(const double* pk_k, size_t np, const double
   }
 }
 
+// Pre-chain part of ric_forward for knot k given kap_k (also called by ric_backward, which has kap_k in registers: one pass, one
+// barrier and one global round trip of kap less per corrector solve).
+template <int M> GDEV void ric_forward_pre(const IpmCtx<M>& c, int k, const double* kap) {
+  using L = IpmLayout<M>;
+  using T = Traits<M>;
+  constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
+  const int N = c.N;
+  const size_t np = c.NP, ne = c.NE;
+  double* const dz = sh_dz<M>(c);
+  const double* const vp = sh_vp<M>(c);
+  (void)vp; (void)ne; (void)N;
+#pragma unroll
+  for (int a = 0; a < NU; ++a) dz[k * NV + NX + a] = kap[a];
+  if (k < N - 1) {
+    const double* bs = c.bs + k;
+    double dk[NX], bk[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += bs[(a * NX + i) * np] * kap[a];
+      bk[i] = v;
+      dk[i] = v + c.ch[i * np + k];
+    }
+    if (kTO) {   // realised state: s_{k+1} = N_{k+1} (Acl_k s_k + d_k + W_{k+1} p_{k+1}),  p_{k+1} = w_{k+1} + P_{k+1} ch_k  (products only)
+      double pj[NX], wt[NX], chv[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) chv[i] = c.ch[i * np + k];
+      packed_mv<M>(c.pk + k + 1, np, chv, pj);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pj[i] += vp[(k + 1) * NX + i];
+      noise_W<M>(c, k + 1, pj, wt);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) wt[i] += dk[i];
+      const double* nm = c.nm + k + 1;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int m = 0; m < NX; ++m) a += nm[(size_t)(i * NX + m) * np] * wt[m];
+        dk[i] = a;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dz[(k + 1) * NV + i] = dk[i];
+  }
+  if (k == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dz[i] = c.rnu[i * ne];
+  }
+}
 // Costates for a new right-hand side (the corrector's): bb_k = rx - K'rs - psi_{k-1}, the backward chain, then
 // kap_k = Lam_k^-1 (rs + Bh_k' pit_k).
-template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
+template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c, bool fuse_forward_pre = false) {
   using L = IpmLayout<M>;
   constexpr int NX = L::NX, NU = L::NU, NTU = L::NTU;
   const int N = c.N;
@@ -1634,14 +1782,15 @@ template <int M> GDEV_NOINLINE void ric_backward(const IpmCtx<M>& c) {
     for (int a = 0; a < NU; ++a) rs[a] = x[a];
     tri_lower_tmv<NU>(Lc, rs, x);
 #pragma unroll
-    for (int a = 0; a < NU; ++a) c.kap[a * np + k] = x[a];
+    for (int a = 0; a < NU; ++a) if (!fuse_forward_pre) c.kap[a * np + k] = x[a];
+    if (fuse_forward_pre) ric_forward_pre<M>(c, k, x);
   }
   G_SYNC();
   if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
 }
 // d_k = Bh_k kap_k + ch_k into the x-slot k+1 of dz, s_0 = rho_0 into slot 0, kap_k into the u-slot k; forward chain; then
 // per knot  u = kap - K s,  x = s + Gam u  and (want_nu) the equality multipliers  dnu_j = F_j^-T (P_j (s_j - ch_{j-1}) - pit_{j-1}).
-template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu) {
+template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu, bool pre_done = false) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
@@ -1650,47 +1799,11 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
   double* const dz = sh_dz<M>(c);
   const double* const vp = sh_vp<M>(c);
   long long tc0 = g_clock();
-  G_PAR_FOR(k, N) {
+  if (!pre_done) G_PAR_FOR(k, N) {
     double kap[NU];
 #pragma unroll
-    for (int a = 0; a < NU; ++a) { kap[a] = c.kap[a * np + k]; dz[k * NV + NX + a] = kap[a]; }
-    if (k < N - 1) {
-      const double* bs = c.bs + k;
-      double dk[NX], bk[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double v = 0.0;
-#pragma unroll
-        for (int a = 0; a < NU; ++a) if (L::dsame(i, T::b_row(a))) v += bs[(a * NX + i) * np] * kap[a];
-        bk[i] = v;
-        dk[i] = v + c.ch[i * np + k];
-      }
-      if (kTO) {   // realised state: s_{k+1} = N_{k+1} (Acl_k s_k + d_k + W_{k+1} p_{k+1}),  p_{k+1} = w_{k+1} + P_{k+1} ch_k  (products only)
-        double pj[NX], wt[NX], chv[NX];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) chv[i] = c.ch[i * np + k];
-        packed_mv<M>(c.pk + k + 1, np, chv, pj);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) pj[i] += vp[(k + 1) * NX + i];
-        noise_W<M>(c, k + 1, pj, wt);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) wt[i] += dk[i];
-        const double* nm = c.nm + k + 1;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-          double a = 0.0;
-#pragma unroll
-          for (int m = 0; m < NX; ++m) a += nm[(size_t)(i * NX + m) * np] * wt[m];
-          dk[i] = a;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NX; ++i) dz[(k + 1) * NV + i] = dk[i];
-    }
-    if (k == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) dz[i] = c.rnu[i * ne];
-    }
+    for (int a = 0; a < NU; ++a) kap[a] = c.kap[a * np + k];
+    ric_forward_pre<M>(c, k, kap);
   }
   G_SYNC();
   if (G_TID == 0 && GUSTO_PROF_CHAINS) c.prof[2] += g_clock() - tc0;
@@ -2312,8 +2425,8 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     const double smu = predictor_pass<M>(c, R.npair, mu, prm.tol, &a_aff);     // affine step, sigma, corrector right-hand side
     cyc_slot += g_clock() - tc0;
     tc0 = g_clock();
-    ric_backward<M>(c);
-    ric_forward<M>(c, true);
+    ric_backward<M>(c, true);
+    ric_forward<M>(c, true, true);
     cyc_sol += g_clock() - tc0;
 #ifdef GUSTO_HOSTSIM
     if (getenv("GUSTO_HOSTSIM_CHECK")) kkt_check<M>(c, "corr");
