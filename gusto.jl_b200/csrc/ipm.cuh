@@ -938,7 +938,7 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
 // (no pivoting: F is a small perturbation of the identity), so the whole pass has no barrier -- the cooperative version (one
 // thread per (knot, row), pivot rows through shared memory, 2 barriers per pivot, 64 / NX knots at a time) took 580 k cycles per
 // solve on the headline batch, 6.5 % of the kernel.  -DGUSTO_SETUP_COOP restores it.
-template <int M, int LO, int HI> GDEV void setup_dynamics_block(const IpmCtx<M>& c, int k) {
+template <int M, int LO, int HI> GDEV void setup_dynamics_block(const IpmCtx<M>& c, int k, double* stg) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
   constexpr int NX = L::NX, NU = L::NU, ANZ = L::ANZ, LDT = L::LDT, n = HI - LO;
@@ -975,14 +975,15 @@ template <int M, int LO, int HI> GDEV void setup_dynamics_block(const IpmCtx<M>&
 #pragma unroll
     for (int j = 0; j < n; ++j) c.fi[(size_t)((LO + i) * NX + LO + j) * np + k] = a[i][j];
   // Gam_k' (column b_row(a) of Fi_k scaled; zero outside the block of the driven coordinate, and for k = 0)
-  double* cr = c.cr + (size_t)k * L::CRW;
+  // (the knot-major record rows go through the shared-memory stage `stg` = [Ah_{k-1}' rows | Gam_k' rows] and are written to
+  // global memory by the whole group, coalesced: one thread per knot storing its own record costs 32 sectors per store instruction)
 #pragma unroll
   for (int q = 0; q < NU; ++q) {
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       double gv = 0.0;
       if (T::b_row(q) >= LO && T::b_row(q) < HI && k > 0) gv = hh * c.bv[q] * a[i][T::b_row(q) - LO];
-      cr[(L::CR_GT + q) * LDT + LO + i] = gv;
+      stg[(NX + q) * LDT + LO + i] = gv;
       c.gs[(size_t)(q * NX + LO + i) * np + k] = gv;
     }
   }
@@ -1000,18 +1001,12 @@ template <int M, int LO, int HI> GDEV void setup_dynamics_block(const IpmCtx<M>&
 #pragma unroll
         for (int i = 0; i < n; ++i) ah[i][T::a_col(e) - LO] += av * a[i][T::a_row(e) - LO];
       }
-    double* crp = c.cr + (size_t)(k - 1) * L::CRW;
 #pragma unroll
     for (int j = 0; j < NX; ++j)
 #pragma unroll
-      for (int i = 0; i < n; ++i) crp[(L::CR_AT + j) * LDT + LO + i] = (j >= LO && j < HI) ? ah[i][j - LO] : 0.0;
+      for (int i = 0; i < n; ++i) stg[j * LDT + LO + i] = (j >= LO && j < HI) ? ah[i][j - LO] : 0.0;
   }
-  if (k == N - 1) {      // no dynamics after the last knot
-#pragma unroll
-    for (int j = 0; j < NX + NU; ++j)
-#pragma unroll
-      for (int i = 0; i < n; ++i) cr[j * LDT + LO + i] = 0.0;
-  }
+  (void)N;
 }
 #ifndef GUSTO_SETUP_COOP
 template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
@@ -1020,14 +1015,34 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
   constexpr int NX = L::NX, NU = L::NU, LDT = L::LDT;
   static_assert(L::dcheck(), "Traits<M>::DSPLIT does not decouple the pattern of A");
   const int N = c.N;
-  G_PAR_FOR(k, N) {
-    if constexpr (T::DSPLIT > 0) {
-      setup_dynamics_block<M, 0, T::DSPLIT>(c, k);
-      setup_dynamics_block<M, T::DSPLIT, NX>(c, k);
-    } else {
-      setup_dynamics_block<M, 0, NX>(c, k);
+  constexpr int RW = (NX + NU) * LDT, W = RW | 1;          // staged rows of one knot; odd slot stride: conflict-free
+  double* const stage = sh_dz<M>(c);                       // the work region and the costate chain behind it are idle here
+  const int avail = L::work_doubles(N) + (int)L::rnd((size_t)(N + 1) * NX);
+  const int KC = avail / W > 0 ? avail / W : 1;
+  static_assert(L::CR_AT == 0 && L::CR_BT == NX && L::CR_GT == NX + NU, "record layout");
+  for (int k0 = 0; k0 < N; k0 += KC) {
+    const int nk = N - k0 < KC ? N - k0 : KC;
+    G_PAR_FOR(kk, nk) {
+      const int k = k0 + kk;
+      double* stg = stage + (size_t)kk * W;
+      if constexpr (T::DSPLIT > 0) {
+        setup_dynamics_block<M, 0, T::DSPLIT>(c, k, stg);
+        setup_dynamics_block<M, T::DSPLIT, NX>(c, k, stg);
+      } else {
+        setup_dynamics_block<M, 0, NX>(c, k, stg);
+      }
     }
+    G_SYNC();
+    G_PAR_FOR(it, nk * RW) {
+      const int kk = it / RW, e = it - kk * RW, k = k0 + kk;
+      if (e % LDT >= NX) continue;                          // padding columns of the tile rows stay at their allocation-time zero
+      const double v = stage[(size_t)kk * W + e];
+      if (e < NX * LDT) { if (k >= 1) c.cr[(size_t)(k - 1) * L::CRW + e] = v; }
+      else c.cr[(size_t)k * L::CRW + L::CR_GT * LDT + (e - NX * LDT)] = v;
+    }
+    G_SYNC();
   }
+  G_PAR_FOR(e, RW) c.cr[(size_t)(N - 1) * L::CRW + e] = 0.0;     // no dynamics after the last knot: Ah', Bh' rows of knot N - 1
   G_SYNC();
 #else
 template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
