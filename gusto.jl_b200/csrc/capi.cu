@@ -71,6 +71,11 @@ constexpr int IPM_THREADS = GUSTO_IPM_THREADS;
 constexpr int IPM_MAX_PACK = GUSTO_IPM_MAX_PACK;   // 7 groups x 64 threads x 144 registers fit the register file of an SM (8 x 128 spilled more)
 static_assert(GUSTO_IPM_THREADS == GUSTO_IPM_GROUP, "ipm.cuh's group size and the launch configuration must agree");
 constexpr int EVAL_THREADS = 128;
+// K4 resident CTAs per SM: 7 x 148 = 1036 slots hold the headline batch (1024 CTAs) in ONE wave; with 4 (128 registers) the second
+// wave was 73 % full
+#ifndef GUSTO_EVAL_MINBLOCKS
+#define GUSTO_EVAL_MINBLOCKS 7
+#endif
 
 // K1+K2.  Grid: ceil(B*N/8) CTAs of 8 warps.  The 8 knots' states and controls are contiguous in HBM
 // ([B][N][NX] knot-major) and are staged into shared memory with two TMA bulk copies per CTA.
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   __shared__ alignas(8) unsigned long long mbar;
   __shared__ double sbv[NU > 0 ? NU : 1];
   __shared__ unsigned char pat[T::ANZ];                    // a_row(e) * NX + a_col(e)
+  __shared__ int kn_b[KPC], kn_k[KPC];                     // instance / knot of the CTA's knots (-1: none or frozen instance)
   const BatchDesc& d = *dp;
   if (threadIdx.x == 0) dyn_B_columns<M>(d.rp, sbv);     // visible after the barrier / mbarrier wait below
   const int total = d.B * d.N;
@@ -111,6 +117,12 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_obs = T::WS > 0 ? d.n_obs : 0, nfield = T::ANZ + 2 * NX + 5 * n_obs;
   if (threadIdx.x < T::ANZ) pat[threadIdx.x] = (unsigned char)(T::a_row(threadIdx.x) * NX + T::a_col(threadIdx.x));
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + KPC) {       // (the write-out below used to divide by N and test `active` per element)
+    const int kk = threadIdx.x - 32, gk = k0 + kk;
+    int b = -1, k = 0;
+    if (kk < nk) { b = gk / d.N; k = gk - b * d.N; if (p.active && !p.active[b]) b = -1; }
+    kn_b[kk] = b; kn_k[kk] = k;
+  }
   for (int i = threadIdx.x; i < KPC * (NX * NX + NX); i += blockDim.x) (&ws[0][0])[i] = 0.0;
   __syncthreads();
   const bool live = warp < nk && !(p.active && !p.active[(k0 + warp) / d.N]);     // (frozen instance: its blocks are never read again)
@@ -128,9 +140,8 @@ __global__ void __launch_bounds__(LIN_KNOTS_PER_CTA * 32) linearize_kernel(const
   const size_t np = g_np(d.N);
   for (int idx = threadIdx.x; idx < nfield * KPC; idx += blockDim.x) {
     const int fld = idx / KPC, kk = idx - fld * KPC;
-    if (kk >= nk) continue;
-    const int gk = k0 + kk, b = gk / d.N, k = gk - b * d.N;
-    if (p.active && !p.active[b]) continue;
+    const int b = kn_b[kk], k = kn_k[kk];
+    if (b < 0) continue;
     const double v = outs[idx];
     if (fld < T::ANZ) p.A[((size_t)b * T::ANZ + fld) * np + k] = v;
     else if (fld < T::ANZ + NX) p.f[((size_t)b * NX + fld - T::ANZ) * np + k] = v;
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) trajopt_compare_kernel(const Bat
 
 // K4.  Grid: B CTAs.
 template <int M>
-__global__ void __launch_bounds__(EVAL_THREADS, 4) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
+__global__ void __launch_bounds__(EVAL_THREADS, GUSTO_EVAL_MINBLOCKS) evaluate_kernel(const BatchDesc* __restrict__ dp, BatchPtrs p, double* out) {
   using T = Traits<M>;
   __shared__ double red[EVAL_THREADS];
   const int b = blockIdx.x;

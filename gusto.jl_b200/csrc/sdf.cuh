@@ -31,8 +31,10 @@ GDEV void signed_distance(const double* r, int kind, const double* a, const doub
       if (q[i] > q[j]) j = i;
     }
     if (outside) {
-      const double d = sqrt(d2);
-      for (int i = 0; i < WS; ++i) nhat[i] = diff[i] / d;
+      // 1 / sqrt(d2) once (g_rsqrt, ~1 ulp) instead of an IEEE sqrt and WS IEEE divisions: K1 is issue-bound and this query is
+      // most of its instructions; outside => d2 > 0
+      const double inv = g_rsqrt(d2), d = d2 * inv;
+      for (int i = 0; i < WS; ++i) nhat[i] = diff[i] * inv;
       *dist = d - R;
     } else {
       nhat[j] = (r[j] - b[j] >= a[j] - r[j]) ? 1.0 : -1.0;
@@ -41,8 +43,8 @@ GDEV void signed_distance(const double* r, int kind, const double* a, const doub
   } else {
     double d2 = 0.0, diff[3];
     for (int i = 0; i < WS; ++i) { diff[i] = r[i] - a[i]; d2 += diff[i] * diff[i]; }
-    const double d = sqrt(d2);
-    for (int i = 0; i < WS; ++i) nhat[i] = diff[i] / d;
+    const double inv = g_rsqrt(d2), d = d2 > 0.0 ? d2 * inv : 0.0;
+    for (int i = 0; i < WS; ++i) nhat[i] = diff[i] * inv;      // (centre on centre: NaN normal, as 0 / 0 gave)
     *dist = d - b[0] - R;
   }
 }
