@@ -165,6 +165,9 @@ constexpr int IPM_NINFO = 8;  // status, iterations, residual, mu, objective, cy
 #ifndef GUSTO_CHAIN_D
 #define GUSTO_CHAIN_D 4
 #endif
+#ifndef GUSTO_RD_FACTOR
+#define GUSTO_RD_FACTOR 0.01
+#endif
 constexpr int CHAIN_STAGES = GUSTO_CHAIN_D;
 
 GHD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
@@ -274,7 +277,7 @@ template <int M> struct IpmCtx {
   static constexpr int NX = L::NX, NU = L::NU, NV = L::NV;
   const BatchDesc* d;
   const double* rp;
-  int N, n_obs, b, nact, pmask, bmask;
+  int N, n_obs, b, nact, pmask, bmask, reset;   // reset: slack reset on (slack_reset_on<M>() and no BoxGoal rows)
   int NP, NE, PP;         // field strides of the knot-minor scratch arrays (IpmLayout::np_of / ne_of / pp_of)
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
@@ -348,14 +351,30 @@ GDEV void pair_stat(const double* st, size_t ss, bool has_t, const Pair& q, Stat
 //           (Mehrotra's mu_aff for any step a, so the predictor needs ONE pass over the rows);
 //   mode 2: apply (ap, ad) and accumulate the new complementarity sum / pair count (for the central-path floor).
 struct StepAcc { double amp, amd, c0, c1, c2, np; };
-GDEV void pair_step(double* st, size_t ss, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a) {
+// quad = dz' (hess c / 2) dz of a quadratic row: the slack is updated linearly, s += ap ds, while the row moves by ap gdz + ap^2 quad,
+// so after a FULL step the row residual c + s [- t] is exactly ap^2 quad -- on the headline batch that second-order remainder
+// (1e-4 on the inactive trust-region rows) is what the last one or two Newton iterations of every solve were spent on, with the
+// dual residual and the complementarity already converged.  Mode 2 therefore moves the slack to where the row puts it (slack
+// reset, as nonlinear interior-point codes do), unless that would take more than 90 % of it (a nearly active row keeps the
+// linear update and its fraction-to-boundary guarantee).  -DGUSTO_NO_SLACK_RESET restores the linear update.
+GDEV double slack_reset(double s1, double ap, double quad) {
+#ifndef GUSTO_NO_SLACK_RESET
+  const double s1q = s1 - ap * ap * quad;
+  return (quad > 0.0 && s1q >= 0.1 * s1) ? s1q : s1;
+#else
+  (void)ap; (void)quad;
+  return s1;
+#endif
+}
+GDEV void pair_step(double* st, size_t ss, bool has_t, const Pair& q, double gdz, int mode, double ap, double ad, StepAcc& a, double quad = 0.0) {
   const double sa = st[0], la = st[ss];
   if (has_t) {
     const double t = st[2 * ss], lb = st[3 * ss];
     const double dt = (q.wa * gdz + q.ba + q.bb - q.rt) * q.iw;
     const double dla = q.wa * (gdz - dt) + q.ba, dlb = -q.wb * dt + q.bb, ds = -q.rc - (gdz - dt);
     if (mode == 2) {
-      const double s1 = sa + ap * ds, t1 = t + ap * dt, l1 = la + ad * dla, b1 = lb + ad * dlb;
+      const double s0 = sa + ap * ds, s1 = slack_reset(s0, ap, quad), t1 = t + ap * dt, b1 = lb + ad * dlb;
+      const double l1 = (la + ad * dla) * (s1 != s0 ? s0 * g_rcp(s1) : 1.0);      // the pair keeps its product: the iterate stays as centred as it was
       st[0] = s1; st[2 * ss] = t1; st[ss] = l1; st[3 * ss] = b1;
       a.c0 += s1 * l1 + t1 * b1; a.np += 2.0;
     } else {
@@ -371,7 +390,7 @@ GDEV void pair_step(double* st, size_t ss, bool has_t, const Pair& q, double gdz
   } else {
     const double dla = q.wa * gdz + q.ba, ds = -q.rc - gdz;
     if (mode == 2) {
-      const double s1 = sa + ap * ds, l1 = la + ad * dla;
+      const double s0 = sa + ap * ds, s1 = slack_reset(s0, ap, quad), l1 = (la + ad * dla) * (s1 != s0 ? s0 * g_rcp(s1) : 1.0);
       st[0] = s1; st[ss] = l1;
       a.c0 += s1 * l1; a.np += 1.0;
     } else {
@@ -1913,6 +1932,13 @@ template <int M> GDEV void l1_rows_step(const IpmCtx<M>& c, double smu, int phas
 // --------------------------------------------------------------------------------------------- slot passes
 // Flat pass over every live row.  FN(st, has_t, c0, gdz) is called once per row; `want_gdz` says whether the
 // directional derivative gv.dz is needed.
+// Slack reset (pair_step): on where the parity tolerances of the test-suite hold with it -- astrobeeSE3 with PointGoal rows
+// (c.reset; the headline configurations).  Elsewhere the minimiser is flat in some directions (attitude inside the quaternion
+// dead-band of astrobeeSE3manifold, position inside a BoxGoal, l1 rows of TrajOpt) or the SCP path is close to a decision boundary
+// (freeflyerSE2's omega-escalation instances): there the end point depends on how the complementarity products are distributed, and
+// with the reset the kernel lands 2e-5 (U) / 5e-4 (X) from the oracle's end point instead of 1e-6 -- inside the solver tolerance,
+// outside the tests' -- so those keep the linear slack update.
+template <int M> GHD constexpr bool slack_reset_on() { return !kTO && M == ASTROBEE_SE3; }
 template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool want_gdz, FN&& fn) {
   using L = IpmLayout<M>;
   using T = Traits<M>;
@@ -1924,16 +1950,19 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)s * SLOT_W * np + k;
     if (T::HAS_TR && s == L::S_TR) {
-      double v = -c.dow, gdz = 0.0;
-      for (int i = 0; i < NX; ++i) { const double dxi = x[i] - c.xps[i * np + k]; v += dxi * dxi; gdz += 2.0 * dxi * sh_dz<M>(c)[k * NV + i]; }
-      fn(st, np, !kTO, v, gdz);
+      double v = -c.dow, gdz = 0.0, quad = 0.0;
+      for (int i = 0; i < NX; ++i) {
+        const double dxi = x[i] - c.xps[i * np + k], dzi = sh_dz<M>(c)[k * NV + i];
+        v += dxi * dxi; gdz += 2.0 * dxi * dzi; quad += dzi * dzi;
+      }
+      fn(st, np, !kTO, v, gdz, c.reset ? quad : 0.0);
     } else {
       SpecEval o;
       spec_eval<M>(c, k, s, x, x + NX, o);
       if (!o.valid) continue;
-      double gdz = 0.0;
-      if (want_gdz) { const double* dv = sh_dz<M>(c) + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) gdz += o.gv[a] * dv[a]; }
-      fn(st, np, o.has_t, o.c0, gdz);
+      double gdz = 0.0, quad = 0.0;
+      if (want_gdz) { const double* dv = sh_dz<M>(c) + k * NV + (o.is_u ? NX : 0) + o.i0; for (int a = 0; a < 4; ++a) if (a < o.n) { gdz += o.gv[a] * dv[a]; quad += 0.5 * o.hq[a] * dv[a] * dv[a]; } }
+      fn(st, np, o.has_t, o.c0, gdz, c.reset ? quad : 0.0);
     }
   }
   if (c.bmask != 0) {
@@ -1941,7 +1970,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
       if (!((c.bmask >> (j >> 1)) & 1)) continue;
       const double* x = sh_z<M>(c) + (N - 1) * NV;
       const double gdz = ((j & 1) == 0 ? 1.0 : -1.0) * sh_dz<M>(c)[(N - 1) * NV + (j >> 1)];
-      fn(c.bslot + (size_t)j * SLOT_W, (size_t)1, false, box_c0<M>(c, j, x), gdz);
+      fn(c.bslot + (size_t)j * SLOT_W, (size_t)1, false, box_c0<M>(c, j, x), gdz, 0.0);
     }
   }
   if (T::WS > 0) {
@@ -1960,7 +1989,7 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
       double v = row[3 * pp], gdz = 0.0;
 #pragma unroll
       for (int a = 0; a < WS; ++a) { const double ra = row[a * pp]; v -= ra * x[a]; gdz -= ra * dv[a]; }
-      fn(ost + p, pp, true, v, gdz);
+      fn(ost + p, pp, true, v, gdz, 0.0);
     }
   }
 }
@@ -1970,10 +1999,10 @@ template <int M, typename FN> GDEV void for_each_row(const IpmCtx<M>& c, bool wa
 template <int M> GDEV_NOINLINE void slot_steps(const IpmCtx<M>& c, int phase, double smu, int mode, double ap, double ad, double* out) {
   StepAcc acc; acc.amp = 1e300; acc.amd = 1e300; acc.c0 = 0.0; acc.c1 = 0.0; acc.c2 = 0.0; acc.np = 0.0;
   const double omega = c.omega;
-  for_each_row<M>(c, true, [&](double* st, size_t ss, bool has_t, double c0, double gdz) {
+  for_each_row<M>(c, true, [&](double* st, size_t ss, bool has_t, double c0, double gdz, double quad) {
     Pair q;
     pair_eval(st, ss, has_t, c0, omega, smu, phase, q);
-    pair_step(st, ss, has_t, q, gdz, mode, ap, ad, acc);
+    pair_step(st, ss, has_t, q, gdz, mode, ap, ad, acc, quad);
   });
   if (kTO) l1_rows_step<M>(c, smu, phase, mode, ap, ad, acc);
   if (mode != 2) {
@@ -2338,6 +2367,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.dow = kTO ? c.Delta : c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
     for (int i = 0; i < NX; ++i) { if (d.goal_type[i] == GOAL_POINT) c.pmask |= 1 << i; if (d.goal_type[i] == GOAL_BOX) c.bmask |= 1 << i; }
+    c.reset = (slack_reset_on<M>() && c.bmask == 0) ? 1 : 0;
     c.Xp = p.Xp + (size_t)b * N * NX; c.Up = p.Up + (size_t)b * N * NU;
     c.Ac = p.A + (size_t)b * L::ANZ * g_np(N); c.g = p.g + (size_t)b * NX * g_np(N);
     c.rows = p.rows + (size_t)b * 5 * d.n_obs * g_np(N);
@@ -2397,6 +2427,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   const long long cyc_setup = g_clock() - tc0;
   double best = 1e300;
   int stall = 0;
+  bool polish = false;
   bool broke = false;
   int restarts = 0;
   for (int iter = 1; iter <= prm.max_iter; ++iter) {
@@ -2412,7 +2443,18 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
 #ifdef GUSTO_HOSTSIM
     if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  ipm %3d rd=%.2e rp=%.2e rc=%.2e mu=%.2e\n", iter, R.rz, R.rp, R.rc, mu);
 #endif
-    if (res <= prm.tol) { status = IPM_OPTIMAL; break; }
+    // With the slack reset (pair_step) the row residuals no longer lag behind, and the first iterate with res <= tol can carry a dual
+    // residual just under the tolerance -- 1e-9 relative, which the weakly curved state directions (cost on U only) turn into 1e-4 in
+    // X.  The solves used to end far below it (the lagging row residual forced one or two more quadratically convergent steps), and
+    // the parity tolerances are calibrated on that; likewise the complementarity, whose average mu times the ~1e3 pairs is the error
+    // of the objective, used to end at its floor 0.1 tol.  So: accept at once when the dual residual is 100x under the tolerance and
+    // mu is at its floor, else take ONE more Newton step and accept then.
+    if (res <= prm.tol) {
+      if (!c.reset || (R.rz / scd <= GUSTO_RD_FACTOR * prm.tol && mu <= 0.15 * prm.tol) || polish) { status = IPM_OPTIMAL; break; }
+      polish = true;
+    } else {
+      polish = false;
+    }
     if (!(res == res) || res > 1e200) { status = IPM_NUMERICAL; break; }
     // The best iterate is kept in Xn / Un (as the oracle keeps it, ipm.py): a solve whose dual residual wanders once the
     // complementarity sits at its floor is stopped after 8 iterations without improvement and answers with that iterate.
@@ -2509,7 +2551,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
   }
   {
     const double omega = c.omega;
-    for_each_row<M>(c, false, [&](double* st, size_t ss, bool has_t, double c0, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2 * ss]); });
+    for_each_row<M>(c, false, [&](double* st, size_t ss, bool has_t, double c0, double, double) { if (has_t) obj += omega * (use_best ? (c0 > 0.0 ? c0 : 0.0) : st[2 * ss]); });
     if (kTO) {   // + mu |d_j(z)|_1 over the dynamics rows (the l1 slacks at their optimal values)
       G_PAR_FOR(j1, N - 1) {
         double v[NX];
