@@ -11,9 +11,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.
 import __graft_entry__ as entry
 
 mode, name, B = sys.argv[1], sys.argv[2], int(sys.argv[3])
+KW = {}
+if name.endswith(":hard"):                       # e.g. astrobeeSE3:hard -- the C3-hard tier of the generator
+    name, KW = name[:-5], dict(hard=True)
 if mode == "gpu":
     pkg = entry.build(); host = pkg.engine()
-    bp = pkg.problems.CONFIGS[name](B=B)
+    bp = pkg.problems.CONFIGS[name](B=B, **KW)
     eng = host.Engine(bp)
     S = host.solve_gusto_batch_device(eng, max_iter=30)          # the device-resident loop (same decisions as the host loop: GPU test)
     np.savez(sys.argv[4], converged=S.converged, successful=S.successful, iterations=S.iterations,
@@ -24,7 +27,7 @@ else:
     from util import gb, to_oracle
     from gusto_oracle.scp import solve_gusto
     n = int(sys.argv[4]); G = np.load(sys.argv[5])
-    bp = gb.problems.CONFIGS[name](B=B)
+    bp = gb.problems.CONFIGS[name](B=B, **KW)
     agree = 0; rows = []
     for b in range(n):
         R = solve_gusto(to_oracle(bp, b), max_iter=30)
