@@ -1584,7 +1584,7 @@ template <int M> GDEV_NOINLINE void chain_forward(const IpmCtx<M>& c) {
       if (k + D - 1 < nt) chain_fetch<M>(c, ring, (k + D - 1) % D, k + D - 1);
       g_cp_async_commit();
       const double* R = ring + (k % D) * L::GT + ir * LDT;
-      double a0 = y[(k + 1) * NV + ir], a1 = 0.0;                // d_k[i]: independent of the chain
+      double a0 = act ? y[(k + 1) * NV + i] : 0.0, a1 = 0.0;     // d_k[i]: independent of the chain (idle lanes read nothing: racecheck-clean)
 #pragma unroll
       for (int m = 0; m < HP; ++m) {
         const g_d2 rv = g_ld2(R + 2 * m);
@@ -1635,7 +1635,7 @@ template <int M> GDEV_NOINLINE void chain_backward(const IpmCtx<M>& c) {
       if (k - (D - 1) >= 0) chain_fetch<M>(c, ring, (st + D - 1) % D, k - (D - 1));
       g_cp_async_commit();
       const double* R = ring + (st % D) * L::GT + ir;
-      double a0 = y[k * NX + ir], a1 = 0.0;
+      double a0 = act ? y[k * NX + i] : 0.0, a1 = 0.0;
 #pragma unroll
       for (int m = 0; m + 1 < NX; m += 2) {
         a0 = fma(R[m * LDT], __shfl_sync(0xffffffffu, sv, m), a0);
