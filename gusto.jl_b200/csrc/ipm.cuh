@@ -153,7 +153,23 @@ struct IpmParams {
   double tol;        // max(|r_dual|/(1+omega), |r_eq|, |r_ineq|, mu) <= tol
   double wn_base;    // terminal (PointGoal) penalty  w_N = wn_base + wn_omega * omega
   double wn_omega;
+  // centred start (slot_init): mu0 = max(mu0_a omega, mu0_b omega vmax), vmax = the largest violated soft-row value at the start point;
+  // mu0 > mu0_cap (a poor start point) or mu0_a <= 0: the tuned default start.  ipm_default_start() fills the defaults.
+  double mu0_a, mu0_b, mu0_cap, mu0_smin;   // mu0_smin: smallest margin of a satisfied obstacle row below which the default start is used
 };
+#ifndef GUSTO_MU0_A
+#define GUSTO_MU0_A 5e-5
+#endif
+#ifndef GUSTO_MU0_B
+#define GUSTO_MU0_B 1.0
+#endif
+#ifndef GUSTO_MU0_CAP
+#define GUSTO_MU0_CAP 1e-3
+#endif
+#ifndef GUSTO_MU0_SMIN
+#define GUSTO_MU0_SMIN 0.0
+#endif
+inline void ipm_default_start(IpmParams& prm) { prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP; prm.mu0_smin = GUSTO_MU0_SMIN; }
 
 // IPM_ALMOST_OPTIMAL: stalled within 1e3*tol of the tolerance AND far below the SCP's own soft-row threshold eps -- the
 // MOI.ALMOST_LOCALLY_SOLVED the reference accepts next to OPTIMAL (scp_gusto.jl:107); the host records it as such.
@@ -281,6 +297,7 @@ template <int M> struct IpmCtx {
   int NP, NE, PP;         // field strides of the knot-minor scratch arrays (IpmLayout::np_of / ne_of / pp_of)
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
+  double mu0_a, mu0_b, mu0_cap, mu0_smin;   // centred start (IpmParams)
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *Ac, *g, *rows, *x_init, *goal_lo, *goal_hi;   // Ac, g, rows: the linearize kernel's blocks, knot-minor, read in place
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
@@ -410,6 +427,27 @@ GDEV void pair_floor(double* st, size_t ss, bool has_t, double floor_) {
 GDEV void slot_init(double* st, size_t ss, bool valid, bool has_t, double c0, double omega, double t_in = 1.0, double lam_split = 0.5) {
   for (int i = 0; i < SLOT_W; ++i) st[i * ss] = 0.0;
   if (!valid) return;
+  if (t_in < 0.0) {
+    // Centred start (round 2, last session): both pairs of the row ON the central path at mu0 = -t_in with zero dual residual of t,
+    //   lam = mu0 / s,  lamb = mu0 / t,  lam + lamb = omega,  s = t - c0   =>   omega t^2 + (omega a - 2 mu0) t - mu0 a = 0,  a = -c0.
+    // The tuned start below leaves e.g. the (far inactive) trust-region pairs at s lam = 0.2 and the solve needs two to three Newton
+    // iterations just to bring mu down; from a centred point at mu0 = 5e-5 omega a first-iteration solve of the headline batch takes 4
+    // Newton iterations instead of 5.7, later SCP iterations 3 instead of 4.  It needs a start point that violates no soft row (a
+    // violated hinge row has t >= c0 and wants mu ~ omega c0): setup() measures that and falls back to the tuned start otherwise
+    // (hard tier, first iterations: 30-50 Newton iterations from a centred point at 1e-4, 7-10 from the tuned one).
+    const double mu0 = -t_in;
+    if (has_t) {
+      const double a = -c0, bq = omega * a - 2.0 * mu0;
+      double t = (-bq + sqrt(bq * bq + 4.0 * omega * mu0 * a)) / (2.0 * omega);
+      if (!(t > 0.0) || !(t + a > 0.0)) t = (c0 > 0 ? c0 : 0.0) + mu0 / omega + 1e-12;
+      const double sa = t + a;
+      st[0] = sa; st[ss] = mu0 / sa; st[2 * ss] = t; st[3 * ss] = mu0 / t;
+    } else {
+      const double sa = -c0 > 1e-6 ? -c0 : 1e-2;
+      st[0] = sa; st[ss] = mu0 / sa;
+    }
+    return;
+  }
   if (has_t) {
     // interior start of the penalty slack: t_in inside (the oracle uses one unit).  0.25 saves 0.85 Newton iterations of 8.85 on
     // astrobeeSE3 but costs restarts on freeflyerSE2 at omega = 25 (measured), so it is a per-model setting
@@ -2221,6 +2259,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   using T = Traits<M>;
   constexpr int NX = L::NX, NU = L::NU, NV = L::NV, ANZ = L::ANZ;
   const int N = c.N;
+  double tin_ = slack_start<M>();
   // start point: X, U <- previous trajectory (set_start_value, scp_gusto.jl:100-102); multipliers 0
   const size_t np = c.NP, ne = c.NE, pp = c.PP;
   G_PAR_FOR(it, N * NV) { const int k = it / NV, i = it - k * NV; sh_z<M>(c)[it] = i < NX ? c.Xp[k * NX + i] : c.Up[k * NU + i - NX]; }
@@ -2252,6 +2291,43 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     if (G_TID == 0) c.nact = 0;
     G_SYNC();
   }
+  // Centred start: on for astrobeeSE3 (GuSTO subproblem) while the penalty weight has not been escalated.  Measured on the CPU build
+  // over real SCP solves as the sum over the launches of the slowest instance's Newton count (what a launch costs): astrobeeSE3
+  // 15 -> 11, its hard tier 167 -> 167 (with the omega gate; instances past an escalation sit on their hinge rows and a start that
+  // close to them stalls: 30-50 iterations), dubins 198 -> 194, freeflyerSE2 158 -> 160, astrobeeSE3manifold 100 -> 146, and the
+  // TrajOpt subproblem grows stragglers (25 iterations): those keep the tuned start.
+  if (!kTO && M == ASTROBEE_SE3 && c.mu0_a > 0.0 && c.omega <= c.d->sp[SP_OMEGA0]) {
+    // centred start when the start point violates no soft row (see slot_init): vmax over the live obstacle rows and the special rows
+    double vloc = 0.0, sloc = 1e300;
+    if (T::WS > 0) G_PAR_FOR(k, N) {
+      const double* x = sh_z<M>(c) + k * NV;
+      const size_t fs = (size_t)c.n_obs * np;
+      for (int i = 0; i < c.n_obs; ++i) {
+        const double* row = c.rows + (size_t)i * np + k;
+        if (!(row[4 * fs] < c.toggle)) continue;
+        double v = row[3 * fs];
+        for (int a2 = 0; a2 < T::WS; ++a2) v -= row[a2 * fs] * x[a2];
+        vloc = v > vloc ? v : vloc;
+        if (v < 0.0 && -v < sloc) sloc = -v;
+      }
+    }
+    G_PAR_FOR(it, N * L::SP) {
+      const int s2 = it / N, k = it - s2 * N;
+      if (T::HAS_TR && s2 == L::S_TR) continue;                  // x = xp at the start: never violated
+      const double* x = sh_z<M>(c) + k * NV;
+      SpecEval o; spec_eval<M>(c, k, s2, x, x + NX, o);
+      if (o.valid && o.c0 > vloc) vloc = o.c0;
+    }
+    const double vmax = block_max(vloc, c.red);
+    const double smin = -block_max(-sloc, c.red);
+#ifdef GUSTO_HOSTSIM
+    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  start: vmax %.3e smin %.3e\n", vmax, smin);
+#endif
+    double mu0 = c.mu0_a * c.omega;
+    if (c.mu0_b * c.omega * vmax > mu0) mu0 = c.mu0_b * c.omega * vmax;
+    if (mu0 <= c.mu0_cap && smin >= c.mu0_smin) tin_ = -mu0;
+  }
+  const double tin = tin_;
   if (T::WS > 0) {
     G_PAR_FOR(k, N) {
       int p = sh_seg<M>(c)[k];
@@ -2265,7 +2341,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
         double v = off;
         for (int a = 0; a < 3; ++a) { const double ra = row[a * fs]; o[a * pp] = ra; if (a < T::WS) v -= ra * x[a]; }
         o[3 * pp] = off; o[4 * pp] = (double)k;
-        slot_init(c.ost + p, pp, true, true, v, c.omega, slack_start<M>(), slack_lam_split<M>());
+        slot_init(c.ost + p, pp, true, true, v, c.omega, tin, slack_lam_split<M>());
         ++p;
       }
     }
@@ -2275,8 +2351,8 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     const int s = it / N, k = it - s * N;
     const double* x = sh_z<M>(c) + k * NV;
     double* st = c.sslot + (size_t)s * SLOT_W * np + k;
-    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, !kTO, -c.dow, c.omega, slack_start<M>(), slack_lam_split<M>());   // x = xp at the start
-    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega, slack_start<M>(), slack_lam_split<M>()); }
+    if (T::HAS_TR && s == L::S_TR) slot_init(st, np, true, !kTO, -c.dow, c.omega, tin, slack_lam_split<M>());   // x = xp at the start
+    else { SpecEval o; spec_eval<M>(c, k, s, x, x + NX, o); slot_init(st, np, o.valid, o.has_t, o.c0, c.omega, tin, slack_lam_split<M>()); }
   }
   G_PAR_FOR(j, L::NBOX) {
     const bool valid = (c.bmask >> (j >> 1)) & 1;
@@ -2380,6 +2456,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.toggle = kTO ? d.rp[RP_CLEAR] + 1.0 : c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];   // scp_gusto.jl:76 | scp_trajopt.jl:65
     // TrajOpt: the noise phase forms P~ = P - X'X at the last knot, where P carries w_N: a smaller penalty keeps that difference
     // accurate (the row error after a step is dnu_N / w_N and vanishes with the step, as a proximal multiplier update does)
+    c.mu0_a = prm.mu0_a; c.mu0_b = prm.mu0_b; c.mu0_cap = prm.mu0_cap; c.mu0_smin = prm.mu0_smin;
     c.wN = kTO ? 1e-3 * (prm.wn_base + prm.wn_omega * c.omega) : prm.wn_base + prm.wn_omega * c.omega;
     c.dow = kTO ? c.Delta : c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
