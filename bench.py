@@ -402,9 +402,9 @@ def main():
             kern[k] = {"ms": ms, "algorithmic_bytes": ab[k] * B, "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(kern, key=lambda k: kern[k]["ms"])
         # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-        # (profiles/r02b_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); null when the workload differs
+        # (profiles/r02c_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); null when the workload differs
         traffic = None
-        for tname in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):
+        for tname in ("r02c_traffic.json", "r02_traffic.json", "r01_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath):
                 tj = json.load(open(tpath))
