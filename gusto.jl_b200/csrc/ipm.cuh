@@ -155,7 +155,7 @@ struct IpmParams {
   double wn_omega;
   // centred start (slot_init): mu0 = max(mu0_a omega, mu0_b omega vmax), vmax = the largest violated soft-row value at the start point;
   // mu0 > mu0_cap (a poor start point) or mu0_a <= 0: the tuned default start.  ipm_default_start() fills the defaults.
-  double mu0_a, mu0_b, mu0_cap, mu0_smin;   // mu0_smin: smallest margin of a satisfied obstacle row below which the default start is used
+  double mu0_a, mu0_b, mu0_cap;
 };
 #ifndef GUSTO_MU0_A
 #define GUSTO_MU0_A 5e-5
@@ -166,10 +166,7 @@ struct IpmParams {
 #ifndef GUSTO_MU0_CAP
 #define GUSTO_MU0_CAP 1e-3
 #endif
-#ifndef GUSTO_MU0_SMIN
-#define GUSTO_MU0_SMIN 0.0
-#endif
-inline void ipm_default_start(IpmParams& prm) { prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP; prm.mu0_smin = GUSTO_MU0_SMIN; }
+inline void ipm_default_start(IpmParams& prm) { prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP; }
 
 // IPM_ALMOST_OPTIMAL: stalled within 1e3*tol of the tolerance AND far below the SCP's own soft-row threshold eps -- the
 // MOI.ALMOST_LOCALLY_SOLVED the reference accepts next to OPTIMAL (scp_gusto.jl:107); the host records it as such.
@@ -297,7 +294,7 @@ template <int M> struct IpmCtx {
   int NP, NE, PP;         // field strides of the knot-minor scratch arrays (IpmLayout::np_of / ne_of / pp_of)
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
-  double mu0_a, mu0_b, mu0_cap, mu0_smin;   // centred start (IpmParams)
+  double mu0_a, mu0_b, mu0_cap;   // centred start (IpmParams)
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *Ac, *g, *rows, *x_init, *goal_lo, *goal_hi;   // Ac, g, rows: the linearize kernel's blocks, knot-minor, read in place
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
@@ -1075,7 +1072,9 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
   constexpr int RW = (NX + NU) * LDT, W = RW | 1;          // staged rows of one knot; odd slot stride: conflict-free
   double* const stage = sh_dz<M>(c);                       // the work region and the costate chain behind it are idle here
   const int avail = L::work_doubles(N) + (int)L::rnd((size_t)(N + 1) * NX);
-  const int KC = avail / W > 0 ? avail / W : 1;
+  constexpr int GW = NU * LDT;                                // Gam' rows of the previous round's last knot, kept behind the slots
+  const int KC = (avail - GW) / W > 0 ? (avail - GW) / W : 1;
+  double* const prevG = stage + (size_t)KC * W;
   static_assert(L::CR_AT == 0 && L::CR_BT == NX && L::CR_GT == NX + NU, "record layout");
   for (int k0 = 0; k0 < N; k0 += KC) {
     const int nk = N - k0 < KC ? N - k0 : KC;
@@ -1099,7 +1098,7 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
       const double* stg = stage + (size_t)kk * W;
       double v = stg[(NX + a) * LDT + i];
       for (int m = L::dlo(i); m < L::dhi(i); ++m) {
-        const double gm = kk >= 1 ? stg[(NX + a) * LDT + m - W] : c.gs[(size_t)(a * NX + m) * c.NP + k - 1];
+        const double gm = kk >= 1 ? stg[(NX + a) * LDT + m - W] : prevG[a * LDT + m];
         v += stg[m * LDT + i] * gm;
       }
       c.bs[(size_t)e * c.NP + k - 1] = v;
@@ -1113,6 +1112,10 @@ template <int M> GDEV_NOINLINE void setup_dynamics(const IpmCtx<M>& c) {
       else c.cr[(size_t)k * L::CRW + L::CR_GT * LDT + (e - NX * LDT)] = v;
     }
     G_SYNC();
+    if (k0 + KC < N) {
+      G_PAR_FOR(t, GW) prevG[t] = stage[(size_t)(nk - 1) * W + NX * LDT + t];
+      G_SYNC();                                                    // before the next round's compute overwrites that slot
+    }
   }
   G_PAR_FOR(e, RW) c.cr[(size_t)(N - 1) * L::CRW + e] = 0.0;     // no dynamics after the last knot: Ah', Bh' rows of knot N - 1
   G_PAR_FOR(r, NU * NX) c.bs[(size_t)r * c.NP + N - 1] = 0.0;
@@ -1952,10 +1955,15 @@ template <int M> GDEV_NOINLINE void ric_forward(const IpmCtx<M>& c, bool want_nu
   if (want_nu) {
     // row 0 (x_0 = x_init): stationarity in x_0,  dnu_0 = rx_0 - Hx_0 dx_0 - E_1' dnu_1,  E_1 = I + h/2 A_0
     if (G_TID == 0) {
-      double dx0[NX], hx[NX], e1[NX];
-      for (int i = 0; i < NX; ++i) { dx0[i] = dz[i]; e1[i] = c.dnu[i * ne + 1]; }
+      // (unrolled: static indices keep e1 in registers and let the loads go out together; rolled, with e1 in local memory, this
+      // one-thread block was 1.7 % of the kernel's stall samples)
+      double dx0[NX], hx[NX], e1[NX], d1[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { dx0[i] = dz[i]; d1[i] = c.dnu[i * ne + 1]; e1[i] = d1[i]; }
       apply_Hx<M>(c, 0, dx0, hx);
-      for (int e = 0; e < L::ANZ; ++e) e1[T::a_col(e)] += c.hh * c.Ac[e * np] * c.dnu[T::a_row(e) * ne + 1];
+#pragma unroll
+      for (int e = 0; e < L::ANZ; ++e) e1[T::a_col(e)] += c.hh * c.Ac[e * np] * d1[T::a_row(e)];
+#pragma unroll
       for (int i = 0; i < NX; ++i) c.dnu[i * ne] = c.r[i * np] - hx[i] - e1[i];
     }
     G_SYNC();
@@ -2291,6 +2299,32 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     if (G_TID == 0) c.nact = 0;
     G_SYNC();
   }
+  // Compaction (thread per knot): the distances of a knot's obstacles are loaded first (independent loads, one round trip) into a
+  // bit mask, then the live rows are copied; their start values go through the record's first field to the flat pass below that
+  // initialises the records once the start point has been measured.  (One loop with the test in front of each row's loads was a
+  // chain of n_obs dependent round trips per thread: 2 % of the kernel's stall samples, three times over.)
+  double vloc = 0.0;
+  if (T::WS > 0) {
+    G_PAR_FOR(k, N) {
+      int p = sh_seg<M>(c)[k];
+      const double* x = sh_z<M>(c) + k * NV;
+      const size_t fs = (size_t)c.n_obs * np;
+      unsigned long long live = 0ull;
+      for (int i = 0; i < c.n_obs; ++i) live |= (unsigned long long)(c.rows[4 * fs + (size_t)i * np + k] < c.toggle ? 1 : 0) << i;
+      for (int i = 0; i < c.n_obs; ++i) {
+        if (!((live >> i) & 1ull)) continue;
+        const double* row = c.rows + (size_t)i * np + k;
+        double* o = c.orow + p;
+        const double off = row[3 * fs];
+        double v = off;
+        for (int a = 0; a < 3; ++a) { const double ra = row[a * fs]; o[a * pp] = ra; if (a < T::WS) v -= ra * x[a]; }
+        o[3 * pp] = off; o[4 * pp] = (double)k;
+        c.ost[p] = v;
+        vloc = v > vloc ? v : vloc;
+        ++p;
+      }
+    }
+  }
   // Centred start: on for astrobeeSE3 (GuSTO subproblem) while the penalty weight has not been escalated.  Measured on the CPU build
   // over real SCP solves as the sum over the launches of the slowest instance's Newton count (what a launch costs): astrobeeSE3
   // 15 -> 11, its hard tier 167 -> 167 (with the omega gate; instances past an escalation sit on their hinge rows and a start that
@@ -2298,19 +2332,6 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   // TrajOpt subproblem grows stragglers (25 iterations): those keep the tuned start.
   if (!kTO && M == ASTROBEE_SE3 && c.mu0_a > 0.0 && c.omega <= c.d->sp[SP_OMEGA0]) {
     // centred start when the start point violates no soft row (see slot_init): vmax over the live obstacle rows and the special rows
-    double vloc = 0.0, sloc = 1e300;
-    if (T::WS > 0) G_PAR_FOR(k, N) {
-      const double* x = sh_z<M>(c) + k * NV;
-      const size_t fs = (size_t)c.n_obs * np;
-      for (int i = 0; i < c.n_obs; ++i) {
-        const double* row = c.rows + (size_t)i * np + k;
-        if (!(row[4 * fs] < c.toggle)) continue;
-        double v = row[3 * fs];
-        for (int a2 = 0; a2 < T::WS; ++a2) v -= row[a2 * fs] * x[a2];
-        vloc = v > vloc ? v : vloc;
-        if (v < 0.0 && -v < sloc) sloc = -v;
-      }
-    }
     G_PAR_FOR(it, N * L::SP) {
       const int s2 = it / N, k = it - s2 * N;
       if (T::HAS_TR && s2 == L::S_TR) continue;                  // x = xp at the start: never violated
@@ -2319,32 +2340,16 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
       if (o.valid && o.c0 > vloc) vloc = o.c0;
     }
     const double vmax = block_max(vloc, c.red);
-    const double smin = -block_max(-sloc, c.red);
-#ifdef GUSTO_HOSTSIM
-    if (getenv("GUSTO_HOSTSIM_VERBOSE")) printf("  start: vmax %.3e smin %.3e\n", vmax, smin);
-#endif
     double mu0 = c.mu0_a * c.omega;
     if (c.mu0_b * c.omega * vmax > mu0) mu0 = c.mu0_b * c.omega * vmax;
-    if (mu0 <= c.mu0_cap && smin >= c.mu0_smin) tin_ = -mu0;
+    if (mu0 <= c.mu0_cap) tin_ = -mu0;
+  } else {
+    G_SYNC();                                                      // the compacted rows are read by other threads below
   }
   const double tin = tin_;
   if (T::WS > 0) {
-    G_PAR_FOR(k, N) {
-      int p = sh_seg<M>(c)[k];
-      const double* x = sh_z<M>(c) + k * NV;
-      for (int i = 0; i < c.n_obs; ++i) {
-        const size_t fs = (size_t)c.n_obs * np;
-        const double* row = c.rows + (size_t)i * np + k;
-        if (!(row[4 * fs] < c.toggle)) continue;
-        double* o = c.orow + p;
-        const double off = row[3 * fs];
-        double v = off;
-        for (int a = 0; a < 3; ++a) { const double ra = row[a * fs]; o[a * pp] = ra; if (a < T::WS) v -= ra * x[a]; }
-        o[3 * pp] = off; o[4 * pp] = (double)k;
-        slot_init(c.ost + p, pp, true, true, v, c.omega, tin, slack_lam_split<M>());
-        ++p;
-      }
-    }
+    const int nact = c.nact;
+    for (int p = G_TID; p < nact; p += G_NTHR) slot_init(c.ost + p, pp, true, true, c.ost[p], c.omega, tin, slack_lam_split<M>());
   }
   // special rows: slacks one unit inside
   G_PAR_FOR(it, N * L::SP) {
@@ -2456,7 +2461,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.toggle = kTO ? d.rp[RP_CLEAR] + 1.0 : c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];   // scp_gusto.jl:76 | scp_trajopt.jl:65
     // TrajOpt: the noise phase forms P~ = P - X'X at the last knot, where P carries w_N: a smaller penalty keeps that difference
     // accurate (the row error after a step is dnu_N / w_N and vanishes with the step, as a proximal multiplier update does)
-    c.mu0_a = prm.mu0_a; c.mu0_b = prm.mu0_b; c.mu0_cap = prm.mu0_cap; c.mu0_smin = prm.mu0_smin;
+    c.mu0_a = prm.mu0_a; c.mu0_b = prm.mu0_b; c.mu0_cap = prm.mu0_cap;
     c.wN = kTO ? 1e-3 * (prm.wn_base + prm.wn_omega * c.omega) : prm.wn_base + prm.wn_omega * c.omega;
     c.dow = kTO ? c.Delta : c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
