@@ -141,3 +141,23 @@ def test_full_scp_on_the_quaternion_model_matches_oracle():
         assert int(S["iterations"][b]) == R.iterations
         assert abs(S["J_true"][b] - R.J_true[-1]) <= 1e-3 * max(1e-6, abs(R.J_true[-1]))
         assert [bool(a[b]) for a in S["accept"][:R.iterations + 1]] == R.accept_solution
+
+
+def test_centred_start_keeps_the_newton_counts_of_the_headline_model_low():
+    """Regression guard for the start point of the convex solve (ipm.cuh slot_init / setup): from the centred start an astrobeeSE3
+    subproblem at the straight-line initialisation takes 4-5 Newton iterations (5-7 from the tuned default start, which
+    GUSTO_IPM_MU0=0 restores) and reaches the same optimum."""
+    import os
+    bp = gb.problems.CONFIGS["astrobeeSE3"](B=6, N=50, seed=3)
+    sp = bp.model.scp_params
+    X0, U0 = bp.init_traj_straightline()
+    hs = hostsim_iterate(bp, X0, U0, sp[1], sp[0], stages=3)
+    os.environ["GUSTO_IPM_MU0"] = "0"
+    try:
+        ref = hostsim_iterate(bp, X0, U0, sp[1], sp[0], stages=3)
+    finally:
+        del os.environ["GUSTO_IPM_MU0"]
+    assert np.all(hs["info"][:, 0] == 0) and np.all(ref["info"][:, 0] == 0)
+    assert hs["info"][:, 1].max() <= 5 and hs["info"][:, 1].mean() < ref["info"][:, 1].mean()
+    assert np.max(np.abs(hs["info"][:, 4] - ref["info"][:, 4])) <= 1e-7 * np.max(np.abs(ref["info"][:, 4]))
+    assert err(hs["Xn"], ref["Xn"]) < 1e-5 and err(hs["Un"], ref["Un"]) < 1e-6
