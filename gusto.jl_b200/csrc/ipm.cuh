@@ -938,9 +938,6 @@ template <int M> GDEV_NOINLINE void assemble(const IpmCtx<M>& c, int phase, doub
           const double re = t - q.p + q.n;
           const double beta = -q.p - q.p * q.rp * q.ilp + q.n + q.n * q.rn * q.iln;
           c.dd[(size_t)i * c.NE + j] = q.p * q.ilp + q.n * q.iln;
-#ifdef GUSTO_HOSTSIM
-          if (getenv("GUSTO_DSCALE")) c.dd[(size_t)i * c.NE + j] *= atof(getenv("GUSTO_DSCALE"));
-#endif
           const double ad = fabs(q.rp) > fabs(q.rn) ? fabs(q.rp) : fabs(q.rn);
           S.rz = ad > S.rz ? ad : S.rz;
           if (!(ad == ad)) S.rz = 1e300;
