@@ -312,21 +312,23 @@ def main():
     if not args.no_e2e:
         nx, nu, N = bp.model.x_dim, bp.model.u_dim, bp.N
         pin = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
-        hb = {"Xh": pin(B, N, nx), "Uh": pin(B, N, nu), "Xc": pin(B, N, nx), "Uc": pin(B, N, nu)}
+        hb = {"Xh": pin(B, N, nx), "Uh": pin(B, N, nu), "Xc": pin(B, N, nx), "Uc": pin(B, N, nu), "X0": pin(B, N, nx), "U0": pin(B, N, nu)}
+        hb["X0"].numpy()[...] = X0; hb["U0"].numpy()[...] = U0      # every solve starts from this pinned copy (uploaded in its first step)
         om, de = pin(B), pin(B)
         oute, infoe = pin(B, host.EVAL_NOUT), pin(B, host.SOLVE_NINFO)
         act8 = torch.empty(B, dtype=torch.uint8).pin_memory()
         st8 = {}
 
         def e2e_reset():
-            hb["Xh"].numpy()[...] = X0; hb["Uh"].numpy()[...] = U0
             st8.update(Delta=np.full(B, sp[0]), omega=np.full(B, sp[1]), iters=np.zeros(B, np.int64), conv=np.zeros(B),
                        active=np.ones(B, bool), k=0)
 
         def e2e_step(record):
             om.numpy()[...] = st8["omega"]; de.numpy()[...] = st8["Delta"]; act8.numpy()[...] = st8["active"]
             # H2D: this step's accepted trajectory, penalties, active flags; kernels; D2H: scalars + the step's result (candidate)
-            eng.iterate_host(hb["Xh"].numpy(), hb["Uh"].numpy(), om.numpy(), de.numpy(), act8.numpy(), oute.numpy(), infoe.numpy(),
+            first = st8["k"] == 0
+            xin, uin = (hb["X0"], hb["U0"]) if first else (hb["Xh"], hb["Uh"])
+            eng.iterate_host(xin.numpy(), uin.numpy(), om.numpy(), de.numpy(), act8.numpy(), oute.numpy(), infoe.numpy(),
                              hb["Xc"].numpy(), hb["Uc"].numpy())
             o = oute.numpy()
             s = host.gusto_update(o, host.solver_status_ok(infoe.numpy()[:, 0]), st8["active"], st8["Delta"], st8["omega"], st8["iters"],
@@ -334,7 +336,9 @@ def main():
             acc = s["accept"]
             if acc.all():                                               # every candidate accepted: swap the pinned buffers
                 hb["Xh"], hb["Xc"] = hb["Xc"], hb["Xh"]; hb["Uh"], hb["Uc"] = hb["Uc"], hb["Uh"]
-            elif acc.any():
+            else:
+                if first:                                               # the accepted trajectory is still the initial one
+                    hb["Xh"].numpy()[...] = hb["X0"].numpy(); hb["Uh"].numpy()[...] = hb["U0"].numpy()
                 np.copyto(hb["Xh"].numpy(), hb["Xc"].numpy(), where=acc[:, None, None])
                 np.copyto(hb["Uh"].numpy(), hb["Uc"].numpy(), where=acc[:, None, None])
             e2e_cnt[0] += int(s["run"].sum())
