@@ -156,6 +156,9 @@ struct IpmParams {
   // centred start (slot_init): mu0 = max(mu0_a omega, mu0_b omega vmax), vmax = the largest violated soft-row value at the start point;
   // mu0 > mu0_cap (a poor start point) or mu0_a <= 0: the tuned default start.  ipm_default_start() fills the defaults.
   double mu0_a, mu0_b, mu0_cap;
+  // ... scaled down with the start point's primal infeasibility rp0 (a nearly converged SCP iteration starts next to its optimum):
+  // mu0 *= min(1, rp0 / mu0_rp), not below mu0_lo omega; only with an unshrunk trust region and every live obstacle row mu0_smin clear
+  double mu0_rp, mu0_lo, mu0_smin;
 };
 #ifndef GUSTO_MU0_A
 #define GUSTO_MU0_A 5e-5
@@ -166,7 +169,19 @@ struct IpmParams {
 #ifndef GUSTO_MU0_CAP
 #define GUSTO_MU0_CAP 1e-3
 #endif
-inline void ipm_default_start(IpmParams& prm) { prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP; }
+#ifndef GUSTO_MU0_RP
+#define GUSTO_MU0_RP 0.1
+#endif
+#ifndef GUSTO_MU0_LO
+#define GUSTO_MU0_LO 1e-9
+#endif
+#ifndef GUSTO_MU0_SMIN
+#define GUSTO_MU0_SMIN 2e-2
+#endif
+inline void ipm_default_start(IpmParams& prm) {
+  prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP;
+  prm.mu0_rp = GUSTO_MU0_RP; prm.mu0_lo = GUSTO_MU0_LO; prm.mu0_smin = GUSTO_MU0_SMIN;
+}
 
 // IPM_ALMOST_OPTIMAL: stalled within 1e3*tol of the tolerance AND far below the SCP's own soft-row threshold eps -- the
 // MOI.ALMOST_LOCALLY_SOLVED the reference accepts next to OPTIMAL (scp_gusto.jl:107); the host records it as such.
@@ -294,7 +309,7 @@ template <int M> struct IpmCtx {
   int NP, NE, PP;         // field strides of the knot-minor scratch arrays (IpmLayout::np_of / ne_of / pp_of)
   double h, hh, omega, Delta, toggle, eps, wN;
   double dow, eow;         // Delta / omega, eps / omega
-  double mu0_a, mu0_b, mu0_cap;   // centred start (IpmParams)
+  double mu0_a, mu0_b, mu0_cap, mu0_rp, mu0_lo, mu0_smin;   // centred start (IpmParams)
   mutable double floor_;   // pending central-path floor of the complementarity pairs (see pair_floor)
   const double *Xp, *Up, *Ac, *g, *rows, *x_init, *goal_lo, *goal_hi;   // Ac, g, rows: the linearize kernel's blocks, knot-minor, read in place
   double bv[NU];          // B has one entry per column: B[b_row(a)][a] = bv[a]
@@ -2300,7 +2315,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
   // bit mask, then the live rows are copied; their start values go through the record's first field to the flat pass below that
   // initialises the records once the start point has been measured.  (One loop with the test in front of each row's loads was a
   // chain of n_obs dependent round trips per thread: 2 % of the kernel's stall samples, three times over.)
-  double vloc = 0.0;
+  double vloc = 0.0, sloc = 1e300;
   if (T::WS > 0) {
     G_PAR_FOR(k, N) {
       int p = sh_seg<M>(c)[k];
@@ -2318,6 +2333,7 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
         o[3 * pp] = off; o[4 * pp] = (double)k;
         c.ost[p] = v;
         vloc = v > vloc ? v : vloc;
+        if (-v < sloc) sloc = -v;
         ++p;
       }
     }
@@ -2338,6 +2354,26 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     }
     const double vmax = block_max(vloc, c.red);
     double mu0 = c.mu0_a * c.omega;
+    // A nearly converged SCP iteration starts next to its optimum: there the solve can start on the central path at (almost) the
+    // final mu and needs ONE Newton step.  The start point's primal infeasibility rp0 (0.1 for a straight line, 3e-4 / 1e-7 in the
+    // second / third iteration of the headline problems) measures that, provided nothing else will make the iterate move: the trust
+    // region has not been shrunk by a rejection and no live obstacle row is within mu0_smin of its hinge (astrobeeSE3 hard tier, CPU
+    // build: instances touching an obstacle stall for 20-34 iterations from such a start; with the two gates its launch maxima are
+    // unchanged).  astrobeeSE3: Newton iterations 4 / 3.2 / 3 -> 4 / 2.6 / 2 over the three SCP iterations of a solve.
+    const double smin = -block_max(-sloc, c.red);
+    if (c.mu0_rp > 0.0 && c.Delta >= c.d->sp[SP_DELTA0] && smin >= c.mu0_smin) {
+      double rpl = 0.0;
+      G_PAR_FOR(j, N + 1) {
+        double v[NX];
+        aeq_row<M>(c, sh_z<M>(c), j, v);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { const double a2 = fabs(v[i] + c.gsum[(size_t)i * c.NE + j]); rpl = a2 > rpl ? a2 : rpl; }
+      }
+      const double rp0 = block_max(rpl, c.red);
+      const double f = rp0 * g_rcp(c.mu0_rp);
+      if (f < 1.0) mu0 *= f;
+      if (mu0 < c.mu0_lo * c.omega) mu0 = c.mu0_lo * c.omega;
+    }
     if (c.mu0_b * c.omega * vmax > mu0) mu0 = c.mu0_b * c.omega * vmax;
     if (mu0 <= c.mu0_cap) tin_ = -mu0;
   } else {
@@ -2458,7 +2494,7 @@ GDEV void ipm_solve_instance(const BatchDesc& d, const BatchPtrs& p, const IpmPa
     c.toggle = kTO ? d.rp[RP_CLEAR] + 1.0 : c.Delta / 8.0 + d.rp[RP_CLEAR]; c.eps = d.sp[SP_EPS];   // scp_gusto.jl:76 | scp_trajopt.jl:65
     // TrajOpt: the noise phase forms P~ = P - X'X at the last knot, where P carries w_N: a smaller penalty keeps that difference
     // accurate (the row error after a step is dnu_N / w_N and vanishes with the step, as a proximal multiplier update does)
-    c.mu0_a = prm.mu0_a; c.mu0_b = prm.mu0_b; c.mu0_cap = prm.mu0_cap;
+    c.mu0_a = prm.mu0_a; c.mu0_b = prm.mu0_b; c.mu0_cap = prm.mu0_cap; c.mu0_rp = prm.mu0_rp; c.mu0_lo = prm.mu0_lo; c.mu0_smin = prm.mu0_smin;
     c.wN = kTO ? 1e-3 * (prm.wn_base + prm.wn_omega * c.omega) : prm.wn_base + prm.wn_omega * c.omega;
     c.dow = kTO ? c.Delta : c.Delta / c.omega; c.eow = c.eps / c.omega;
     c.pmask = 0; c.bmask = 0;
