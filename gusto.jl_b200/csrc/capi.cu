@@ -416,10 +416,10 @@ int32_t gusto_create(const gusto_config* cfg, const int32_t* obs_kind, const dou
   // configuration are accepted and ignored since round 2 (the Riccati solve has no regularisation and no refinement)
   ctx->prm.wn_base = 1e8; ctx->prm.wn_omega = 1e4;
   ipm_default_start(ctx->prm);
-  if (const char* ev = getenv("GUSTO_IPM_MU0")) {      // developer override: "A[,B[,cap[,rp]]]" (rp = 0: no scaling with the start point's infeasibility), "0" = the tuned default start everywhere
-    double a = 0, b2 = ctx->prm.mu0_b, cp = ctx->prm.mu0_cap, rp = ctx->prm.mu0_rp;
-    const int n = sscanf(ev, "%lf,%lf,%lf,%lf", &a, &b2, &cp, &rp);
-    if (n >= 1) { ctx->prm.mu0_a = a; ctx->prm.mu0_b = b2; ctx->prm.mu0_cap = cp; ctx->prm.mu0_rp = rp; }
+  if (const char* ev = getenv("GUSTO_IPM_MU0")) {      // developer override: "A[,B[,cap[,rp[,lo[,smin]]]]]" (rp = 0: no scaling with the start point's infeasibility), "0" = the tuned default start everywhere
+    double a = 0, b2 = ctx->prm.mu0_b, cp = ctx->prm.mu0_cap, rp = ctx->prm.mu0_rp, lo = ctx->prm.mu0_lo, sm = ctx->prm.mu0_smin;
+    const int n = sscanf(ev, "%lf,%lf,%lf,%lf,%lf,%lf", &a, &b2, &cp, &rp, &lo, &sm);
+    if (n >= 1) { ctx->prm.mu0_a = a; ctx->prm.mu0_b = b2; ctx->prm.mu0_cap = cp; ctx->prm.mu0_rp = rp; ctx->prm.mu0_lo = lo; ctx->prm.mu0_smin = sm; }
   }
 
   const size_t B = cfg->B, N = cfg->N, no = h.n_obs > 0 ? h.n_obs : 1;

@@ -176,7 +176,7 @@ struct IpmParams {
 #define GUSTO_MU0_LO 1e-9
 #endif
 #ifndef GUSTO_MU0_SMIN
-#define GUSTO_MU0_SMIN 2e-2
+#define GUSTO_MU0_SMIN 5e-2
 #endif
 inline void ipm_default_start(IpmParams& prm) {
   prm.mu0_a = GUSTO_MU0_A; prm.mu0_b = GUSTO_MU0_B; prm.mu0_cap = GUSTO_MU0_CAP;
@@ -2357,9 +2357,11 @@ template <int M> GDEV_NOINLINE void setup(IpmCtx<M>& c) {
     // A nearly converged SCP iteration starts next to its optimum: there the solve can start on the central path at (almost) the
     // final mu and needs ONE Newton step.  The start point's primal infeasibility rp0 (0.1 for a straight line, 3e-4 / 1e-7 in the
     // second / third iteration of the headline problems) measures that, provided nothing else will make the iterate move: the trust
-    // region has not been shrunk by a rejection and no live obstacle row is within mu0_smin of its hinge (astrobeeSE3 hard tier, CPU
-    // build: instances touching an obstacle stall for 20-34 iterations from such a start; with the two gates its launch maxima are
-    // unchanged).  astrobeeSE3: Newton iterations 4 / 3.2 / 3 -> 4 / 2.6 / 2 over the three SCP iterations of a solve.
+    // region has not been shrunk by a rejection and no live obstacle row is within mu0_smin (5 cm) of its hinge.  astrobeeSE3 hard
+    // tier: instances about to touch an obstacle stall for 20-38 iterations from such a start; sum over the 17 launches of a B = 1024
+    // solve of the slowest instance's Newton count (GPU): 241 without the scaling, 267 / 243 / 241 with the gate at 2 / 5 / 7 cm, while
+    // the headline batch (margins 5-20 cm) keeps its full gain up to 5 cm (bench 388 k -> 453 k instance-iterations/s; 415 k at 7 cm).
+    // astrobeeSE3: Newton iterations 4 / 3.2 / 3 -> 4 / 2.6 / 2 over the three SCP iterations of a solve.
     const double smin = -block_max(-sloc, c.red);
     if (c.mu0_rp > 0.0 && c.Delta >= c.d->sp[SP_DELTA0] && smin >= c.mu0_smin) {
       double rpl = 0.0;

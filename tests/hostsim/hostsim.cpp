@@ -99,10 +99,10 @@ extern "C" int hostsim_iterate(const gusto_config* cfg, const int32_t* obs_kind,
   prm.tol = cfg->ipm_tol > 0 ? cfg->ipm_tol : 1e-8;
   prm.wn_base = 1e8; prm.wn_omega = 1e4;
   ipm_default_start(prm);
-  if (const char* ev = getenv("GUSTO_IPM_MU0")) {      // developer override: "A[,B[,cap[,rp]]]" (rp = 0: no scaling with the start point's infeasibility), "0" = the tuned default start everywhere
-    double a = 0, b2 = prm.mu0_b, cp = prm.mu0_cap, rp = prm.mu0_rp;
-    const int n = sscanf(ev, "%lf,%lf,%lf,%lf", &a, &b2, &cp, &rp);
-    if (n >= 1) { prm.mu0_a = a; prm.mu0_b = b2; prm.mu0_cap = cp; prm.mu0_rp = rp; }
+  if (const char* ev = getenv("GUSTO_IPM_MU0")) {      // developer override: "A[,B[,cap[,rp[,lo[,smin]]]]]" (rp = 0: no scaling with the start point's infeasibility), "0" = the tuned default start everywhere
+    double a = 0, b2 = prm.mu0_b, cp = prm.mu0_cap, rp = prm.mu0_rp, lo = prm.mu0_lo, sm = prm.mu0_smin;
+    const int n = sscanf(ev, "%lf,%lf,%lf,%lf,%lf,%lf", &a, &b2, &cp, &rp, &lo, &sm);
+    if (n >= 1) { prm.mu0_a = a; prm.mu0_b = b2; prm.mu0_cap = cp; prm.mu0_rp = rp; prm.mu0_lo = lo; prm.mu0_smin = sm; }
   }
 #define HS_CASE(MM)                                                                                                         \
   case MM:                                                                                                                  \
