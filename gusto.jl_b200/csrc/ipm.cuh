@@ -1362,7 +1362,6 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
       double* const tv = tile + L::F_NVEC;
       double* const ptil = tv + L::KP;
       double* const wv = ptil + L::KP;
-      int* const ipiv = reinterpret_cast<int*>(wv + L::KP);
       // Fi_j and D_j to shared memory, then W = Fi D Fi'
       G_PAR_FOR(it, NX * NX + NX) {
         if (it < NX * NX) { const int i = it / NX, m = it - i * NX; Vt[i * LDN + m] = L::dsame(i, m) ? c.fi[(size_t)(i * NX + m) * np + j] : 0.0; }
@@ -1393,30 +1392,38 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
         }
       }
       G_SYNC();
-      // N = (I + W P)^-1 by Gauss-Jordan with row pivoting, one thread per row.  (The textbook forms  N = I - V T^-1 V'P,
-      // P~ = P - P V T^-1 V'P  cancel catastrophically once a defect row is relaxed -- D = p / lam_p ~ 1e6 -- and P~ ~ W^-1 << P.)
+      // N = (I + W P)^-1 by Gauss-Jordan with row pivoting.  (The textbook forms  N = I - V T^-1 V'P,  P~ = P - P V T^-1 V'P
+      // cancel catastrophically once a defect row is relaxed -- D = p / lam_p ~ 1e6 -- and P~ ~ W^-1 << P.)  No row is moved:
+      // every thread repeats the pivot search of a column among the rows not used yet (broadcast reads, the same result in every
+      // thread, kept as a nibble list in a register), and the whole group updates the live (row, column) pairs of the step --
+      // columns left of the pivot column are dead and the pivot column is never read again -- so a column costs ONE barrier.
+      static_assert(NX <= 16, "pivot rows are kept as nibbles of one 64-bit register");
+      unsigned long long perm = 0;
+      unsigned used = 0;
       for (int cc = 0; cc < NX; ++cc) {
-        if (G_TID == 0) {
-          int pr = cc;
-          double best = fabs(Aug[cc * LD2 + cc]);
-          for (int r = cc + 1; r < NX; ++r) { const double v = fabs(Aug[r * LD2 + cc]); if (v > best) { best = v; pr = r; } }
-          if (!(best > 1e-300)) bad = 1.0;
-          ipiv[0] = pr;
+        int pr = -1;
+        double best = -1.0;
+#pragma unroll
+        for (int r = 0; r < NX; ++r) {
+          const double v = fabs(Aug[r * LD2 + cc]);
+          if (!((used >> r) & 1u) && v > best) { best = v; pr = r; }
         }
-        G_SYNC();
-        const int pr = ipiv[0];
-        if (pr != cc) G_PAR_FOR(q, LD2) { const double t2 = Aug[cc * LD2 + q]; Aug[cc * LD2 + q] = Aug[pr * LD2 + q]; Aug[pr * LD2 + q] = t2; }
-        G_SYNC();
-        G_PAR_FOR(r, NX) {
-          if (r == cc) continue;
-          const double f = Aug[r * LD2 + cc] * g_rcp(Aug[cc * LD2 + cc]);
-          for (int q = 0; q < LD2; ++q) Aug[r * LD2 + q] -= f * Aug[cc * LD2 + q];
+        if (!(best > 1e-300)) bad = 1.0;
+        used |= 1u << pr;
+        perm |= (unsigned long long)pr << (4 * cc);
+        const double rp = g_rcp(Aug[pr * LD2 + cc]);
+        const int live = LD2 - 1 - cc;                          // columns cc + 1 .. 2 NX - 1
+        G_PAR_FOR(it, (NX - 1) * live) {
+          const int r0 = it / live, q = cc + 1 + (it - r0 * live);
+          const int r = r0 + (r0 >= pr ? 1 : 0);
+          Aug[r * LD2 + q] -= Aug[r * LD2 + cc] * rp * Aug[pr * LD2 + q];
         }
         G_SYNC();
       }
       G_PAR_FOR(it, NX * NX) {
         const int i = it / NX, q = it - i * NX;
-        const double a = Aug[i * LD2 + NX + q] * g_rcp(Aug[i * LD2 + i]);
+        const int pr = (int)((perm >> (4 * i)) & 15u);
+        const double a = Aug[pr * LD2 + NX + q] * g_rcp(Aug[pr * LD2 + i]);
         Nt[i * LDN + q] = a;
         c.nm[(size_t)it * np + j] = a;
       }
