@@ -277,12 +277,22 @@ template <int M> struct IpmLayout {
   static constexpr int F_SB = F_HU + NUP * LDU;             // two of them
   static constexpr int F_VEC = F_SB + 2 * SBW;              // q[2][KP] | ru[2][KU] | pit[KP]
   static constexpr int V_Q = 0, V_RU = 2 * KP, V_PIT = V_RU + 2 * KU, VECW = V_PIT + KP;
-  // TrajOpt noise phase: F_j^-1 | W = F^-1 D F^-T, then P~ | [I + W P | I] (two tiles) | N = (I + W P)^-1 | Acl of the knot |
-  // vectors D_j, p~, w, pivot index
+  // TrajOpt noise phase.  Its tiles live in regions of the sweep that are dead while it runs (it is the first thing of a knot
+  // step), so that the group's slice of shared memory stays small enough for 7 groups per SM like GuSTO's:
+  //   F_j^-1                   in S' | Lam      (written in phases A / B)
+  //   W, then P~               in the first rows of the OTHER staged dynamics record (re-staged for knot k - 1 right after)
+  //   [I + W P | I]            in Z1             (written in phase A)
+  //   N = (I + W P)^-1         in the tile P_k is built in (phase C); the chain tile G_k = N_{k+1} Acl_k at the end of the step
+  //                            re-reads N from global scratch (c.nm)
+  //   Acl_k (phase D)          in the tile of P_{k+1} / M' (dead after phase C2)
+  // Nothing else relies on those regions: only rows / columns that a later phase rewrites completely, or whose products are
+  // masked or meet exact zeros of the other operand, are touched (L^-1, whose rows beyond n_u must STAY zero, is not).  Own
+  // storage: the vectors D_j, p~, w.
   static constexpr int LDN = NX | 1;                        // odd row stride: column walks are conflict-free
   static constexpr int NTILE = NX * LDN;
-  static constexpr int F_NV = F_VEC + VECW, F_NZ = F_NV + NTILE, F_NT = F_NZ + NTILE, F_NY = F_NT + NTILE, F_NN = F_NY + NTILE,
-                       F_NA = F_NN + NTILE, F_NVEC = F_NA + NTILE;
+  static constexpr int F_NV = F_SM, F_NT = F_Z1, F_NVEC = F_VEC + VECW;
+  static_assert(!kTO || (NTILE <= (NXP + NUP) * LDU && NTILE <= (NX + NU) * LDT && 2 * NX * NX <= RXS * LDT && NTILE <= TILE),
+                "noise-phase tiles do not fit the regions they alias");
   static constexpr int FAC_DOUBLES = kTO ? F_NVEC + 3 * KP + 2 : F_VEC + VECW;
   static constexpr int GJ_ROWS = (64 / NX) * NX;            // setup_dynamics: (knot, row) pairs of one Gauss-Jordan batch
   static constexpr int GJ_DOUBLES = GJ_ROWS * 2 * NX;
@@ -1356,9 +1366,9 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
       const int j = k + 1;
       const size_t np = c.NP, ne = c.NE;
       double* const Vt = tile + L::F_NV;
-      double* const Zt = tile + L::F_NZ;
-      double* const Aug = tile + L::F_NT;                       // [NX][2 NX], spans F_NT and F_NY
-      double* const Nt = tile + L::F_NN;
+      double* const Zt = tile + L::F_XS + nxt * L::XSR * LDT;
+      double* const Aug = tile + L::F_NT;                       // [NX][2 NX]
+      double* const Nt = Wn;
       double* const tv = tile + L::F_NVEC;
       double* const ptil = tv + L::KP;
       double* const wv = ptil + L::KP;
@@ -1560,7 +1570,7 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
     if (w1) {
       g_tile_grid<KSU, MT_X, MT_X, false, false>(BL, LDU, 0, Yt, LDU, 0, [&](int r, int q, double v) {
         if (r < NX && q < NX) {
-          if (kTO && k < N - 1) tile[L::F_NA + r * L::LDN + q] = XS[q * LDT + r] - v;      // multiplied by N_{k+1} below
+          if (kTO && k < N - 1) Mt[r * L::LDN + q] = XS[q * LDT + r] - v;                  // multiplied by N_{k+1} below (M' is dead)
           else c.acl[(size_t)k * L::GT + r * LDT + q] = XS[q * LDT + r] - v;
         }
       });
@@ -1576,12 +1586,14 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
     }
     G_SYNC();
     if (kTO && k < N - 1) {                                       // chain tile G_k = N_{k+1} Acl_k
-      const double* Nt = tile + L::F_NN;
-      const double* At = tile + L::F_NA;
+      const double* Ng = c.nm + (k + 1);                           // N_{k+1}, written in this step's noise phase
+      const double* At = Mt;
+      const size_t np = c.NP;
       G_PAR_FOR(it, NX * NX) {
         const int r = it / NX, q = it - r * NX;
         double a = 0.0;
-        for (int m = 0; m < NX; ++m) a += Nt[r * L::LDN + m] * At[m * L::LDN + q];
+#pragma unroll
+        for (int m = 0; m < NX; ++m) a += Ng[(size_t)(r * NX + m) * np] * At[m * L::LDN + q];
         c.acl[(size_t)k * L::GT + r * LDT + q] = a;
       }
       G_SYNC();
