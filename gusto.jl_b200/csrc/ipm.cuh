@@ -1347,6 +1347,20 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
 #else
 #define GUSTO_PROF_TICK(slot) ((void)0)
 #endif
+  // TrajOpt: F_j^-1 (its non-zero blocks) and D_j of the NEXT knot step's noise phase, issued once their shared-memory regions
+  // are dead at the end of a step: the round trip to global scratch hides behind the chain-tile product and the barriers between
+  auto noise_prefetch = [&](int j) {
+    double* const Vt = tile + L::F_NV;
+    double* const tv = tile + L::F_NVEC;
+    const size_t np = c.NP, ne = c.NE;
+    G_PAR_FOR(it, NX * NX + NX) {
+      if (it < NX * NX) {
+        const int i = it / NX, m = it - i * NX;
+        if (L::dsame(i, m)) g_cp_async8(Vt + i * L::LDN + m, c.fi + (size_t)(i * NX + m) * np + j);
+        else Vt[i * L::LDN + m] = 0.0;
+      } else g_cp_async8(tv + (it - NX * NX), c.dd + (size_t)(it - NX * NX) * ne + j);
+    }
+  };
   for (int k = N - 1; k >= 0; --k) {
     const int cur = k & 1, nxt = cur ^ 1;
     const double* XS = tile + L::F_XS + cur * L::XSR * LDT;        // rows: Ah' (NX) | Bh' (NU) | ch | 0.. | Gam' at row RXS
@@ -1372,11 +1386,8 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
       double* const tv = tile + L::F_NVEC;
       double* const ptil = tv + L::KP;
       double* const wv = ptil + L::KP;
-      // Fi_j and D_j to shared memory, then W = Fi D Fi'
-      G_PAR_FOR(it, NX * NX + NX) {
-        if (it < NX * NX) { const int i = it / NX, m = it - i * NX; Vt[i * LDN + m] = L::dsame(i, m) ? c.fi[(size_t)(i * NX + m) * np + j] : 0.0; }
-        else tv[it - NX * NX] = c.dd[(size_t)(it - NX * NX) * ne + j];
-      }
+      // Fi_j and D_j are on their way to shared memory since the end of the previous knot step (noise_prefetch); W = Fi D Fi'
+      g_cp_async_wait();
       G_SYNC();
       G_PAR_FOR(it, NX * NX) {
         const int i = it / NX, m = it - i * NX;
@@ -1422,11 +1433,14 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
         used |= 1u << pr;
         perm |= (unsigned long long)pr << (4 * cc);
         const double rp = g_rcp(Aug[pr * LD2 + cc]);
-        const int live = LD2 - 1 - cc;                          // columns cc + 1 .. 2 NX - 1
-        G_PAR_FOR(it, (NX - 1) * live) {
-          const int r0 = it / live, q = cc + 1 + (it - r0 * live);
-          const int r = r0 + (r0 >= pr ? 1 : 0);
-          Aug[r * LD2 + q] -= Aug[r * LD2 + cc] * rp * Aug[pr * LD2 + q];
+        constexpr int RG = GUSTO_IPM_GROUP / LD2 > 0 ? GUSTO_IPM_GROUP / LD2 : 1;   // a thread owns one column and every RG-th row
+        G_PAR_FOR(t, RG * LD2) {
+          const int g = t / LD2, q = t - g * LD2;
+          if (q > cc) {                                         // columns cc + 1 .. 2 NX - 1 are live
+            const double pq = Aug[pr * LD2 + q];
+            for (int r = g; r < NX; r += RG)
+              if (r != pr) Aug[r * LD2 + q] -= Aug[r * LD2 + cc] * rp * pq;
+          }
         }
         G_SYNC();
       }
@@ -1585,6 +1599,7 @@ template <int M> GDEV_NOINLINE bool riccati_factor(const IpmCtx<M>& c) {
       }
     }
     G_SYNC();
+    if (kTO && k >= 1) noise_prefetch(k);
     if (kTO && k < N - 1) {                                       // chain tile G_k = N_{k+1} Acl_k
       const double* Ng = c.nm + (k + 1);                           // N_{k+1}, written in this step's noise phase
       const double* At = Mt;
